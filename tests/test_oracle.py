@@ -1,0 +1,181 @@
+"""Pins the CPU oracle (oracle/) with everything the reference offers for this path.
+
+The reference has no tests or golden vectors, so the pins are: the
+element-wise definition from notebooks/benchmarks.ipynb (tconv4), adjointness, the tconv3
+shift-and-stack identity, agreement between the NumPy and plain-C restatements, the algebraic
+Gram/recurrence forms the CUDA kernels use, MU monotonicity, driver/convergence semantics
+(src/algs/alternating.jl, src/model.jl:91-107) and the committed golden fixtures.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as co
+from oracle import cnmf_oracle as po
+from oracle import restructured as rs
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _rand(N, T, K, L, seed=0):
+    rng = np.random.default_rng(seed)
+    return rng.random((K, N, L)), rng.random((K, T)), rng.random((N, T))
+
+
+@pytest.mark.parametrize("dims", [(13, 57, 3, 5), (4, 6, 2, 6), (5, 3, 2, 7), (1, 1, 1, 1)])
+def test_definitions_match_naive(dims):
+    N, T, K, L = dims
+    W, H, X = _rand(*dims)
+    assert np.allclose(po.tensor_conv(W, H), po.naive_conv(W, H), atol=1e-13)
+    assert np.allclose(po.tensor_transconv(W, X), po.naive_transconv(W, X), atol=1e-13)
+    assert np.allclose(po.corr_w(H, X, L), po.naive_corr_w(H, X, L), atol=1e-13)
+
+
+def test_c_twin_matches_numpy():
+    W, H, X = _rand(31, 203, 4, 9, seed=3)
+    assert np.allclose(co.tensor_conv(W, H), po.tensor_conv(W, H), atol=1e-12)
+    assert np.allclose(co.tensor_transconv(W, X), po.tensor_transconv(W, X), atol=1e-12)
+    assert np.allclose(co.corr_w(H, X, 9), po.corr_w(H, X, 9), atol=1e-11)
+
+
+def test_adjoint_identities():
+    W, H, X = _rand(17, 91, 3, 8, seed=1)
+    a = np.vdot(po.tensor_conv(W, H), X)
+    b = np.vdot(H, po.tensor_transconv(W, X))
+    c = np.vdot(W, po.corr_w(H, X, 8))
+    assert abs(a - b) < 1e-10 * abs(a) and abs(a - c) < 1e-10 * abs(a)
+
+
+def test_shift_and_stack_identity():
+    # notebooks/benchmarks.ipynb tconv3: conv = W_unf * shift_and_stack(H)
+    W, H, _ = _rand(11, 64, 3, 6, seed=2)
+    Wu = rs.unfold_W(W)  # KL x N
+    assert np.allclose(Wu.T @ po.shift_and_stack(H, 6), po.tensor_conv(W, H), atol=1e-13)
+
+
+def test_toy_data_exact_integers():
+    # datasets/toy.jl: small-integer W, sparse H -> conv is exact in floating point
+    X, W, H = po.toy_data()
+    assert X.shape == (7, 250)
+    assert np.array_equal(X, po.naive_conv(W, H))
+    assert np.array_equal(co.tensor_conv(W, H), X)
+    assert np.array_equal(X * 2, np.round(X * 2))
+
+
+@pytest.mark.parametrize("dims", [(11, 64, 3, 6), (7, 9, 2, 5), (6, 5, 2, 5)])
+def test_gram_forms_equal_literal(dims):
+    N, T, K, L = dims
+    W, H, X = _rand(*dims, seed=5)
+    est = po.tensor_conv(W, H)
+    assert np.allclose(rs.denomW_gram(W, H), po.corr_w(H, est, L), rtol=1e-12, atol=1e-12)
+    assert np.allclose(rs.denomH_gram(W, H), po.tensor_transconv(W, est), rtol=1e-12, atol=1e-12)
+    assert np.allclose(rs.build_G(H, L), po.shift_and_stack(H, L) @ po.shift_and_stack(H, L).T,
+                       atol=1e-12)
+    assert abs(rs.loss_expansion(X, W, H) - po.compute_loss(X, W, H)) < 1e-12
+
+
+def test_mu_gram_iteration_equals_literal():
+    N, T, K, L = 23, 120, 3, 7
+    W, H, X = _rand(N, T, K, L, seed=7)
+    reg = dict(l1W=0.1, l2W=0.5, l1H=0.1, l2H=0.2)
+    Wl, Hl = W.copy(), H.copy()
+    rule = po.MultUpdate(X, Wl, Hl)
+    Wg, Hg = W.copy(), H.copy()
+    for _ in range(5):
+        rule.update_motifs(X, Wl, Hl, **reg)
+        loss_l = rule.update_feature_maps(X, Wl, Hl, **reg)
+        Wg, Hg, loss_g = rs.mu_iteration_gram(X, Wg, Hg, **reg)
+        assert abs(loss_l - loss_g) < 1e-12
+    assert np.allclose(Wl, Wg, rtol=1e-11) and np.allclose(Hl, Hg, rtol=1e-11)
+
+
+def test_mu_c_twin_equals_numpy():
+    N, T, K, L = 19, 150, 4, 6
+    W, H, X = _rand(N, T, K, L, seed=8)
+    reg = dict(l1W=0.05, l2W=0.1, l1H=0.02, l2H=0.3)
+    rp = po.fit(po.MultUpdate(X, W, H), X, W, H, 12, check_convergence=False, **reg)
+    rc = co.fit(co.MultUpdate, X, W, H, 12, check_convergence=False, **reg)
+    assert np.allclose(rp.loss_hist, rc.loss_hist, rtol=1e-12)
+    assert np.allclose(rp.W, rc.W, rtol=1e-10) and np.allclose(rp.H, rc.H, rtol=1e-10)
+
+
+def test_hals_c_twin_and_gram_equal_literal():
+    N, T, K, L = 11, 64, 3, 6
+    W, H, X = _rand(N, T, K, L, seed=9)
+    reg = dict(l1W=0.1, l2W=0.5, l1H=0.1, l2H=0.2)
+    rp = po.fit(po.HALSUpdate(X, W, H), X, W, H, 6, check_convergence=False, **reg)
+    rc = co.fit(co.HALSUpdate, X, W, H, 6, check_convergence=False, **reg)
+    assert np.allclose(rp.loss_hist, rc.loss_hist, rtol=1e-12)
+    assert np.allclose(rp.W, rc.W, atol=1e-12) and np.allclose(rp.H, rc.H, atol=1e-12)
+    Wg, Hg = W.copy(), H.copy()
+    for i in range(6):
+        Wg, Hg, loss = rs.hals_iteration_gram(X, Wg, Hg, **reg)
+        assert abs(loss - rp.loss_hist[i + 1]) < 1e-12
+    assert np.allclose(Wg, rp.W, atol=1e-12) and np.allclose(Hg, rp.H, atol=1e-12)
+
+
+def test_hals_short_T_tail():
+    # T < 2L: every column of H is in the truncated tail (hals.jl:137 w = min(T-t+1, L))
+    N, T, K, L = 5, 7, 2, 5
+    W, H, X = _rand(N, T, K, L, seed=10)
+    rp = po.fit(po.HALSUpdate(X, W, H), X, W, H, 3, check_convergence=False)
+    Wg, Hg = W.copy(), H.copy()
+    for i in range(3):
+        Wg, Hg, loss = rs.hals_iteration_gram(X, Wg, Hg)
+        assert abs(loss - rp.loss_hist[i + 1]) < 1e-12
+
+
+def test_mu_monotone_on_synthetic():
+    data, _, _ = po.synthetic_sequences(K=3, N=60, L=8, T=300, rng=np.random.default_rng(1234))
+    r = po.fit_cnmf(data, L=8, K=3, alg="mult", max_itr=40, seed=0, check_convergence=False)
+    lh = np.asarray(r.loss_hist)
+    assert len(lh) == 41 and np.all(np.diff(lh) <= 1e-12)
+
+
+def test_converged_semantics():
+    # src/model.jl:91-107
+    assert not po.converged([1.0, 1.0, 1.0], 3, 1e-4)  # length <= patience
+    assert po.converged([1.0, 1.0, 1.0, 1.0], 3, 1e-4)
+    assert not po.converged([1.0, 0.9, 0.9, 0.9], 3, 1e-4)
+    assert po.converged([5.0, 0.9, 0.90001, 0.90002, 0.90001], 3, 1e-4)
+
+
+def test_driver_history_and_early_stop():
+    data, _, _ = po.synthetic_sequences(K=2, N=20, L=4, T=80, rng=np.random.default_rng(1))
+    msgs = []
+    r = po.fit_cnmf(data, L=4, K=2, alg="mult", max_itr=500, seed=0, tol=1e-3, printer=msgs.append)
+    assert len(r.loss_hist) == len(r.time_hist) < 501 and r.time_hist[0] == 0.0
+    assert msgs == ["Converged early."]
+    r2 = po.fit_cnmf(data, L=4, K=2, alg="mult", max_itr=0, seed=0)
+    assert len(r2.loss_hist) == 1
+    # eval_mode skips the motif update (alternating.jl:51-53)
+    W0 = np.random.default_rng(3).random((2, 20, 4))
+    r3 = po.fit_cnmf(data, L=4, K=2, max_itr=3, W_init=W0, eval_mode=True, check_convergence=False)
+    assert np.array_equal(r3.W, W0)
+
+
+def test_init_rand_alpha_is_least_squares_scale():
+    data, _, _ = po.synthetic_sequences(K=2, N=15, L=4, T=60, rng=np.random.default_rng(2))
+    W, H = po.init_rand(data, 4, 2, np.random.default_rng(0))
+    est = po.tensor_conv(W, H)
+    # after the rescale, <data, est> == ||est||^2  (alpha == 1)
+    assert abs(np.vdot(data, est) / np.vdot(est, est) - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["mu_small", "mu_reg_small", "hals_small", "hals_reg_small", "prims"])
+def test_golden_fixtures(name):
+    path = os.path.join(GOLD, name + ".npz")
+    g = np.load(path)
+    if name == "prims":
+        assert np.allclose(po.tensor_conv(g["W"], g["H"]), g["conv"], rtol=1e-13, atol=1e-13)
+        assert np.allclose(po.tensor_transconv(g["W"], g["X"]), g["transconv"], rtol=1e-13, atol=1e-13)
+        assert np.allclose(po.corr_w(g["H"], g["X"], g["W"].shape[2]), g["corr"], rtol=1e-13, atol=1e-12)
+        return
+    reg = {k: float(g[k]) for k in ("l1W", "l2W", "l1H", "l2H")}
+    alg = str(g["alg"])
+    rule = {"mult": co.MultUpdate, "hals": co.HALSUpdate}[alg]
+    r = co.fit(rule, g["X"], g["W0"], g["H0"], int(g["max_itr"]), check_convergence=False, **reg)
+    assert np.allclose(r.loss_hist, g["loss_hist"], rtol=1e-11)
+    assert np.allclose(r.W, g["W"], rtol=1e-9, atol=1e-12)
+    assert np.allclose(r.H, g["H"], rtol=1e-9, atol=1e-12)
