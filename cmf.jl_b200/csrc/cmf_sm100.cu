@@ -1,0 +1,768 @@
+// libcmf_sm100: C ABI + host orchestration of the B200 CNMF fit path (see include/cmf_sm100.h).
+//
+// One handle = one time-shard on one GPU.  All device memory is owned here; host arrays are
+// copied during the call.  Errors never escape as C++ exceptions.
+#include "../../include/cmf_sm100.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "kernels_simt.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+struct CmfError : std::runtime_error {
+    int code;
+    CmfError(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            throw CmfError(CMF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));     \
+    } while (0)
+
+#define REQUIRE(cond, msg)                                                                         \
+    do {                                                                                           \
+        if (!(cond)) throw CmfError(CMF_ERR_ARG, std::string(msg));                                \
+    } while (0)
+
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count) {
+        free();
+        n = count;
+        if (count) {
+            CK(cudaMalloc(&p, count * sizeof(T)));
+            CK(cudaMemset(p, 0, count * sizeof(T)));
+        }
+    }
+    void free() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { free(); }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------
+struct cmf_ctx {
+    int64_t N = 0, T = 0, t0 = 0, t1 = 0, Tl = 0, K = 0, L = 0;
+    int dtype = 0, alg = 0, device = 0, engine = 0;
+    bool is_first = true, is_last = true;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int64_t launches = 0;
+    double data_norm = 0.0;
+    bool have_data = false, have_factors = false;
+    virtual ~cmf_ctx() {}
+    virtual void set_data(const void *X, int64_t first_col) = 0;
+    virtual void synth_data(uint64_t seed, int64_t Kt, int64_t Lt, double p_h, double noise) = 0;
+    virtual double data_sumsq() = 0;
+    virtual void set_factors(const void *W, const void *H, int64_t first_col) = 0;
+    virtual void init_rand(uint64_t seed) = 0;
+    virtual void init_scale_partials(double out[2]) = 0;
+    virtual void scale_factors(double s) = 0;
+    virtual void get_factors(void *W, void *H) = 0;
+    virtual void w_partials() = 0;
+    virtual void w_apply(double l1W, double l2W) = 0;
+    virtual void h_update(double l1H, double l2H) = 0;
+    virtual double loss_partial() = 0;
+    virtual void hals_update_motifs(double l1W, double l2W) = 0;
+    virtual double hals_update_feature_maps(double l1H, double l2H) = 0;
+    virtual void exchange_buffer(int which, void **p, int64_t *count, int *dt) = 0;
+    virtual void halo_buffers(void **sl, void **sr, void **rl, void **rr, int64_t *count) = 0;
+    virtual void prim_conv(void *out_host) = 0;
+    virtual void prim_transconv(const void *X_host, void *out_host) = 0;
+    virtual void prim_corr(const void *X_host, void *out_host) = 0;
+};
+
+namespace {
+
+using namespace cmf;
+
+template <typename S>
+struct Ctx : cmf_ctx {
+    DevBuf<S> X, Hbuf, Wi, Wtmp, numW, denW, GS, Cf, numH, denH, R, tailC;
+    DevBuf<double> exch1, corr_part, loss_part, scal;
+    S *H = nullptr;  // owned column 0 inside Hbuf
+    int nsplit_w = 1, nsplit_g = 1;
+    int64_t split_w = 0, split_g = 0;
+    int conv_blocks_max = 0;
+
+    // conv tiling per dtype
+    static constexpr int TN = sizeof(S) == 4 ? 8 : 4;
+    static constexpr int TT = 8, TY = 16;
+    static constexpr int BN = 16 * TN, BT = TY * TT;
+
+    int64_t KL() const { return K * L; }
+
+    void init() {
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        own_stream = true;
+        const int64_t hal = L - 1;
+        X.alloc((size_t)((Tl + hal) * N));
+        Hbuf.alloc((size_t)((Tl + 2 * hal) * K));
+        H = Hbuf.p + hal * K;
+        Wi.alloc((size_t)(KL() * N));
+        Wtmp.alloc((size_t)(KL() * N));
+        numW.alloc((size_t)(KL() * N));
+        denW.alloc((size_t)(KL() * N));
+        GS.alloc((size_t)(KL() * KL()));
+        Cf.alloc((size_t)((2 * L - 1) * K * K));
+        numH.alloc((size_t)(Tl * K));
+        denH.alloc((size_t)(std::max<int64_t>(Tl * K, Tl)));
+        exch1.alloc((size_t)(L * K * K + hal * K + 1));
+        scal.alloc(8);
+        if (alg == CMF_HALS) {
+            R.alloc((size_t)((Tl + hal) * N));
+            tailC.alloc((size_t)(L * L));
+        }
+        // corr splits: numW (Nin = N) and Gram (Nin = K)
+        plan_split(N, Tl + hal, nsplit_w, split_w);
+        plan_split(K, Tl + hal, nsplit_g, split_g);
+        corr_part.alloc((size_t)std::max<int64_t>((int64_t)nsplit_w * KL() * N, (int64_t)nsplit_g * KL() * K));
+        conv_blocks_max = (int)(cdiv(N, BN) * cdiv(Tl + hal, BT));
+        loss_part.alloc((size_t)std::max(2 * conv_blocks_max, 1024));
+        CK(cudaStreamSynchronize(stream));
+    }
+
+    ~Ctx() override {
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+
+    void plan_split(int64_t Nin, int64_t tau_hi, int &nsplit, int64_t &split_len) {
+        const int64_t ngrp = cdiv(L, 8);
+        const int64_t bxy = cdiv(Nin, 128) * cdiv(K * ngrp, CORR_PB);
+        int64_t ns = std::min<int64_t>(std::max<int64_t>(cdiv(592, bxy), 1), 64);
+        split_len = cdiv(cdiv(tau_hi, ns), CORR_BTAU) * CORR_BTAU;
+        if (split_len < CORR_BTAU) split_len = CORR_BTAU;
+        nsplit = (int)cdiv(tau_hi, split_len);
+    }
+
+    void post_launch() {
+        ++launches;
+        CK(cudaGetLastError());
+    }
+
+    // ---------------------------------------------------------------- kernel launch helpers
+    // est over local columns [t_lo, t_hi) from (Wsrc, Hsrc) with dims (Kc, Lc).
+    void launch_conv(const S *Wsrc, const S *Hsrc, int64_t Kc, int64_t Lc, int64_t h_lo, int64_t h_hi,
+                     int64_t t_lo, int64_t t_hi, int flags, S *out, double *partial, uint64_t seed = 0,
+                     double noise = 0.0) {
+        if (t_hi <= t_lo) return;
+        ConvArgs<S> a;
+        a.Wi = Wsrc; a.H = Hsrc; a.X = X.p; a.out = out; a.partial = partial;
+        a.N = N; a.K = Kc; a.L = Lc; a.t_lo = t_lo; a.t_hi = t_hi; a.h_lo = h_lo; a.h_hi = h_hi;
+        a.flags = flags; a.seed = seed; a.t_global0 = t0; a.noise = noise;
+        const int Lpad = (int)(cdiv(Lc, 8) * 8);
+        const int HW = BT + Lpad - 1;
+        const size_t ws_bytes = (size_t)CONV_LC * BN * sizeof(S);
+        const size_t budget = 160 * 1024 - ws_bytes;
+        int KC = (int)std::min<int64_t>(Kc, (int64_t)(budget / ((size_t)HW * sizeof(S))));
+        REQUIRE(KC >= 1, "conv: L too large for the shared-memory H window");
+        a.KC = KC;
+        const size_t smem = (size_t)KC * HW * sizeof(S) + ws_bytes;
+        auto kern = conv_kernel<S, TN, TT, TY>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)cdiv(N, BN), (unsigned)cdiv(t_hi - t_lo, BT));
+        kern<<<grid, dim3(16, TY), smem, stream>>>(a);
+        post_launch();
+    }
+    int conv_nblocks(int64_t t_lo, int64_t t_hi) const { return (int)(cdiv(N, BN) * cdiv(t_hi - t_lo, BT)); }
+
+    void reduce_scalar(const double *part, int64_t n, double *dst) {
+        reduce_sum_kernel<<<1, 1024, 0, stream>>>(part, n, dst);
+        post_launch();
+    }
+    double fetch_scalar(const double *dst) {
+        double v;
+        CK(cudaMemcpyAsync(&v, dst, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        return v;
+    }
+
+    // out[t][k] for t in [0, t_out)
+    void launch_transconv(const S *Wg, const S *Xin, S *out, int64_t Nin, int64_t Kout, int64_t Lin,
+                          int64_t ldx, int64_t t_out, int64_t x_cols) {
+        if (t_out <= 0) return;
+        // choose TK / kgroups minimising padding
+        int best_tk = 8, best_kg = 1;
+        double best_waste = 1e30;
+        const int tks[3] = {8, 5, 4};
+        for (int tk : tks) {
+            int kg = 1;
+            while (kg < 16 && kg * tk < Kout) kg *= 2;
+            const int64_t kp = (int64_t)kg * tk;
+            const double waste = (double)(cdiv(Kout, kp) * kp - Kout) / (double)Kout;
+            if (waste < best_waste - 1e-9) { best_waste = waste; best_tk = tk; best_kg = kg; }
+        }
+        int tg = std::max(128 / best_kg, 8);
+        while (tg * best_kg > 32 && cdiv(t_out, (int64_t)tg * 8) < 296) tg /= 2;
+        TransArgs<S> a;
+        a.Wg = Wg; a.Xin = Xin; a.out = out; a.Nin = Nin; a.Kout = Kout; a.Lin = Lin; a.ldx = ldx;
+        a.t_out = t_out; a.x_cols = x_cols; a.kgroups = best_kg; a.tgroups = tg;
+        const int BTt = tg * 8, Lpad = (int)(cdiv(Lin, 8) * 8);
+        const int XW = BTt + Lpad, XWP = XW + XW / 8 + 1, KP = best_kg * best_tk;
+        const size_t smem = ((size_t)TR_NC * XWP + (size_t)8 * TR_NC * KP) * sizeof(S);
+        REQUIRE(smem <= 200 * 1024, "transconv: L too large for the shared-memory window");
+        dim3 grid((unsigned)cdiv(t_out, BTt), (unsigned)cdiv(Kout, KP));
+        const int nthr = best_kg * tg;
+#define LAUNCH_TR(TKV)                                                                             \
+    {                                                                                              \
+        auto kern = transconv_kernel<S, TKV, 8>;                                                   \
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        kern<<<grid, nthr, smem, stream>>>(a);                                                     \
+    }
+        if (best_tk == 8) LAUNCH_TR(8) else if (best_tk == 5) LAUNCH_TR(5) else LAUNCH_TR(4)
+#undef LAUNCH_TR
+        post_launch();
+    }
+
+    // out_S / out_D [(l*K+k)*Nin + n] = sum_tau hm(tau-l)[k] Xin[tau][n]
+    void launch_corr(const S *Xin, int64_t Nin, int64_t ldx, int64_t tau_hi, int nsplit, int64_t split_len,
+                     S *out_s, double *out_d) {
+        CorrArgs<S> a;
+        a.H = H; a.Xin = Xin; a.part = corr_part.p; a.Nin = Nin; a.K = K; a.L = L; a.ldx = ldx;
+        a.u_hi = Tl; a.tau_hi = tau_hi; a.split_len = split_len;
+        const int64_t ngrp = cdiv(L, 8);
+        dim3 grid((unsigned)cdiv(Nin, 128), (unsigned)cdiv(K * ngrp, CORR_PB), (unsigned)nsplit);
+        corr_kernel<S><<<grid, dim3(16, 16), 0, stream>>>(a);
+        post_launch();
+        const int64_t n = KL() * Nin;
+        reduce_partials_kernel<S><<<(unsigned)cdiv(n, 256), 256, 0, stream>>>(corr_part.p, nsplit, n, out_s, out_d);
+        post_launch();
+    }
+
+    template <bool TB>
+    void launch_gemm(const S *A, const S *B, S *C, int64_t M, int64_t Nn, int64_t Kg, int64_t lda, int64_t ldb,
+                     int64_t ldc) {
+        dim3 grid((unsigned)cdiv(Nn, 64), (unsigned)cdiv(M, 64));
+        gemm_kernel<S, TB><<<grid, 256, 0, stream>>>(A, B, C, M, Nn, Kg, lda, ldb, ldc);
+        post_launch();
+    }
+
+    void launch_mu(S *x, const S *num, const S *den, double l1, double l2, int64_t n) {
+        mu_update_kernel<S><<<(unsigned)cdiv(n, 256), 256, 0, stream>>>(x, num, den, (S)l1, (S)l2, n);
+        post_launch();
+    }
+
+    // ---------------------------------------------------------------- data
+    void set_data(const void *Xh, int64_t first_col) override {
+        REQUIRE(Xh != nullptr, "set_data: null pointer");
+        REQUIRE(first_col <= t0, "set_data: host array starts after the shard's first column");
+        const int64_t hi = std::min(t1 + (L - 1), T);
+        CK(cudaMemsetAsync(X.p, 0, X.n * sizeof(S), stream));
+        const S *src = static_cast<const S *>(Xh) + (t0 - first_col) * N;
+        CK(cudaMemcpyAsync(X.p, src, (size_t)((hi - t0) * N) * sizeof(S), cudaMemcpyHostToDevice, stream));
+        finish_data();
+    }
+    void finish_data() {
+        data_norm = std::sqrt(data_sumsq());
+        have_data = true;
+    }
+    double data_sumsq() override {
+        dot_partial_kernel<S><<<1024, 256, 0, stream>>>(X.p, X.p, Tl * N, loss_part.p);
+        post_launch();
+        reduce_scalar(loss_part.p, 1024, scal.p);
+        return fetch_scalar(scal.p);
+    }
+
+    void synth_data(uint64_t seed, int64_t Kt, int64_t Lt, double p_h, double noise) override {
+        REQUIRE(Kt >= 1 && Lt >= 1, "synth_data: bad ground-truth dims");
+        DevBuf<S> Wt, Ht;
+        Wt.alloc((size_t)(Kt * Lt * N));
+        const int64_t cols_out = std::min(Tl + (L - 1), T - t0);   // local columns to produce
+        const int64_t hcols = cols_out + (Lt - 1);
+        Ht.alloc((size_t)(hcols * Kt));
+        synth_W_kernel<S><<<(unsigned)cdiv(N, 128), 128, 0, stream>>>(Wt.p, Kt, N, Lt, seed, 0.1, 0.2);
+        post_launch();
+        synth_H_kernel<S><<<(unsigned)cdiv(hcols * Kt, 256), 256, 0, stream>>>(Ht.p, Kt, t0 - (Lt - 1), hcols, T, seed, p_h);
+        post_launch();
+        CK(cudaMemsetAsync(X.p, 0, X.n * sizeof(S), stream));
+        launch_conv(Wt.p, Ht.p + (Lt - 1) * Kt, Kt, Lt, -(Lt - 1), cols_out, 0, cols_out, 8, X.p, nullptr, seed, noise);
+        CK(cudaStreamSynchronize(stream));
+        finish_data();
+    }
+
+    // ---------------------------------------------------------------- factors
+    void set_factors(const void *Wh, const void *Hh, int64_t first_col) override {
+        REQUIRE(Wh && Hh, "set_factors: null pointer");
+        const int64_t lo = std::max<int64_t>(t0 - (L - 1), 0), hi = std::min(t1 + (L - 1), T);
+        REQUIRE(first_col <= lo, "set_factors: host H starts after the shard's left halo");
+        CK(cudaMemcpyAsync(Wtmp.p, Wh, Wi.n * sizeof(S), cudaMemcpyHostToDevice, stream));
+        w_julia_to_internal<S><<<(unsigned)cdiv(KL() * N, 256), 256, 0, stream>>>(Wtmp.p, Wi.p, K, N, L);
+        post_launch();
+        CK(cudaMemsetAsync(Hbuf.p, 0, Hbuf.n * sizeof(S), stream));
+        const S *src = static_cast<const S *>(Hh) + (lo - first_col) * K;
+        CK(cudaMemcpyAsync(H + (lo - t0) * K, src, (size_t)((hi - lo) * K) * sizeof(S), cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
+        have_factors = true;
+        if (alg == CMF_HALS && have_data) refresh_resid(false);
+    }
+
+    void init_rand(uint64_t seed) override {
+        // W in Julia order (k + K*(n + N*l)) so the draw for element (k,n,l) does not depend on layout
+        uniform_kernel<S><<<(unsigned)cdiv(KL() * N, 256), 256, 0, stream>>>(Wtmp.p, KL() * N, seed, 100, 0);
+        post_launch();
+        w_julia_to_internal<S><<<(unsigned)cdiv(KL() * N, 256), 256, 0, stream>>>(Wtmp.p, Wi.p, K, N, L);
+        post_launch();
+        const int64_t lo = std::max<int64_t>(t0 - (L - 1), 0), hi = std::min(t1 + (L - 1), T);
+        CK(cudaMemsetAsync(Hbuf.p, 0, Hbuf.n * sizeof(S), stream));
+        uniform_kernel<S><<<(unsigned)cdiv((hi - lo) * K, 256), 256, 0, stream>>>(H + (lo - t0) * K, (hi - lo) * K, seed, 101, lo * K);
+        post_launch();
+        CK(cudaStreamSynchronize(stream));
+        have_factors = true;
+    }
+
+    void init_scale_partials(double out[2]) override {
+        REQUIRE(have_data && have_factors, "init_scale_partials: data and factors must be set");
+        const int nb = conv_nblocks(0, Tl);
+        launch_conv(Wi.p, H, K, L, -(L - 1), Tl + (L - 1), 0, Tl, 16, nullptr, loss_part.p);
+        // partial layout: [2*b] = <est, X>, [2*b+1] = ||est||^2  -> de-interleave by strided sums
+        std::vector<double> hp((size_t)2 * nb);
+        CK(cudaMemcpyAsync(hp.data(), loss_part.p, hp.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        double a = 0.0, b = 0.0;
+        for (int i = 0; i < nb; ++i) { a += hp[2 * i]; b += hp[2 * i + 1]; }
+        out[0] = a; out[1] = b;
+    }
+
+    void scale_factors(double s) override {
+        scale_kernel<S><<<(unsigned)cdiv(KL() * N, 256), 256, 0, stream>>>(Wi.p, (S)s, KL() * N);
+        post_launch();
+        scale_kernel<S><<<(unsigned)cdiv((int64_t)Hbuf.n, 256), 256, 0, stream>>>(Hbuf.p, (S)s, (int64_t)Hbuf.n);
+        post_launch();
+        if (alg == CMF_HALS && have_data) refresh_resid(false);
+    }
+
+    void get_factors(void *Wo, void *Ho) override {
+        if (Wo) {
+            w_internal_to_julia<S><<<(unsigned)cdiv(KL() * N, 256), 256, 0, stream>>>(Wi.p, Wtmp.p, K, N, L);
+            post_launch();
+            CK(cudaMemcpyAsync(Wo, Wtmp.p, Wi.n * sizeof(S), cudaMemcpyDeviceToHost, stream));
+        }
+        if (Ho) CK(cudaMemcpyAsync(Ho, H, (size_t)(Tl * K) * sizeof(S), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+    }
+
+    // ---------------------------------------------------------------- MU (src/algs/mult.jl)
+    void w_partials() override {
+        REQUIRE(have_data && have_factors, "update: data and factors must be set first");
+        // numW partial over the owned u (mult.jl:32): Xin = X incl. right halo
+        launch_corr(X.p, N, N, Tl + (L - 1), nsplit_w, split_w, numW.p, nullptr);
+        // Gram partial Rg[d][k][k'] = sum_u H[u][k] H[u+d][k'] (owned u, right halo for u+d)
+        launch_corr(H, K, K, Tl + (L - 1), nsplit_g, split_g, nullptr, exch1.p);
+        if (L > 1) {
+            h_tail_kernel<S><<<(unsigned)cdiv((L - 1) * K, 256), 256, 0, stream>>>(H, exch1.p + L * K * K, K, L, Tl, is_last ? 1 : 0);
+            post_launch();
+        }
+    }
+
+    void build_G() {
+        build_G_kernel<S><<<(unsigned)cdiv(KL() * KL(), 256), 256, 0, stream>>>(exch1.p, exch1.p + L * K * K, GS.p, K, L);
+        post_launch();
+    }
+
+    void w_apply(double l1W, double l2W) override {
+        build_G();
+        launch_gemm<false>(GS.p, Wi.p, denW.p, KL(), N, KL(), KL(), N, N);   // denomW = G * Wi (mult.jl:28,33)
+        launch_mu(Wi.p, numW.p, denW.p, l1W, l2W, KL() * N);                  // mult.jl:37-38
+    }
+
+    void lag_tables() {
+        launch_gemm<true>(Wi.p, Wi.p, GS.p, KL(), KL(), N, N, N, KL());       // S2 = Wi Wi'
+        lag_table_kernel<S><<<(unsigned)cdiv((2 * L - 1) * K * K, 256), 256, 0, stream>>>(GS.p, Cf.p, K, L);
+        post_launch();
+    }
+
+    void h_update(double l1H, double l2H) override {
+        REQUIRE(have_data && have_factors, "update: data and factors must be set first");
+        launch_transconv(Wi.p, X.p, numH.p, N, K, L, N, Tl, Tl + (L - 1));    // numH (mult.jl:47)
+        lag_tables();
+        // denomH = C (*) H on all owned columns (mult.jl:44,48), then the truncated tail
+        launch_transconv(Cf.p, Hbuf.p, denH.p, K, K, 2 * L - 1, K, Tl, Tl + 2 * (L - 1));
+        if (is_last && L > 1) {
+            dim3 grid((unsigned)(L - 1), (unsigned)K);
+            denomH_tail_kernel<S><<<grid, 256, 0, stream>>>(GS.p, H, denH.p, K, L, Tl, -(L - 1));
+            post_launch();
+        }
+        launch_mu(H, numH.p, denH.p, l1H, l2H, Tl * K);                       // mult.jl:51-52
+    }
+
+    double loss_partial() override {
+        REQUIRE(have_data && have_factors, "loss: data and factors must be set first");
+        const int nb = conv_nblocks(0, Tl);
+        launch_conv(Wi.p, H, K, L, -(L - 1), Tl + (L - 1), 0, Tl, 4, nullptr, loss_part.p);  // mult.jl:55-57
+        reduce_scalar(loss_part.p, nb, scal.p);
+        return fetch_scalar(scal.p);
+    }
+
+    // ---------------------------------------------------------------- HALS (src/algs/hals.jl)
+    double refresh_resid(bool want_loss) {
+        const int nb = conv_nblocks(0, Tl);
+        launch_conv(Wi.p, H, K, L, -(L - 1), Tl + (L - 1), 0, Tl, 2 | 4, R.p, loss_part.p);   // hals.jl:22
+        if (!want_loss) return 0.0;
+        reduce_scalar(loss_part.p, nb, scal.p);
+        return fetch_scalar(scal.p);
+    }
+
+    void hals_update_motifs(double l1W, double l2W) override {
+        REQUIRE(have_data && have_factors, "update: data and factors must be set first");
+        // P[j][n] = sum_t R[n,t] Htilde[j,t]  (hals.jl:111 projections for every column at once)
+        launch_corr(R.p, N, N, Tl + (L - 1), nsplit_w, split_w, numW.p, nullptr);
+        launch_corr(H, K, K, Tl + (L - 1), nsplit_g, split_g, nullptr, exch1.p);
+        if (L > 1) {
+            h_tail_kernel<S><<<(unsigned)cdiv((L - 1) * K, 256), 256, 0, stream>>>(H, exch1.p + L * K * K, K, L, Tl, 1);
+            post_launch();
+        }
+        build_G();
+        const size_t smem = (size_t)KL() * sizeof(S);
+        REQUIRE(smem <= 200 * 1024, "HALS W sweep: K*L too large for shared memory");
+        auto kern = hals_w_sweep_kernel<S>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)N, 256, smem, stream>>>(GS.p, numW.p, Wi.p, K, L, N, (S)l1W, (S)l2W);   // hals.jl:90-112
+        post_launch();
+        refresh_resid(false);
+    }
+
+    double hals_update_feature_maps(double l1H, double l2H) override {
+        REQUIRE(have_data && have_factors, "update: data and factors must be set first");
+        launch_transconv(Wi.p, R.p, numH.p, N, K, L, N, Tl, Tl + (L - 1));    // Q = transconv(W, R)
+        lag_tables();
+        const size_t smem = (size_t)(2 * L + 32 + L) * sizeof(S);
+        auto kern = hals_h_sweep_kernel<S>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<1, 1024, smem, stream>>>(Cf.p, GS.p, numH.p, H, denH.p, tailC.p, K, L, Tl, (S)l1H, (S)l2H);  // hals.jl:121-154
+        post_launch();
+        return refresh_resid(true);                                            // hals.jl:41
+    }
+
+    // ---------------------------------------------------------------- exchange
+    void exchange_buffer(int which, void **p, int64_t *count, int *dt) override {
+        if (which == 0) { *p = numW.p; *count = KL() * N; *dt = dtype; }
+        else if (which == 1) { *p = exch1.p; *count = L * K * K + (L - 1) * K; *dt = CMF_F64; }
+        else throw CmfError(CMF_ERR_ARG, "exchange_buffer: which must be 0 or 1");
+    }
+    void halo_buffers(void **sl, void **sr, void **rl, void **rr, int64_t *count) override {
+        *sl = H; *sr = H + (Tl - (L - 1)) * K; *rl = Hbuf.p; *rr = H + Tl * K; *count = (L - 1) * K;
+    }
+
+    // ---------------------------------------------------------------- primitives
+    void prim_conv(void *out_host) override {
+        DevBuf<S> out;
+        out.alloc((size_t)(N * Tl));
+        launch_conv(Wi.p, H, K, L, -(L - 1), Tl + (L - 1), 0, Tl, 1, out.p, nullptr);
+        CK(cudaMemcpyAsync(out_host, out.p, out.n * sizeof(S), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+    }
+    void prim_transconv(const void *X_host, void *out_host) override {
+        set_data(X_host, 0);
+        launch_transconv(Wi.p, X.p, numH.p, N, K, L, N, Tl, Tl + (L - 1));
+        CK(cudaMemcpyAsync(out_host, numH.p, numH.n * sizeof(S), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+    }
+    void prim_corr(const void *X_host, void *out_host) override {
+        set_data(X_host, 0);
+        launch_corr(X.p, N, N, Tl + (L - 1), nsplit_w, split_w, numW.p, nullptr);
+        w_internal_to_julia<S><<<(unsigned)cdiv(KL() * N, 256), 256, 0, stream>>>(numW.p, Wtmp.p, K, N, L);
+        post_launch();
+        CK(cudaMemcpyAsync(out_host, Wtmp.p, Wtmp.n * sizeof(S), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+    }
+};
+
+cmf_ctx *make_ctx(int64_t N, int64_t T, int64_t t0, int64_t t1, int64_t K, int64_t L, int dtype, int alg, int device) {
+    REQUIRE(N >= 1 && K >= 1 && L >= 1 && T >= 1, "dimensions must be positive");
+    REQUIRE(L <= T, "need L <= T (src/common.jl:28-31)");
+    REQUIRE(0 <= t0 && t0 < t1 && t1 <= T, "bad shard range");
+    REQUIRE(dtype == CMF_F64 || dtype == CMF_F32, "dtype must be 0 (f64) or 1 (f32)");
+    REQUIRE(alg == CMF_MULT || alg == CMF_HALS, "alg must be 0 (mult) or 1 (hals)");
+    const bool sharded = !(t0 == 0 && t1 == T);
+    if (sharded) {
+        REQUIRE(t1 - t0 >= L - 1, "each shard needs at least L-1 columns");
+        if (alg == CMF_HALS) throw CmfError(CMF_ERR_UNSUPPORTED, "HALS is single-shard only in this version");
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        throw CmfError(CMF_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) + "); libcmf_sm100 has no CPU fallback");
+    REQUIRE(device >= 0 && device < ndev, "bad device ordinal");
+    cmf_ctx *c = (dtype == CMF_F64) ? static_cast<cmf_ctx *>(new Ctx<double>()) : static_cast<cmf_ctx *>(new Ctx<float>());
+    c->N = N; c->T = T; c->t0 = t0; c->t1 = t1; c->Tl = t1 - t0; c->K = K; c->L = L;
+    c->dtype = dtype; c->alg = alg; c->device = device;
+    c->is_first = (t0 == 0); c->is_last = (t1 == T);
+    try {
+        if (dtype == CMF_F64) static_cast<Ctx<double> *>(c)->init();
+        else static_cast<Ctx<float> *>(c)->init();
+    } catch (...) {
+        delete c;
+        throw;
+    }
+    return c;
+}
+
+template <typename F>
+int guarded(F &&f) {
+    try {
+        f();
+        return CMF_OK;
+    } catch (const CmfError &e) {
+        g_err = e.what();
+        return e.code;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return CMF_ERR_ARG;
+    } catch (...) {
+        g_err = "unknown error";
+        return CMF_ERR_ARG;
+    }
+}
+
+void use(cmf_handle h) {
+    REQUIRE(h != nullptr, "null handle");
+    CK(cudaSetDevice(h->device));
+}
+
+// src/model.jl:91-107
+bool converged(const double *loss_hist, int64_t n, int patience, double tol) {
+    if (n <= patience) return false;
+    for (int64_t i = n - patience; i < n; ++i)
+        if (!(std::fabs(loss_hist[i] - loss_hist[i - 1]) < tol)) return false;
+    return true;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *cmf_last_error(void) { return g_err.c_str(); }
+
+int cmf_create(cmf_handle *out, int64_t N, int64_t T, int64_t K, int64_t L, int dtype, int alg, int device) {
+    return guarded([&] {
+        REQUIRE(out != nullptr, "null output pointer");
+        *out = make_ctx(N, T, 0, T, K, L, dtype, alg, device);
+    });
+}
+
+int cmf_create_shard(cmf_handle *out, int64_t N, int64_t T_global, int64_t t_begin, int64_t t_end, int64_t K,
+                     int64_t L, int dtype, int alg, int device) {
+    return guarded([&] {
+        REQUIRE(out != nullptr, "null output pointer");
+        *out = make_ctx(N, T_global, t_begin, t_end, K, L, dtype, alg, device);
+    });
+}
+
+int cmf_destroy(cmf_handle h) {
+    return guarded([&] {
+        if (!h) return;
+        cudaSetDevice(h->device);
+        delete h;
+    });
+}
+
+int cmf_set_data(cmf_handle h, const void *X, int64_t first_col) {
+    return guarded([&] { use(h); h->set_data(X, first_col); });
+}
+int cmf_synth_data(cmf_handle h, uint64_t seed, int64_t K_true, int64_t L_true, double p_h, double noise) {
+    return guarded([&] { use(h); h->synth_data(seed, K_true, L_true, p_h, noise); });
+}
+int cmf_data_sumsq(cmf_handle h, double *out) {
+    return guarded([&] { use(h); REQUIRE(out, "null output"); REQUIRE(h->have_data, "no data"); *out = h->data_sumsq(); });
+}
+int cmf_set_data_norm(cmf_handle h, double norm) {
+    return guarded([&] { use(h); h->data_norm = norm; });
+}
+int cmf_set_factors(cmf_handle h, const void *W, const void *H, int64_t first_col) {
+    return guarded([&] { use(h); h->set_factors(W, H, first_col); });
+}
+int cmf_init_rand(cmf_handle h, uint64_t seed) {
+    return guarded([&] { use(h); h->init_rand(seed); });
+}
+int cmf_init_scale_partials(cmf_handle h, double out[2]) {
+    return guarded([&] { use(h); REQUIRE(out, "null output"); h->init_scale_partials(out); });
+}
+int cmf_scale_factors(cmf_handle h, double s) {
+    return guarded([&] { use(h); h->scale_factors(s); });
+}
+int cmf_get_factors(cmf_handle h, void *W_out, void *H_out) {
+    return guarded([&] { use(h); REQUIRE(h->have_factors, "no factors"); h->get_factors(W_out, H_out); });
+}
+
+int cmf_update_motifs(cmf_handle h, double l1W, double l2W) {
+    return guarded([&] {
+        use(h);
+        if (h->alg == CMF_HALS) { h->hals_update_motifs(l1W, l2W); return; }
+        REQUIRE(h->is_first && h->is_last, "sharded handles use the split-phase calls");
+        h->w_partials();
+        h->w_apply(l1W, l2W);
+    });
+}
+
+int cmf_update_feature_maps(cmf_handle h, double l1H, double l2H, double *loss_out) {
+    return guarded([&] {
+        use(h);
+        double loss;
+        if (h->alg == CMF_HALS) {
+            loss = std::sqrt(h->hals_update_feature_maps(l1H, l2H)) / h->data_norm;
+        } else {
+            REQUIRE(h->is_first && h->is_last, "sharded handles use the split-phase calls");
+            h->h_update(l1H, l2H);
+            loss = std::sqrt(h->loss_partial()) / h->data_norm;
+        }
+        if (loss_out) *loss_out = loss;
+    });
+}
+
+int cmf_loss(cmf_handle h, double *loss_out) {
+    return guarded([&] {
+        use(h);
+        REQUIRE(loss_out, "null output");
+        REQUIRE(h->is_first && h->is_last, "sharded handles use cmf_loss_partial");
+        *loss_out = std::sqrt(h->loss_partial()) / h->data_norm;
+    });
+}
+
+int cmf_fit(cmf_handle h, int64_t max_itr, double max_time, int eval_mode, int check_convergence, int patience,
+            double tol, double l1W, double l2W, double l1H, double l2H, double *loss_hist, double *time_hist,
+            int64_t cap, int64_t *n_hist, int *converged_early) {
+    return guarded([&] {
+        use(h);
+        REQUIRE(loss_hist && time_hist && n_hist, "null history pointers");
+        REQUIRE(patience >= 1, "patience must be >= 1 (src/algs/alternating.jl:30)");
+        REQUIRE(cap >= 1, "history capacity must be >= 1");
+        REQUIRE(h->is_first && h->is_last, "cmf_fit drives a single shard; sharded fits use the split-phase calls");
+        if (converged_early) *converged_early = 0;
+        int64_t n = 0;
+        loss_hist[n] = std::sqrt(h->loss_partial()) / h->data_norm;   // alternating.jl:37
+        time_hist[n] = 0.0;
+        ++n;
+        int64_t itr = 1;
+        while ((max_itr < 0 || itr <= max_itr) && time_hist[n - 1] <= max_time) {   // alternating.jl:45
+            ++itr;
+            REQUIRE(n < cap, "history capacity exhausted");
+            auto t_start = std::chrono::steady_clock::now();
+            double loss;
+            if (h->alg == CMF_HALS) {
+                if (!eval_mode) h->hals_update_motifs(l1W, l2W);
+                loss = std::sqrt(h->hals_update_feature_maps(l1H, l2H)) / h->data_norm;
+            } else {
+                if (!eval_mode) { h->w_partials(); h->w_apply(l1W, l2W); }
+                h->h_update(l1H, l2H);
+                loss = std::sqrt(h->loss_partial()) / h->data_norm;
+            }
+            const double dur = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+            time_hist[n] = time_hist[n - 1] + dur;
+            loss_hist[n] = loss;
+            ++n;
+            if (check_convergence && converged(loss_hist, n, patience, tol)) {   // alternating.jl:63-66
+                if (converged_early) *converged_early = 1;
+                break;
+            }
+        }
+        *n_hist = n;
+    });
+}
+
+int cmf_w_partials(cmf_handle h) {
+    return guarded([&] { use(h); REQUIRE(h->alg == CMF_MULT, "split-phase calls are MultUpdate only"); h->w_partials(); });
+}
+int cmf_w_apply(cmf_handle h, double l1W, double l2W) {
+    return guarded([&] { use(h); REQUIRE(h->alg == CMF_MULT, "split-phase calls are MultUpdate only"); h->w_apply(l1W, l2W); });
+}
+int cmf_h_update(cmf_handle h, double l1H, double l2H) {
+    return guarded([&] { use(h); REQUIRE(h->alg == CMF_MULT, "split-phase calls are MultUpdate only"); h->h_update(l1H, l2H); });
+}
+int cmf_loss_partial(cmf_handle h, double *sumsq_out) {
+    return guarded([&] { use(h); REQUIRE(sumsq_out, "null output"); *sumsq_out = h->loss_partial(); });
+}
+int cmf_exchange_buffer(cmf_handle h, int which, void **dev_ptr, int64_t *count, int *dtype) {
+    return guarded([&] { use(h); REQUIRE(dev_ptr && count && dtype, "null output"); h->exchange_buffer(which, dev_ptr, count, dtype); });
+}
+int cmf_halo_buffers(cmf_handle h, void **sl, void **sr, void **rl, void **rr, int64_t *count) {
+    return guarded([&] { use(h); REQUIRE(sl && sr && rl && rr && count, "null output"); h->halo_buffers(sl, sr, rl, rr, count); });
+}
+int cmf_sync(cmf_handle h) {
+    return guarded([&] { use(h); CK(cudaStreamSynchronize(h->stream)); });
+}
+int cmf_launch_count(cmf_handle h, int64_t *out) {
+    return guarded([&] { REQUIRE(h && out, "null argument"); *out = h->launches; });
+}
+int cmf_stream(cmf_handle h, void **stream_out) {
+    return guarded([&] { REQUIRE(h && stream_out, "null argument"); *stream_out = (void *)h->stream; });
+}
+int cmf_set_stream(cmf_handle h, void *stream) {
+    return guarded([&] {
+        use(h);
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+        h->own_stream = false;
+        h->stream = (cudaStream_t)stream;
+    });
+}
+int cmf_set_engine(cmf_handle h, int engine) {
+    return guarded([&] {
+        REQUIRE(h, "null handle");
+        REQUIRE(engine == 0 || engine == 1, "engine must be 0 (SIMT) or 1 (tcgen05)");
+        if (engine == 1) throw CmfError(CMF_ERR_UNSUPPORTED, "tcgen05 engine not built into this library version");
+        h->engine = engine;
+    });
+}
+
+int cmf_tensor_conv(int64_t N, int64_t T, int64_t K, int64_t L, int dtype, const void *W, const void *H, void *out) {
+    return guarded([&] {
+        REQUIRE(W && H && out, "null pointer");
+        cmf_ctx *c = make_ctx(N, T, 0, T, K, L, dtype, CMF_MULT, 0);
+        try { c->set_factors(W, H, 0); c->prim_conv(out); } catch (...) { delete c; throw; }
+        delete c;
+    });
+}
+int cmf_tensor_transconv(int64_t N, int64_t T, int64_t K, int64_t L, int dtype, const void *W, const void *X, void *out) {
+    return guarded([&] {
+        REQUIRE(W && X && out, "null pointer");
+        cmf_ctx *c = make_ctx(N, T, 0, T, K, L, dtype, CMF_MULT, 0);
+        try {
+            std::vector<char> Hz((size_t)(K * T) * (dtype == CMF_F64 ? 8 : 4), 0);
+            c->set_factors(W, Hz.data(), 0);
+            c->prim_transconv(X, out);
+        } catch (...) { delete c; throw; }
+        delete c;
+    });
+}
+int cmf_corr_w(int64_t N, int64_t T, int64_t K, int64_t L, int dtype, const void *H, const void *X, void *out) {
+    return guarded([&] {
+        REQUIRE(H && X && out, "null pointer");
+        cmf_ctx *c = make_ctx(N, T, 0, T, K, L, dtype, CMF_MULT, 0);
+        try {
+            std::vector<char> Wz((size_t)(K * N * L) * (dtype == CMF_F64 ? 8 : 4), 0);
+            c->set_factors(Wz.data(), H, 0);
+            c->prim_corr(X, out);
+        } catch (...) { delete c; throw; }
+        delete c;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,796 @@
+// SIMT (CUDA-core) kernels of the CNMF fit path, templated on the scalar type S (double/float).
+// These are the fp64 engine and the fp32 fallback engine; the tcgen05 engine (kernels_tc.cuh)
+// replaces the three big contractions for fp32 when K*L is large.
+//
+// Device layouts, all t-major so that a time shift is a pointer offset:
+//   X  [t][N]   (identical to Julia's column-major N x T), valid local columns [0, Tl + L-1)
+//   H  [t][K]   (identical to Julia's column-major K x T), valid local columns [-(L-1), Tl + L-1)
+//   Wi [j][N]   with j = l*K + k  (the unfolded row index of src/algs/hals.jl:102), n contiguous
+//
+// Reference semantics (file:line relative to /root/reference):
+//   conv       src/common.jl:24-34     est[n,t]  = sum_{l,k} W[k,n,l] H[k,t-l]
+//   transconv  src/common.jl:71-81     out[k,t]  = sum_{l,n} W[k,n,l] X[n,t+l]
+//   corr       src/algs/mult.jl:31-34  num[k,n,l]= sum_u   H[k,u]   X[n,u+l]
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cmf {
+
+#define CMF_EPS 2.220446049250313e-16 /* src/CMF.jl:20 */
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum of one double per thread; result valid in thread 0.  `red` holds >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double *red) {
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int nthr = blockDim.x * blockDim.y;
+    v = warp_sum(v);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (tid < 32) {
+        r = (tid < (nthr + 31) / 32) ? red[tid] : 0.0;
+        r = warp_sum(r);
+    }
+    return r;
+}
+
+// Deterministic second stage: one block sums `n` doubles in a fixed order.
+__global__ void reduce_sum_kernel(const double *__restrict__ in, int64_t n, double *__restrict__ out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += in[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// conv (+ residual, + loss):   est[t][n] = sum_{l<L,k<K} Wi[l*K+k][n] * H[t-l][k]
+//   block (16, TY) threads, micro-tile TN (n) x TT (t); tile BN = 16*TN, BT = TY*TT.
+//   smem: H window of KC components  Hs[KC][BT + Lpad - 1], W chunk Ws[LC][BN] of one k.
+//   flags: bit0 store est, bit1 store est - X, bit2 accumulate sum((est-X)^2) into partial[block],
+//          bit3 synth epilogue out = max(0, est + noise*gauss(seed, n, t_global)),
+//          bit4 partial[2b] = <est,X>, partial[2b+1] = ||est||^2 (init_rand rescale, src/model.jl:119-120).
+// ------------------------------------------------------------------------------------------
+template <typename S>
+struct ConvArgs {
+    const S *Wi;     // [L*K][N]
+    const S *H;      // owned column 0; valid [-(hlo), Tl + hhi)
+    const S *X;      // owned column 0 (flags 2|4)
+    S *out;          // [t][N] local columns (flags 1|2|8)
+    double *partial; // one per block (flag 4)
+    int64_t N, K, L;
+    int64_t t_lo, t_hi;   // local column range to produce [t_lo, t_hi)
+    int64_t h_lo, h_hi;   // valid local column range of H: [h_lo, h_hi), zero outside
+    int flags;
+    uint64_t seed;        // synth
+    int64_t t_global0;    // global index of local column 0 (synth)
+    double noise;         // synth
+    int KC;               // components staged per H window
+};
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+// counter-based uniform in (0,1): keyed on (seed, stream, index)
+__device__ __forceinline__ double u01(uint64_t seed, uint64_t stream, uint64_t idx) {
+    uint64_t h = mix64(mix64(seed ^ (stream * 0xd1342543de82ef95ull)) + idx);
+    return ((double)(h >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ double gauss01(uint64_t seed, uint64_t stream, uint64_t idx) {
+    const double u1 = u01(seed, stream, 2 * idx), u2 = u01(seed, stream, 2 * idx + 1);
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+constexpr int CONV_LC = 32; // lags per staged W chunk
+
+template <typename S, int TN, int TT, int TY>
+__global__ void __launch_bounds__(16 * TY) conv_kernel(ConvArgs<S> a) {
+    constexpr int BN = 16 * TN, BT = TY * TT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int64_t N = a.N, K = a.K, L = a.L;
+    const int Lpad = (int)((L + 7) / 8 * 8);
+    const int HW = BT + Lpad - 1;
+    S *Hs = reinterpret_cast<S *>(smem_raw);            // [KC][HW]
+    S *Ws = Hs + (size_t)a.KC * HW;                      // [CONV_LC][BN]
+    __shared__ double red[32];
+
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * 16 + tx, nthr = 16 * TY;
+    const int64_t n0 = (int64_t)blockIdx.x * BN;
+    const int64_t t0 = a.t_lo + (int64_t)blockIdx.y * BT;
+
+    S acc[TT][TN];
+#pragma unroll
+    for (int j = 0; j < TT; ++j)
+#pragma unroll
+        for (int i = 0; i < TN; ++i) acc[j][i] = S(0);
+
+    for (int64_t kc0 = 0; kc0 < K; kc0 += a.KC) {
+        const int kc = (int)min((int64_t)a.KC, K - kc0);
+        __syncthreads();
+        // stage the H window: Hs[k][i] = H[t0 - (Lpad-1) + i][kc0 + k]
+        for (int idx = tid; idx < kc * HW; idx += nthr) {
+            const int k = idx % kc, i = idx / kc;
+            const int64_t t = t0 - (Lpad - 1) + i;
+            S v = S(0);
+            if (t >= a.h_lo && t < a.h_hi) v = a.H[t * K + kc0 + k];
+            Hs[(size_t)k * HW + i] = v;
+        }
+        for (int k = 0; k < kc; ++k) {
+            const S *hrow = Hs + (size_t)k * HW + ty * TT + (Lpad - 1) - 7;
+            for (int lc0 = 0; lc0 < Lpad; lc0 += CONV_LC) {
+                const int lcn = min(CONV_LC, Lpad - lc0);
+                __syncthreads();
+                for (int idx = tid; idx < lcn * BN; idx += nthr) {
+                    const int n = idx % BN, dl = idx / BN;
+                    const int64_t l = lc0 + dl;
+                    S v = S(0);
+                    if (l < L && n0 + n < N) v = a.Wi[((l * K) + kc0 + k) * N + n0 + n];
+                    Ws[dl * BN + n] = v;
+                }
+                __syncthreads();
+                for (int l8 = 0; l8 < lcn; l8 += 8) {
+                    S hw[TT + 7];
+#pragma unroll
+                    for (int i = 0; i < TT + 7; ++i) hw[i] = hrow[i - (lc0 + l8)];
+#pragma unroll
+                    for (int dl = 0; dl < 8; ++dl) {
+                        S wv[TN];
+                        const S *wp = Ws + (l8 + dl) * BN + tx * TN;
+#pragma unroll
+                        for (int i = 0; i < TN; ++i) wv[i] = wp[i];
+#pragma unroll
+                        for (int j = 0; j < TT; ++j) {
+                            const S h = hw[7 - dl + j];
+#pragma unroll
+                            for (int i = 0; i < TN; ++i) acc[j][i] = fma(wv[i], h, acc[j][i]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // epilogue
+    double sq = 0.0, dxe = 0.0;
+#pragma unroll
+    for (int j = 0; j < TT; ++j) {
+        const int64_t t = t0 + ty * TT + j;
+        if (t >= a.t_hi) continue;
+        S part = S(0), pdot = S(0);
+#pragma unroll
+        for (int i = 0; i < TN; ++i) {
+            const int64_t n = n0 + tx * TN + i;
+            if (n >= N) continue;
+            const S e = acc[j][i];
+            if (a.flags & 1) a.out[t * N + n] = e;
+            if (a.flags & 16) {  // init_rand rescale partials: <est, X> and ||est||^2
+                pdot = fma(e, a.X[t * N + n], pdot);
+                part = fma(e, e, part);
+            }
+            if (a.flags & 8) {
+                const double g = gauss01(a.seed, 3, (uint64_t)((a.t_global0 + t) * N + n));
+                const double v = (double)e + a.noise * g;
+                a.out[t * N + n] = (S)(v > 0.0 ? v : 0.0);
+            }
+            if (a.flags & 6) {
+                const S r = e - a.X[t * N + n];
+                if (a.flags & 2) a.out[t * N + n] = r;
+                part = fma(r, r, part);
+            }
+        }
+        sq += (double)part;
+        dxe += (double)pdot;
+    }
+    if (a.flags & 4) {
+        sq = block_sum(sq, red);
+        if (tid == 0) a.partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = sq;
+    }
+    if (a.flags & 16) {
+        const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+        dxe = block_sum(dxe, red);
+        if (tid == 0) a.partial[2 * b] = dxe;
+        sq = block_sum(sq, red);
+        if (tid == 0) a.partial[2 * b + 1] = sq;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// transconv (generic):  out[t][k] = sum_{l<Lin} sum_{n<Nin} Wg[(l*Kout + k)*Nin + n] * Xin[(t+l)*ldx + n]
+//   used for numH (Wg = Wi, Xin = X) and for denomH (Wg = C table, Xin = H with halos).
+//   block = kgroups x tgroups threads, micro-tile TK (k) x TT (t), lane index = kg fastest.
+//   smem: Xs[NC][XWP] (t contiguous per n, one pad word every 8), Ws[8][NC][KP].
+// ------------------------------------------------------------------------------------------
+template <typename S>
+struct TransArgs {
+    const S *Wg;
+    const S *Xin;   // column 0 of the window; valid columns [0, x_cols)
+    S *out;         // [t][Kout], t in [0, t_out)
+    int64_t Nin, Kout, Lin, ldx;
+    int64_t t_out, x_cols;
+    int kgroups, tgroups;
+};
+
+constexpr int TR_NC = 16;
+
+template <typename S, int TK, int TT>
+__global__ void __launch_bounds__(256) transconv_kernel(TransArgs<S> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int kgroups = a.kgroups, tgroups = a.tgroups;
+    const int BT = tgroups * TT;
+    const int Lpad = (int)((a.Lin + 7) / 8 * 8);
+    const int XW = BT + Lpad;               // logical window length (t0 .. t0 + BT + Lpad - 1)
+    const int XWP = XW + XW / 8 + 1;        // padded: phys(i) = i + i/8
+    const int KP = kgroups * TK;
+    S *Xs = reinterpret_cast<S *>(smem_raw);        // [TR_NC][XWP]
+    S *Ws = Xs + (size_t)TR_NC * XWP;               // [8][TR_NC][KP]
+
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int kg = tid % kgroups, tg = tid / kgroups;
+    const int64_t t0 = (int64_t)blockIdx.x * BT;
+    const int64_t kb = (int64_t)blockIdx.y * KP;     // first k of this block
+
+    S acc[TT][TK];
+#pragma unroll
+    for (int j = 0; j < TT; ++j)
+#pragma unroll
+        for (int i = 0; i < TK; ++i) acc[j][i] = S(0);
+
+    for (int64_t nc0 = 0; nc0 < a.Nin; nc0 += TR_NC) {
+        __syncthreads();
+        // stage X window (transposed): Xs[n][phys(i)] = Xin[(t0+i)*ldx + nc0 + n]
+        for (int idx = tid; idx < TR_NC * XW; idx += nthr) {
+            const int n = idx % TR_NC, i = idx / TR_NC;
+            const int64_t t = t0 + i;
+            S v = S(0);
+            if (t < a.x_cols && nc0 + n < a.Nin) v = a.Xin[t * a.ldx + nc0 + n];
+            Xs[(size_t)n * XWP + i + i / 8] = v;
+        }
+        for (int lc0 = 0; lc0 < Lpad; lc0 += 8) {
+            __syncthreads();
+            // stage W chunk: Ws[dl][n][k] = Wg[((lc0+dl)*Kout + kb + k)*Nin + nc0 + n]
+            for (int idx = tid; idx < 8 * TR_NC * KP; idx += nthr) {
+                const int n = idx % TR_NC, k = (idx / TR_NC) % KP, dl = idx / (TR_NC * KP);
+                const int64_t l = lc0 + dl;
+                S v = S(0);
+                if (l < a.Lin && kb + k < a.Kout && nc0 + n < a.Nin)
+                    v = a.Wg[((l * a.Kout) + kb + k) * a.Nin + nc0 + n];
+                Ws[((size_t)dl * TR_NC + n) * KP + k] = v;
+            }
+            __syncthreads();
+            // thread's window base: logical index tg*TT + lc0 (a multiple of 8 when TT == 8)
+            const int base = tg * TT + lc0;
+#pragma unroll 2
+            for (int n = 0; n < TR_NC; ++n) {
+                S xw[TT + 7];
+                const S *xr = Xs + (size_t)n * XWP;
+#pragma unroll
+                for (int i = 0; i < TT + 7; ++i) {
+                    const int li = base + i;
+                    xw[i] = xr[li + li / 8];
+                }
+#pragma unroll
+                for (int dl = 0; dl < 8; ++dl) {
+                    S wv[TK];
+                    const S *wp = Ws + ((size_t)dl * TR_NC + n) * KP + kg * TK;
+#pragma unroll
+                    for (int i = 0; i < TK; ++i) wv[i] = wp[i];
+#pragma unroll
+                    for (int j = 0; j < TT; ++j) {
+                        const S x = xw[j + dl];
+#pragma unroll
+                        for (int i = 0; i < TK; ++i) acc[j][i] = fma(wv[i], x, acc[j][i]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < TT; ++j) {
+        const int64_t t = t0 + tg * TT + j;
+        if (t >= a.t_out) continue;
+#pragma unroll
+        for (int i = 0; i < TK; ++i) {
+            const int64_t k = kb + kg * TK + i;
+            if (k < a.Kout) a.out[t * a.Kout + k] = acc[j][i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// corr (generic):  part[split][(l*K + k)*Nin + n] = sum_{tau in split} hm(tau - l)[k] * Xin[tau*ldx + n]
+//   hm(u) = H[u*K + k] for u in [0, u_hi), zero outside (owned columns only).
+//   block (16, 16): tx -> 8 consecutive n, ty -> pair p = (k, lag group of 8); reduction over tau.
+//   fp32 accumulators are flushed into the double partial every CORR_FLUSH columns.
+// ------------------------------------------------------------------------------------------
+template <typename S>
+struct CorrArgs {
+    const S *H;      // owned column 0, [u][K]
+    const S *Xin;    // column 0, [tau][ldx]
+    double *part;    // [nsplit][L*K*Nin]
+    int64_t Nin, K, L, ldx;
+    int64_t u_hi;    // owned columns (H valid for u in [0,u_hi))
+    int64_t tau_hi;  // Xin valid for tau in [0, tau_hi)
+    int64_t split_len;
+};
+
+constexpr int CORR_BTAU = 32;
+constexpr int CORR_PB = 16;
+constexpr int CORR_FLUSH = 2048;
+
+template <typename S>
+__global__ void __launch_bounds__(256) corr_kernel(CorrArgs<S> a) {
+    constexpr int TN = 8, BN = 16 * TN, HWN = CORR_BTAU + 7;
+    __shared__ __align__(16) S Xs[CORR_BTAU][BN];
+    __shared__ S Hs[CORR_PB][HWN + 1];
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 16 + tx;
+    const int64_t n0 = (int64_t)blockIdx.x * BN;
+    const int64_t p = (int64_t)blockIdx.y * CORR_PB + ty;
+    const int64_t ngrp = (a.L + 7) / 8;
+    const bool pvalid = p < a.K * ngrp;
+    const int64_t k = pvalid ? p % a.K : 0, l0 = pvalid ? (p / a.K) * 8 : 0;
+    const int64_t tau_a = (int64_t)blockIdx.z * a.split_len;
+    const int64_t tau_b = min(a.tau_hi, tau_a + a.split_len);
+    double *part = a.part + (size_t)blockIdx.z * (size_t)(a.L * a.K * a.Nin);
+
+    S acc[8][TN];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = S(0);
+    bool flushed_once = false;
+    int since_flush = 0;
+
+    auto flush = [&]() {
+        if (!pvalid) return;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t l = l0 + i;
+            if (l >= a.L) continue;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const int64_t n = n0 + tx * TN + j;
+                if (n >= a.Nin) continue;
+                double *d = part + (l * a.K + k) * a.Nin + n;
+                *d = flushed_once ? (*d + (double)acc[i][j]) : (double)acc[i][j];
+                acc[i][j] = S(0);
+            }
+        }
+        flushed_once = true;
+    };
+
+    for (int64_t tau0 = tau_a; tau0 < tau_b; tau0 += CORR_BTAU) {
+        __syncthreads();
+        for (int idx = tid; idx < CORR_BTAU * BN; idx += 256) {
+            const int n = idx % BN, dt = idx / BN;
+            const int64_t tau = tau0 + dt;
+            S v = S(0);
+            if (tau < tau_b && n0 + n < a.Nin) v = a.Xin[tau * a.ldx + n0 + n];
+            Xs[dt][n] = v;
+        }
+        for (int idx = tid; idx < CORR_PB * HWN; idx += 256) {
+            const int i = idx % HWN, pp = idx / HWN;
+            const int64_t q = (int64_t)blockIdx.y * CORR_PB + pp;
+            S v = S(0);
+            if (q < a.K * ngrp) {
+                const int64_t kk = q % a.K, ll0 = (q / a.K) * 8;
+                const int64_t u = tau0 - ll0 - 7 + i;
+                if (u >= 0 && u < a.u_hi) v = a.H[u * a.K + kk];
+            }
+            Hs[pp][i] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int t8 = 0; t8 < CORR_BTAU; t8 += 8) {
+            S hw[15];
+#pragma unroll
+            for (int i = 0; i < 15; ++i) hw[i] = Hs[ty][t8 + i];
+#pragma unroll
+            for (int dt = 0; dt < 8; ++dt) {
+                S xv[TN];
+#pragma unroll
+                for (int j = 0; j < TN; ++j) xv[j] = Xs[t8 + dt][tx * TN + j];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const S h = hw[dt - i + 7];
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) acc[i][j] = fma(h, xv[j], acc[i][j]);
+                }
+            }
+        }
+        since_flush += CORR_BTAU;
+        if (sizeof(S) == 4 && since_flush >= CORR_FLUSH) {
+            flush();
+            since_flush = 0;
+        }
+    }
+    flush();
+}
+
+// out[i] = (S) sum_s part[s][i]   (fixed order -> deterministic)
+template <typename S>
+__global__ void reduce_partials_kernel(const double *__restrict__ part, int nsplit, int64_t n,
+                                       S *__restrict__ out, double *__restrict__ out_d) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int sp = 0; sp < nsplit; ++sp) s += part[(size_t)sp * n + i];
+    if (out) out[i] = (S)s;
+    if (out_d) out_d[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// plain GEMM  C[M][Nn] = A[M][Kg] * B   (row-major; TRANSB: B is [Nn][Kg], else [Kg][Nn])
+//   64x64 tile, BK 16, 256 threads, 4x4 micro-tile.  Used for G*Wi and Wi*Wi' (<1% of the FLOPs).
+// ------------------------------------------------------------------------------------------
+template <typename S, bool TRANSB>
+__global__ void __launch_bounds__(256) gemm_kernel(const S *__restrict__ A, const S *__restrict__ B,
+                                                   S *__restrict__ C, int64_t M, int64_t Nn,
+                                                   int64_t Kg, int64_t lda, int64_t ldb, int64_t ldc) {
+    constexpr int BM = 64, BNt = 64, BK = 16;
+    __shared__ S As[BK][BM + 1];
+    __shared__ S Bs[BK][BNt + 1];
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int64_t m0 = (int64_t)blockIdx.y * BM, c0 = (int64_t)blockIdx.x * BNt;
+    S acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = S(0);
+    for (int64_t k0 = 0; k0 < Kg; k0 += BK) {
+        __syncthreads();
+        for (int idx = tid; idx < BM * BK; idx += 256) {
+            const int kk = idx % BK, mm = idx / BK;
+            S v = S(0);
+            if (m0 + mm < M && k0 + kk < Kg) v = A[(m0 + mm) * lda + k0 + kk];
+            As[kk][mm] = v;
+        }
+        for (int idx = tid; idx < BNt * BK; idx += 256) {
+            S v = S(0);
+            if (TRANSB) {
+                const int kk = idx % BK, nn = idx / BK;
+                if (c0 + nn < Nn && k0 + kk < Kg) v = B[(c0 + nn) * ldb + k0 + kk];
+                Bs[kk][nn] = v;
+            } else {
+                const int nn = idx % BNt, kk = idx / BNt;
+                if (c0 + nn < Nn && k0 + kk < Kg) v = B[(k0 + kk) * ldb + c0 + nn];
+                Bs[kk][nn] = v;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            S av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t m = m0 + ty * 4 + i, c = c0 + tx * 4 + j;
+            if (m < M && c < Nn) C[m * ldc + c] = acc[i][j];
+        }
+}
+
+// ------------------------------------------------------------------------------------------
+// G = Htilde Htilde'  from the Toeplitz part Rg[d][k][k'] and the tail Ht[c][k] = H[T-(L-1)+c][k]
+//   G[(l,k)][(l',k')] = (l>=l' ? Rg[l-l'][k][k'] : Rg[l'-l][k'][k]) - sum_{i<min(l,l')} Ht[L-1-l+i][k] Ht[L-1-l'+i][k']
+// ------------------------------------------------------------------------------------------
+template <typename S>
+__global__ void build_G_kernel(const double *__restrict__ Rg, const double *__restrict__ Ht,
+                               S *__restrict__ G, int64_t K, int64_t L) {
+    const int64_t KL = K * L;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= KL * KL) return;
+    const int64_t jp = idx % KL, j = idx / KL;
+    const int64_t k = j % K, l = j / K, kp = jp % K, lp = jp / K;
+    double g = (l >= lp) ? Rg[((l - lp) * K + k) * K + kp] : Rg[((lp - l) * K + kp) * K + k];
+    const int64_t m = l < lp ? l : lp;
+    double tail = 0.0;
+    for (int64_t i = 0; i < m; ++i) tail += Ht[(L - 1 - l + i) * K + k] * Ht[(L - 1 - lp + i) * K + kp];
+    G[idx] = (S)(g - tail);
+}
+
+// Cf[(d+L-1)][k][k'] = sum_{l, 0<=l-d<L} S2[(l,k)][(l-d,k')]      (S2 = Wi Wi', KL x KL)
+template <typename S>
+__global__ void lag_table_kernel(const S *__restrict__ S2, S *__restrict__ Cf, int64_t K, int64_t L) {
+    const int64_t KL = K * L;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (2 * L - 1) * K * K) return;
+    const int64_t kp = idx % K, k = (idx / K) % K, d = idx / (K * K) - (L - 1);
+    double s = 0.0;
+    for (int64_t l = (d > 0 ? d : 0); l < L && l - d < L; ++l) s += (double)S2[(l * K + k) * KL + (l - d) * K + kp];
+    Cf[idx] = (S)s;
+}
+
+// Truncated tail of denomH (columns with w = T - t < L):
+//   den[t][k] = sum_{l<w} sum_{l'<L} sum_{k'} S2[(l,k)][(l',k')] * H[t + l - l'][k']
+// one block per (tail column, k).
+template <typename S>
+__global__ void __launch_bounds__(256) denomH_tail_kernel(const S *__restrict__ S2, const S *__restrict__ H,
+                                                           S *__restrict__ den, int64_t K, int64_t L,
+                                                           int64_t Tl, int64_t h_lo) {
+    __shared__ double red[32];
+    const int64_t KL = K * L;
+    const int64_t c = blockIdx.x;                 // tail column index: t = Tl - (L-1) + c
+    const int64_t k = blockIdx.y;
+    const int64_t t = Tl - (L - 1) + c;
+    if (t < 0) return;
+    const int64_t w = Tl - t;                     // 1 .. L-1
+    double s = 0.0;
+    const int64_t total = w * KL;                 // (l, l', k')
+    for (int64_t idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int64_t jp = idx % KL, l = idx / KL;
+        const int64_t kp = jp % K, lp = jp / K;
+        const int64_t u = t + l - lp;
+        if (u < h_lo) continue;
+        s += (double)S2[(l * K + k) * KL + jp] * (double)H[u * K + kp];
+    }
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) den[t * K + k] = (S)s;
+}
+
+// ------------------------------------------------------------------------------------------
+// element-wise pieces
+// ------------------------------------------------------------------------------------------
+// src/algs/mult.jl:37-38 / :51-52   x <- max(eps, x * num / (den + l1 + 2*l2*x + eps))
+template <typename S>
+__global__ void mu_update_kernel(S *__restrict__ x, const S *__restrict__ num, const S *__restrict__ den,
+                                 S l1, S l2, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const S eps = (S)CMF_EPS;
+    S v = x[i];
+    v = v * (num[i] / (den[i] + l1 + S(2) * l2 * v + eps));
+    x[i] = v > eps ? v : eps;
+}
+
+template <typename S>
+__global__ void scale_kernel(S *__restrict__ x, S s, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] *= s;
+}
+
+// partial[block] = sum over a grid-stride slice of a[i]*b[i]  (b may alias a)
+template <typename S>
+__global__ void dot_partial_kernel(const S *__restrict__ a, const S *__restrict__ b, int64_t n,
+                                   double *__restrict__ partial) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        s += (double)a[i] * (double)b[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// Julia W[k + K*(n + N*l)]  <->  Wi[(l*K + k)*N + n]
+template <typename S>
+__global__ void w_julia_to_internal(const S *__restrict__ Wj, S *__restrict__ Wi, int64_t K, int64_t N, int64_t L) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= K * N * L) return;
+    const int64_t n = idx % N, k = (idx / N) % K, l = idx / (N * K);
+    Wi[idx] = Wj[k + K * (n + N * l)];
+}
+template <typename S>
+__global__ void w_internal_to_julia(const S *__restrict__ Wi, S *__restrict__ Wj, int64_t K, int64_t N, int64_t L) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= K * N * L) return;
+    const int64_t k = idx % K, n = (idx / K) % N, l = idx / (K * N);
+    Wj[idx] = Wi[(l * K + k) * N + n];
+}
+
+// tail[c][k] (double) = H[Tl-(L-1)+c][k]; zeros when this shard is not the last one
+template <typename S>
+__global__ void h_tail_kernel(const S *__restrict__ H, double *__restrict__ tail, int64_t K, int64_t L,
+                              int64_t Tl, int is_last) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (L - 1) * K) return;
+    const int64_t c = idx / K, k = idx % K;
+    tail[idx] = is_last ? (double)H[(Tl - (L - 1) + c) * K + k] : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// counter-based generators (synthetic data model of datasets/synthetic.jl:29-61, and init_rand)
+// ------------------------------------------------------------------------------------------
+template <typename S>
+__global__ void uniform_kernel(S *__restrict__ x, int64_t n, uint64_t seed, uint64_t stream, int64_t idx0) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = (S)u01(seed, stream, (uint64_t)(idx0 + i));
+}
+
+// ground-truth H: Exponential(1) * Bernoulli(p_h), keyed on the global (t, k); zero for t < 0 or t >= T
+template <typename S>
+__global__ void synth_H_kernel(S *__restrict__ H, int64_t K, int64_t t_first, int64_t cols, int64_t T,
+                               uint64_t seed, double p_h) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * cols) return;
+    const int64_t k = i % K, t = t_first + i / K;
+    S v = S(0);
+    if (t >= 0 && t < T) {
+        const uint64_t id = (uint64_t)(t * K + k);
+        if (u01(seed, 1, id) < p_h) v = (S)(-log(u01(seed, 2, id)));
+    }
+    H[i] = v;
+}
+
+// Marsaglia-Tsang Gamma(alpha<1 via boost) with counter-based draws
+__device__ inline double gamma_draw(double alpha, uint64_t seed, uint64_t stream, uint64_t id) {
+    const double a = alpha + 1.0, d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    double g = d;
+    for (uint64_t it = 0; it < 32; ++it) {
+        const double x = gauss01(seed, stream, id * 64 + it);
+        const double v0 = 1.0 + c * x;
+        if (v0 <= 0.0) continue;
+        const double v = v0 * v0 * v0, u = u01(seed, stream + 1, id * 64 + it);
+        if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) { g = d * v; break; }
+    }
+    return g * pow(u01(seed, stream + 2, id), 1.0 / alpha);
+}
+
+// ground-truth W in the internal layout: Dirichlet(alpha) weights over k for each unit n, times a
+// Gaussian bump over the lag axis linspace(-1,1,L) centred at U(-1,1)   (datasets/synthetic.jl:42-51)
+template <typename S>
+__global__ void synth_W_kernel(S *__restrict__ Wi, int64_t K, int64_t N, int64_t L, uint64_t seed,
+                               double alpha, double sigma) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    double tot = 0.0;
+    for (int64_t k = 0; k < K; ++k) tot += gamma_draw(alpha, seed, 10, (uint64_t)(n * K + k));
+    for (int64_t k = 0; k < K; ++k) {
+        const double wgt = gamma_draw(alpha, seed, 10, (uint64_t)(n * K + k)) / tot;
+        const double cent = 2.0 * u01(seed, 20, (uint64_t)(n * K + k)) - 1.0;
+        for (int64_t l = 0; l < L; ++l) {
+            const double x = (L > 1) ? (-1.0 + 2.0 * (double)l / (double)(L - 1)) : -1.0;
+            const double z = (x - cent) / sigma;
+            Wi[(l * K + k) * N + n] = (S)(wgt * exp(-0.5 * z * z) / (sigma * 2.5066282746310002));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// HALS sweeps (src/algs/hals.jl:90-154) in the Gram / recurrence form of oracle/restructured.py
+// ------------------------------------------------------------------------------------------
+// W sweep: one block per unit n.  P row and W row live in shared memory.
+//   for k, for l:  j = l*K+k;  g = G[j][j];  w' = max((w*g - P[j] - l1)/(g + eps + l2), 0);
+//                  P[:] += (w'-w) * G[j][:]
+template <typename S>
+__global__ void __launch_bounds__(256) hals_w_sweep_kernel(const S *__restrict__ G, const S *__restrict__ P /*[KL][N]*/,
+                                                            S *__restrict__ Wi /*[KL][N]*/, int64_t K, int64_t L,
+                                                            int64_t N, S l1, S l2) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int64_t KL = K * L;
+    S *Ps = reinterpret_cast<S *>(smem_raw);
+    __shared__ S delta_s;
+    const int64_t n = blockIdx.x;
+    for (int64_t j = threadIdx.x; j < KL; j += blockDim.x) Ps[j] = P[j * N + n];
+    __syncthreads();
+    for (int64_t k = 0; k < K; ++k)
+        for (int64_t l = 0; l < L; ++l) {
+            const int64_t j = l * K + k;
+            if (threadIdx.x == 0) {
+                const S g = G[j * KL + j];
+                const S w = Wi[j * N + n];
+                S v = (w * g - Ps[j] - l1) / (g + (S)CMF_EPS + l2);
+                v = v > S(0) ? v : S(0);
+                Wi[j * N + n] = v;
+                delta_s = v - w;
+            }
+            __syncthreads();
+            const S d = delta_s;
+            if (d != S(0)) {
+                const S *grow = G + j * KL;
+                for (int64_t jj = threadIdx.x; jj < KL; jj += blockDim.x) Ps[jj] = fma(d, grow[jj], Ps[jj]);
+            }
+            __syncthreads();
+        }
+}
+
+// H sweep, single block (sequential in k, sequential in t inside warp 0, block-parallel Q update).
+//   Q[t][k] = transconv(W, R);  Cf[(d+L-1)][k][k'] interior table;  S2 for the truncated tail.
+//   for k: for t: w = min(L, T-t); c0 = C_w[k,k,0];
+//          h' = max((h*c0 - Q[t][k] - pend(t) - l1)/(c0 + eps + l2), 0);  delta[t] = h'-h
+//          pend(t+s) += delta * C_w[k,k,s]   (s = 1..L-1, same component, future columns)
+//     then for all k' != k ... only k' > k matter: Q[t'][k'] += sum_t delta[t] * C_{w(t)}[k,k',t'-t]
+template <typename S>
+__global__ void __launch_bounds__(1024) hals_h_sweep_kernel(const S *__restrict__ Cf, const S *__restrict__ S2,
+                                                             S *__restrict__ Q, S *__restrict__ H,
+                                                             S *__restrict__ delta /*[T]*/,
+                                                             S *__restrict__ tailC /*[L][L] scratch*/,
+                                                             int64_t K, int64_t L, int64_t T, S l1, S l2) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    S *pend = reinterpret_cast<S *>(smem_raw);  // ring of RB entries
+    S *ckk = pend + 2 * L + 32;                 // Cf[k,k,s], s = 0..L-1
+    const int64_t KL = K * L;
+    const int RB = (int)(2 * L + 32);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int64_t Tint = T - (L - 1);           // columns t < Tint have the full window (w = L)
+
+    for (int64_t k = 0; k < K; ++k) {
+        // per-component tables
+        for (int64_t s = tid; s < L; s += nthr) ckk[s] = Cf[((s + L - 1) * K + k) * K + k];
+        for (int64_t i = tid; i < RB; i += nthr) pend[i] = S(0);
+        // tailC[w][s] = C_w[k,k,s] = sum_{l<w, l-s>=0} S2[(l,k)][(l-s,k)],  w = 1..L-1 (index w), s = 0..L-1
+        for (int64_t idx = tid; idx < L * L; idx += nthr) {
+            const int64_t w = idx / L, s = idx % L;
+            double acc = 0.0;
+            for (int64_t l = s; l < w; ++l) acc += (double)S2[(l * K + k) * KL + (l - s) * K + k];
+            tailC[idx] = (S)acc;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            const int lane = tid;
+            for (int64_t t = 0; t < T; ++t) {
+                const int64_t w = (T - t < L) ? (T - t) : L;
+                const S c0 = (w == L) ? ckk[0] : tailC[w * L + 0];
+                const int slot = (int)(t % RB);
+                const S h = H[t * K + k];
+                const S q = Q[t * K + k] + pend[slot];
+                S v = (h * c0 - q - l1) / (c0 + (S)CMF_EPS + l2);
+                v = v > S(0) ? v : S(0);
+                const S d = v - h;
+                __syncwarp();
+                if (lane == 0) {
+                    H[t * K + k] = v;
+                    delta[t] = d;
+                    pend[slot] = S(0);
+                }
+                if (d != S(0)) {
+                    // future columns of the same component: t + s <= T-1, s <= L-1 (and s <= w-1 in the tail)
+                    for (int64_t s = 1 + lane; s < w; s += 32) {
+                        const S c = (w == L) ? ckk[s] : tailC[w * L + s];
+                        pend[(int)((t + s) % RB)] += d * c;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // propagate to the later components:  Q[t'][k'] += sum_t delta[t] * C_{w(t)}[k,k',t'-t]
+        const int64_t nk = K - 1 - k;
+        for (int64_t idx = tid; idx < nk * T; idx += nthr) {
+            const int64_t kp = k + 1 + idx % nk, tp = idx / nk;
+            double acc = 0.0;
+            const int64_t ta = tp - (L - 1) > 0 ? tp - (L - 1) : 0;
+            const int64_t tb = tp + (L - 1) < T - 1 ? tp + (L - 1) : T - 1;
+            for (int64_t t = ta; t <= tb; ++t) {
+                const S d = delta[t];
+                if (d == S(0)) continue;
+                const int64_t dd = tp - t;
+                if (t < Tint) {
+                    acc += (double)d * (double)Cf[((dd + L - 1) * K + k) * K + kp];
+                } else {
+                    const int64_t w = T - t;  // C_w[k,k',dd] = sum_{l<w, 0<=l-dd<L} S2[(l,k)][(l-dd,k')]
+                    double c = 0.0;
+                    for (int64_t l = (dd > 0 ? dd : 0); l < w && l - dd < L; ++l)
+                        c += (double)S2[(l * K + k) * KL + (l - dd) * K + kp];
+                    acc += (double)d * c;
+                }
+            }
+            Q[tp * K + kp] += (S)acc;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace cmf

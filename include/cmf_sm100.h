@@ -1,0 +1,175 @@
+/* libcmf_sm100 -- C ABI of the B200 (sm_100a) convolutive-NMF fit path.
+ *
+ * Drop-in boundary for the update-rule plugin interface of degleris1/CMF.jl
+ * (`abstract type AbstractCFUpdate`, src/algs/alternating.jl:8): a rule is constructed from
+ * (data, W, H) (src/model.jl:79), `update_motifs!` mutates W (alternating.jl:52) and
+ * `update_feature_maps!` mutates H and returns the relative loss (alternating.jl:54).
+ * Julia binds these entry points with `ccall` (see INTEGRATION.md and julia/CMFsm100.jl);
+ * the Python mirror in cmf.jl_b200/ binds the same symbols with ctypes.
+ *
+ * Conventions
+ *  - All HOST arrays are Julia column-major:  data N x T  (X[n + N*t]),
+ *    W  K x N x L (W[k + K*(n + N*l)], current-src layout, src/common.jl:18,25),
+ *    H  K x T     (H[k + K*t]).  Element type is double (dtype 0) or float (dtype 1).
+ *  - The caller owns every host array; the library copies during the call and never keeps
+ *    a host pointer.  The library owns all device memory behind the handle.
+ *  - Every function returns 0 on success, non-zero on error; the message is available from
+ *    cmf_last_error() (thread-local).  No C++ exception crosses this boundary.  There is no
+ *    CPU fallback: without a CUDA device every compute entry point fails with CMF_ERR_CUDA.
+ *  - One host thread per handle.
+ *
+ * Sharding (time axis): a handle may own the column range
+ * [t_begin, t_end) of a global problem of T columns.  The exchange steps between ranks
+ * (all-reduce of the W-side partials, L-1 column halo exchange of H, all-reduce of the loss
+ * partial) are done by the HOST with whatever collective library it has (torch.distributed /
+ * NCCL.jl / MPI) on the device pointers exposed by cmf_exchange_buffer / cmf_halo_buffers.
+ */
+#ifndef CMF_SM100_H
+#define CMF_SM100_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cmf_ctx *cmf_handle;
+
+enum { CMF_F64 = 0, CMF_F32 = 1 };   /* dtype: arithmetic type of the kernels            */
+enum { CMF_MULT = 0, CMF_HALS = 1 }; /* alg:   MultUpdate (src/algs/mult.jl) / HALSUpdate */
+enum {
+    CMF_OK = 0,
+    CMF_ERR_ARG = 1,   /* bad dimensions / null pointer / wrong state                  */
+    CMF_ERR_CUDA = 2,  /* CUDA runtime error (including "no device")                   */
+    CMF_ERR_UNSUPPORTED = 3
+};
+
+/* ---- lifecycle ---------------------------------------------------------------------- */
+
+/* Replaces the rule constructors MultUpdate(data,W,H) / HALSUpdate(data,W,H)
+ * (src/algs/mult.jl:11-20, src/algs/hals.jl:18-28) together with cmf_set_data and
+ * cmf_set_factors.  Requires 1 <= L <= T (src/common.jl:28-31 would index out of range
+ * otherwise).  `device` is the CUDA ordinal. */
+int cmf_create(cmf_handle *out, int64_t N, int64_t T, int64_t K, int64_t L, int dtype, int alg,
+               int device);
+
+/* Same, for one time-shard [t_begin, t_end) of a T_global-column problem (no reference
+ * counterpart: the reference is single-process).  Needs t_end - t_begin >= L-1.
+ * HALS is single-shard only in this version (CMF_ERR_UNSUPPORTED otherwise). */
+int cmf_create_shard(cmf_handle *out, int64_t N, int64_t T_global, int64_t t_begin, int64_t t_end,
+                     int64_t K, int64_t L, int dtype, int alg, int device);
+
+int cmf_destroy(cmf_handle h);
+
+/* Thread-local message of the last failing call on this thread. */
+const char *cmf_last_error(void);
+
+/* ---- data and factors ----------------------------------------------------------------- */
+
+/* `X` is a column-major N x (something) host array whose first column is global column
+ * `first_col`; the library reads columns [t_begin, min(t_end + L-1, T)) (owned + right halo)
+ * and computes ||X_owned||^2.  Replaces the `data` argument of the rule constructor
+ * (src/model.jl:79) and `data_norm = norm(data)` (mult.jl:13, hals.jl:23). */
+int cmf_set_data(cmf_handle h, const void *X, int64_t first_col);
+
+/* Synthetic data generated in HBM (benchmarks): the reference's
+ * data model (datasets/synthetic.jl:29-61) with a counter-based generator keyed on the global
+ * (seed, n, t), so the data are identical for any sharding.  K_true/L_true are the ground-truth
+ * rank and lag count, p_h the activation probability, noise the Gaussian noise std. */
+int cmf_synth_data(cmf_handle h, uint64_t seed, int64_t K_true, int64_t L_true, double p_h,
+                   double noise);
+
+/* sum of squares of the owned columns of X (double), and the global norm used as the loss
+ * denominator (defaults to the local one; a sharded host all-reduces and sets it). */
+int cmf_data_sumsq(cmf_handle h, double *out);
+int cmf_set_data_norm(cmf_handle h, double norm);
+
+/* W: K x N x L host array.  H: column-major K x (something) whose first column is global
+ * column `first_col`; the library reads [t_begin-(L-1), t_end+(L-1)) clipped to [0,T)
+ * (owned + both halos).  Replaces the W,H arguments of the rule constructor / the deepcopy at
+ * src/algs/alternating.jl:33-34.  For HALS this also (re)computes the persistent residual
+ * (hals.jl:22). */
+int cmf_set_factors(cmf_handle h, const void *W, const void *H, int64_t first_col);
+
+/* Uniform [0,1) initialisation in HBM keyed on the global (seed,k,n,l) / (seed,k,t)
+ * (src/model.jl:116-117 restated with a counter-based generator), WITHOUT the alpha rescale:
+ * cmf_init_scale_partials returns the local <X, est> and ||est||^2 (model.jl:119-120); the host
+ * sums them over shards and calls cmf_scale_factors(sqrt(|alpha|)) (model.jl:121-122). */
+int cmf_init_rand(cmf_handle h, uint64_t seed);
+int cmf_init_scale_partials(cmf_handle h, double out_dot_norm2[2]);
+int cmf_scale_factors(cmf_handle h, double s);
+
+/* Copies W (K x N x L) and the owned columns of H (K x (t_end-t_begin)) to host arrays. */
+int cmf_get_factors(cmf_handle h, void *W_out, void *H_out);
+
+/* ---- the update rule (single shard) --------------------------------------------------- */
+
+/* update_motifs!(rule, data, W, H; l1W, l2W)      src/algs/mult.jl:23-39, hals.jl:31-34 */
+int cmf_update_motifs(cmf_handle h, double l1W, double l2W);
+/* loss = update_feature_maps!(rule, data, W, H; l1H, l2H)   mult.jl:42-58, hals.jl:37-42 */
+int cmf_update_feature_maps(cmf_handle h, double l1H, double l2H, double *loss_out);
+/* compute_loss(data, W, H)                         src/common.jl:54-55 */
+int cmf_loss(cmf_handle h, double *loss_out);
+
+/* The whole alternating loop on the device (src/algs/alternating.jl:16-71):
+ * max_itr < 0 means Inf; loss_hist/time_hist are caller-allocated with capacity `cap`
+ * (>= max_itr+1 when max_itr >= 0); *n_hist receives the number of entries written
+ * (iterations + 1); *converged_early is set when the early stop of alternating.jl:63-66 fired
+ * (the caller prints "Converged early." as the reference does). */
+int cmf_fit(cmf_handle h, int64_t max_itr, double max_time, int eval_mode, int check_convergence,
+            int patience, double tol, double l1W, double l2W, double l1H, double l2H,
+            double *loss_hist, double *time_hist, int64_t cap, int64_t *n_hist,
+            int *converged_early);
+
+/* ---- split-phase steps for time-sharded fits (MultUpdate only) -------------------------- */
+
+/* 1. local W-side partials: numW (src/algs/mult.jl:32), the H cross-correlation that yields
+ *    denomW (mult.jl:28,33 via G = Htilde Htilde'), and the last L-1 columns of H on the last
+ *    shard, all into exchange buffers 0 and 1. */
+int cmf_w_partials(cmf_handle h);
+/* 2. host all-reduces (sum) exchange buffers 0 and 1, then: W update (mult.jl:37-38). */
+int cmf_w_apply(cmf_handle h, double l1W, double l2W);
+/* 3. H update on the owned columns (mult.jl:44-52); afterwards the host exchanges halos. */
+int cmf_h_update(cmf_handle h, double l1H, double l2H);
+/* 4. after the halo exchange: local sum of squared residuals (mult.jl:55-57 numerator^2). */
+int cmf_loss_partial(cmf_handle h, double *sumsq_out);
+
+/* Exchange buffer `which`: 0 = numW partial (count = K*N*L elements of the handle dtype),
+ * 1 = Gram/tail partial (double).  Returns the device pointer, element count and dtype. */
+int cmf_exchange_buffer(cmf_handle h, int which, void **dev_ptr, int64_t *count, int *dtype);
+/* H halo regions, each (L-1)*K contiguous elements of the handle dtype:
+ * send_left  = first L-1 owned columns (goes to the left neighbour's recv_right),
+ * send_right = last  L-1 owned columns (goes to the right neighbour's recv_left). */
+int cmf_halo_buffers(cmf_handle h, void **send_left, void **send_right, void **recv_left,
+                     void **recv_right, int64_t *count);
+
+/* Blocks until all work queued by this handle has finished (for host-side timing). */
+int cmf_sync(cmf_handle h);
+/* Number of kernels this handle has launched so far (bench.py's `gpu_launches`). */
+int cmf_launch_count(cmf_handle h, int64_t *out);
+/* The CUDA stream (cudaStream_t) the handle launches on, for event timing by the host. */
+int cmf_stream(cmf_handle h, void **stream_out);
+/* Makes the handle launch on a caller-owned stream (e.g. the host framework's current stream,
+ * so that host-side collectives on the exchange buffers are stream-ordered with the kernels
+ * and no host synchronisation is needed between steps).  NULL selects the legacy default stream. */
+int cmf_set_stream(cmf_handle h, void *stream);
+/* Selects the contraction engine: 0 = SIMT kernels (fp64 and fp32), 1 = tcgen05 tensor-core
+ * kernels (fp32 data, split-bf16 operands) where available.  Default: best available. */
+int cmf_set_engine(cmf_handle h, int engine);
+
+/* ---- primitives (tests; one-shot, host in / host out) ----------------------------------- */
+
+/* tensor_conv(W, H)       src/common.jl:17-34     out: N x T */
+int cmf_tensor_conv(int64_t N, int64_t T, int64_t K, int64_t L, int dtype, const void *W,
+                    const void *H, void *out);
+/* tensor_transconv(W, X)  src/common.jl:62-81     out: K x T */
+int cmf_tensor_transconv(int64_t N, int64_t T, int64_t K, int64_t L, int dtype, const void *W,
+                         const void *X, void *out);
+/* numW of src/algs/mult.jl:31-34                  out: K x N x L */
+int cmf_corr_w(int64_t N, int64_t T, int64_t K, int64_t L, int dtype, const void *H,
+               const void *X, void *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMF_SM100_H */

@@ -1,0 +1,296 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the Python mirror of the reference
+interface) against the CPU oracle on the same seeded inputs, against the committed golden
+fixtures, and through size-independent properties at larger sizes.
+
+Tolerances (BASELINE.json north_star): fp64 kernels within 1e-9 relative of the Float64
+reference arithmetic on W, H and loss_hist; fp32 within 1e-4 relative on the loss after 100
+iterations."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+F64_RTOL = 1e-9
+F32_LOSS_RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def cmf():
+    import __graft_entry__ as ge
+
+    ge.build()
+    import cmf_jl_b200
+
+    return cmf_jl_b200
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import c_oracle, cnmf_oracle, restructured
+
+    class O:
+        po, co, rs = cnmf_oracle, c_oracle, restructured
+
+    return O
+
+
+def _rand(N, T, K, L, seed=0):
+    rng = np.random.default_rng(seed)
+    return rng.random((K, N, L)), rng.random((K, T)), rng.random((N, T))
+
+
+def _relerr(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+PRIM_DIMS = [(13, 57, 3, 5), (1, 1, 1, 1), (5, 7, 2, 7), (130, 300, 20, 9), (500, 2000, 5, 10),
+             (64, 257, 64, 33), (33, 140, 7, 1), (150, 1000, 15, 100), (17, 90, 130, 3)]
+
+
+@pytest.mark.parametrize("dims", PRIM_DIMS)
+@pytest.mark.parametrize("dtype,tol", [("f64", 1e-12), ("f32", 2e-5)])
+def test_primitives_match_oracle(cmf, orc, dims, dtype, tol):
+    N, T, K, L = dims
+    W, H, X = _rand(*dims, seed=sum(dims))
+    assert _relerr(cmf.tensor_conv(W, H, dtype), orc.co.tensor_conv(W, H)) < tol
+    assert _relerr(cmf.tensor_transconv(W, X, dtype), orc.co.tensor_transconv(W, X)) < tol
+    assert _relerr(cmf.corr_w(H, X, L, dtype), orc.co.corr_w(H, X, L)) < tol
+
+
+def test_toy_data_is_bit_exact(cmf, orc):
+    # datasets/toy.jl: small integers and halves -> every partial sum is exact in fp32 and fp64
+    X, W, H = orc.po.toy_data()
+    assert np.array_equal(cmf.tensor_conv(W, H, "f64"), X)
+    assert np.array_equal(cmf.tensor_conv(W, H, "f32").astype(np.float64), X)
+
+
+def test_golden_primitives(cmf):
+    g = np.load(os.path.join(GOLD, "prims.npz"))
+    assert _relerr(cmf.tensor_conv(g["W"], g["H"]), g["conv"]) < 1e-12
+    assert _relerr(cmf.tensor_transconv(g["W"], g["X"]), g["transconv"]) < 1e-12
+    assert _relerr(cmf.corr_w(g["H"], g["X"], g["W"].shape[2]), g["corr"]) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["mu_small", "mu_reg_small", "hals_small", "hals_reg_small"])
+def test_golden_fits_fp64(cmf, name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    reg = {k: float(g[k]) for k in ("l1W", "l2W", "l1H", "l2H")}
+    K, N, L = g["W0"].shape
+    r = cmf.fit_cnmf(g["X"], L=L, K=K, alg=str(g["alg"]), max_itr=int(g["max_itr"]), W_init=g["W0"],
+                     H_init=g["H0"], check_convergence=False, layout="KNL", **reg)
+    assert len(r.loss_hist) == int(g["max_itr"]) + 1
+    assert np.allclose(r.loss_hist, g["loss_hist"], rtol=F64_RTOL)
+    assert np.allclose(r.W, g["W"], rtol=F64_RTOL, atol=1e-13)
+    assert np.allclose(r.H, g["H"], rtol=F64_RTOL, atol=1e-13)
+
+
+def _config1(orc, N=500, T=2000):
+    # BASELINE.json configs[0]: synthetic N=500, T=2000, fit K=5 L=10 (datasets/synthetic.jl data model)
+    X, _, _ = orc.po.synthetic_sequences(K=3, N=N, L=20, T=T, rng=np.random.default_rng(1234))
+    W0, H0 = orc.po.init_rand(X, 10, 5, np.random.default_rng(0))
+    return X, W0, H0
+
+
+def test_config1_mu_fp64_100_iterations(cmf, orc):
+    X, W0, H0 = _config1(orc)
+    ref = orc.co.fit(orc.co.MultUpdate, X, W0, H0, 100, check_convergence=False)
+    r = cmf.fit_cnmf(X, L=10, K=5, alg="mult", max_itr=100, W_init=W0, H_init=H0, check_convergence=False,
+                     layout="KNL")
+    assert len(r.loss_hist) == 101 and r.time_hist[0] == 0.0
+    assert np.allclose(r.loss_hist, ref.loss_hist, rtol=F64_RTOL)
+    assert np.allclose(r.W, ref.W, rtol=F64_RTOL, atol=1e-13)
+    assert np.allclose(r.H, ref.H, rtol=F64_RTOL, atol=1e-13)
+    assert np.all(np.diff(r.loss_hist) <= 1e-12)      # MU is monotone
+
+
+def test_config1_mu_fp32_loss_within_1e4(cmf, orc):
+    X, W0, H0 = _config1(orc)
+    ref = orc.co.fit(orc.co.MultUpdate, X, W0, H0, 100, check_convergence=False)
+    r = cmf.fit_cnmf(X, L=10, K=5, alg="mult", max_itr=100, W_init=W0, H_init=H0, check_convergence=False,
+                     dtype="f32", layout="KNL")
+    rel = np.abs(np.asarray(r.loss_hist) - np.asarray(ref.loss_hist)) / np.asarray(ref.loss_hist)
+    assert rel[-1] < F32_LOSS_RTOL and rel.max() < F32_LOSS_RTOL, rel.max()
+
+
+def test_config2_hals_regularised_fp64(cmf, orc):
+    # BASELINE.json configs[1]: same data, HALS with l1_H=0.1, l2_H=0.2, l1_W=0.1, l2_W=0.5 (README.md:52)
+    X, W0, H0 = _config1(orc)
+    reg = dict(l1W=0.1, l2W=0.5, l1H=0.1, l2H=0.2)
+    ref = orc.co.fit(orc.co.HALSUpdate, X, W0, H0, 25, check_convergence=False, **reg)
+    r = cmf.fit_cnmf(X, L=10, K=5, alg=":hals", max_itr=25, W_init=W0, H_init=H0, check_convergence=False,
+                     layout="KNL", l1_W=0.1, l2_W=0.5, l1_H=0.1, l2_H=0.2)      # README spellings
+    assert np.allclose(r.loss_hist, ref.loss_hist, rtol=F64_RTOL)
+    assert np.allclose(r.W, ref.W, rtol=1e-8, atol=1e-11)
+    assert np.allclose(r.H, ref.H, rtol=1e-8, atol=1e-11)
+
+
+def test_config2_hals_fp32_loss_within_1e4(cmf, orc):
+    X, W0, H0 = _config1(orc, N=200, T=800)
+    reg = dict(l1W=0.1, l2W=0.5, l1H=0.1, l2H=0.2)
+    ref = orc.co.fit(orc.co.HALSUpdate, X, W0, H0, 30, check_convergence=False, **reg)
+    r = cmf.fit_cnmf(X, L=10, K=5, alg="hals", max_itr=30, W_init=W0, H_init=H0, check_convergence=False,
+                     dtype="f32", layout="KNL", **reg)
+    rel = np.abs(np.asarray(r.loss_hist) - np.asarray(ref.loss_hist)) / np.asarray(ref.loss_hist)
+    assert rel[-1] < F32_LOSS_RTOL, rel
+
+
+def test_hals_short_T_all_tail(cmf, orc):
+    N, T, K, L = 5, 7, 2, 5
+    W, H, X = _rand(N, T, K, L, seed=10)
+    ref = orc.co.fit(orc.co.HALSUpdate, X, W, H, 3, check_convergence=False)
+    r = cmf.fit_cnmf(X, L=L, K=K, alg="hals", max_itr=3, W_init=W, H_init=H, check_convergence=False, layout="KNL")
+    assert np.allclose(r.loss_hist, ref.loss_hist, rtol=F64_RTOL)
+    ref = orc.co.fit(orc.co.MultUpdate, X, W, H, 3, check_convergence=False)
+    r = cmf.fit_cnmf(X, L=L, K=K, alg="mult", max_itr=3, W_init=W, H_init=H, check_convergence=False, layout="KNL")
+    assert np.allclose(r.loss_hist, ref.loss_hist, rtol=F64_RTOL)
+
+
+def test_rule_interface_in_place_semantics(cmf, orc):
+    # the plugin boundary: Rule(data,W,H); update_motifs!(...) mutates W; update_feature_maps!(...) -> loss
+    N, T, K, L = 23, 120, 3, 7
+    W, H, X = _rand(N, T, K, L, seed=7)
+    Wo, Ho = np.asfortranarray(W.copy()), np.asfortranarray(H.copy())
+    ro = orc.co.MultUpdate(X, Wo, Ho)
+    Wg, Hg = W.copy(), H.copy()
+    rg = cmf.MultUpdate(X, Wg, Hg)
+    for _ in range(3):
+        ro.update_motifs(X, Wo, Ho, l1W=0.1, l2W=0.2)
+        rg.update_motifs(X, Wg, Hg, l1W=0.1, l2W=0.2)
+        assert np.allclose(Wg, Wo, rtol=F64_RTOL)
+        lo = ro.update_feature_maps(X, Wo, Ho, l1H=0.3)
+        lg = rg.update_feature_maps(X, Wg, Hg, l1H=0.3)
+        assert abs(lo - lg) < F64_RTOL * lo and np.allclose(Hg, Ho, rtol=F64_RTOL)
+    assert rg.launch_count() > 0
+    rg.close()
+
+
+def test_host_stepped_fit_equals_device_loop(cmf, orc):
+    X, W0, H0 = _config1(orc, N=60, T=300)
+    a = cmf.fit_cnmf(X, L=10, K=5, max_itr=8, W_init=W0, H_init=H0, check_convergence=False, layout="KNL")
+    rule = cmf.MultUpdate(X, W0, H0)
+    b = cmf.fit(cmf.AlternatingOptimizer(rule, 8), X, 10, 5, W0, H0, check_convergence=False, layout="KNL")
+    assert np.array_equal(a.loss_hist, b.loss_hist) and np.array_equal(a.W, b.W) and np.array_equal(a.H, b.H)
+
+
+def test_driver_semantics(cmf, orc):
+    X, W0, H0 = _config1(orc, N=40, T=200)
+    msgs = []
+    r = cmf.fit_cnmf(X, L=10, K=5, max_itr=400, W_init=W0, H_init=H0, tol=1e-3, printer=msgs.append)
+    ref = orc.co.fit(orc.co.MultUpdate, X, W0, H0, 400, tol=1e-3, printer=lambda s: None)
+    assert msgs == ["Converged early."] and len(r.loss_hist) == len(ref.loss_hist) < 401
+    assert r.W.shape == (10, 40, 5)                                   # default layout L x N x K
+    r0 = cmf.fit_cnmf(X, L=10, K=5, max_itr=0, W_init=W0, H_init=H0)
+    assert len(r0.loss_hist) == 1 and abs(r0.loss_hist[0] - orc.po.compute_loss(X, W0, H0)) < 1e-12
+    re = cmf.fit_cnmf(X, L=10, K=5, max_itr=3, W_init=W0, H_init=H0, eval_mode=True, check_convergence=False,
+                      layout="KNL")
+    assert np.allclose(re.W, W0, rtol=1e-15)                          # eval_mode skips update_motifs!
+    rs_ = cmf.fit_cnmf(X, L=4, K=2, max_itr=2, seed=3)                # seeded random init path
+    assert len(rs_.loss_hist) == 3 and rs_.loss_hist[0] < 1.0
+    with pytest.raises(ValueError):
+        cmf.fit_cnmf(X, L=4, K=2, alg="anls")
+
+
+def test_init_rand_rescale(cmf, orc):
+    X, _, _ = _config1(orc, N=30, T=150)
+    W, H = cmf.init_rand(X, 6, 3, seed=5)
+    est = orc.po.tensor_conv(W, H)
+    assert abs(np.vdot(X, est) / np.vdot(est, est) - 1.0) < 1e-10
+
+
+def _lockstep(shards, iters, reg):
+    """Drives several DeviceShard handles on ONE GPU in lockstep, doing the collectives by hand
+    (sum of the exchange tensors, halo copies) -- emulates the ranks without multi-process spins."""
+    import math
+
+    ss = sum(s.data_sumsq() for s in shards)
+    for s in shards:
+        s.set_data_norm(math.sqrt(ss))
+    hist = []
+
+    def loss():
+        return math.sqrt(sum(s.loss_partial() for s in shards)) / math.sqrt(ss)
+
+    hist.append(loss())
+    for _ in range(iters):
+        for s in shards:
+            s.w_partials()
+        for which in (0, 1):
+            tot = sum(s.exchange[which].clone() for s in shards)
+            for s in shards:
+                s.exchange[which].copy_(tot)
+        for s in shards:
+            s.w_apply(reg.get("l1W", 0.0), reg.get("l2W", 0.0))
+        for s in shards:
+            s.h_update(reg.get("l1H", 0.0), reg.get("l2H", 0.0))
+        for a, b in zip(shards[:-1], shards[1:]):
+            b.recv_left.copy_(a.send_right)
+            a.recv_right.copy_(b.send_left)
+        hist.append(loss())
+    return hist
+
+
+@pytest.mark.parametrize("dtype,tol", [("f64", F64_RTOL), ("f32", 5e-5)])
+def test_sharded_device_path_matches_oracle(cmf, orc, dtype, tol):
+    import torch
+
+    N, T, K, L, iters = 37, 301, 4, 9, 6
+    W0, H0, X = _rand(N, T, K, L, seed=21)
+    reg = dict(l1W=0.1, l2W=0.5, l1H=0.1, l2H=0.2)
+    ref = orc.co.fit(orc.co.MultUpdate, X, W0, H0, iters, check_convergence=False, **reg)
+    plan = cmf.ShardPlan(T, 3, L)
+    shards = []
+    for (t0, t1) in plan.ranges:
+        s = cmf.DeviceShard(N, T, t0, t1, K, L, dtype=dtype, device=0)
+        s.set_data(X, 0)
+        s.set_factors(W0, H0, 0)
+        shards.append(s)
+    hist = _lockstep(shards, iters, reg)
+    torch.cuda.synchronize()
+    assert np.allclose(hist, ref.loss_hist, rtol=tol)
+    H = np.concatenate([s.get_factors()[1] for s in shards], axis=1)
+    for s in shards:
+        assert np.allclose(s.get_factors()[0], ref.W, rtol=max(tol, 1e-9) * 50, atol=1e-12)
+    assert np.allclose(H, ref.H, rtol=max(tol, 1e-9) * 50, atol=1e-12)
+    for s in shards:
+        s.close()
+
+
+def test_synth_data_and_init_are_sharding_invariant(cmf):
+    import ctypes
+
+    N, T, K, L = 48, 500, 4, 8
+
+    def losses(world):
+        plan = cmf.ShardPlan(T, world, L)
+        shards = []
+        for (t0, t1) in plan.ranges:
+            s = cmf.DeviceShard(N, T, t0, t1, K, L, dtype="f64", device=0)
+            s.synth_data(1234, K, L, 0.05, 0.1)
+            s.init_rand(0)
+            shards.append(s)
+        dot = sum(s.init_scale_partials()[0] for s in shards)
+        nrm = sum(s.init_scale_partials()[1] for s in shards)
+        for s in shards:
+            s.scale_factors(np.sqrt(abs(dot / nrm)))
+        h = _lockstep(shards, 3, {})
+        for s in shards:
+            s.close()
+        return h
+
+    a, b = losses(1), losses(2)
+    assert a[0] < 1.0 and a[-1] < a[0]
+    assert np.allclose(a, b, rtol=1e-10)
+
+
+def test_adjointness_at_medium_size_fp32(cmf):
+    # size-independent property: <conv(W,H), X> == <H, transconv(W,X)> == <W, corr(H,X)>
+    N, T, K, L = 256, 20000, 16, 24
+    W, H, X = _rand(N, T, K, L, seed=99)
+    a = np.vdot(cmf.tensor_conv(W, H, "f32").astype(np.float64), X)
+    b = np.vdot(H, cmf.tensor_transconv(W, X, "f32").astype(np.float64))
+    c = np.vdot(W, cmf.corr_w(H, X, L, "f32").astype(np.float64))
+    assert abs(a - b) < 1e-5 * abs(a) and abs(a - c) < 1e-5 * abs(a)
