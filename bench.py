@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- CNMF iterations/s of the B200 fit path on BASELINE.json's headline workload.
+
+    python bench.py --gpus N --steps K --warmup W            (this repo's CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...  (the reference's CPU algorithm, oracle port)
+
+One "step" = one full MU iteration (update_motifs! + update_feature_maps! incl. the loss,
+src/algs/alternating.jl:51-54) over the whole synthetic data set.  N > 1 shards the time axis
+(strong scaling: the workload is fixed).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# BASELINE.json configs (fp32 MU).  "c4" is the configuration the metric is quoted on; it fits
+# one B200 (X = 64 GiB fp32), so it is the N=1 workload too.
+CONFIGS = {
+    "c4": dict(N=4096, T=1 << 22, K=64, L=100),
+    "c3": dict(N=1024, T=1 << 20, K=20, L=50),
+    "c1": dict(N=500, T=2000, K=5, L=10),
+}
+SEED_DATA, SEED_INIT, P_H, NOISE = 1234, 0, 0.05, 0.1
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"], tensor=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor=1400.0, src="fallback")
+
+
+def flops_contraction(N, T, K, L):
+    return 2.0 * N * K * (L * T - L * (L - 1) / 2.0)          # SURVEY.md section 8d  F_c
+
+
+def bytes_iteration(N, T, K, L, s=4):
+    return s * (2.0 * N * T + 4.0 * K * T + 6.0 * K * N * L)  # SURVEY.md section 8d  B_alg
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (oracle port, NumPy/OpenBLAS per-lag GEMMs like src/common.jl)
+# ------------------------------------------------------------------------------------------------
+def cpu_iteration_time(cfg, T_sample, steps, warmup):
+    """Seconds per literal MU iteration (src/algs/mult.jl:23-58) on a T_sample-column slice of the
+    workload (same N, K, L), Float64 like the reference, all host threads OpenBLAS gives us."""
+    import numpy as np
+
+    from oracle import cnmf_oracle as po
+
+    N, K, L = cfg["N"], cfg["K"], cfg["L"]
+    rng = np.random.default_rng(SEED_DATA)
+    X = rng.random((N, T_sample))
+    W = rng.random((K, N, L))
+    H = rng.random((K, T_sample))
+    rule = po.MultUpdate.__new__(po.MultUpdate)     # skip the ctor's extra conv: we time the iteration only
+    rule.data_norm = float(np.linalg.norm(X))
+    rule.est = np.zeros_like(X)
+    rule.resids = None
+    for _ in range(warmup):
+        rule.update_motifs(X, W, H)
+        rule.update_feature_maps(X, W, H)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        rule.update_motifs(X, W, H)
+        rule.update_feature_maps(X, W, H)
+    return (time.perf_counter() - t0) / steps
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+
+        return max([p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"] or [os.cpu_count()])
+    except Exception:
+        return os.cpu_count()
+
+
+def cpu_sample_T(cfg):
+    # ~10-30 s of CPU work per bounded sample: 7 contractions of 2*N*K*L*T_sample FLOP at O(100) GFLOP/s
+    target_flops = 1.0e12
+    per_col = 7 * 2.0 * cfg["N"] * cfg["K"] * cfg["L"]
+    Ts = int(max(4 * cfg["L"], min(cfg["T"], target_flops / per_col)))
+    return max(cfg["L"], (Ts // 256) * 256 or Ts)
+
+
+def run_reference(args, cfg, name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    Ts = cpu_sample_T(cfg)
+    sec = cpu_iteration_time(cfg, Ts, max(args.steps, 1), max(args.warmup, 1))
+    its = 1.0 / (sec * cfg["T"] / Ts)                 # cost is exactly linear in T
+    sample = f"literal MU iteration timed on a T={Ts} slice (same N,K,L), extrapolated x{cfg['T'] / Ts:.0f} to T={cfg['T']}"
+    cores = cpu_threads()
+    line = {
+        "impl": "reference", "metric": "CNMF iterations/sec", "value": its, "unit": "iterations/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / its,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{name}: MU N={cfg['N']} T={cfg['T']} K={cfg['K']} L={cfg['L']}", "alg": "mult"},
+        "cpu_baseline": {"value": its, "unit": "iterations/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": its, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "Julia is not installed in this image, so the reference itself cannot run; this is the "
+                "NumPy/OpenBLAS restatement of src/algs/mult.jl (oracle/cnmf_oracle.py), same per-lag GEMM structure",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, cfg, name):
+    import numpy as np
+    import torch
+
+    import __graft_entry__ as ge
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+    if rank == 0:
+        ge.build()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        dist.barrier()
+    torch.cuda.set_device(local_rank)
+    import cmf_jl_b200 as cmf
+
+    N, T, K, L = cfg["N"], cfg["T"], cfg["K"], cfg["L"]
+    plan = cmf.ShardPlan(T, world, L)
+    t0, t1 = plan.ranges[rank]
+    shard = cmf.DeviceShard(N, T, t0, t1, K, L, dtype="f32", device=local_rank)
+    fitter = cmf.ShardedMultFit(shard, rank, world, dist)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # synthetic data of BASELINE's shape, generated in HBM; random-init factors + alpha rescale
+    shard.synth_data(SEED_DATA, K, L, P_H, NOISE)
+    fitter.setup_data_norm()
+    shard.init_rand(SEED_INIT)
+    fitter.rescale_init()
+    loss0 = fitter.loss()
+
+    for _ in range(args.warmup):
+        fitter.iterate()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    shard.profile(True)
+    launches0 = shard.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    losses = []
+    for _ in range(args.steps):
+        losses.append(fitter.iterate())
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = shard.profile_read()
+    shard.profile(False)
+    launches = shard.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    ms_per_step = ms / args.steps
+    value = 1e3 / ms_per_step
+
+    # ---- end-to-end through the public API with HOST buffers (upload inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        hi = min(t1 + (L - 1), T)                 # owned columns + the static right halo of X
+        host = torch.empty((hi - t0, N), dtype=torch.float32, pin_memory=True)   # [t][n] == Julia N x cols
+        Xh = host.numpy().T                       # N x cols, Fortran-ordered view of the pinned buffer
+        shard.get_data(Xh, with_halo=True)
+        Wh, Hh = shard.get_factors()
+        W0 = np.asfortranarray(Wh, dtype=np.float32)
+        H0 = np.asfortranarray(Hh, dtype=np.float32)
+        shard.close()
+        del shard, fitter, Wh, Hh
+        torch.cuda.empty_cache()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sh2 = cmf.DeviceShard(N, T, t0, t1, K, L, dtype="f32", device=local_rank)
+        f2 = cmf.ShardedMultFit(sh2, rank, world, dist)
+        sh2.set_data(Xh, t0)                      # H2D of this rank's columns from pinned host memory
+        f2.setup_data_norm()
+        # factors: host W (replicated) and this rank's columns of H (+ halos are exchanged, not uploaded)
+        _set_sharded_factors(sh2, f2, W0, H0, t0)
+        el = [f2.loss()]
+        for _ in range(args.steps):
+            el.append(f2.iterate())               # each iteration reads its loss back (8 bytes D2H)
+        We, He = sh2.get_factors()                # D2H of the result
+        e1.record()
+        barrier()
+        ems = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ems], dtype=torch.float64, device=f"cuda:{local_rank}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        h2d = (Xh.nbytes + W0.size * 4 + H0.size * 4) * world / args.steps
+        d2h = ((We.size + He.size) * 4 * world + 8 * (args.steps + 1)) / args.steps
+        e2e = {"value": args.steps / (ems / 1e3), "unit": "iterations/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "iterations": args.steps,
+               "note": "fit through the public API from pinned host buffers: one upload of X/W/H, K iterations "
+                       "each reading its loss back, one download of W/H; bytes are totals divided by K",
+               "final_loss": el[-1]}
+        sh2.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    Fc = flops_contraction(N, T, K, L)
+    # dominant kernel = the contraction class with the largest device time in the timed region
+    dom = max(prof, key=lambda k: prof[k][0])
+    dom_ms, dom_n = prof[dom]
+    per_launch_ms = dom_ms / max(dom_n, 1)
+    Fc_rank = Fc / world
+    achieved_tf = Fc_rank / (per_launch_ms * 1e-3) / 1e12
+    contr_share = sum(v[0] for v in prof.values()) / (ms_per_step * args.steps) if ms > 0 else None
+    roofline = {
+        "bound": "tensor", "kernel": dom, "achieved": achieved_tf, "peak": pk["tensor"], "unit": "TFLOP/s",
+        "frac": achieved_tf / pk["tensor"], "traffic": None, "peak_source": f"{pk['src']} bf16 sustained",
+        "flops_per_launch": Fc_rank, "ms_per_launch": per_launch_ms,
+        "note": "arithmetic intensity K*L/2 = %d FLOP/B >> machine balance: the contraction is tensor/FMA bound, "
+                "not HBM bound (SURVEY.md section 8d); algorithmic FLOPs 2*N*K*(L*T - L(L-1)/2) per contraction launch" % (K * L // 2),
+        "kernel_ms": {k: {"total_ms": v[0], "launches": v[1]} for k, v in prof.items()},
+        "contraction_share_of_step": contr_share,
+    }
+    B = bytes_iteration(N, T, K, L) / world
+    hbm = {"achieved": B / (ms_per_step * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+           "frac": B / (ms_per_step * 1e-3) / 1e9 / pk["hbm"],
+           "note": "whole-iteration algorithmic bytes s*(2NT + 4KT + 6KNL) per GPU over the step time (the % HBM figure the metric asks for)"}
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        Ts = cpu_sample_T(cfg)
+        sec = cpu_iteration_time(cfg, Ts, 1, 1)
+        cpu = {"value": 1.0 / (sec * T / Ts), "unit": "iterations/s", "cores": cpu_threads(), "kind": "port",
+               "sample": f"one literal Float64 MU iteration on a T={Ts} slice (same N,K,L), extrapolated x{T / Ts:.0f}"}
+
+    line = {
+        "metric": "CNMF iterations/sec", "value": value, "unit": "iterations/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{name}: MU N={N} T={T} K={K} L={L}", "alg": "mult", "parallelism": f"T-shard x{world}",
+                   "l2": "inputs (X = %.1f GiB per GPU) exceed the 126 MB L2" % (4.0 * N * (t1 - t0) / 2 ** 30),
+                   "seeds": {"data": SEED_DATA, "init": SEED_INIT}, "p_h": P_H, "noise": NOISE},
+        "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_hbm": hbm, "cpu_baseline": cpu,
+        "clocks": clocks, "loss": {"initial": loss0, "final": losses[-1] if losses else None},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _set_sharded_factors(shard, fitter, W, H_owned, t0):
+    """Uploads W and this rank's owned H columns, then fills the halos by exchange."""
+    import numpy as np
+
+    L, K = shard.L, shard.K
+    lo = max(t0 - (L - 1), 0)
+    hi = min(shard.t1 + (L - 1), shard.T)
+    buf = np.zeros((K, hi - lo), dtype=H_owned.dtype, order="F")
+    buf[:, t0 - lo : t0 - lo + H_owned.shape[1]] = H_owned
+    shard.set_factors(W, buf, lo)
+    fitter.exchange_halos()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
+    ap.add_argument("--T", type=int, default=None, help="override T (development only; reported in config.workload)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    name = args.config
+    if args.T:
+        cfg["T"] = args.T
+        name += f"(T overridden to {args.T})"
+    if args.impl == "reference":
+        run_reference(args, cfg, name)
+    else:
+        run_ours(args, cfg, name)
+
+
+if __name__ == "__main__":
+    main()

@@ -23,6 +23,7 @@ SIGNATURES = {
     "cmf_destroy": [_h],
     "cmf_set_data": [_h, _vp, _i64],
     "cmf_synth_data": [_h, _c.c_uint64, _i64, _i64, _dbl, _dbl],
+    "cmf_get_data": [_h, _vp, _int],
     "cmf_data_sumsq": [_h, _c.POINTER(_dbl)],
     "cmf_set_data_norm": [_h, _dbl],
     "cmf_set_factors": [_h, _vp, _vp, _i64],
@@ -47,6 +48,8 @@ SIGNATURES = {
     "cmf_stream": [_h, _c.POINTER(_vp)],
     "cmf_set_stream": [_h, _vp],
     "cmf_set_engine": [_h, _int],
+    "cmf_profile": [_h, _int],
+    "cmf_profile_read": [_h, _int, _c.POINTER(_dbl), _c.POINTER(_i64)],
     "cmf_tensor_conv": [_i64, _i64, _i64, _i64, _int, _vp, _vp, _vp],
     "cmf_tensor_transconv": [_i64, _i64, _i64, _i64, _int, _vp, _vp, _vp],
     "cmf_corr_w": [_i64, _i64, _i64, _i64, _int, _vp, _vp, _vp],

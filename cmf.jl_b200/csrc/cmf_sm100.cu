@@ -74,7 +74,30 @@ struct cmf_ctx {
     int64_t launches = 0;
     double data_norm = 0.0;
     bool have_data = false, have_factors = false;
-    virtual ~cmf_ctx() {}
+    // optional per-kernel-class event timing (bench.py's roofline): class -> list of event pairs
+    bool profiling = false;
+    struct ProfEv { int which; cudaEvent_t a, b; };
+    std::vector<ProfEv> prof_events;
+    int prof_open = -1;
+    void prof_begin(int which) {
+        if (!profiling) return;
+        ProfEv e; e.which = which;
+        cudaEventCreate(&e.a); cudaEventCreate(&e.b);
+        cudaEventRecord(e.a, stream);
+        prof_events.push_back(e);
+        prof_open = (int)prof_events.size() - 1;
+    }
+    void prof_end() {
+        if (!profiling || prof_open < 0) return;
+        cudaEventRecord(prof_events[prof_open].b, stream);
+        prof_open = -1;
+    }
+    void prof_clear() {
+        for (auto &e : prof_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+        prof_events.clear();
+    }
+    virtual ~cmf_ctx() { prof_clear(); }
+    virtual void get_data(void *X_out, int with_halo) = 0;
     virtual void set_data(const void *X, int64_t first_col) = 0;
     virtual void synth_data(uint64_t seed, int64_t Kt, int64_t Lt, double p_h, double noise) = 0;
     virtual double data_sumsq() = 0;
@@ -95,6 +118,8 @@ struct cmf_ctx {
     virtual void prim_transconv(const void *X_host, void *out_host) = 0;
     virtual void prim_corr(const void *X_host, void *out_host) = 0;
 };
+
+enum { PROF_CONV = 0, PROF_TRANSCONV = 1, PROF_CORR = 2, PROF_NCLASS = 3 };
 
 namespace {
 
@@ -185,8 +210,10 @@ struct Ctx : cmf_ctx {
         const size_t smem = (size_t)KC * HW * sizeof(S) + ws_bytes;
         auto kern = conv_kernel<S, TN, TT, TY>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid((unsigned)cdiv(N, BN), (unsigned)cdiv(t_hi - t_lo, BT));
+        dim3 grid((unsigned)cdiv(t_hi - t_lo, BT), (unsigned)cdiv(N, BN));
+        prof_begin(PROF_CONV);
         kern<<<grid, dim3(16, TY), smem, stream>>>(a);
+        prof_end();
         post_launch();
     }
     int conv_nblocks(int64_t t_lo, int64_t t_hi) const { return (int)(cdiv(N, BN) * cdiv(t_hi - t_lo, BT)); }
@@ -234,8 +261,10 @@ struct Ctx : cmf_ctx {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
         kern<<<grid, nthr, smem, stream>>>(a);                                                     \
     }
+        if (Nin == N) prof_begin(PROF_TRANSCONV);
         if (best_tk == 8) LAUNCH_TR(8) else if (best_tk == 5) LAUNCH_TR(5) else LAUNCH_TR(4)
 #undef LAUNCH_TR
+        prof_end();
         post_launch();
     }
 
@@ -247,7 +276,9 @@ struct Ctx : cmf_ctx {
         a.u_hi = Tl; a.tau_hi = tau_hi; a.split_len = split_len;
         const int64_t ngrp = cdiv(L, 8);
         dim3 grid((unsigned)cdiv(Nin, 128), (unsigned)cdiv(K * ngrp, CORR_PB), (unsigned)nsplit);
+        if (Nin == N) prof_begin(PROF_CORR);
         corr_kernel<S><<<grid, dim3(16, 16), 0, stream>>>(a);
+        prof_end();
         post_launch();
         const int64_t n = KL() * Nin;
         reduce_partials_kernel<S><<<(unsigned)cdiv(n, 256), 256, 0, stream>>>(corr_part.p, nsplit, n, out_s, out_d);
@@ -276,6 +307,11 @@ struct Ctx : cmf_ctx {
         const S *src = static_cast<const S *>(Xh) + (t0 - first_col) * N;
         CK(cudaMemcpyAsync(X.p, src, (size_t)((hi - t0) * N) * sizeof(S), cudaMemcpyHostToDevice, stream));
         finish_data();
+    }
+    void get_data(void *X_out, int with_halo) override {
+        const int64_t cols = with_halo ? std::min(t1 + (L - 1), T) - t0 : Tl;
+        CK(cudaMemcpyAsync(X_out, X.p, (size_t)(cols * N) * sizeof(S), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
     }
     void finish_data() {
         data_norm = std::sqrt(data_sumsq());
@@ -713,6 +749,36 @@ int cmf_launch_count(cmf_handle h, int64_t *out) {
 }
 int cmf_stream(cmf_handle h, void **stream_out) {
     return guarded([&] { REQUIRE(h && stream_out, "null argument"); *stream_out = (void *)h->stream; });
+}
+int cmf_get_data(cmf_handle h, void *X_out, int with_halo) {
+    return guarded([&] { use(h); REQUIRE(X_out, "null output"); REQUIRE(h->have_data, "no data"); h->get_data(X_out, with_halo); });
+}
+int cmf_profile(cmf_handle h, int enable) {
+    return guarded([&] {
+        use(h);
+        CK(cudaStreamSynchronize(h->stream));
+        h->prof_clear();
+        h->profiling = enable != 0;
+    });
+}
+int cmf_profile_read(cmf_handle h, int which, double *ms_total, int64_t *count) {
+    return guarded([&] {
+        use(h);
+        REQUIRE(ms_total && count, "null output");
+        REQUIRE(which >= 0 && which < PROF_NCLASS, "which must be 0 (conv), 1 (transconv) or 2 (corr)");
+        CK(cudaStreamSynchronize(h->stream));
+        double tot = 0.0;
+        int64_t n = 0;
+        for (auto &e : h->prof_events) {
+            if (e.which != which) continue;
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, e.a, e.b));
+            tot += ms;
+            ++n;
+        }
+        *ms_total = tot;
+        *count = n;
+    });
 }
 int cmf_set_stream(cmf_handle h, void *stream) {
     return guarded([&] {

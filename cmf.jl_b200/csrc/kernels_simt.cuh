@@ -109,8 +109,8 @@ __global__ void __launch_bounds__(16 * TY) conv_kernel(ConvArgs<S> a) {
 
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int tid = ty * 16 + tx, nthr = 16 * TY;
-    const int64_t n0 = (int64_t)blockIdx.x * BN;
-    const int64_t t0 = a.t_lo + (int64_t)blockIdx.y * BT;
+    const int64_t n0 = (int64_t)blockIdx.y * BN;          // grid.x runs over time tiles (can be > 65535)
+    const int64_t t0 = a.t_lo + (int64_t)blockIdx.x * BT;
 
     S acc[TT][TN];
 #pragma unroll

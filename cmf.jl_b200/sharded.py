@@ -114,6 +114,28 @@ class DeviceShard:
         check(_lib.load().cmf_data_sumsq(self._h, ctypes.byref(out)))
         return out.value
 
+    def get_data(self, out=None, with_halo=False):
+        """Owned columns of X (plus the right halo, clipped to T, with ``with_halo``) as a
+        Fortran-ordered N x cols array (optionally into a caller buffer)."""
+        cols = (min(self.t1 + self.L - 1, self.T) if with_halo else self.t1) - self.t0
+        if out is None:
+            out = np.empty((self.N, cols), dtype=np_dtype(self.dtype), order="F")
+        assert out.shape == (self.N, cols) and out.flags.f_contiguous
+        check(_lib.load().cmf_get_data(self._h, fptr(out), int(with_halo)))
+        return out
+
+    def profile(self, enable=True):
+        check(_lib.load().cmf_profile(self._h, int(enable)))
+
+    def profile_read(self):
+        """{class: (total_ms, launches)} for conv / transconv / corr."""
+        res = {}
+        for which, name in enumerate(("conv", "transconv", "corr")):
+            ms, n = ctypes.c_double(), ctypes.c_int64()
+            check(_lib.load().cmf_profile_read(self._h, which, ctypes.byref(ms), ctypes.byref(n)))
+            res[name] = (ms.value, n.value)
+        return res
+
     def set_data_norm(self, v):
         check(_lib.load().cmf_set_data_norm(self._h, float(v)))
 

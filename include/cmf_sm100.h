@@ -79,6 +79,11 @@ int cmf_set_data(cmf_handle h, const void *X, int64_t first_col);
 int cmf_synth_data(cmf_handle h, uint64_t seed, int64_t K_true, int64_t L_true, double p_h,
                    double noise);
 
+/* Copies the owned columns of X (N x (t_end-t_begin)), plus the right halo clipped to T when
+ * with_halo != 0, back to a host array (used by benchmarks to obtain a host copy of the
+ * device-generated synthetic data). */
+int cmf_get_data(cmf_handle h, void *X_out, int with_halo);
+
 /* sum of squares of the owned columns of X (double), and the global norm used as the loss
  * denominator (defaults to the local one; a sharded host all-reduces and sets it). */
 int cmf_data_sumsq(cmf_handle h, double *out);
@@ -153,6 +158,12 @@ int cmf_stream(cmf_handle h, void **stream_out);
  * so that host-side collectives on the exchange buffers are stream-ordered with the kernels
  * and no host synchronisation is needed between steps).  NULL selects the legacy default stream. */
 int cmf_set_stream(cmf_handle h, void *stream);
+/* Per-kernel-class CUDA-event timing on the handle's stream (bench.py's roofline numbers):
+ * cmf_profile(h, 1) starts recording an event pair around every launch of the three contraction
+ * kernels; cmf_profile_read returns the summed device time and launch count of class
+ * `which` (0 = conv/residual/loss, 1 = transposed conv for numH, 2 = correlation for numW). */
+int cmf_profile(cmf_handle h, int enable);
+int cmf_profile_read(cmf_handle h, int which, double *ms_total, int64_t *count);
 /* Selects the contraction engine: 0 = SIMT kernels (fp64 and fp32), 1 = tcgen05 tensor-core
  * kernels (fp32 data, split-bf16 operands) where available.  Default: best available. */
 int cmf_set_engine(cmf_handle h, int engine);
