@@ -15,7 +15,10 @@
 #include <string>
 #include <vector>
 
+#include <type_traits>
+
 #include "kernels_simt.cuh"
+#include "kernels_tc.cuh"
 
 namespace {
 
@@ -98,6 +101,7 @@ struct cmf_ctx {
     }
     virtual ~cmf_ctx() { prof_clear(); }
     virtual void get_data(void *X_out, int with_halo) = 0;
+    virtual bool tc_available() const = 0;
     virtual void set_data(const void *X, int64_t first_col) = 0;
     virtual void synth_data(uint64_t seed, int64_t Kt, int64_t Lt, double p_h, double noise) = 0;
     virtual double data_sumsq() = 0;
@@ -125,8 +129,55 @@ namespace {
 
 using namespace cmf;
 
+
+// ------------------------------------------------------------------------------------------
+// tcgen05 engine state (fp32 handles only): bf16 hi/lo operand copies and their TMA tensor maps
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !ptr) throw CmfError(CMF_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+        fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor map: dim0 (contiguous) x dim1 with row stride `stride1` bytes (rows may overlap)
+CUtensorMap make_map_2d(void *base, uint64_t dim0, uint64_t dim1, uint64_t stride1, uint32_t box0, uint32_t box1,
+                        CUtensorMapSwizzle swz) {
+    CUtensorMap m;
+    cuuint64_t gdim[2] = {dim0, dim1};
+    cuuint64_t gstr[1] = {stride1};
+    cuuint32_t box[2] = {box0, box1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstr, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw CmfError(CMF_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return m;
+}
+
+struct TcState {
+    bool ok = false;
+    int Kp = 0, G = 0, num_sms = 148;
+    int64_t KLp = 0, rows_u = 0, groups = 0, hrows = 0;
+    DevBuf<__nv_bfloat16> X_hi, X_lo, Hw_hi, Hw_lo, Hm_hi, Hm_lo, Wc_hi, Wc_lo, Wu_hi, Wu_lo;
+    CUtensorMap mWc[2], mHw[2], mHm[2], mWu[2], mXk[2], mXmn[2];
+    int nsplit = 1;
+    int64_t split_len = 0, tiles_m = 0, tiles_n = 0;
+    bool x_dirty = true, w_dirty = true;
+};
+
 template <typename S>
 struct Ctx : cmf_ctx {
+    TcState tcs;
     DevBuf<S> X, Hbuf, Wi, Wtmp, numW, denW, GS, Cf, numH, denH, R, tailC;
     DevBuf<double> exch1, corr_part, loss_part, scal;
     S *H = nullptr;  // owned column 0 inside Hbuf
@@ -169,7 +220,159 @@ struct Ctx : cmf_ctx {
         corr_part.alloc((size_t)std::max<int64_t>((int64_t)nsplit_w * KL() * N, (int64_t)nsplit_g * KL() * K));
         conv_blocks_max = (int)(cdiv(N, BN) * cdiv(Tl + hal, BT));
         loss_part.alloc((size_t)std::max(2 * conv_blocks_max, 1024));
+        tc_setup();
         CK(cudaStreamSynchronize(stream));
+    }
+
+    // ---------------------------------------------------------------- tcgen05 engine (fp32 only)
+    bool tc_active() const { return engine == 1 && tcs.ok; }
+    bool tc_available() const override { return tcs.ok; }
+
+    void tc_setup() {
+        if constexpr (!std::is_same<S, float>::value) { return; } else {
+            TcState &t = tcs;
+            if (alg != CMF_MULT || K > 128 || N % 8 != 0) return;
+            t.Kp = K <= 16 ? 16 : K <= 32 ? 32 : K <= 64 ? 64 : 128;
+            t.G = 128 / t.Kp;
+            t.KLp = cdiv(L * t.Kp, tc::BK) * tc::BK;
+            t.groups = cdiv(L, t.G);
+            t.rows_u = t.groups * 128;
+            const int64_t hal = L - 1;
+            t.hrows = Tl + hal;                                   // window rows addressed (X columns incl. right halo)
+            cudaDeviceProp prop;
+            CK(cudaGetDeviceProperties(&prop, device));
+            if (prop.major != 10) return;                         // tcgen05 needs sm_100
+            t.num_sms = prop.multiProcessorCount;
+            const size_t hw_elems = (size_t)((Tl + 2 * hal) * t.Kp + t.KLp + 64);
+            t.X_hi.alloc(X.n); t.X_lo.alloc(X.n);
+            t.Hw_hi.alloc(hw_elems); t.Hw_lo.alloc(hw_elems);
+            t.Hm_hi.alloc(hw_elems); t.Hm_lo.alloc(hw_elems);
+            t.Wc_hi.alloc((size_t)(N * t.KLp)); t.Wc_lo.alloc((size_t)(N * t.KLp));
+            t.Wu_hi.alloc((size_t)(t.rows_u * N)); t.Wu_lo.alloc((size_t)(t.rows_u * N));
+            // tensor maps (index 0 = hi plane, 1 = lo plane)
+            __nv_bfloat16 *wc[2] = {t.Wc_hi.p, t.Wc_lo.p}, *hw[2] = {t.Hw_hi.p, t.Hw_lo.p}, *hm[2] = {t.Hm_hi.p, t.Hm_lo.p};
+            __nv_bfloat16 *wu[2] = {t.Wu_hi.p, t.Wu_lo.p}, *xs[2] = {t.X_hi.p, t.X_lo.p};
+            for (int i = 0; i < 2; ++i) {
+                t.mWc[i] = make_map_2d(wc[i], (uint64_t)t.KLp, (uint64_t)N, (uint64_t)t.KLp * 2, tc::BK, tc::BM, CU_TENSOR_MAP_SWIZZLE_64B);
+                // overlapping-row "window" map: row t starts at element t*Kp and is KLp long
+                t.mHw[i] = make_map_2d(hw[i], (uint64_t)t.KLp, (uint64_t)t.hrows, (uint64_t)t.Kp * 2, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
+                t.mHm[i] = make_map_2d(hm[i], (uint64_t)t.KLp, (uint64_t)t.hrows, (uint64_t)t.Kp * 2, 64, tc::BK, CU_TENSOR_MAP_SWIZZLE_128B);
+                t.mWu[i] = make_map_2d(wu[i], (uint64_t)N, (uint64_t)t.rows_u, (uint64_t)N * 2, tc::BK, tc::BM, CU_TENSOR_MAP_SWIZZLE_64B);
+                t.mXk[i] = make_map_2d(xs[i], (uint64_t)N, (uint64_t)(Tl + hal), (uint64_t)N * 2, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
+                t.mXmn[i] = make_map_2d(xs[i], (uint64_t)N, (uint64_t)(Tl + hal), (uint64_t)N * 2, 64, tc::BK, CU_TENSOR_MAP_SWIZZLE_128B);
+            }
+            // correlation work split: balance persistent CTAs, keep splits >= FLUSH_T columns
+            t.tiles_m = cdiv(t.KLp, tc::BM);
+            t.tiles_n = cdiv(N, tc::BN);
+            const int64_t tau = Tl + hal, base = t.tiles_m * t.tiles_n;
+            double best = -1.0;
+            for (int ns = 1; ns <= 16; ++ns) {
+                const int64_t sl = cdiv(cdiv(tau, ns), tc::BK) * tc::BK;
+                if (ns > 1 && sl < tc::FLUSH_T) break;
+                const int64_t units = base * cdiv(tau, sl);
+                const double eff = (double)units / (double)(cdiv(units, t.num_sms) * t.num_sms);
+                if (eff > best + 1e-9) { best = eff; t.nsplit = (int)cdiv(tau, sl); t.split_len = sl; }
+            }
+            const size_t need = (size_t)t.nsplit * (size_t)(KL() * N);
+            if (corr_part.n < need) corr_part.alloc(need);
+            const size_t need_lp = (size_t)(tc::EPI_WARPS * cdiv(Tl, tc::BN) * cdiv(N, tc::BM));
+            if (loss_part.n < need_lp) loss_part.alloc(need_lp);
+            CK(cudaFuncSetAttribute(tc::tc_kernel<tc::TC_CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+            CK(cudaFuncSetAttribute(tc::tc_kernel<tc::TC_TRANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+            CK(cudaFuncSetAttribute(tc::tc_kernel<tc::TC_CORR>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+            t.ok = true;
+            // default engine: tensor cores when the contraction is big enough to fill 128x256 tiles
+            if (N >= 256 && Tl >= 4096 && K * L >= 256) engine = 1;
+        }
+    }
+
+    tc::Params tc_base_params() {
+        tc::Params q;
+        memset(&q, 0, sizeof(q));
+        q.N = N; q.K = K; q.L = L; q.Tl = Tl; q.G = tcs.G; q.Kp = tcs.Kp;
+        return q;
+    }
+
+    void tc_split_X() {
+        if constexpr (std::is_same<S, float>::value) {
+            if (!tcs.ok || !tcs.x_dirty) return;
+            tc::split_plain_kernel<<<(unsigned)cdiv((int64_t)X.n, 256), 256, 0, stream>>>(X.p, tcs.X_hi.p, tcs.X_lo.p, (int64_t)X.n);
+            post_launch();
+            tcs.x_dirty = false;
+        }
+    }
+    void tc_split_W() {
+        if constexpr (std::is_same<S, float>::value) {
+            if (!tcs.w_dirty) return;
+            tc::split_W_kernel<<<(unsigned)cdiv(L * tcs.Kp * N, 256), 256, 0, stream>>>(
+                Wi.p, tcs.Wc_hi.p, tcs.Wc_lo.p, tcs.Wu_hi.p, tcs.Wu_lo.p, N, K, L, tcs.Kp, tcs.KLp);
+            post_launch();
+            tcs.w_dirty = false;
+        }
+    }
+    void tc_split_H(bool masked) {
+        if constexpr (std::is_same<S, float>::value) {
+            const int64_t rows = Tl + 2 * (L - 1);
+            tc::split_H_kernel<<<(unsigned)cdiv(rows * tcs.Kp, 256), 256, 0, stream>>>(
+                Hbuf.p, masked ? tcs.Hm_hi.p : tcs.Hw_hi.p, masked ? tcs.Hm_lo.p : tcs.Hw_lo.p, rows, K, tcs.Kp,
+                L - 1, L - 1 + Tl, masked ? 1 : 0);
+            post_launch();
+        }
+    }
+
+    // numW via tensor cores (mult.jl:32)
+    void tc_corr() {
+        if constexpr (std::is_same<S, float>::value) {
+            tc_split_X();
+            tc_split_H(true);
+            tc::Params q = tc_base_params();
+            q.tiles_m = tcs.tiles_m; q.tiles_n = tcs.tiles_n; q.split_len = tcs.split_len; q.tau_hi = Tl + (L - 1);
+            q.units = tcs.tiles_m * tcs.tiles_n * tcs.nsplit;
+            q.part = corr_part.p;
+            const unsigned grid = (unsigned)std::min<int64_t>(q.units, tcs.num_sms);
+            prof_begin(PROF_CORR);
+            tc::tc_kernel<tc::TC_CORR><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tcs.mHm[0], tcs.mHm[1], tcs.mXmn[0], tcs.mXmn[1], q);
+            prof_end();
+            post_launch();
+            const int64_t n = KL() * N;
+            reduce_partials_kernel<S><<<(unsigned)cdiv(n, 256), 256, 0, stream>>>(corr_part.p, tcs.nsplit, n, numW.p, nullptr);
+            post_launch();
+        }
+    }
+    // numH via tensor cores (mult.jl:47)
+    void tc_transconv() {
+        if constexpr (std::is_same<S, float>::value) {
+            tc_split_X();
+            tc_split_W();
+            tc::Params q = tc_base_params();
+            q.groups = tcs.groups; q.nblocks = cdiv(N, tc::BK); q.own = tc::BN - (tcs.G - 1);
+            q.units = cdiv(Tl, q.own);
+            q.out = numH.p;
+            const unsigned grid = (unsigned)std::min<int64_t>(q.units, tcs.num_sms);
+            prof_begin(PROF_TRANSCONV);
+            tc::tc_kernel<tc::TC_TRANS><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tcs.mWu[0], tcs.mWu[1], tcs.mXk[0], tcs.mXk[1], q);
+            prof_end();
+            post_launch();
+        }
+    }
+    // sum of squared residuals via tensor cores (mult.jl:55-57); returns the number of partials written
+    int64_t tc_conv_loss() {
+        if constexpr (std::is_same<S, float>::value) {
+            tc_split_W();
+            tc_split_H(false);
+            tc::Params q = tc_base_params();
+            q.tiles_n = cdiv(N, tc::BM);
+            q.nkb = tcs.KLp / tc::BK;
+            q.units = q.tiles_n * cdiv(Tl, tc::BN);
+            q.X = X.p; q.partial = loss_part.p;
+            const unsigned grid = (unsigned)std::min<int64_t>(q.units, tcs.num_sms);
+            prof_begin(PROF_CONV);
+            tc::tc_kernel<tc::TC_CONV><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tcs.mWc[0], tcs.mWc[1], tcs.mHw[0], tcs.mHw[1], q);
+            prof_end();
+            post_launch();
+            return tc::EPI_WARPS * q.units;
+        }
+        return 0;
     }
 
     ~Ctx() override {
@@ -314,6 +517,7 @@ struct Ctx : cmf_ctx {
         CK(cudaStreamSynchronize(stream));
     }
     void finish_data() {
+        tcs.x_dirty = true;
         data_norm = std::sqrt(data_sumsq());
         have_data = true;
     }
@@ -354,6 +558,7 @@ struct Ctx : cmf_ctx {
         CK(cudaMemcpyAsync(H + (lo - t0) * K, src, (size_t)((hi - lo) * K) * sizeof(S), cudaMemcpyHostToDevice, stream));
         CK(cudaStreamSynchronize(stream));
         have_factors = true;
+        tcs.w_dirty = true;
         if (alg == CMF_HALS && have_data) refresh_resid(false);
     }
 
@@ -369,6 +574,7 @@ struct Ctx : cmf_ctx {
         post_launch();
         CK(cudaStreamSynchronize(stream));
         have_factors = true;
+        tcs.w_dirty = true;
     }
 
     void init_scale_partials(double out[2]) override {
@@ -389,6 +595,7 @@ struct Ctx : cmf_ctx {
         post_launch();
         scale_kernel<S><<<(unsigned)cdiv((int64_t)Hbuf.n, 256), 256, 0, stream>>>(Hbuf.p, (S)s, (int64_t)Hbuf.n);
         post_launch();
+        tcs.w_dirty = true;
         if (alg == CMF_HALS && have_data) refresh_resid(false);
     }
 
@@ -406,7 +613,8 @@ struct Ctx : cmf_ctx {
     void w_partials() override {
         REQUIRE(have_data && have_factors, "update: data and factors must be set first");
         // numW partial over the owned u (mult.jl:32): Xin = X incl. right halo
-        launch_corr(X.p, N, N, Tl + (L - 1), nsplit_w, split_w, numW.p, nullptr);
+        if (tc_active()) tc_corr();
+        else launch_corr(X.p, N, N, Tl + (L - 1), nsplit_w, split_w, numW.p, nullptr);
         // Gram partial Rg[d][k][k'] = sum_u H[u][k] H[u+d][k'] (owned u, right halo for u+d)
         launch_corr(H, K, K, Tl + (L - 1), nsplit_g, split_g, nullptr, exch1.p);
         if (L > 1) {
@@ -424,6 +632,7 @@ struct Ctx : cmf_ctx {
         build_G();
         launch_gemm<false>(GS.p, Wi.p, denW.p, KL(), N, KL(), KL(), N, N);   // denomW = G * Wi (mult.jl:28,33)
         launch_mu(Wi.p, numW.p, denW.p, l1W, l2W, KL() * N);                  // mult.jl:37-38
+        tcs.w_dirty = true;
     }
 
     void lag_tables() {
@@ -434,7 +643,8 @@ struct Ctx : cmf_ctx {
 
     void h_update(double l1H, double l2H) override {
         REQUIRE(have_data && have_factors, "update: data and factors must be set first");
-        launch_transconv(Wi.p, X.p, numH.p, N, K, L, N, Tl, Tl + (L - 1));    // numH (mult.jl:47)
+        if (tc_active()) tc_transconv();
+        else launch_transconv(Wi.p, X.p, numH.p, N, K, L, N, Tl, Tl + (L - 1));    // numH (mult.jl:47)
         lag_tables();
         // denomH = C (*) H on all owned columns (mult.jl:44,48), then the truncated tail
         launch_transconv(Cf.p, Hbuf.p, denH.p, K, K, 2 * L - 1, K, Tl, Tl + 2 * (L - 1));
@@ -448,8 +658,9 @@ struct Ctx : cmf_ctx {
 
     double loss_partial() override {
         REQUIRE(have_data && have_factors, "loss: data and factors must be set first");
-        const int nb = conv_nblocks(0, Tl);
-        launch_conv(Wi.p, H, K, L, -(L - 1), Tl + (L - 1), 0, Tl, 4, nullptr, loss_part.p);  // mult.jl:55-57
+        int64_t nb = conv_nblocks(0, Tl);
+        if (tc_active()) nb = tc_conv_loss();
+        else launch_conv(Wi.p, H, K, L, -(L - 1), Tl + (L - 1), 0, Tl, 4, nullptr, loss_part.p);  // mult.jl:55-57
         reduce_scalar(loss_part.p, nb, scal.p);
         return fetch_scalar(scal.p);
     }
@@ -498,7 +709,9 @@ struct Ctx : cmf_ctx {
     void exchange_buffer(int which, void **p, int64_t *count, int *dt) override {
         if (which == 0) { *p = numW.p; *count = KL() * N; *dt = dtype; }
         else if (which == 1) { *p = exch1.p; *count = L * K * K + (L - 1) * K; *dt = CMF_F64; }
-        else throw CmfError(CMF_ERR_ARG, "exchange_buffer: which must be 0 or 1");
+        else if (which == 2) { *p = numH.p; *count = Tl * K; *dt = dtype; }   // diagnostics: numH [t][K]
+        else if (which == 3) { *p = denH.p; *count = Tl * K; *dt = dtype; }   // diagnostics: denomH [t][K]
+        else throw CmfError(CMF_ERR_ARG, "exchange_buffer: which must be 0..3");
     }
     void halo_buffers(void **sl, void **sr, void **rl, void **rr, int64_t *count) override {
         *sl = H; *sr = H + (Tl - (L - 1)) * K; *rl = Hbuf.p; *rr = H + Tl * K; *count = (L - 1) * K;
@@ -793,9 +1006,14 @@ int cmf_set_engine(cmf_handle h, int engine) {
     return guarded([&] {
         REQUIRE(h, "null handle");
         REQUIRE(engine == 0 || engine == 1, "engine must be 0 (SIMT) or 1 (tcgen05)");
-        if (engine == 1) throw CmfError(CMF_ERR_UNSUPPORTED, "tcgen05 engine not built into this library version");
+        if (engine == 1 && !h->tc_available())
+            throw CmfError(CMF_ERR_UNSUPPORTED, "tcgen05 engine needs an fp32 MultUpdate handle with K <= 128 and N % 8 == 0 on sm_100");
         h->engine = engine;
     });
+}
+
+int cmf_get_engine(cmf_handle h, int *engine_out) {
+    return guarded([&] { REQUIRE(h && engine_out, "null argument"); *engine_out = h->engine; });
 }
 
 int cmf_tensor_conv(int64_t N, int64_t T, int64_t K, int64_t L, int dtype, const void *W, const void *H, void *out) {

@@ -85,7 +85,7 @@ class DeviceShard:
         dev = f"cuda:{self.device}"
         ts = {_lib.F64: "<f8", _lib.F32: "<f4"}
         self.exchange = []
-        for which in (0, 1):
+        for which in (0, 1, 2, 3):
             p, n, dt = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_int()
             check(lib.cmf_exchange_buffer(self._h, which, ctypes.byref(p), ctypes.byref(n), ctypes.byref(dt)))
             self.exchange.append(torch.as_tensor(_CudaView(p.value, n.value, ts[dt.value]), device=dev))
@@ -97,6 +97,15 @@ class DeviceShard:
         else:
             v = [torch.empty(0, device=dev)] * 4
         self.send_left, self.send_right, self.recv_left, self.recv_right = v
+
+    def set_engine(self, engine):
+        """0 = SIMT kernels, 1 = tcgen05 tensor-core kernels (raises if the handle cannot use them)."""
+        check(_lib.load().cmf_set_engine(self._h, int(engine)))
+
+    def get_engine(self):
+        out = ctypes.c_int()
+        check(_lib.load().cmf_get_engine(self._h, ctypes.byref(out)))
+        return out.value
 
     def scalar_tensor(self, values):
         return self.torch.tensor(values, dtype=self.torch.float64, device=f"cuda:{self.device}")

@@ -140,7 +140,8 @@ int cmf_h_update(cmf_handle h, double l1H, double l2H);
 int cmf_loss_partial(cmf_handle h, double *sumsq_out);
 
 /* Exchange buffer `which`: 0 = numW partial (count = K*N*L elements of the handle dtype),
- * 1 = Gram/tail partial (double).  Returns the device pointer, element count and dtype. */
+ * 1 = Gram/tail partial (double); diagnostics only: 2 = numH, 3 = denomH of the last cmf_h_update
+ * ([t][K], handle dtype).  Returns the device pointer, element count and dtype. */
 int cmf_exchange_buffer(cmf_handle h, int which, void **dev_ptr, int64_t *count, int *dtype);
 /* H halo regions, each (L-1)*K contiguous elements of the handle dtype:
  * send_left  = first L-1 owned columns (goes to the left neighbour's recv_right),
@@ -167,6 +168,8 @@ int cmf_profile_read(cmf_handle h, int which, double *ms_total, int64_t *count);
 /* Selects the contraction engine: 0 = SIMT kernels (fp64 and fp32), 1 = tcgen05 tensor-core
  * kernels (fp32 data, split-bf16 operands) where available.  Default: best available. */
 int cmf_set_engine(cmf_handle h, int engine);
+/* The engine currently selected (0 / 1). */
+int cmf_get_engine(cmf_handle h, int *engine_out);
 
 /* ---- primitives (tests; one-shot, host in / host out) ----------------------------------- */
 
