@@ -168,10 +168,16 @@ struct TcState {
     bool ok = false;
     int Kp = 0, G = 0, num_sms = 148;
     int64_t KLp = 0, rows_u = 0, groups = 0, hrows = 0;
-    DevBuf<__nv_bfloat16> X_hi, X_lo, Hw_hi, Hw_lo, Hm_hi, Hm_lo, Wc_hi, Wc_lo, Wu_hi, Wu_lo;
+    DevBuf<__nv_bfloat16> X_hi, X_lo, Hw_hi, Hw_lo, Hm_hi, Hm_lo, Wc_hi, Wc_lo, Wu_hi, Wu_lo, Cc_hi, Cc_lo;
     CUtensorMap mWc[2], mHw[2], mHm[2], mWu[2], mXk[2], mXmn[2];
-    int nsplit = 1;
-    int64_t split_len = 0, tiles_m = 0, tiles_n = 0;
+    CUtensorMap mHmn[2];   // H (owned + right halo) as the MN-major "X" operand of the Gram correlation
+    CUtensorMap mCu[2];    // C table as the A operand of denomH
+    CUtensorMap mHk[2];    // H (both halos) as the K-major "X" operand of denomH
+    CUtensorMap mGc[2];    // G = Htilde Htilde' as the A operand of G*W
+    CUtensorMap mWuB[2], mWcB[2];   // Wu / Wc with 256-row boxes (B operands of the plain GEMMs)
+    DevBuf<__nv_bfloat16> Gc_hi, Gc_lo;
+    int nsplit = 1, nsplit_g = 1;
+    int64_t split_len = 0, split_len_g = 0, tiles_m = 0, tiles_n = 0, groups_c = 0, rows_c = 0;
     bool x_dirty = true, w_dirty = true;
 };
 
@@ -249,6 +255,11 @@ struct Ctx : cmf_ctx {
             t.Hm_hi.alloc(hw_elems); t.Hm_lo.alloc(hw_elems);
             t.Wc_hi.alloc((size_t)(N * t.KLp)); t.Wc_lo.alloc((size_t)(N * t.KLp));
             t.Wu_hi.alloc((size_t)(t.rows_u * N)); t.Wu_lo.alloc((size_t)(t.rows_u * N));
+            t.groups_c = cdiv(2 * L - 1, t.G);
+            t.rows_c = t.groups_c * 128;
+            t.Cc_hi.alloc((size_t)(t.rows_c * t.Kp)); t.Cc_lo.alloc((size_t)(t.rows_c * t.Kp));
+            t.Gc_hi.alloc((size_t)(KL() * t.KLp)); t.Gc_lo.alloc((size_t)(KL() * t.KLp));
+            if (GS.n < (size_t)(t.rows_u * t.rows_u)) GS.alloc((size_t)(t.rows_u * t.rows_u));
             // tensor maps (index 0 = hi plane, 1 = lo plane)
             __nv_bfloat16 *wc[2] = {t.Wc_hi.p, t.Wc_lo.p}, *hw[2] = {t.Hw_hi.p, t.Hw_lo.p}, *hm[2] = {t.Hm_hi.p, t.Hm_lo.p};
             __nv_bfloat16 *wu[2] = {t.Wu_hi.p, t.Wu_lo.p}, *xs[2] = {t.X_hi.p, t.X_lo.p};
@@ -260,6 +271,16 @@ struct Ctx : cmf_ctx {
                 t.mWu[i] = make_map_2d(wu[i], (uint64_t)N, (uint64_t)t.rows_u, (uint64_t)N * 2, tc::BK, tc::BM, CU_TENSOR_MAP_SWIZZLE_64B);
                 t.mXk[i] = make_map_2d(xs[i], (uint64_t)N, (uint64_t)(Tl + hal), (uint64_t)N * 2, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
                 t.mXmn[i] = make_map_2d(xs[i], (uint64_t)N, (uint64_t)(Tl + hal), (uint64_t)N * 2, 64, tc::BK, CU_TENSOR_MAP_SWIZZLE_128B);
+                // Gram: "X" = H rows from owned column 0 (owned + right halo), [t][Kp] MN-major
+                t.mHmn[i] = make_map_2d(hw[i] + hal * t.Kp, (uint64_t)t.Kp, (uint64_t)(Tl + hal), (uint64_t)t.Kp * 2, 64, tc::BK, CU_TENSOR_MAP_SWIZZLE_128B);
+                // denomH: A = C table rows (d'*Kp + k) x Kp, "X" = H rows from the left halo on, K-major
+                __nv_bfloat16 *cc[2] = {t.Cc_hi.p, t.Cc_lo.p};
+                t.mCu[i] = make_map_2d(cc[i], (uint64_t)t.Kp, (uint64_t)t.rows_c, (uint64_t)t.Kp * 2, tc::BK, tc::BM, CU_TENSOR_MAP_SWIZZLE_64B);
+                t.mHk[i] = make_map_2d(hw[i], (uint64_t)t.Kp, (uint64_t)(Tl + 2 * hal), (uint64_t)t.Kp * 2, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
+                __nv_bfloat16 *gc[2] = {t.Gc_hi.p, t.Gc_lo.p};
+                t.mWuB[i] = make_map_2d(wu[i], (uint64_t)N, (uint64_t)t.rows_u, (uint64_t)N * 2, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
+                t.mWcB[i] = make_map_2d(wc[i], (uint64_t)t.KLp, (uint64_t)N, (uint64_t)t.KLp * 2, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
+                t.mGc[i] = make_map_2d(gc[i], (uint64_t)t.KLp, (uint64_t)KL(), (uint64_t)t.KLp * 2, tc::BK, tc::BM, CU_TENSOR_MAP_SWIZZLE_64B);
             }
             // correlation work split: balance persistent CTAs, keep splits >= FLUSH_T columns
             t.tiles_m = cdiv(t.KLp, tc::BM);
@@ -273,13 +294,22 @@ struct Ctx : cmf_ctx {
                 const double eff = (double)units / (double)(cdiv(units, t.num_sms) * t.num_sms);
                 if (eff > best + 1e-9) { best = eff; t.nsplit = (int)cdiv(tau, sl); t.split_len = sl; }
             }
-            const size_t need = (size_t)t.nsplit * (size_t)(KL() * N);
+            // Gram correlation (one n tile): enough splits to fill the machine
+            {
+                const int64_t want = std::max<int64_t>(1, cdiv(2 * t.num_sms, t.tiles_m));
+                const int64_t maxs = std::max<int64_t>(1, tau / tc::FLUSH_T);
+                const int64_t ns = std::min(want, maxs);
+                t.split_len_g = cdiv(cdiv(tau, ns), tc::BK) * tc::BK;
+                t.nsplit_g = (int)cdiv(tau, t.split_len_g);
+            }
+            const size_t need = std::max((size_t)t.nsplit * (size_t)(KL() * N), (size_t)t.nsplit_g * (size_t)(KL() * K));
             if (corr_part.n < need) corr_part.alloc(need);
             const size_t need_lp = (size_t)(tc::EPI_WARPS * cdiv(Tl, tc::BN) * cdiv(N, tc::BM));
             if (loss_part.n < need_lp) loss_part.alloc(need_lp);
             CK(cudaFuncSetAttribute(tc::tc_kernel<tc::TC_CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
             CK(cudaFuncSetAttribute(tc::tc_kernel<tc::TC_TRANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
             CK(cudaFuncSetAttribute(tc::tc_kernel<tc::TC_CORR>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+            CK(cudaFuncSetAttribute(tc::tc_kernel<tc::TC_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
             t.ok = true;
             // default engine: tensor cores when the contraction is big enough to fill 128x256 tiles
             if (N >= 256 && Tl >= 4096 && K * L >= 256) engine = 1;
@@ -290,6 +320,8 @@ struct Ctx : cmf_ctx {
         tc::Params q;
         memset(&q, 0, sizeof(q));
         q.N = N; q.K = K; q.L = L; q.Tl = Tl; q.G = tcs.G; q.Kp = tcs.Kp;
+        q.Kp_log2 = 0;
+        while ((1 << q.Kp_log2) < tcs.Kp) ++q.Kp_log2;
         return q;
     }
 
@@ -336,6 +368,59 @@ struct Ctx : cmf_ctx {
             post_launch();
             const int64_t n = KL() * N;
             reduce_partials_kernel<S><<<(unsigned)cdiv(n, 256), 256, 0, stream>>>(corr_part.p, tcs.nsplit, n, numW.p, nullptr);
+            post_launch();
+        }
+    }
+    // plain GEMM out[m*ldo + n] = sum_k A[m][k] B[n][k] on tensor cores (operands given as hi/lo tensor maps)
+    void tc_plain(const CUtensorMap *mA, const CUtensorMap *mB, S *out, int64_t Mrows, int64_t Ncols, int64_t Kdim, int64_t ldo) {
+        if constexpr (std::is_same<S, float>::value) {
+            tc::Params q = tc_base_params();
+            q.tiles_n = cdiv(Ncols, tc::BN);
+            q.nkb = cdiv(Kdim, tc::BK);
+            q.units = q.tiles_n * cdiv(Mrows, tc::BM);
+            q.out = out; q.Mrows = Mrows; q.Ncols = Ncols; q.ldo = ldo;
+            const unsigned grid = (unsigned)std::min<int64_t>(q.units, tcs.num_sms);
+            tc::tc_kernel<tc::TC_PLAIN><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(mA[0], mA[1], mB[0], mB[1], q);
+            post_launch();
+        }
+    }
+    // denomW = G * Wi (mult.jl:28,33): G is built straight into bf16 planes in the K-dim order of Wc
+    void tc_denomW() {
+        if constexpr (std::is_same<S, float>::value) {
+            tc::build_G_split_kernel<<<(unsigned)cdiv(KL() * tcs.KLp, 256), 256, 0, stream>>>(
+                exch1.p, exch1.p + L * K * K, tcs.Gc_hi.p, tcs.Gc_lo.p, K, L, tcs.Kp, tcs.KLp);
+            post_launch();
+            tc_split_W();
+            tc_plain(tcs.mGc, tcs.mWcB, denW.p, KL(), N, tcs.KLp, N);
+        }
+    }
+    // Gram partial Rg[d][k][k'] = sum_u H[u][k] H[u+d][k'] via tensor cores (needs tc_split_H(true) and (false) done)
+    void tc_gram() {
+        if constexpr (std::is_same<S, float>::value) {
+            tc::Params q = tc_base_params();
+            q.N = K;                                   // output row stride / column bound: Rg is [L][K][K]
+            q.tiles_m = tcs.tiles_m; q.tiles_n = 1; q.split_len = tcs.split_len_g; q.tau_hi = Tl + (L - 1);
+            q.units = tcs.tiles_m * tcs.nsplit_g;
+            q.part = corr_part.p;
+            const unsigned grid = (unsigned)std::min<int64_t>(q.units, tcs.num_sms);
+            tc::tc_kernel<tc::TC_CORR><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tcs.mHm[0], tcs.mHm[1], tcs.mHmn[0], tcs.mHmn[1], q);
+            post_launch();
+            const int64_t n = L * K * K;
+            reduce_partials_kernel<S><<<(unsigned)cdiv(n, 256), 256, 0, stream>>>(corr_part.p, tcs.nsplit_g, n, nullptr, exch1.p);
+            post_launch();
+        }
+    }
+    // denomH = C (*) H via tensor cores (mult.jl:44,48); needs lag_tables() and tc_split_H(false) done
+    void tc_denomH() {
+        if constexpr (std::is_same<S, float>::value) {
+            tc::split_C_kernel<<<(unsigned)cdiv(tcs.rows_c * tcs.Kp, 256), 256, 0, stream>>>(Cf.p, tcs.Cc_hi.p, tcs.Cc_lo.p, K, 2 * L - 1, tcs.Kp, tcs.rows_c);
+            post_launch();
+            tc::Params q = tc_base_params();
+            q.groups = tcs.groups_c; q.nblocks = cdiv(tcs.Kp, tc::BK); q.own = tc::BN - (tcs.G - 1);
+            q.units = cdiv(Tl, q.own);
+            q.out = denH.p;
+            const unsigned grid = (unsigned)std::min<int64_t>(q.units, tcs.num_sms);
+            tc::tc_kernel<tc::TC_TRANS><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tcs.mCu[0], tcs.mCu[1], tcs.mHk[0], tcs.mHk[1], q);
             post_launch();
         }
     }
@@ -616,7 +701,8 @@ struct Ctx : cmf_ctx {
         if (tc_active()) tc_corr();
         else launch_corr(X.p, N, N, Tl + (L - 1), nsplit_w, split_w, numW.p, nullptr);
         // Gram partial Rg[d][k][k'] = sum_u H[u][k] H[u+d][k'] (owned u, right halo for u+d)
-        launch_corr(H, K, K, Tl + (L - 1), nsplit_g, split_g, nullptr, exch1.p);
+        if (tc_active()) { tc_split_H(false); tc_gram(); }
+        else launch_corr(H, K, K, Tl + (L - 1), nsplit_g, split_g, nullptr, exch1.p);
         if (L > 1) {
             h_tail_kernel<S><<<(unsigned)cdiv((L - 1) * K, 256), 256, 0, stream>>>(H, exch1.p + L * K * K, K, L, Tl, is_last ? 1 : 0);
             post_launch();
@@ -629,15 +715,29 @@ struct Ctx : cmf_ctx {
     }
 
     void w_apply(double l1W, double l2W) override {
-        build_G();
-        launch_gemm<false>(GS.p, Wi.p, denW.p, KL(), N, KL(), KL(), N, N);   // denomW = G * Wi (mult.jl:28,33)
+        if (tc_active()) {
+            tc_denomW();                                                          // denomW = G * Wi on tensor cores
+        } else {
+            build_G();
+            launch_gemm<false>(GS.p, Wi.p, denW.p, KL(), N, KL(), KL(), N, N);   // denomW = G * Wi (mult.jl:28,33)
+        }
         launch_mu(Wi.p, numW.p, denW.p, l1W, l2W, KL() * N);                  // mult.jl:37-38
         tcs.w_dirty = true;
     }
 
+    // layout of the W W' product held in GS: S2[(l*s2_ks + k)*s2_ld + l'*s2_ks + k']
+    int64_t s2_ks = 0, s2_ld = 0;
+
     void lag_tables() {
-        launch_gemm<true>(Wi.p, Wi.p, GS.p, KL(), KL(), N, N, N, KL());       // S2 = Wi Wi'
-        lag_table_kernel<S><<<(unsigned)cdiv((2 * L - 1) * K * K, 256), 256, 0, stream>>>(GS.p, Cf.p, K, L);
+        if (tc_active()) {
+            tc_split_W();
+            tc_plain(tcs.mWu, tcs.mWuB, GS.p, tcs.rows_u, tcs.rows_u, N, tcs.rows_u);   // S2 = Wu Wu' on tensor cores
+            s2_ks = tcs.Kp; s2_ld = tcs.rows_u;
+        } else {
+            launch_gemm<true>(Wi.p, Wi.p, GS.p, KL(), KL(), N, N, N, KL());              // S2 = Wi Wi'
+            s2_ks = K; s2_ld = KL();
+        }
+        lag_table_kernel<S><<<(unsigned)cdiv((2 * L - 1) * K * K, 256), 256, 0, stream>>>(GS.p, Cf.p, K, L, s2_ks, s2_ld);
         post_launch();
     }
 
@@ -647,10 +747,11 @@ struct Ctx : cmf_ctx {
         else launch_transconv(Wi.p, X.p, numH.p, N, K, L, N, Tl, Tl + (L - 1));    // numH (mult.jl:47)
         lag_tables();
         // denomH = C (*) H on all owned columns (mult.jl:44,48), then the truncated tail
-        launch_transconv(Cf.p, Hbuf.p, denH.p, K, K, 2 * L - 1, K, Tl, Tl + 2 * (L - 1));
+        if (tc_active()) { tc_split_H(false); tc_denomH(); }
+        else launch_transconv(Cf.p, Hbuf.p, denH.p, K, K, 2 * L - 1, K, Tl, Tl + 2 * (L - 1));
         if (is_last && L > 1) {
             dim3 grid((unsigned)(L - 1), (unsigned)K);
-            denomH_tail_kernel<S><<<grid, 256, 0, stream>>>(GS.p, H, denH.p, K, L, Tl, -(L - 1));
+            denomH_tail_kernel<S><<<grid, 256, 0, stream>>>(GS.p, H, denH.p, K, L, Tl, -(L - 1), s2_ks, s2_ld);
             post_launch();
         }
         launch_mu(H, numH.p, denH.p, l1H, l2H, Tl * K);                       // mult.jl:51-52

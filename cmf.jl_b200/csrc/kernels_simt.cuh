@@ -512,15 +512,16 @@ __global__ void build_G_kernel(const double *__restrict__ Rg, const double *__re
     G[idx] = (S)(g - tail);
 }
 
-// Cf[(d+L-1)][k][k'] = sum_{l, 0<=l-d<L} S2[(l,k)][(l-d,k')]      (S2 = Wi Wi', KL x KL)
+// Cf[(d+L-1)][k][k'] = sum_{l, 0<=l-d<L} S2[(l,k)][(l-d,k')]      (S2 = W W' over the unfolded rows)
+// S2 is addressed as S2[(l*Ks + k) * ld + (l'*Ks + k')]: (Ks, ld) = (K, K*L) for the SIMT product and
+// (Kp, rows_u) for the tensor-core product over the padded rows.
 template <typename S>
-__global__ void lag_table_kernel(const S *__restrict__ S2, S *__restrict__ Cf, int64_t K, int64_t L) {
-    const int64_t KL = K * L;
+__global__ void lag_table_kernel(const S *__restrict__ S2, S *__restrict__ Cf, int64_t K, int64_t L, int64_t Ks, int64_t ld) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (2 * L - 1) * K * K) return;
     const int64_t kp = idx % K, k = (idx / K) % K, d = idx / (K * K) - (L - 1);
     double s = 0.0;
-    for (int64_t l = (d > 0 ? d : 0); l < L && l - d < L; ++l) s += (double)S2[(l * K + k) * KL + (l - d) * K + kp];
+    for (int64_t l = (d > 0 ? d : 0); l < L && l - d < L; ++l) s += (double)S2[(l * Ks + k) * ld + (l - d) * Ks + kp];
     Cf[idx] = (S)s;
 }
 
@@ -530,7 +531,7 @@ __global__ void lag_table_kernel(const S *__restrict__ S2, S *__restrict__ Cf, i
 template <typename S>
 __global__ void __launch_bounds__(256) denomH_tail_kernel(const S *__restrict__ S2, const S *__restrict__ H,
                                                            S *__restrict__ den, int64_t K, int64_t L,
-                                                           int64_t Tl, int64_t h_lo) {
+                                                           int64_t Tl, int64_t h_lo, int64_t Ks, int64_t ld) {
     __shared__ double red[32];
     const int64_t KL = K * L;
     const int64_t c = blockIdx.x;                 // tail column index: t = Tl - (L-1) + c
@@ -545,7 +546,7 @@ __global__ void __launch_bounds__(256) denomH_tail_kernel(const S *__restrict__ 
         const int64_t kp = jp % K, lp = jp / K;
         const int64_t u = t + l - lp;
         if (u < h_lo) continue;
-        s += (double)S2[(l * K + k) * KL + jp] * (double)H[u * K + kp];
+        s += (double)S2[(l * Ks + k) * ld + lp * Ks + kp] * (double)H[u * K + kp];
     }
     s = block_sum(s, red);
     if (threadIdx.x == 0) den[t * K + k] = (S)s;

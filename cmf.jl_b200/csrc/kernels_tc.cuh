@@ -15,6 +15,8 @@
 //   TC_CORR   D[j, n]      = sum_t Hwin[t][j] * X[t][n]             (both MN-major, SW128)
 //             epilogue: every TC_FLUSH_T columns of t, part[(l,k)][n] (+)= D  in double
 //                                                                      (src/algs/mult.jl:31-34)
+//   TC_PLAIN  D[m, n]      = sum_k A[m][k] * B[n][k]                (K-major, SW64)  plain GEMM for the two small
+//             epilogue: outp[m*ldo + n] = D                          T-independent products G*W and W*W'
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -33,9 +35,9 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
 constexpr int EPI_WARPS = 8;                         // epilogue / promotion warps (2 per TMEM lane quarter)
 constexpr int THREADS = 128 + 32 * EPI_WARPS;        // warpgroup 0: warp 0 TMA, warp 1 MMA + TMEM alloc (2,3 idle); warpgroups 1-2: epilogue
 constexpr int PROMO = 4;                             // k-blocks accumulated in TMEM before promotion to registers
-constexpr int FLUSH_T = 8192;                        // TC_CORR: fp32 accumulation length before the fp64 flush
+constexpr int FLUSH_T = 65536;                       // TC_CORR: columns of t accumulated in fp32 registers (RN) before the fp64 flush
 
-enum Mode { TC_CONV = 0, TC_TRANS = 1, TC_CORR = 2 };
+enum Mode { TC_CONV = 0, TC_TRANS = 1, TC_CORR = 2, TC_PLAIN = 3 };
 
 struct Params {
     // work decomposition
@@ -45,7 +47,7 @@ struct Params {
     int64_t nkb;            // CONV: k-blocks per tile
     // TRANS
     int64_t groups, nblocks;   // lag groups, n blocks of BK
-    int G, Kp;                 // lags per group (128 / Kp), padded K
+    int G, Kp, Kp_log2;        // lags per group (128 / Kp), padded K (power of two)
     int64_t own;               // owned columns per t tile = BN - (G-1)
     // CORR
     int64_t split_len;         // t columns per split (multiple of BK)
@@ -55,7 +57,8 @@ struct Params {
     // epilogue pointers
     const float *X;            // CONV: fp32 data [t][N]
     double *partial;           // CONV: EPI_WARPS partials per unit
-    float *out;                // TRANS: numH [t][K]
+    float *out;                // TRANS: numH [t][K];  PLAIN: output matrix
+    int64_t Mrows, Ncols, ldo; // PLAIN: output bounds and row stride
     double *part;              // CORR: [split][L*K*N]
 };
 
@@ -156,7 +159,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ float stage_s[MODE == TC_CORR ? EPI_WARPS : 1][32][17];   // TC_CORR flush staging
+    __shared__ float stage_s[(MODE == TC_CORR || MODE == TC_PLAIN) ? EPI_WARPS : 1][32][17];   // write-out staging
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -186,7 +189,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
         return c > 0 ? c : 1;
     };
     auto segment_kb = [&](int64_t unit, int64_t seg, int64_t &kb0, int64_t &kbn) {
-        if (MODE == TC_CONV) { kb0 = 0; kbn = p.nkb; }
+        if (MODE == TC_CONV || MODE == TC_PLAIN) { kb0 = 0; kbn = p.nkb; }
         else if (MODE == TC_TRANS) { kb0 = 0; kbn = p.groups * p.nblocks; }
         else {
             const int64_t sp = unit / (p.tiles_m * p.tiles_n);
@@ -208,6 +211,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
             for (int64_t unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
                 int64_t mt = 0, nt = 0;
                 if (MODE == TC_CONV) { nt = unit % p.tiles_n; mt = unit / p.tiles_n; }          // nt: n tile, mt: t tile
+                if (MODE == TC_PLAIN) { nt = unit % p.tiles_n; mt = unit / p.tiles_n; }         // nt: column tile, mt: row tile
                 if (MODE == TC_CORR) { const int64_t r = unit % (p.tiles_m * p.tiles_n); mt = r % p.tiles_m; nt = r / p.tiles_m; }   // j tiles fastest: concurrent CTAs share the X tile
                 const int64_t nseg = n_segments(unit);
                 for (int64_t seg = 0; seg < nseg; ++seg) {
@@ -223,6 +227,12 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                             tma_load_2d(st + A_PLANE, &mapA_lo, &full_bar[s], j0, (int32_t)(nt * BM));
                             tma_load_2d(st + 2 * A_PLANE, &mapB_hi, &full_bar[s], j0, (int32_t)(mt * BN));
                             tma_load_2d(st + 2 * A_PLANE + B_PLANE, &mapB_lo, &full_bar[s], j0, (int32_t)(mt * BN));
+                        } else if (MODE == TC_PLAIN) {
+                            const int32_t k0 = (int32_t)(kb * BK);
+                            tma_load_2d(st, &mapA_hi, &full_bar[s], k0, (int32_t)(mt * BM));
+                            tma_load_2d(st + A_PLANE, &mapA_lo, &full_bar[s], k0, (int32_t)(mt * BM));
+                            tma_load_2d(st + 2 * A_PLANE, &mapB_hi, &full_bar[s], k0, (int32_t)(nt * BN));
+                            tma_load_2d(st + 2 * A_PLANE + B_PLANE, &mapB_lo, &full_bar[s], k0, (int32_t)(nt * BN));
                         } else if (MODE == TC_TRANS) {
                             const int64_t nb = kb / p.groups, g = kb % p.groups;   // n-block outer, lag group inner: the X sub-window stays in L2
                             const int32_t c0 = (int32_t)(nb * BK);
@@ -311,7 +321,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
         float racc[BN / 2];
         for (int64_t unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
             int64_t mt = 0, nt = 0, sp = 0;
-            if (MODE == TC_CONV) { nt = unit % p.tiles_n; mt = unit / p.tiles_n; }
+            if (MODE == TC_CONV || MODE == TC_PLAIN) { nt = unit % p.tiles_n; mt = unit / p.tiles_n; }
             if (MODE == TC_CORR) { sp = unit / (p.tiles_m * p.tiles_n); const int64_t r = unit % (p.tiles_m * p.tiles_n); mt = r % p.tiles_m; nt = r / p.tiles_m; }
             const int64_t nseg = n_segments(unit);
             for (int64_t seg = 0; seg < nseg; ++seg) {
@@ -372,6 +382,23 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                         }
                         if (p.G > 1) asm volatile("bar.sync 1, 256;" ::: "memory");
                     }
+                } else if (MODE == TC_PLAIN) {
+                    // fp32 store through the per-warp staging tile (coalesced 64-byte row segments)
+                    float(*stg)[17] = stage_s[warp - 4];
+#pragma unroll
+                    for (int cc = 0; cc < BN / 2; cc += 16) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) stg[lane][c] = racc[cc + c];
+                        __syncwarp();
+#pragma unroll 1
+                        for (int it = 0; it < 16; ++it) {
+                            const int r = it * 2 + (lane >> 4), c = lane & 15;
+                            const int64_t m = mt * BM + quarter * 32 + r;
+                            const int64_t n = nt * BN + col0 + cc + c;
+                            if (m < p.Mrows && n < p.Ncols) p.out[m * p.ldo + n] = stg[r][c];
+                        }
+                        __syncwarp();
+                    }
                 } else {
                     // fp64 flush through a per-warp shared staging tile: registers -> smem with static
                     // indices, then a compact loop does the coalesced double read-modify-write
@@ -386,7 +413,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                         for (int it = 0; it < 16; ++it) {
                             const int r = it * 2 + (lane >> 4), c = lane & 15;
                             const int64_t j = mt * BM + quarter * 32 + r;
-                            const int64_t lp = j / p.Kp, k = j % p.Kp;
+                            const int64_t lp = j >> p.Kp_log2, k = j & (p.Kp - 1);   // Kp is a power of two
                             const int64_t n = nt * BN + col0 + cc + c;
                             if (lp < p.L && k < p.K && n < p.N) {
                                 double *d = pbase + ((p.L - 1 - lp) * p.K + k) * p.N + n;
@@ -457,6 +484,45 @@ __global__ void split_W_kernel(const float *__restrict__ Wi, __nv_bfloat16 *__re
     wu_hi[idx] = h; wu_lo[idx] = lo_;
     const int64_t j = (L - 1 - l) * Kp + k;
     wc_hi[n * KLp + j] = h; wc_lo[n * KLp + j] = lo_;
+}
+
+// G = Htilde Htilde' (see build_G_kernel) written as bf16 hi/lo planes Gc[j][jj]: rows j = l*K + k (Wi order),
+// columns jj = (L-1-l')*Kp + k' (the K-dim order of Wc), row length KLp, zero padded.      [G*W A operand]
+__global__ void build_G_split_kernel(const double *__restrict__ Rg, const double *__restrict__ Ht, __nv_bfloat16 *__restrict__ hi,
+                                     __nv_bfloat16 *__restrict__ lo, int64_t K, int64_t L, int Kp, int64_t KLp) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= K * L * KLp) return;
+    const int64_t jj = idx % KLp, j = idx / KLp;
+    const int64_t k = j % K, l = j / K;
+    const int64_t kp = jj % Kp, lrev = jj / Kp;
+    float v = 0.f;
+    if (kp < K && lrev < L) {
+        const int64_t lp = L - 1 - lrev;
+        double g = (l >= lp) ? Rg[((l - lp) * K + k) * K + kp] : Rg[((lp - l) * K + kp) * K + k];
+        const int64_t m = l < lp ? l : lp;
+        double tail = 0.0;
+        for (int64_t i = 0; i < m; ++i) tail += Ht[(L - 1 - l + i) * K + k] * Ht[(L - 1 - lp + i) * K + kp];
+        v = (float)(g - tail);
+    }
+    __nv_bfloat16 h, l_;
+    split_bf16(v, h, l_);
+    hi[idx] = h; lo[idx] = l_;
+}
+
+// Cf[(d')][k][k'] fp32 ((2L-1) x K x K) -> Cc[(d'*Kp + k)][Kp] hi/lo (rows_c rows, zero padded)  [denomH A operand]
+__global__ void split_C_kernel(const float *__restrict__ Cf, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo,
+                               int64_t K, int64_t D, int Kp, int64_t rows_c) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows_c * Kp) return;
+    const int kp = (int)(idx % Kp);
+    const int64_t r = idx / Kp;
+    const int64_t d = r / Kp;
+    const int k = (int)(r % Kp);
+    float v = 0.f;
+    if (d < D && k < K && kp < K) v = Cf[(d * K + k) * K + kp];
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[idx] = h; lo[idx] = l;
 }
 
 }  // namespace tc

@@ -65,11 +65,19 @@ def test_tc_contractions_match_oracle(cmf, orc, dims):
     torch.cuda.synchronize()
     numW = s.exchange[0].cpu().numpy().reshape(L, K, N).transpose(1, 2, 0)
     assert _scale_err(numW, orc.co.corr_w(H, X, L)) < 3e-5
+    # Gram partial Rg[d][k][k'] (tensor-core correlation of H with itself)
+    from oracle import restructured as rs
+
+    Rg = s.exchange[1].cpu().numpy()[: L * K * K].reshape(L, K, K).transpose(1, 2, 0)
+    assert _scale_err(Rg, rs.gram_R(H, L)) < 3e-5
     # TC_TRANS: numH [t][K]
     s.h_update(0.0, 0.0)
     torch.cuda.synchronize()
     numH = s.exchange[2].cpu().numpy().reshape(T, K).T
     assert _scale_err(numH, orc.co.tensor_transconv(W, X)) < 3e-5
+    # denomH = C (*) H on tensor cores + truncated tail
+    denH = s.exchange[3].cpu().numpy().reshape(T, K).T
+    assert _scale_err(denH, orc.co.tensor_transconv(W, orc.co.tensor_conv(W, H))) < 3e-5
     s.close()
 
 
