@@ -164,6 +164,21 @@ CUtensorMap make_map_2d(void *base, uint64_t dim0, uint64_t dim1, uint64_t strid
     return m;
 }
 
+// 3-D bf16 map for MN-major operands: (64 contiguous elements, rows with stride `row_stride` bytes,
+// groups of 64 elements 128 bytes apart); box = (64, box_rows, box_groups), SWIZZLE_128B.
+CUtensorMap make_map_mn(void *base, uint64_t rows, uint64_t row_stride, uint64_t groups, uint32_t box_rows, uint32_t box_groups) {
+    CUtensorMap m;
+    cuuint64_t gdim[3] = {64, rows, groups};
+    cuuint64_t gstr[2] = {row_stride, 128};
+    cuuint32_t box[3] = {64, box_rows, box_groups};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, gdim, gstr, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw CmfError(CMF_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with code " + std::to_string((int)r));
+    return m;
+}
+
 struct TcState {
     bool ok = false;
     int Kp = 0, G = 0, num_sms = 148;
@@ -240,7 +255,7 @@ struct Ctx : cmf_ctx {
             if (alg != CMF_MULT || K > 128 || N % 8 != 0) return;
             t.Kp = K <= 16 ? 16 : K <= 32 ? 32 : K <= 64 ? 64 : 128;
             t.G = 128 / t.Kp;
-            t.KLp = cdiv(L * t.Kp, tc::BK) * tc::BK;
+            t.KLp = cdiv(L * t.Kp, 64) * 64;
             t.groups = cdiv(L, t.G);
             t.rows_u = t.groups * 128;
             const int64_t hal = L - 1;
@@ -250,7 +265,7 @@ struct Ctx : cmf_ctx {
             if (prop.major != 10) return;                         // tcgen05 needs sm_100
             t.num_sms = prop.multiProcessorCount;
             const size_t hw_elems = (size_t)((Tl + 2 * hal) * t.Kp + t.KLp + 64);
-            t.X_hi.alloc(X.n); t.X_lo.alloc(X.n);
+            t.X_hi.alloc(X.n + 64); t.X_lo.alloc(X.n + 64);          // +64: the 3-D maps may touch one atom past the last row
             t.Hw_hi.alloc(hw_elems); t.Hw_lo.alloc(hw_elems);
             t.Hm_hi.alloc(hw_elems); t.Hm_lo.alloc(hw_elems);
             t.Wc_hi.alloc((size_t)(N * t.KLp)); t.Wc_lo.alloc((size_t)(N * t.KLp));
@@ -267,12 +282,12 @@ struct Ctx : cmf_ctx {
                 t.mWc[i] = make_map_2d(wc[i], (uint64_t)t.KLp, (uint64_t)N, (uint64_t)t.KLp * 2, tc::BK, tc::BM, CU_TENSOR_MAP_SWIZZLE_64B);
                 // overlapping-row "window" map: row t starts at element t*Kp and is KLp long
                 t.mHw[i] = make_map_2d(hw[i], (uint64_t)t.KLp, (uint64_t)t.hrows, (uint64_t)t.Kp * 2, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
-                t.mHm[i] = make_map_2d(hm[i], (uint64_t)t.KLp, (uint64_t)t.hrows, (uint64_t)t.Kp * 2, 64, tc::BK, CU_TENSOR_MAP_SWIZZLE_128B);
+                t.mHm[i] = make_map_mn(hm[i], (uint64_t)t.hrows, (uint64_t)t.Kp * 2, (uint64_t)(t.KLp / 64), tc::BK, 2);
                 t.mWu[i] = make_map_2d(wu[i], (uint64_t)N, (uint64_t)t.rows_u, (uint64_t)N * 2, tc::BK, tc::BM, CU_TENSOR_MAP_SWIZZLE_64B);
                 t.mXk[i] = make_map_2d(xs[i], (uint64_t)N, (uint64_t)(Tl + hal), (uint64_t)N * 2, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
-                t.mXmn[i] = make_map_2d(xs[i], (uint64_t)N, (uint64_t)(Tl + hal), (uint64_t)N * 2, 64, tc::BK, CU_TENSOR_MAP_SWIZZLE_128B);
+                t.mXmn[i] = make_map_mn(xs[i], (uint64_t)(Tl + hal), (uint64_t)N * 2, (uint64_t)cdiv(N, 64), tc::BK, 4);
                 // Gram: "X" = H rows from owned column 0 (owned + right halo), [t][Kp] MN-major
-                t.mHmn[i] = make_map_2d(hw[i] + hal * t.Kp, (uint64_t)t.Kp, (uint64_t)(Tl + hal), (uint64_t)t.Kp * 2, 64, tc::BK, CU_TENSOR_MAP_SWIZZLE_128B);
+                t.mHmn[i] = make_map_mn(hw[i] + hal * t.Kp, (uint64_t)(Tl + hal), (uint64_t)t.Kp * 2, (uint64_t)cdiv(t.Kp, 64), tc::BK, 4);
                 // denomH: A = C table rows (d'*Kp + k) x Kp, "X" = H rows from the left halo on, K-major
                 __nv_bfloat16 *cc[2] = {t.Cc_hi.p, t.Cc_lo.p};
                 t.mCu[i] = make_map_2d(cc[i], (uint64_t)t.Kp, (uint64_t)t.rows_c, (uint64_t)t.Kp * 2, tc::BK, tc::BM, CU_TENSOR_MAP_SWIZZLE_64B);

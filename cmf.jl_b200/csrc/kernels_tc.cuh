@@ -89,6 +89,12 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int32_t c0, int32_t c1, int32_t c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -242,17 +248,13 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                             tma_load_2d(st + 2 * A_PLANE, &mapB_hi, &full_bar[s], c0, rowB);
                             tma_load_2d(st + 2 * A_PLANE + B_PLANE, &mapB_lo, &full_bar[s], c0, rowB);
                         } else {
+                            // MN-major operands come through 3-D maps (64 contiguous elements, t rows, 64-element
+                            // groups), so one TMA per plane fills all the 4 KB swizzle atoms of the tile
                             const int32_t trow = (int32_t)(kb * BK);
-#pragma unroll
-                            for (int b = 0; b < 2; ++b) {
-                                tma_load_2d(st + b * 4096, &mapA_hi, &full_bar[s], (int32_t)(mt * BM + b * 64), trow);
-                                tma_load_2d(st + A_PLANE + b * 4096, &mapA_lo, &full_bar[s], (int32_t)(mt * BM + b * 64), trow);
-                            }
-#pragma unroll
-                            for (int b = 0; b < 4; ++b) {
-                                tma_load_2d(st + 2 * A_PLANE + b * 4096, &mapB_hi, &full_bar[s], (int32_t)(nt * BN + b * 64), trow);
-                                tma_load_2d(st + 2 * A_PLANE + B_PLANE + b * 4096, &mapB_lo, &full_bar[s], (int32_t)(nt * BN + b * 64), trow);
-                            }
+                            tma_load_3d(st, &mapA_hi, &full_bar[s], 0, trow, (int32_t)(mt * 2));
+                            tma_load_3d(st + A_PLANE, &mapA_lo, &full_bar[s], 0, trow, (int32_t)(mt * 2));
+                            tma_load_3d(st + 2 * A_PLANE, &mapB_hi, &full_bar[s], 0, trow, (int32_t)(nt * 4));
+                            tma_load_3d(st + 2 * A_PLANE + B_PLANE, &mapB_lo, &full_bar[s], 0, trow, (int32_t)(nt * 4));
                         }
                         if (++s == STAGES) { s = 0; ph ^= 1; }
                     }
