@@ -194,6 +194,7 @@ def run_ours(args, cfg, name):
     plan = cmf.ShardPlan(T, world, L)
     t0, t1 = plan.ranges[rank]
     shard = cmf.DeviceShard(N, T, t0, t1, K, L, dtype="f32", device=local_rank)
+    shard.set_loss_mode(args.loss_mode)
     fitter = cmf.ShardedMultFit(shard, rank, world, dist)
 
     def barrier():
@@ -238,6 +239,27 @@ def run_ours(args, cfg, name):
         launches = int(lt.item())
     ms_per_step = ms / args.steps
     value = 1e3 / ms_per_step
+    engine = shard.get_engine()
+
+    # secondary: the same iteration with the loss evaluated by the direct conv + residual pass (mult.jl:55-57 literally)
+    value_direct = None
+    if args.loss_mode == 1:
+        shard.set_loss_mode(0)
+        fitter.iterate()
+        barrier()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for _ in range(args.steps):
+            fitter.iterate()
+        d1.record()
+        barrier()
+        dms = d0.elapsed_time(d1)
+        if world > 1:
+            t = torch.tensor([dms], dtype=torch.float64, device=f"cuda:{local_rank}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dms = float(t.item())
+        value_direct = args.steps / (dms / 1e3)
+        shard.set_loss_mode(1)
 
     # ---- end-to-end through the public API with HOST buffers (upload inside the timed region)
     e2e = None
@@ -256,6 +278,7 @@ def run_ours(args, cfg, name):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         sh2 = cmf.DeviceShard(N, T, t0, t1, K, L, dtype="f32", device=local_rank)
+        sh2.set_loss_mode(args.loss_mode)
         f2 = cmf.ShardedMultFit(sh2, rank, world, dist)
         sh2.set_data(Xh, t0)                      # H2D of this rank's columns from pinned host memory
         f2.setup_data_norm()
@@ -322,7 +345,11 @@ def run_ours(args, cfg, name):
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{name}: MU N={N} T={T} K={K} L={L}", "alg": "mult", "parallelism": f"T-shard x{world}",
                    "l2": "inputs (X = %.1f GiB per GPU) exceed the 126 MB L2" % (4.0 * N * (t1 - t0) / 2 ** 30),
-                   "seeds": {"data": SEED_DATA, "init": SEED_INIT}, "p_h": P_H, "noise": NOISE},
+                   "seeds": {"data": SEED_DATA, "init": SEED_INIT}, "p_h": P_H, "noise": NOISE,
+                   "engine": "tcgen05 split-bf16 (3 MMAs per product, fp32 accumulate)" if engine == 1 else "SIMT fp32",
+                   "loss": ("algebraic expansion ||X||^2 - 2<numH,H> + <WW',HtHt'> (exact identity, falls back to the direct "
+                            "pass below 20% loss)" if args.loss_mode == 1 else "direct conv + residual pass")},
+        "value_direct_loss": value_direct,
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_hbm": hbm, "cpu_baseline": cpu,
         "clocks": clocks, "loss": {"initial": loss0, "final": losses[-1] if losses else None},
     }
@@ -347,11 +374,13 @@ def _set_sharded_factors(shard, fitter, W, H_owned, t0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
     ap.add_argument("--T", type=int, default=None, help="override T (development only; reported in config.workload)")
+    ap.add_argument("--loss-mode", type=int, default=1, choices=[0, 1],
+                    help="1: loss by the algebraic expansion on resident numH / W W' (default); 0: direct residual pass")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

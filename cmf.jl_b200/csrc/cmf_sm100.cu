@@ -76,6 +76,10 @@ struct cmf_ctx {
     bool own_stream = false;
     int64_t launches = 0;
     double data_norm = 0.0;
+    double data_sumsq_local = 0.0;   // ||X_owned||^2 of this shard
+    int loss_mode = 0;               // 0 = direct residual pass, 1 = algebraic expansion when its inputs are resident
+    bool numH_valid = false;         // numH buffer == transconv(current W, X) and GS == W W' of the current W
+    bool gram_valid = false;         // exchange buffer 1 holds the local Gram/tail partial of the current H
     bool have_data = false, have_factors = false;
     // optional per-kernel-class event timing (bench.py's roofline): class -> list of event pairs
     bool profiling = false;
@@ -240,7 +244,7 @@ struct Ctx : cmf_ctx {
         plan_split(K, Tl + hal, nsplit_g, split_g);
         corr_part.alloc((size_t)std::max<int64_t>((int64_t)nsplit_w * KL() * N, (int64_t)nsplit_g * KL() * K));
         conv_blocks_max = (int)(cdiv(N, BN) * cdiv(Tl + hal, BT));
-        loss_part.alloc((size_t)std::max(2 * conv_blocks_max, 1024));
+        loss_part.alloc((size_t)std::max(2 * conv_blocks_max, 4096));
         tc_setup();
         CK(cudaStreamSynchronize(stream));
     }
@@ -320,7 +324,7 @@ struct Ctx : cmf_ctx {
             const size_t need = std::max((size_t)t.nsplit * (size_t)(KL() * N), (size_t)t.nsplit_g * (size_t)(KL() * K));
             if (corr_part.n < need) corr_part.alloc(need);
             const size_t need_lp = (size_t)(tc::EPI_WARPS * cdiv(Tl, tc::BN) * cdiv(N, tc::BM));
-            if (loss_part.n < need_lp) loss_part.alloc(need_lp);
+            if (loss_part.n < need_lp) loss_part.alloc(std::max<size_t>(need_lp, 4096));
             CK(cudaFuncSetAttribute(tc::tc_kernel<tc::TC_CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
             CK(cudaFuncSetAttribute(tc::tc_kernel<tc::TC_TRANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
             CK(cudaFuncSetAttribute(tc::tc_kernel<tc::TC_CORR>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
@@ -426,10 +430,12 @@ struct Ctx : cmf_ctx {
         }
     }
     // denomH = C (*) H via tensor cores (mult.jl:44,48); needs lag_tables() and tc_split_H(false) done
-    void tc_denomH() {
+    void tc_denomH(bool resplit_C = true) {
         if constexpr (std::is_same<S, float>::value) {
-            tc::split_C_kernel<<<(unsigned)cdiv(tcs.rows_c * tcs.Kp, 256), 256, 0, stream>>>(Cf.p, tcs.Cc_hi.p, tcs.Cc_lo.p, K, 2 * L - 1, tcs.Kp, tcs.rows_c);
-            post_launch();
+            if (resplit_C) {
+                tc::split_C_kernel<<<(unsigned)cdiv(tcs.rows_c * tcs.Kp, 256), 256, 0, stream>>>(Cf.p, tcs.Cc_hi.p, tcs.Cc_lo.p, K, 2 * L - 1, tcs.Kp, tcs.rows_c);
+                post_launch();
+            }
             tc::Params q = tc_base_params();
             q.groups = tcs.groups_c; q.nblocks = cdiv(tcs.Kp, tc::BK); q.own = tc::BN - (tcs.G - 1);
             q.units = cdiv(Tl, q.own);
@@ -618,7 +624,9 @@ struct Ctx : cmf_ctx {
     }
     void finish_data() {
         tcs.x_dirty = true;
-        data_norm = std::sqrt(data_sumsq());
+        numH_valid = false;
+        data_sumsq_local = data_sumsq();
+        data_norm = std::sqrt(data_sumsq_local);
         have_data = true;
     }
     double data_sumsq() override {
@@ -659,6 +667,8 @@ struct Ctx : cmf_ctx {
         CK(cudaStreamSynchronize(stream));
         have_factors = true;
         tcs.w_dirty = true;
+        numH_valid = false;
+        gram_valid = false;
         if (alg == CMF_HALS && have_data) refresh_resid(false);
     }
 
@@ -675,6 +685,8 @@ struct Ctx : cmf_ctx {
         CK(cudaStreamSynchronize(stream));
         have_factors = true;
         tcs.w_dirty = true;
+        numH_valid = false;
+        gram_valid = false;
     }
 
     void init_scale_partials(double out[2]) override {
@@ -696,6 +708,8 @@ struct Ctx : cmf_ctx {
         scale_kernel<S><<<(unsigned)cdiv((int64_t)Hbuf.n, 256), 256, 0, stream>>>(Hbuf.p, (S)s, (int64_t)Hbuf.n);
         post_launch();
         tcs.w_dirty = true;
+        numH_valid = false;
+        gram_valid = false;
         if (alg == CMF_HALS && have_data) refresh_resid(false);
     }
 
@@ -715,8 +729,14 @@ struct Ctx : cmf_ctx {
         // numW partial over the owned u (mult.jl:32): Xin = X incl. right halo
         if (tc_active()) tc_corr();
         else launch_corr(X.p, N, N, Tl + (L - 1), nsplit_w, split_w, numW.p, nullptr);
-        // Gram partial Rg[d][k][k'] = sum_u H[u][k] H[u+d][k'] (owned u, right halo for u+d)
-        if (tc_active()) { tc_split_H(false); tc_gram(); }
+        // Gram partial Rg[d][k][k'] = sum_u H[u][k] H[u+d][k'] (owned u, right halo for u+d); already resident
+        // when the expansion loss of the previous iteration computed it for the same H
+        if (!gram_valid) gram_partial();
+        gram_valid = false;     // the host all-reduces the buffer in place: it is consumed by this step
+    }
+
+    void gram_partial() {
+        if (tc_active()) { tc_split_H(true); tc_split_H(false); tc_gram(); }
         else launch_corr(H, K, K, Tl + (L - 1), nsplit_g, split_g, nullptr, exch1.p);
         if (L > 1) {
             h_tail_kernel<S><<<(unsigned)cdiv((L - 1) * K, 256), 256, 0, stream>>>(H, exch1.p + L * K * K, K, L, Tl, is_last ? 1 : 0);
@@ -738,6 +758,7 @@ struct Ctx : cmf_ctx {
         }
         launch_mu(Wi.p, numW.p, denW.p, l1W, l2W, KL() * N);                  // mult.jl:37-38
         tcs.w_dirty = true;
+        numH_valid = false;
     }
 
     // layout of the W W' product held in GS: S2[(l*s2_ks + k)*s2_ld + l'*s2_ks + k']
@@ -770,15 +791,37 @@ struct Ctx : cmf_ctx {
             post_launch();
         }
         launch_mu(H, numH.p, denH.p, l1H, l2H, Tl * K);                       // mult.jl:51-52
+        numH_valid = (alg == CMF_MULT);
+        gram_valid = false;
     }
 
     double loss_partial() override {
         REQUIRE(have_data && have_factors, "loss: data and factors must be set first");
+        if (loss_mode == 1 && tc_active() && numH_valid) return loss_partial_expansion();
         int64_t nb = conv_nblocks(0, Tl);
         if (tc_active()) nb = tc_conv_loss();
         else launch_conv(Wi.p, H, K, L, -(L - 1), Tl + (L - 1), 0, Tl, 4, nullptr, loss_part.p);  // mult.jl:55-57
         reduce_scalar(loss_part.p, nb, scal.p);
         return fetch_scalar(scal.p);
+    }
+
+    // ||conv(W,H) - X||^2 = ||X||^2 - 2 <transconv(W,X), H> + <W W', Htilde Htilde'>, summed over the owned columns
+    // (the global sum over shards is exact; a single shard's value is not its own residual).  numH and W W' are
+    // resident from the H update with the current W; the Gram of the new H is computed here and reused by the
+    // next cmf_w_partials (the halos must not change in between).
+    double loss_partial_expansion() {
+        gram_partial();
+        gram_valid = true;
+        s2_dot_G_kernel<S><<<1024, 256, 0, stream>>>(GS.p, s2_ks, s2_ld, exch1.p, exch1.p + L * K * K, K, L, loss_part.p + 1024);
+        post_launch();
+        reduce_scalar(loss_part.p + 1024, 1024, scal.p + 1);
+        dot_partial_kernel<S><<<1024, 256, 0, stream>>>(numH.p, H, Tl * K, loss_part.p);
+        post_launch();
+        reduce_scalar(loss_part.p, 1024, scal.p);
+        double bc[2];
+        CK(cudaMemcpyAsync(bc, scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        return data_sumsq_local - 2.0 * bc[0] + bc[1];
     }
 
     // ---------------------------------------------------------------- HALS (src/algs/hals.jl)
@@ -1043,6 +1086,9 @@ int cmf_fit(cmf_handle h, int64_t max_itr, double max_time, int eval_mode, int c
             time_hist[n] = time_hist[n - 1] + dur;
             loss_hist[n] = loss;
             ++n;
+            // the expansion cancels like 1/loss^2: its error is ~1.6e-6/loss^2 relative (measured), so below 20%
+            // relative loss fall back to the direct residual pass (keeps the loss within 1e-4 of the reference)
+            if (h->loss_mode == 1 && !(loss > 0.2)) h->loss_mode = 0;
             if (check_convergence && converged(loss_hist, n, patience, tol)) {   // alternating.jl:63-66
                 if (converged_early) *converged_early = 1;
                 break;
@@ -1128,6 +1174,13 @@ int cmf_set_engine(cmf_handle h, int engine) {
     });
 }
 
+int cmf_set_loss_mode(cmf_handle h, int mode) {
+    return guarded([&] {
+        REQUIRE(h, "null handle");
+        REQUIRE(mode == 0 || mode == 1, "loss mode must be 0 (direct) or 1 (expansion)");
+        h->loss_mode = mode;
+    });
+}
 int cmf_get_engine(cmf_handle h, int *engine_out) {
     return guarded([&] { REQUIRE(h && engine_out, "null argument"); *engine_out = h->engine; });
 }

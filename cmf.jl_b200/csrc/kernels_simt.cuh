@@ -512,6 +512,26 @@ __global__ void build_G_kernel(const double *__restrict__ Rg, const double *__re
     G[idx] = (S)(g - tail);
 }
 
+// partial[block] = sum over a grid-stride slice of S2[j][j'] * G[j][j'], with G = Htilde Htilde' formed on the fly
+// from Rg and the tail exactly as in build_G_kernel:  ||conv(W,H)||^2 = <W W', Htilde Htilde'>.
+template <typename S>
+__global__ void s2_dot_G_kernel(const S *__restrict__ S2, int64_t Ks, int64_t ld, const double *__restrict__ Rg,
+                                const double *__restrict__ Ht, int64_t K, int64_t L, double *__restrict__ partial) {
+    __shared__ double red[32];
+    const int64_t KL = K * L;
+    double acc = 0.0;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < KL * KL; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t jp = idx % KL, j = idx / KL;
+        const int64_t k = j % K, l = j / K, kp = jp % K, lp = jp / K;
+        double g = (l >= lp) ? Rg[((l - lp) * K + k) * K + kp] : Rg[((lp - l) * K + kp) * K + k];
+        const int64_t m = l < lp ? l : lp;
+        for (int64_t i = 0; i < m; ++i) g -= Ht[(L - 1 - l + i) * K + k] * Ht[(L - 1 - lp + i) * K + kp];
+        acc += g * (double)S2[(l * Ks + k) * ld + lp * Ks + kp];
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
 // Cf[(d+L-1)][k][k'] = sum_{l, 0<=l-d<L} S2[(l,k)][(l-d,k')]      (S2 = W W' over the unfolded rows)
 // S2 is addressed as S2[(l*Ks + k) * ld + (l'*Ks + k')]: (Ks, ld) = (K, K*L) for the SIMT product and
 // (Kp, rows_u) for the tensor-core product over the padded rows.

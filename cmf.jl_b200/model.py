@@ -30,7 +30,7 @@ from ._lib import F32, F64, HALS, MULT, CMFError, check, fptr, julia_array, np_d
 _REG_ALIASES = {"l1_W": "l1W", "l2_W": "l2W", "l1_H": "l1H", "l2_H": "l2H"}
 _INIT_ALIASES = {"initW": "W_init", "initH": "H_init"}
 _KNOWN = {"l1W", "l2W", "l1H", "l2H", "seed", "W_init", "H_init", "check_convergence", "patience",
-          "eval_mode", "tol", "verbose", "dtype", "device", "layout", "printer", "engine"}
+          "eval_mode", "tol", "verbose", "dtype", "device", "layout", "printer", "engine", "loss_mode"}
 
 
 def _normalise_kwargs(kwargs):
@@ -102,7 +102,7 @@ class AbstractCFUpdate:
 
     _ALG = None
 
-    def __init__(self, data, W, H, dtype="f64", device=0, sync_host=True, engine=None):
+    def __init__(self, data, W, H, dtype="f64", device=0, sync_host=True, engine=None, loss_mode=None):
         lib = _lib.load()
         self.dtype = parse_dtype(dtype)
         data = np.asarray(data)
@@ -119,6 +119,8 @@ class AbstractCFUpdate:
         check(lib.cmf_create(ctypes.byref(self._h), N, self.T, K, L, self.dtype, self._ALG, device))
         if engine is not None:
             check(lib.cmf_set_engine(self._h, int(engine)))
+        if loss_mode is not None:
+            check(lib.cmf_set_loss_mode(self._h, int(loss_mode)))
         Xj = julia_array(data, self.dtype)
         check(lib.cmf_set_data(self._h, fptr(Xj), 0))
         self.set_factors(W, H)
@@ -317,7 +319,7 @@ def fit_cnmf(data, L=10, K=5, alg=MultUpdate, max_itr=100, max_time=math.inf, **
         raise ValueError(f"W_init must be {(K, N, L)} and H_init {(K, T)}; got {W0.shape}, {H0.shape}")
 
     rule = rule_cls(data, W0, H0, dtype=dtype, device=device, sync_host=False,
-                    engine=kw.get("engine"))                                 # model.jl:79
+                    engine=kw.get("engine"), loss_mode=kw.get("loss_mode"))  # model.jl:79
     try:
         if need_rescale:
             _rescale(rule)

@@ -102,6 +102,11 @@ class DeviceShard:
         """0 = SIMT kernels, 1 = tcgen05 tensor-core kernels (raises if the handle cannot use them)."""
         check(_lib.load().cmf_set_engine(self._h, int(engine)))
 
+    def set_loss_mode(self, mode):
+        """0 = direct residual pass, 1 = algebraic expansion on resident numH / C (tcgen05 engine only)."""
+        check(_lib.load().cmf_set_loss_mode(self._h, int(mode)))
+        self.loss_mode = int(mode)
+
     def get_engine(self):
         out = ctypes.c_int()
         check(_lib.load().cmf_get_engine(self._h, ctypes.byref(out)))
@@ -271,7 +276,10 @@ class ShardedMultFit:
             s.w_apply(l1W, l2W)                  # identical W update on every rank
         s.h_update(l1H, l2H)                     # owned columns of H
         self.exchange_halos()                    # L-1 columns each way
-        return self.loss()                       # all-reduce of one double
+        loss = self.loss()                       # all-reduce of one double
+        if getattr(s, "loss_mode", 0) == 1 and not loss > 0.2:
+            s.set_loss_mode(0)                   # the expansion cancels like 1/loss^2 (same rule on every rank)
+        return loss
 
     def fit(self, max_itr=100, check_convergence=True, patience=3, tol=1e-4, **reg):
         """src/algs/alternating.jl:16-71 over shards (every rank takes the same branch because the

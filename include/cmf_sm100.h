@@ -168,6 +168,14 @@ int cmf_profile_read(cmf_handle h, int which, double *ms_total, int64_t *count);
 /* Selects the contraction engine: 0 = SIMT kernels (fp64 and fp32), 1 = tcgen05 tensor-core
  * kernels (fp32 data, split-bf16 operands) where available.  Default: best available. */
 int cmf_set_engine(cmf_handle h, int engine);
+/* How the tcgen05 engine evaluates the loss inside the iteration (mult.jl:55-57): 0 = direct fused
+ * conv + residual pass (default; always used by the SIMT/fp64 engines), 1 = the exact identity
+ * ||conv(W,H)-X||^2 = ||X||^2 - 2<transconv(W,X),H> + <W W', Htilde Htilde'> on the numH and W W' that the
+ * H update leaves resident plus the Gram of the new H, which the next cmf_w_partials reuses (a third of the
+ * contraction work is saved; the halos must not change between cmf_loss_partial and cmf_w_partials).  The
+ * identity cancels like 1/loss^2, (measured error ~1.6e-6/loss^2 relative), so callers switch back to 0 when the relative loss drops below 20%
+ * (cmf_fit and the sharded host loop do). */
+int cmf_set_loss_mode(cmf_handle h, int mode);
 /* The engine currently selected (0 / 1). */
 int cmf_get_engine(cmf_handle h, int *engine_out);
 

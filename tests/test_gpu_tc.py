@@ -95,6 +95,20 @@ def test_tc_fit_matches_oracle_loss(cmf, orc):
     assert np.linalg.norm(r.H - ref.H) / np.linalg.norm(ref.H) < 1e-3
 
 
+@pytest.mark.parametrize("noise,p_h", [(1.0, 0.5), (0.05, 0.1)])
+def test_tc_expansion_loss_matches_oracle(cmf, orc, noise, p_h):
+    # loss evaluated by the algebraic expansion on the resident numH / C table (cmf_set_loss_mode 1)
+    N, T, K, L = 256, 4096, 8, 10
+    X, _, _ = orc.po.synthetic_sequences(K=4, N=N, L=L, T=T, noise_scale=noise, p_h=p_h,
+                                         rng=np.random.default_rng(1234))
+    W0, H0 = orc.po.init_rand(X, L, K, np.random.default_rng(0))
+    ref = orc.co.fit(orc.co.MultUpdate, X, W0, H0, 40, check_convergence=False)
+    r = cmf.fit_cnmf(X, L=L, K=K, alg="mult", max_itr=40, W_init=W0, H_init=H0, check_convergence=False,
+                     dtype="f32", engine=1, loss_mode=1, layout="KNL")
+    rel = np.abs(np.asarray(r.loss_hist) - np.asarray(ref.loss_hist)) / np.asarray(ref.loss_hist)
+    assert rel.max() < 1e-4, (rel.max(), ref.loss_hist[-1])
+
+
 def test_tc_sharded_matches_single(cmf, orc):
     import math
 
@@ -103,12 +117,13 @@ def test_tc_sharded_matches_single(cmf, orc):
     N, T, K, L, iters = 256, 12000, 16, 9, 4
     W0, H0, X = _rand(N, T, K, L, seed=5)
 
-    def run(world):
+    def run(world, loss_mode=0):
         plan = cmf.ShardPlan(T, world, L)
         shards = []
         for (t0, t1) in plan.ranges:
             s = cmf.DeviceShard(N, T, t0, t1, K, L, dtype="f32", device=0)
             s.set_engine(1)
+            s.set_loss_mode(loss_mode)
             s.set_data(X, 0)
             s.set_factors(W0, H0, 0)
             shards.append(s)
@@ -135,7 +150,8 @@ def test_tc_sharded_matches_single(cmf, orc):
             s.close()
         return np.asarray(hist)
 
-    a, b = run(1), run(3)
+    a, b, c = run(1), run(3), run(3, loss_mode=1)
     ref = orc.co.fit(orc.co.MultUpdate, X, W0, H0, iters, check_convergence=False)
     assert np.allclose(a, ref.loss_hist[1:], rtol=1e-4)
     assert np.allclose(a, b, rtol=2e-6)
+    assert np.allclose(c, ref.loss_hist[1:], rtol=1e-4)      # expansion loss summed over shards
