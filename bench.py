@@ -322,6 +322,9 @@ def run_ours(args, cfg, name):
         "bound": "tensor", "kernel": dom, "achieved": achieved_tf, "peak": pk["tensor"], "unit": "TFLOP/s",
         "frac": achieved_tf / pk["tensor"], "traffic": None, "peak_source": f"{pk['src']} bf16 sustained",
         "flops_per_launch": Fc_rank, "ms_per_launch": per_launch_ms,
+        "executed": {"tflops": 3.0 * achieved_tf if engine == 1 else achieved_tf,
+                     "frac": (3.0 * achieved_tf if engine == 1 else achieved_tf) / pk["tensor"],
+                     "note": "bf16 tensor FLOPs actually issued: every fp32 product is 3 bf16 MMAs (hi*hi + hi*lo + lo*hi)"},
         "note": "arithmetic intensity K*L/2 = %d FLOP/B >> machine balance: the contraction is tensor/FMA bound, "
                 "not HBM bound (SURVEY.md section 8d); algorithmic FLOPs 2*N*K*(L*T - L(L-1)/2) per contraction launch" % (K * L // 2),
         "kernel_ms": {k: {"total_ms": v[0], "launches": v[1]} for k, v in prof.items()},

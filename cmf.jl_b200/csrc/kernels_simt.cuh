@@ -553,20 +553,25 @@ __global__ void __launch_bounds__(256) denomH_tail_kernel(const S *__restrict__ 
                                                            S *__restrict__ den, int64_t K, int64_t L,
                                                            int64_t Tl, int64_t h_lo, int64_t Ks, int64_t ld) {
     __shared__ double red[32];
-    const int64_t KL = K * L;
+    const int KL = (int)(K * L), Ki = (int)K;
     const int64_t c = blockIdx.x;                 // tail column index: t = Tl - (L-1) + c
     const int64_t k = blockIdx.y;
     const int64_t t = Tl - (L - 1) + c;
     if (t < 0) return;
-    const int64_t w = Tl - t;                     // 1 .. L-1
+    const int w = (int)(Tl - t);                  // 1 .. L-1
     double s = 0.0;
-    const int64_t total = w * KL;                 // (l, l', k')
-    for (int64_t idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int64_t jp = idx % KL, l = idx / KL;
-        const int64_t kp = jp % K, lp = jp / K;
-        const int64_t u = t + l - lp;
-        if (u < h_lo) continue;
-        s += (double)S2[(l * Ks + k) * ld + lp * Ks + kp] * (double)H[u * K + kp];
+    // thread -> fixed set of (l', k') pairs (32-bit index math), loop over the w lags of row (l, k)
+    for (int jp = threadIdx.x; jp < KL; jp += blockDim.x) {
+        const int lp = jp / Ki, kp = jp - lp * Ki;
+        const S *s2col = S2 + (int64_t)lp * Ks + kp;
+        const S *hcol = H + kp;
+        S acc = S(0);                                 // <= L terms per chain, accumulated in the handle's type
+        for (int l = 0; l < w; ++l) {
+            const int64_t u = t + l - lp;
+            if (u < h_lo) continue;
+            acc = fma(s2col[((int64_t)l * Ks + k) * ld], hcol[u * K], acc);
+        }
+        s += (double)acc;
     }
     s = block_sum(s, red);
     if (threadIdx.x == 0) den[t * K + k] = (S)s;
