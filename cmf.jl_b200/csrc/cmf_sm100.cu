@@ -203,7 +203,9 @@ struct TcState {
 template <typename S>
 struct Ctx : cmf_ctx {
     TcState tcs;
-    DevBuf<S> X, Hbuf, Wi, Wtmp, numW, denW, GS, Cf, numH, denH, R, tailC;
+    DevBuf<S> X, Hbuf, Wi, Wtmp, numW, denW, GS, Cf, numH, denH, tailC;
+    DevBuf<int> progress;
+    int hals_grid = 0;
     DevBuf<double> exch1, corr_part, loss_part, scal;
     S *H = nullptr;  // owned column 0 inside Hbuf
     int nsplit_w = 1, nsplit_g = 1;
@@ -236,8 +238,19 @@ struct Ctx : cmf_ctx {
         exch1.alloc((size_t)(L * K * K + hal * K + 1));
         scal.alloc(8);
         if (alg == CMF_HALS) {
-            R.alloc((size_t)((Tl + hal) * N));
-            tailC.alloc((size_t)(L * L));
+            // wavefront H sweep: one cooperative launch, CTA b owns components b, b+grid, ...
+            REQUIRE(L - 1 <= HW_TC, "HALS: L-1 must not exceed the sweep chunk (256 columns)");
+            const size_t smem = (size_t)(HW_TC + 2 * L + 32 + L) * sizeof(S);
+            int per_sm = 0, sms = 0, coop = 0;
+            CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+            CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+            REQUIRE(coop != 0, "HALS needs cooperative launch support");
+            CK(cudaFuncSetAttribute(hals_h_wave_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hals_h_wave_kernel<S>, HW_TC, smem));
+            hals_grid = (int)std::min<int64_t>(K, (int64_t)per_sm * sms);
+            REQUIRE(hals_grid >= 1, "HALS: H sweep kernel does not fit on the device");
+            tailC.alloc((size_t)hals_grid * (size_t)(L * L));
+            progress.alloc((size_t)K);
         }
         // corr splits: numW (Nin = N) and Gram (Nin = K)
         plan_split(N, Tl + hal, nsplit_w, split_w);
@@ -256,7 +269,7 @@ struct Ctx : cmf_ctx {
     void tc_setup() {
         if constexpr (!std::is_same<S, float>::value) { return; } else {
             TcState &t = tcs;
-            if (alg != CMF_MULT || K > 128 || N % 8 != 0) return;
+            if (K > 128 || N % 8 != 0) return;
             t.Kp = K <= 16 ? 16 : K <= 32 ? 32 : K <= 64 ? 64 : 128;
             t.G = 128 / t.Kp;
             t.KLp = cdiv(L * t.Kp, 64) * 64;
@@ -669,7 +682,6 @@ struct Ctx : cmf_ctx {
         tcs.w_dirty = true;
         numH_valid = false;
         gram_valid = false;
-        if (alg == CMF_HALS && have_data) refresh_resid(false);
     }
 
     void init_rand(uint64_t seed) override {
@@ -710,7 +722,6 @@ struct Ctx : cmf_ctx {
         tcs.w_dirty = true;
         numH_valid = false;
         gram_valid = false;
-        if (alg == CMF_HALS && have_data) refresh_resid(false);
     }
 
     void get_factors(void *Wo, void *Ho) override {
@@ -750,6 +761,7 @@ struct Ctx : cmf_ctx {
     }
 
     void w_apply(double l1W, double l2W) override {
+        if (alg == CMF_HALS) { hals_w_apply(l1W, l2W); return; }
         if (tc_active()) {
             tc_denomW();                                                          // denomW = G * Wi on tensor cores
         } else {
@@ -825,43 +837,60 @@ struct Ctx : cmf_ctx {
     }
 
     // ---------------------------------------------------------------- HALS (src/algs/hals.jl)
-    double refresh_resid(bool want_loss) {
-        const int nb = conv_nblocks(0, Tl);
-        launch_conv(Wi.p, H, K, L, -(L - 1), Tl + (L - 1), 0, Tl, 2 | 4, R.p, loss_part.p);   // hals.jl:22
-        if (!want_loss) return 0.0;
-        reduce_scalar(loss_part.p, nb, scal.p);
-        return fetch_scalar(scal.p);
-    }
-
-    void hals_update_motifs(double l1W, double l2W) override {
-        REQUIRE(have_data && have_factors, "update: data and factors must be set first");
-        // P[j][n] = sum_t R[n,t] Htilde[j,t]  (hals.jl:111 projections for every column at once)
-        launch_corr(R.p, N, N, Tl + (L - 1), nsplit_w, split_w, numW.p, nullptr);
-        launch_corr(H, K, K, Tl + (L - 1), nsplit_g, split_g, nullptr, exch1.p);
-        if (L > 1) {
-            h_tail_kernel<S><<<(unsigned)cdiv((L - 1) * K, 256), 256, 0, stream>>>(H, exch1.p + L * K * K, K, L, Tl, 1);
-            post_launch();
-        }
-        build_G();
+    // The HALS gradients come from the same four quantities as MU (no residual matrix is kept):
+    //   P = R Htilde' = denomW - numW   (hals.jl:111 projections for every column at once)
+    //   Q = transconv(W, R) = denomH - numH
+    // with R = conv(W,H) - X (hals.jl:22).  w_partials() / the Gram all-reduce are shared with MU.
+    void hals_w_apply(double l1W, double l2W) {
+        if (tc_active()) tc_denomW();
+        build_G();                                                            // G as a matrix for the sweep (GS)
+        if (!tc_active()) launch_gemm<false>(GS.p, Wi.p, denW.p, KL(), N, KL(), KL(), N, N);
+        sub_kernel<S><<<(unsigned)cdiv(KL() * N, 256), 256, 0, stream>>>(numW.p, denW.p, numW.p, KL() * N);   // P
+        post_launch();
         const size_t smem = (size_t)KL() * sizeof(S);
         REQUIRE(smem <= 200 * 1024, "HALS W sweep: K*L too large for shared memory");
         auto kern = hals_w_sweep_kernel<S>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)N, 256, smem, stream>>>(GS.p, numW.p, Wi.p, K, L, N, (S)l1W, (S)l2W);   // hals.jl:90-112
         post_launch();
-        refresh_resid(false);
+        tcs.w_dirty = true;
+        numH_valid = false;
+    }
+
+    void hals_update_motifs(double l1W, double l2W) override {
+        w_partials();
+        hals_w_apply(l1W, l2W);
     }
 
     double hals_update_feature_maps(double l1H, double l2H) override {
         REQUIRE(have_data && have_factors, "update: data and factors must be set first");
-        launch_transconv(Wi.p, R.p, numH.p, N, K, L, N, Tl, Tl + (L - 1));    // Q = transconv(W, R)
+        REQUIRE(is_first && is_last, "HALS H sweep is single-shard");
+        if (tc_active()) tc_transconv();
+        else launch_transconv(Wi.p, X.p, numH.p, N, K, L, N, Tl, Tl + (L - 1));
         lag_tables();
-        const size_t smem = (size_t)(2 * L + 32 + L) * sizeof(S);
-        auto kern = hals_h_sweep_kernel<S>;
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<1, 1024, smem, stream>>>(Cf.p, GS.p, numH.p, H, denH.p, tailC.p, K, L, Tl, (S)l1H, (S)l2H);  // hals.jl:121-154
+        if (tc_active()) { tc_split_H(false); tc_denomH(); }
+        else launch_transconv(Cf.p, Hbuf.p, denH.p, K, K, 2 * L - 1, K, Tl, Tl + 2 * (L - 1));
+        if (L > 1) {
+            dim3 grid((unsigned)(L - 1), (unsigned)K);
+            denomH_tail_kernel<S><<<grid, 256, 0, stream>>>(GS.p, H, denH.p, K, L, Tl, -(L - 1), s2_ks, s2_ld);
+            post_launch();
+        }
+        sub_kernel<S><<<(unsigned)cdiv(Tl * K, 256), 256, 0, stream>>>(numH.p, denH.p, numH.p, Tl * K);        // Q
         post_launch();
-        return refresh_resid(true);                                            // hals.jl:41
+        // wavefront sweep (hals.jl:121-154); Delta H goes to denH
+        CK(cudaMemsetAsync(progress.p, 0, progress.n * sizeof(int), stream));
+        const size_t smem = (size_t)(HW_TC + 2 * L + 32 + L) * sizeof(S);
+        const S *cf = Cf.p, *s2 = GS.p, *q = numH.p;
+        S *hh = H, *dd = denH.p, *tc_ = tailC.p;
+        int *pr = progress.p;
+        int64_t Kk = K, Ll = L, Tt = Tl, ks = s2_ks, ldv = s2_ld;
+        S a1 = (S)l1H, a2 = (S)l2H;
+        void *args[] = {&cf, &s2, &q, &hh, &dd, &tc_, &pr, &Kk, &Ll, &Tt, &ks, &ldv, &a1, &a2};
+        CK(cudaLaunchCooperativeKernel((void *)hals_h_wave_kernel<S>, dim3((unsigned)hals_grid), dim3(HW_TC), args, smem, stream));
+        post_launch();
+        gram_valid = false;
+        numH_valid = false;
+        return loss_partial();                                                // hals.jl:41
     }
 
     // ---------------------------------------------------------------- exchange
@@ -1099,10 +1128,10 @@ int cmf_fit(cmf_handle h, int64_t max_itr, double max_time, int eval_mode, int c
 }
 
 int cmf_w_partials(cmf_handle h) {
-    return guarded([&] { use(h); REQUIRE(h->alg == CMF_MULT, "split-phase calls are MultUpdate only"); h->w_partials(); });
+    return guarded([&] { use(h); h->w_partials(); });
 }
 int cmf_w_apply(cmf_handle h, double l1W, double l2W) {
-    return guarded([&] { use(h); REQUIRE(h->alg == CMF_MULT, "split-phase calls are MultUpdate only"); h->w_apply(l1W, l2W); });
+    return guarded([&] { use(h); h->w_apply(l1W, l2W); });
 }
 int cmf_h_update(cmf_handle h, double l1H, double l2H) {
     return guarded([&] { use(h); REQUIRE(h->alg == CMF_MULT, "split-phase calls are MultUpdate only"); h->h_update(l1H, l2H); });

@@ -732,91 +732,135 @@ __global__ void __launch_bounds__(256) hals_w_sweep_kernel(const S *__restrict__
         }
 }
 
-// H sweep, single block (sequential in k, sequential in t inside warp 0, block-parallel Q update).
-//   Q[t][k] = transconv(W, R);  Cf[(d+L-1)][k][k'] interior table;  S2 for the truncated tail.
-//   for k: for t: w = min(L, T-t); c0 = C_w[k,k,0];
-//          h' = max((h*c0 - Q[t][k] - pend(t) - l1)/(c0 + eps + l2), 0);  delta[t] = h'-h
-//          pend(t+s) += delta * C_w[k,k,s]   (s = 1..L-1, same component, future columns)
-//     then for all k' != k ... only k' > k matter: Q[t'][k'] += sum_t delta[t] * C_{w(t)}[k,k',t'-t]
+// H sweep (hals.jl:121-154) as a wavefront over (component k, time chunk c) in ONE cooperative launch.
+//   Q[t][k] = transconv(W, conv(W,H) - X)[k,t] at the start of the sweep (gradient of the H step),
+//   Cf[(d+L-1)][k][k'] interior lag table, S2 = W W' for the truncated tail tables, D[t][k] = Delta H (output).
+// Cell (k, c) = columns [c*HW_TC, (c+1)*HW_TC) of component k:
+//   pull  : qeff[t'] = Q[t'][k] + sum_{k'<k} sum_{|t-t'|<L} D[t][k'] * C_{w(t)}[k',k,t'-t]      (all threads, no races)
+//   sweep : for t: h' = max((h*c0 - qeff[t] - pend(t) - l1)/(c0 + eps + l2), 0);  D[t][k] = h'-h;
+//           pend(t+s) += D[t][k] * C_w[k,k,s]                                                  (warp 0, sequential)
+// Component k may run cell c once component k-1 has finished cell c+1 (its corrections reach L-1 columns back)
+// and its own cell c-1; CTA b owns components b, b+grid, ...; progress[k] counts finished cells of k.
+// Every Q element has exactly one reader/writer at a time, so the result is deterministic and identical to
+// the sequential k-outer / t-inner sweep of the reference.
+constexpr int HW_TC = 256;
+
 template <typename S>
-__global__ void __launch_bounds__(1024) hals_h_sweep_kernel(const S *__restrict__ Cf, const S *__restrict__ S2,
-                                                             S *__restrict__ Q, S *__restrict__ H,
-                                                             S *__restrict__ delta /*[T]*/,
-                                                             S *__restrict__ tailC /*[L][L] scratch*/,
-                                                             int64_t K, int64_t L, int64_t T, S l1, S l2) {
+__global__ void __launch_bounds__(HW_TC) hals_h_wave_kernel(const S *__restrict__ Cf, const S *__restrict__ S2,
+                                                             const S *__restrict__ Q, S *__restrict__ H, S *__restrict__ D,
+                                                             S *__restrict__ tailC_all /*[grid][L*L]*/, int *progress /*[K]*/,
+                                                             int64_t K, int64_t L, int64_t T, int64_t Ks, int64_t ld,
+                                                             S l1, S l2) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    S *pend = reinterpret_cast<S *>(smem_raw);  // ring of RB entries
-    S *ckk = pend + 2 * L + 32;                 // Cf[k,k,s], s = 0..L-1
-    const int64_t KL = K * L;
+    S *qeff = reinterpret_cast<S *>(smem_raw);       // [HW_TC]
+    S *pend = qeff + HW_TC;                          // ring of RB entries
+    S *ckk = pend + (2 * L + 32);                    // Cf[k,k,s], s = 0..L-1
     const int RB = (int)(2 * L + 32);
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int64_t Tint = T - (L - 1);           // columns t < Tint have the full window (w = L)
+    const int64_t nC = (T + HW_TC - 1) / HW_TC;
+    const int64_t Tint = T - (L - 1);                // columns t < Tint have the full lag window (w = L)
+    S *tailC = tailC_all + (size_t)blockIdx.x * (size_t)(L * L);
 
-    for (int64_t k = 0; k < K; ++k) {
+    for (int64_t k = blockIdx.x; k < K; k += gridDim.x) {
         // per-component tables
         for (int64_t s = tid; s < L; s += nthr) ckk[s] = Cf[((s + L - 1) * K + k) * K + k];
-        for (int64_t i = tid; i < RB; i += nthr) pend[i] = S(0);
-        // tailC[w][s] = C_w[k,k,s] = sum_{l<w, l-s>=0} S2[(l,k)][(l-s,k)],  w = 1..L-1 (index w), s = 0..L-1
+        // tailC[w][s] = C_w[k,k,s] = sum_{l<w, l-s>=0} S2[(l,k)][(l-s,k)],  w = 1..L-1, s = 0..L-1
         for (int64_t idx = tid; idx < L * L; idx += nthr) {
             const int64_t w = idx / L, s = idx % L;
             double acc = 0.0;
-            for (int64_t l = s; l < w; ++l) acc += (double)S2[(l * K + k) * KL + (l - s) * K + k];
+            for (int64_t l = s; l < w; ++l) acc += (double)S2[(l * Ks + k) * ld + (l - s) * Ks + k];
             tailC[idx] = (S)acc;
         }
+        for (int i = tid; i < RB; i += nthr) pend[i] = S(0);
         __syncthreads();
-        if (tid < 32) {
-            const int lane = tid;
-            for (int64_t t = 0; t < T; ++t) {
-                const int64_t w = (T - t < L) ? (T - t) : L;
-                const S c0 = (w == L) ? ckk[0] : tailC[w * L + 0];
-                const int slot = (int)(t % RB);
-                const S h = H[t * K + k];
-                const S q = Q[t * K + k] + pend[slot];
-                S v = (h * c0 - q - l1) / (c0 + (S)CMF_EPS + l2);
-                v = v > S(0) ? v : S(0);
-                const S d = v - h;
-                __syncwarp();
-                if (lane == 0) {
-                    H[t * K + k] = v;
-                    delta[t] = d;
-                    pend[slot] = S(0);
-                }
-                if (d != S(0)) {
-                    // future columns of the same component: t + s <= T-1, s <= L-1 (and s <= w-1 in the tail)
-                    for (int64_t s = 1 + lane; s < w; s += 32) {
-                        const S c = (w == L) ? ckk[s] : tailC[w * L + s];
-                        pend[(int)((t + s) % RB)] += d * c;
+
+        for (int64_t c = 0; c < nC; ++c) {
+            const int64_t t0 = c * HW_TC;
+            // ---- wait: component k-1 must have finished cell min(c+1, nC-1)
+            if (k > 0 && tid == 0) {
+                const int need = (int)((c + 2 < nC) ? c + 2 : nC);
+                volatile int *pr = progress + (k - 1);
+                while (*pr < need) { __nanosleep(64); }
+            }
+            __syncthreads();
+            __threadfence();
+            // ---- pull: corrections from all earlier components
+            {
+                const int64_t tp = t0 + tid;
+                S q = S(0);
+                if (tp < T) {
+                    double acc = (double)Q[tp * K + k];
+                    const int64_t ta = tp - (L - 1) > 0 ? tp - (L - 1) : 0;
+                    const int64_t tb = tp + (L - 1) < T - 1 ? tp + (L - 1) : T - 1;
+                    for (int64_t t = ta; t <= tb; ++t) {
+                        const int64_t dd = tp - t;
+                        const S *drow = D + t * K;
+                        if (t < Tint) {
+                            const S *crow = Cf + (dd + L - 1) * K * K + k;      // Cf[(dd+L-1)][k'][k], stride K over k'
+                            S a = S(0);
+                            for (int64_t kp = 0; kp < k; ++kp) a = fma(__ldcg(drow + kp), crow[kp * K], a);
+                            acc += (double)a;
+                        } else {
+                            const int64_t w = T - t;    // C_w[k',k,dd] = sum_{l<w, 0<=l-dd<L} S2[(l,k')][(l-dd,k)]
+                            for (int64_t kp = 0; kp < k; ++kp) {
+                                const S d = __ldcg(drow + kp);
+                                if (d == S(0)) continue;
+                                double cw = 0.0;
+                                for (int64_t l = (dd > 0 ? dd : 0); l < w && l - dd < L; ++l)
+                                    cw += (double)S2[(l * Ks + kp) * ld + (l - dd) * Ks + k];
+                                acc += (double)d * cw;
+                            }
+                        }
                     }
+                    q = (S)acc;
                 }
-                __syncwarp();
+                qeff[tid] = q;
             }
-        }
-        __syncthreads();
-        // propagate to the later components:  Q[t'][k'] += sum_t delta[t] * C_{w(t)}[k,k',t'-t]
-        const int64_t nk = K - 1 - k;
-        for (int64_t idx = tid; idx < nk * T; idx += nthr) {
-            const int64_t kp = k + 1 + idx % nk, tp = idx / nk;
-            double acc = 0.0;
-            const int64_t ta = tp - (L - 1) > 0 ? tp - (L - 1) : 0;
-            const int64_t tb = tp + (L - 1) < T - 1 ? tp + (L - 1) : T - 1;
-            for (int64_t t = ta; t <= tb; ++t) {
-                const S d = delta[t];
-                if (d == S(0)) continue;
-                const int64_t dd = tp - t;
-                if (t < Tint) {
-                    acc += (double)d * (double)Cf[((dd + L - 1) * K + k) * K + kp];
-                } else {
-                    const int64_t w = T - t;  // C_w[k,k',dd] = sum_{l<w, 0<=l-dd<L} S2[(l,k)][(l-dd,k')]
-                    double c = 0.0;
-                    for (int64_t l = (dd > 0 ? dd : 0); l < w && l - dd < L; ++l)
-                        c += (double)S2[(l * K + k) * KL + (l - dd) * K + kp];
-                    acc += (double)d * c;
+            __syncthreads();
+            // ---- sweep: the sequential recurrence of component k over this chunk (warp 0)
+            if (tid < 32) {
+                const int lane = tid;
+                const int64_t t1 = (t0 + HW_TC < T) ? t0 + HW_TC : T;
+                for (int64_t t = t0; t < t1; ++t) {
+                    const int64_t w = (T - t < L) ? (T - t) : L;
+                    const S c0 = (w == L) ? ckk[0] : tailC[w * L + 0];
+                    const int slot = (int)(t % RB);
+                    const S h = H[t * K + k];
+                    const S q = qeff[t - t0] + pend[slot];
+                    S v = (h * c0 - q - l1) / (c0 + (S)CMF_EPS + l2);
+                    v = v > S(0) ? v : S(0);
+                    const S d = v - h;
+                    __syncwarp();
+                    if (lane == 0) {
+                        H[t * K + k] = v;
+                        D[t * K + k] = d;
+                        pend[slot] = S(0);
+                    }
+                    if (d != S(0)) {
+                        for (int64_t s = 1 + lane; s < w; s += 32) {
+                            const S cc = (w == L) ? ckk[s] : tailC[w * L + s];
+                            pend[(int)((t + s) % RB)] += d * cc;
+                        }
+                    }
+                    __syncwarp();
                 }
             }
-            Q[tp * K + kp] += (S)acc;
+            __syncthreads();
+            // ---- publish
+            if (tid == 0) {
+                __threadfence();
+                atomicExch(progress + k, (int)(c + 1));
+            }
         }
         __syncthreads();
     }
+}
+
+// x[i] = a[i] - b[i]   (P = denomW - numW, Q = denomH - numH: the HALS gradients from the MU quantities)
+template <typename S>
+__global__ void sub_kernel(S *x, const S *a, const S *b, int64_t n) {   // x may alias a or b
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = a[i] - b[i];
 }
 
 }  // namespace cmf

@@ -155,3 +155,28 @@ def test_tc_sharded_matches_single(cmf, orc):
     assert np.allclose(a, ref.loss_hist[1:], rtol=1e-4)
     assert np.allclose(a, b, rtol=2e-6)
     assert np.allclose(c, ref.loss_hist[1:], rtol=1e-4)      # expansion loss summed over shards
+
+
+def test_tc_hals_matches_oracle(cmf, orc):
+    # HALS on the tensor-core engine: gradients P = denomW - numW, Q = denomH - numH from the tcgen05 contractions,
+    # per-unit W sweep and the cooperative wavefront H sweep
+    N, T, K, L = 256, 4096, 8, 10
+    X, _, _ = orc.po.synthetic_sequences(K=4, N=N, L=L, T=T, rng=np.random.default_rng(1234))
+    W0, H0 = orc.po.init_rand(X, L, K, np.random.default_rng(0))
+    reg = dict(l1W=0.1, l2W=0.5, l1H=0.1, l2H=0.2)
+    ref = orc.co.fit(orc.co.HALSUpdate, X, W0, H0, 12, check_convergence=False, **reg)
+    r = cmf.fit_cnmf(X, L=L, K=K, alg="hals", max_itr=12, W_init=W0, H_init=H0, check_convergence=False,
+                     dtype="f32", engine=1, layout="KNL", **reg)
+    rel = np.abs(np.asarray(r.loss_hist) - np.asarray(ref.loss_hist)) / np.asarray(ref.loss_hist)
+    assert rel.max() < 1e-4, rel
+
+
+def test_hals_wavefront_many_components_fp64(cmf, orc):
+    # more components than fit one wave of the pipeline order, several time chunks, truncated tail
+    N, T, K, L = 24, 700, 9, 6
+    W, H, X = _rand(N, T, K, L, seed=3)
+    ref = orc.co.fit(orc.co.HALSUpdate, X, W, H, 4, check_convergence=False, l1H=0.05, l2W=0.1)
+    r = cmf.fit_cnmf(X, L=L, K=K, alg="hals", max_itr=4, W_init=W, H_init=H, check_convergence=False,
+                     layout="KNL", l1H=0.05, l2W=0.1)
+    assert np.allclose(r.loss_hist, ref.loss_hist, rtol=1e-9)
+    assert np.allclose(r.H, ref.H, rtol=1e-8, atol=1e-11) and np.allclose(r.W, ref.W, rtol=1e-8, atol=1e-11)
