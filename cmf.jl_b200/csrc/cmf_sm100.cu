@@ -239,8 +239,8 @@ struct Ctx : cmf_ctx {
         scal.alloc(8);
         if (alg == CMF_HALS) {
             // wavefront H sweep: one cooperative launch, CTA b owns components b, b+grid, ...
-            REQUIRE(L - 1 <= HW_TC, "HALS: L-1 must not exceed the sweep chunk (256 columns)");
-            const size_t smem = (size_t)(HW_TC + 2 * L + 32 + L) * sizeof(S);
+            REQUIRE(L - 1 <= HW_TC, "HALS: L-1 must not exceed the sweep chunk (1024 columns)");
+            const size_t smem = hals_wave_smem_elems<S>(L) * sizeof(S);
             int per_sm = 0, sms = 0, coop = 0;
             CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
             CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
@@ -879,7 +879,7 @@ struct Ctx : cmf_ctx {
         post_launch();
         // wavefront sweep (hals.jl:121-154); Delta H goes to denH
         CK(cudaMemsetAsync(progress.p, 0, progress.n * sizeof(int), stream));
-        const size_t smem = (size_t)(HW_TC + 2 * L + 32 + L) * sizeof(S);
+        const size_t smem = hals_wave_smem_elems<S>(L) * sizeof(S);
         const S *cf = Cf.p, *s2 = GS.p, *q = numH.p;
         S *hh = H, *dd = denH.p, *tc_ = tailC.p;
         int *pr = progress.p;

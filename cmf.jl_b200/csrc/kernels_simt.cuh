@@ -743,7 +743,15 @@ __global__ void __launch_bounds__(256) hals_w_sweep_kernel(const S *__restrict__
 // and its own cell c-1; CTA b owns components b, b+grid, ...; progress[k] counts finished cells of k.
 // Every Q element has exactly one reader/writer at a time, so the result is deterministic and identical to
 // the sequential k-outer / t-inner sweep of the reference.
-constexpr int HW_TC = 256;
+constexpr int HW_TC = 1024;  // columns per cell = threads per CTA
+// earlier components staged per pull step (sized so the transposed Delta window fits shared memory)
+template <typename S> __host__ __device__ constexpr int hw_kb() { return sizeof(S) == 4 ? 32 : 16; }
+// dynamic shared memory of hals_h_wave_kernel in elements of S
+template <typename S>
+inline size_t hals_wave_smem_elems(int64_t L) {
+    const size_t WW = HW_TC + 2 * (L - 1);
+    return 2 * HW_TC + (2 * L + 32) + L + (2 * L - 1) * hw_kb<S>() + hw_kb<S>() * ((WW | 1));
+}
 
 template <typename S>
 __global__ void __launch_bounds__(HW_TC) hals_h_wave_kernel(const S *__restrict__ Cf, const S *__restrict__ S2,
@@ -751,10 +759,14 @@ __global__ void __launch_bounds__(HW_TC) hals_h_wave_kernel(const S *__restrict_
                                                              S *__restrict__ tailC_all /*[grid][L*L]*/, int *progress /*[K]*/,
                                                              int64_t K, int64_t L, int64_t T, int64_t Ks, int64_t ld,
                                                              S l1, S l2) {
+    constexpr int HW_KB = hw_kb<S>();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     S *qeff = reinterpret_cast<S *>(smem_raw);       // [HW_TC]
     S *pend = qeff + HW_TC;                          // ring of RB entries
     S *ckk = pend + (2 * L + 32);                    // Cf[k,k,s], s = 0..L-1
+    S *hch = ckk + L;                                // [HW_TC] H of the current cell
+    S *Cs = hch + HW_TC;                             // [(2L-1)][HW_KB] lag-table slice of the pull phase
+    S *Dwin = Cs + (2 * L - 1) * HW_KB;              // [HW_KB][WWP]   transposed Delta window of the pull phase
     const int RB = (int)(2 * L + 32);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int64_t nC = (T + HW_TC - 1) / HW_TC;
@@ -784,73 +796,111 @@ __global__ void __launch_bounds__(HW_TC) hals_h_wave_kernel(const S *__restrict_
             }
             __syncthreads();
             __threadfence();
-            // ---- pull: corrections from all earlier components
+            // ---- pull: corrections from all earlier components, 32 components at a time through shared memory
+            //      (D window transposed so lanes read consecutive t; lag-table slice broadcast)
             {
                 const int64_t tp = t0 + tid;
-                S q = S(0);
-                if (tp < T) {
-                    double acc = (double)Q[tp * K + k];
-                    const int64_t ta = tp - (L - 1) > 0 ? tp - (L - 1) : 0;
+                const int WW = HW_TC + 2 * (int)(L - 1), WWP = WW | 1;
+                S acc = (tp < T) ? Q[tp * K + k] : S(0);
+                for (int64_t kp0 = 0; kp0 < k; kp0 += HW_KB) {
+                    const int kb = (int)((k - kp0 < HW_KB) ? k - kp0 : HW_KB);
+                    __syncthreads();
+                    for (int idx = tid; idx < WW * HW_KB; idx += nthr) {
+                        const int kk = idx % HW_KB, i = idx / HW_KB;
+                        const int64_t t = t0 - (L - 1) + i;
+                        S v = S(0);
+                        if (kk < kb && t >= 0 && t < Tint) v = __ldcg(D + t * K + kp0 + kk);   // tail columns: slow path below
+                        Dwin[kk * WWP + i] = v;
+                    }
+                    for (int idx = tid; idx < (2 * L - 1) * HW_KB; idx += nthr) {
+                        const int kk = idx % HW_KB;
+                        const int64_t j = idx / HW_KB;
+                        Cs[idx] = (kk < kb) ? Cf[(j * K + kp0 + kk) * K + k] : S(0);
+                    }
+                    __syncthreads();
+                    for (int64_t j = 0; j < 2 * L - 1; ++j) {
+                        const int i = tid + 2 * (int)(L - 1) - (int)j;     // window index of t = tp - dd, dd = j - (L-1)
+                        const S *cr = Cs + j * HW_KB;
+                        S a = S(0);
+#pragma unroll 8
+                        for (int kk = 0; kk < HW_KB; ++kk) a = fma(Dwin[kk * WWP + i], cr[kk], a);
+                        acc += a;
+                    }
+                }
+                // truncated tail columns t >= Tint (only the last chunks see them): C_w from S2 on the fly
+                if (tp < T && tp + (L - 1) >= Tint) {
+                    double accd = 0.0;
+                    const int64_t ta = (tp - (L - 1) > Tint) ? tp - (L - 1) : Tint;
                     const int64_t tb = tp + (L - 1) < T - 1 ? tp + (L - 1) : T - 1;
-                    for (int64_t t = ta; t <= tb; ++t) {
+                    for (int64_t t = (ta > 0 ? ta : 0); t <= tb; ++t) {
                         const int64_t dd = tp - t;
-                        const S *drow = D + t * K;
-                        if (t < Tint) {
-                            const S *crow = Cf + (dd + L - 1) * K * K + k;      // Cf[(dd+L-1)][k'][k], stride K over k'
-                            S a = S(0);
-                            for (int64_t kp = 0; kp < k; ++kp) a = fma(__ldcg(drow + kp), crow[kp * K], a);
-                            acc += (double)a;
-                        } else {
-                            const int64_t w = T - t;    // C_w[k',k,dd] = sum_{l<w, 0<=l-dd<L} S2[(l,k')][(l-dd,k)]
-                            for (int64_t kp = 0; kp < k; ++kp) {
-                                const S d = __ldcg(drow + kp);
-                                if (d == S(0)) continue;
-                                double cw = 0.0;
-                                for (int64_t l = (dd > 0 ? dd : 0); l < w && l - dd < L; ++l)
-                                    cw += (double)S2[(l * Ks + kp) * ld + (l - dd) * Ks + k];
-                                acc += (double)d * cw;
-                            }
+                        const int64_t w = T - t;    // C_w[k',k,dd] = sum_{l<w, 0<=l-dd<L} S2[(l,k')][(l-dd,k)]
+                        for (int64_t kp = 0; kp < k; ++kp) {
+                            const S d = __ldcg(D + t * K + kp);
+                            if (d == S(0)) continue;
+                            double cw = 0.0;
+                            for (int64_t l = (dd > 0 ? dd : 0); l < w && l - dd < L; ++l)
+                                cw += (double)S2[(l * Ks + kp) * ld + (l - dd) * Ks + k];
+                            accd += (double)d * cw;
                         }
                     }
-                    q = (S)acc;
+                    acc += (S)accd;
                 }
-                qeff[tid] = q;
+                __syncthreads();
+                qeff[tid] = acc;
             }
             __syncthreads();
-            // ---- sweep: the sequential recurrence of component k over this chunk (warp 0)
+            // ---- sweep: the sequential recurrence of component k over this chunk (warp 0), entirely in shared
+            //      memory: H of the chunk is prefetched by all threads, results are written back by all threads
+            {
+                const int64_t tp = t0 + tid;
+                hch[tid] = (tp < T) ? H[tp * K + k] : S(0);
+            }
+            __syncthreads();
             if (tid < 32) {
                 const int lane = tid;
-                const int64_t t1 = (t0 + HW_TC < T) ? t0 + HW_TC : T;
-                for (int64_t t = t0; t < t1; ++t) {
-                    const int64_t w = (T - t < L) ? (T - t) : L;
-                    const S c0 = (w == L) ? ckk[0] : tailC[w * L + 0];
-                    const int slot = (int)(t % RB);
-                    const S h = H[t * K + k];
-                    const S q = qeff[t - t0] + pend[slot];
+                const int n = (int)((t0 + HW_TC < T) ? HW_TC : T - t0);
+                int slot = (int)(t0 % RB);
+                for (int i = 0; i < n; ++i) {
+                    const int64_t t = t0 + i;
+                    const int w = (int)((T - t < L) ? (T - t) : L);
+                    const S c0 = (w == (int)L) ? ckk[0] : tailC[w * L + 0];
+                    const S h = hch[i];
+                    const S q = qeff[i] + pend[slot];
                     S v = (h * c0 - q - l1) / (c0 + (S)CMF_EPS + l2);
                     v = v > S(0) ? v : S(0);
                     const S d = v - h;
                     __syncwarp();
                     if (lane == 0) {
-                        H[t * K + k] = v;
-                        D[t * K + k] = d;
+                        hch[i] = v;
+                        qeff[i] = d;            // Delta H of this column (qeff[i] is dead now)
                         pend[slot] = S(0);
                     }
                     if (d != S(0)) {
-                        for (int64_t s = 1 + lane; s < w; s += 32) {
-                            const S cc = (w == L) ? ckk[s] : tailC[w * L + s];
-                            pend[(int)((t + s) % RB)] += d * cc;
+                        const S *ctab = (w == (int)L) ? ckk : tailC + (size_t)w * L;
+                        for (int sft = 1 + lane; sft < w; sft += 32) {
+                            int ps = slot + sft;
+                            if (ps >= RB) ps -= RB;
+                            pend[ps] += d * ctab[sft];
                         }
                     }
+                    if (++slot == RB) slot = 0;
                     __syncwarp();
                 }
             }
             __syncthreads();
-            // ---- publish
-            if (tid == 0) {
-                __threadfence();
-                atomicExch(progress + k, (int)(c + 1));
+            {
+                const int64_t tp = t0 + tid;
+                if (tp < T) {
+                    H[tp * K + k] = hch[tid];
+                    D[tp * K + k] = qeff[tid];
+                }
             }
+            __syncthreads();
+            // ---- publish (every thread fences its own H / Delta stores, then one thread raises the counter)
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicExch(progress + k, (int)(c + 1));
         }
         __syncthreads();
     }

@@ -61,7 +61,7 @@ class _CudaView:
 class DeviceShard:
     """One rank's shard on one GPU: a libcmf_sm100 handle plus torch views of its exchange buffers."""
 
-    def __init__(self, N, T, t0, t1, K, L, dtype="f32", device=0, use_torch_stream=True):
+    def __init__(self, N, T, t0, t1, K, L, dtype="f32", device=0, use_torch_stream=True, alg="mult"):
         import torch
 
         self.torch = torch
@@ -70,10 +70,11 @@ class DeviceShard:
         self.dtype = parse_dtype(dtype)
         self.device = device
         self._h = ctypes.c_void_p()
+        algc = {"mult": _lib.MULT, "hals": _lib.HALS}[alg]
         if t0 == 0 and t1 == T:
-            check(lib.cmf_create(ctypes.byref(self._h), N, T, K, L, self.dtype, _lib.MULT, device))
+            check(lib.cmf_create(ctypes.byref(self._h), N, T, K, L, self.dtype, algc, device))
         else:
-            check(lib.cmf_create_shard(ctypes.byref(self._h), N, T, t0, t1, K, L, self.dtype, _lib.MULT, device))
+            check(lib.cmf_create_shard(ctypes.byref(self._h), N, T, t0, t1, K, L, self.dtype, algc, device))
         if use_torch_stream:
             with torch.cuda.device(device):
                 s = torch.cuda.current_stream().cuda_stream
@@ -184,6 +185,16 @@ class DeviceShard:
 
     def h_update(self, l1H, l2H):
         check(_lib.load().cmf_h_update(self._h, float(l1H), float(l2H)))
+
+    def update_motifs(self, l1W=0.0, l2W=0.0):
+        """Single-shard update_motifs! (MU or HALS)."""
+        check(_lib.load().cmf_update_motifs(self._h, float(l1W), float(l2W)))
+
+    def update_feature_maps(self, l1H=0.0, l2H=0.0):
+        """Single-shard update_feature_maps! (MU or HALS); returns the relative loss."""
+        out = ctypes.c_double()
+        check(_lib.load().cmf_update_feature_maps(self._h, float(l1H), float(l2H), ctypes.byref(out)))
+        return out.value
 
     def loss_partial(self):
         out = ctypes.c_double()
