@@ -6,14 +6,14 @@ whose kernels are hand-written CUDA for sm_100a (csrc/).  Import as ``cmf_jl_b20
 """
 from ._lib import CMFError, F32, F64, HALS, MULT, SO_PATH  # noqa: F401
 from .model import (  # noqa: F401
-    AbstractCFUpdate, AlternatingOptimizer, CNMF_results, HALSUpdate, MultUpdate, compute_loss,
+    AbstractCFUpdate, AlternatingOptimizer, CNMF_results, HALSUpdate, MultUpdate, PGDUpdate, compute_loss,
     converged, corr_w, fit, fit_cnmf, init_rand, num_components, num_iter, num_lags, num_units,
     tensor_conv, tensor_transconv,
 )
 from .sharded import DeviceShard, ShardedMultFit, ShardPlan  # noqa: F401
 
 __all__ = [
-    "fit_cnmf", "init_rand", "MultUpdate", "HALSUpdate", "AbstractCFUpdate", "AlternatingOptimizer",
+    "fit_cnmf", "init_rand", "MultUpdate", "HALSUpdate", "PGDUpdate", "AbstractCFUpdate", "AlternatingOptimizer",
     "fit", "CNMF_results", "converged", "compute_loss", "tensor_conv", "tensor_transconv", "corr_w",
     "num_lags", "num_units", "num_components", "num_iter", "ShardPlan", "DeviceShard",
     "ShardedMultFit", "CMFError",

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libcmf_sm100.so")
 
 F64, F32 = 0, 1
-MULT, HALS = 0, 1
+MULT, HALS, PGD = 0, 1, 2
 _c = ctypes
 _i64, _dbl, _int, _vp = _c.c_int64, _c.c_double, _c.c_int, _c.c_void_p
 _h = _c.c_void_p

@@ -78,6 +78,7 @@ struct cmf_ctx {
     double data_norm = 0.0;
     double data_sumsq_local = 0.0;   // ||X_owned||^2 of this shard
     int loss_mode = 0;               // 0 = direct residual pass, 1 = algebraic expansion when its inputs are resident
+    double pgd_stepW = 5.0, pgd_stepH = 5.0, pgd_cur_loss = 0.0;   // PGDUpdate state (pgd.jl:147-151)
     bool numH_valid = false;         // numH buffer == transconv(current W, X) and GS == W W' of the current W
     bool gram_valid = false;         // exchange buffer 1 holds the local Gram/tail partial of the current H
     bool have_data = false, have_factors = false;
@@ -120,6 +121,8 @@ struct cmf_ctx {
     virtual double loss_partial() = 0;
     virtual void hals_update_motifs(double l1W, double l2W) = 0;
     virtual double hals_update_feature_maps(double l1H, double l2H) = 0;
+    virtual void pgd_update_motifs(double l1W, double l2W) = 0;
+    virtual double pgd_update_feature_maps(double l1H, double l2H) = 0;
     virtual void exchange_buffer(int which, void **p, int64_t *count, int *dt) = 0;
     virtual void halo_buffers(void **sl, void **sr, void **rl, void **rr, int64_t *count) = 0;
     virtual void prim_conv(void *out_host) = 0;
@@ -640,6 +643,7 @@ struct Ctx : cmf_ctx {
         numH_valid = false;
         data_sumsq_local = data_sumsq();
         data_norm = std::sqrt(data_sumsq_local);
+        pgd_cur_loss = data_norm;
         have_data = true;
     }
     double data_sumsq() override {
@@ -682,6 +686,8 @@ struct Ctx : cmf_ctx {
         tcs.w_dirty = true;
         numH_valid = false;
         gram_valid = false;
+        pgd_stepW = pgd_stepH = 5.0;            // a new rule instance (pgd.jl:147-149)
+        pgd_cur_loss = data_norm;
     }
 
     void init_rand(uint64_t seed) override {
@@ -762,6 +768,7 @@ struct Ctx : cmf_ctx {
 
     void w_apply(double l1W, double l2W) override {
         if (alg == CMF_HALS) { hals_w_apply(l1W, l2W); return; }
+        REQUIRE(alg == CMF_MULT, "the split-phase W update serves MultUpdate and HALSUpdate");
         if (tc_active()) {
             tc_denomW();                                                          // denomW = G * Wi on tensor cores
         } else {
@@ -893,6 +900,54 @@ struct Ctx : cmf_ctx {
         return loss_partial();                                                // hals.jl:41
     }
 
+    // ---------------------------------------------------------------- PGD (src/algs/pgd.jl, SquareLoss)
+    // The gradients are the MU quantities again: dW = 2 (denomW - numW), dH = 2 (denomH - numH) (pgd.jl:206-221).
+    void pgd_step(S *x, S *g, int64_t n, double &step) {
+        dot_partial_kernel<S><<<1024, 256, 0, stream>>>(g, g, n, loss_part.p);
+        post_launch();
+        reduce_scalar(loss_part.p, 1024, scal.p + 2);                                   // ||grad||^2 stays on the device
+        pgd_step_kernel<S><<<(unsigned)cdiv(n, 256), 256, 0, stream>>>(x, g, step, scal.p + 2, n);   // pgd.jl:236-240
+        post_launch();
+    }
+    void pgd_adapt(double loss, double &step) {
+        step *= (loss < pgd_cur_loss) ? 1.05 : 0.70;                                    // pgd.jl:247-251
+        pgd_cur_loss = loss;
+    }
+
+    void pgd_update_motifs(double l1W, double l2W) override {
+        REQUIRE(is_first && is_last, "PGD is single-shard");
+        w_partials();
+        if (tc_active()) tc_denomW();
+        else { build_G(); launch_gemm<false>(GS.p, Wi.p, denW.p, KL(), N, KL(), KL(), N, N); }
+        pgd_grad_kernel<S><<<(unsigned)cdiv(KL() * N, 256), 256, 0, stream>>>(denW.p, denW.p, numW.p, Wi.p, (S)l1W, (S)l2W, KL() * N);
+        post_launch();
+        pgd_step(Wi.p, denW.p, KL() * N, pgd_stepW);
+        tcs.w_dirty = true;
+        numH_valid = false;
+        pgd_adapt(loss_partial(), pgd_stepW);                                           // pgd.jl:244-252
+    }
+
+    double pgd_update_feature_maps(double l1H, double l2H) override {
+        REQUIRE(is_first && is_last, "PGD is single-shard");
+        if (tc_active()) tc_transconv();
+        else launch_transconv(Wi.p, X.p, numH.p, N, K, L, N, Tl, Tl + (L - 1));
+        lag_tables();
+        if (tc_active()) { tc_split_H(false); tc_denomH(); }
+        else launch_transconv(Cf.p, Hbuf.p, denH.p, K, K, 2 * L - 1, K, Tl, Tl + 2 * (L - 1));
+        if (L > 1) {
+            dim3 grid((unsigned)(L - 1), (unsigned)K);
+            denomH_tail_kernel<S><<<grid, 256, 0, stream>>>(GS.p, H, denH.p, K, L, Tl, -(L - 1), s2_ks, s2_ld);
+            post_launch();
+        }
+        pgd_grad_kernel<S><<<(unsigned)cdiv(Tl * K, 256), 256, 0, stream>>>(denH.p, denH.p, numH.p, H, (S)l1H, (S)l2H, Tl * K);
+        post_launch();
+        pgd_step(H, denH.p, Tl * K, pgd_stepH);
+        gram_valid = false;
+        numH_valid = true;                                                              // W unchanged: the expansion loss may reuse numH / W W'
+        pgd_adapt(loss_partial(), pgd_stepH);
+        return pgd_cur_loss;                                                            // caller: sqrt(cur_loss / datanorm^2), pgd.jl:202
+    }
+
     // ---------------------------------------------------------------- exchange
     void exchange_buffer(int which, void **p, int64_t *count, int *dt) override {
         if (which == 0) { *p = numW.p; *count = KL() * N; *dt = dtype; }
@@ -934,11 +989,11 @@ cmf_ctx *make_ctx(int64_t N, int64_t T, int64_t t0, int64_t t1, int64_t K, int64
     REQUIRE(L <= T, "need L <= T (src/common.jl:28-31)");
     REQUIRE(0 <= t0 && t0 < t1 && t1 <= T, "bad shard range");
     REQUIRE(dtype == CMF_F64 || dtype == CMF_F32, "dtype must be 0 (f64) or 1 (f32)");
-    REQUIRE(alg == CMF_MULT || alg == CMF_HALS, "alg must be 0 (mult) or 1 (hals)");
+    REQUIRE(alg == CMF_MULT || alg == CMF_HALS || alg == CMF_PGD, "alg must be 0 (mult), 1 (hals) or 2 (pgd)");
     const bool sharded = !(t0 == 0 && t1 == T);
     if (sharded) {
         REQUIRE(t1 - t0 >= L - 1, "each shard needs at least L-1 columns");
-        if (alg == CMF_HALS) throw CmfError(CMF_ERR_UNSUPPORTED, "HALS is single-shard only in this version");
+        if (alg != CMF_MULT) throw CmfError(CMF_ERR_UNSUPPORTED, "HALS and PGD are single-shard only in this version");
     }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1053,6 +1108,7 @@ int cmf_update_motifs(cmf_handle h, double l1W, double l2W) {
     return guarded([&] {
         use(h);
         if (h->alg == CMF_HALS) { h->hals_update_motifs(l1W, l2W); return; }
+        if (h->alg == CMF_PGD) { h->pgd_update_motifs(l1W, l2W); return; }
         REQUIRE(h->is_first && h->is_last, "sharded handles use the split-phase calls");
         h->w_partials();
         h->w_apply(l1W, l2W);
@@ -1065,6 +1121,8 @@ int cmf_update_feature_maps(cmf_handle h, double l1H, double l2H, double *loss_o
         double loss;
         if (h->alg == CMF_HALS) {
             loss = std::sqrt(h->hals_update_feature_maps(l1H, l2H)) / h->data_norm;
+        } else if (h->alg == CMF_PGD) {
+            loss = std::sqrt(h->pgd_update_feature_maps(l1H, l2H)) / h->data_norm;
         } else {
             REQUIRE(h->is_first && h->is_last, "sharded handles use the split-phase calls");
             h->h_update(l1H, l2H);
@@ -1106,6 +1164,9 @@ int cmf_fit(cmf_handle h, int64_t max_itr, double max_time, int eval_mode, int c
             if (h->alg == CMF_HALS) {
                 if (!eval_mode) h->hals_update_motifs(l1W, l2W);
                 loss = std::sqrt(h->hals_update_feature_maps(l1H, l2H)) / h->data_norm;
+            } else if (h->alg == CMF_PGD) {
+                if (!eval_mode) h->pgd_update_motifs(l1W, l2W);
+                loss = std::sqrt(h->pgd_update_feature_maps(l1H, l2H)) / h->data_norm;
             } else {
                 if (!eval_mode) { h->w_partials(); h->w_apply(l1W, l2W); }
                 h->h_update(l1H, l2H);
@@ -1134,7 +1195,7 @@ int cmf_w_apply(cmf_handle h, double l1W, double l2W) {
     return guarded([&] { use(h); h->w_apply(l1W, l2W); });
 }
 int cmf_h_update(cmf_handle h, double l1H, double l2H) {
-    return guarded([&] { use(h); REQUIRE(h->alg == CMF_MULT, "split-phase calls are MultUpdate only"); h->h_update(l1H, l2H); });
+    return guarded([&] { use(h); REQUIRE(h->alg == CMF_MULT, "the split-phase H update is MultUpdate only"); h->h_update(l1H, l2H); });
 }
 int cmf_loss_partial(cmf_handle h, double *sumsq_out) {
     return guarded([&] { use(h); REQUIRE(sumsq_out, "null output"); *sumsq_out = h->loss_partial(); });

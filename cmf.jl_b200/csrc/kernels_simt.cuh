@@ -906,6 +906,26 @@ __global__ void __launch_bounds__(HW_TC) hals_h_wave_kernel(const S *__restrict_
     }
 }
 
+// Projected gradient descent pieces (src/algs/pgd.jl:224-255, SquareLoss):
+//   g = 2*(den - num) + 2*l2*x + l1*sign(x)      gradient of ||conv - X||^2 plus Square/Absolute penalties (:30-32,:77-88)
+//   x = max(eps, x - step/(||g|| + eps) * g)      descent step and NonnegConstraint projection (:236-240,:93-95)
+template <typename S>
+__global__ void pgd_grad_kernel(S *g, const S *den, const S *num, const S *__restrict__ x, S l1, S l2, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const S xv = x[i];
+    const S sg = xv > S(0) ? S(1) : (xv < S(0) ? S(-1) : S(0));
+    g[i] = S(2) * (den[i] - num[i]) + S(2) * l2 * xv + l1 * sg;      // g may alias den
+}
+template <typename S>
+__global__ void pgd_step_kernel(S *__restrict__ x, const S *__restrict__ g, double step, const double *__restrict__ nrm2, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const S alpha = (S)(step / (sqrt(nrm2[0]) + CMF_EPS));
+    const S v = x[i] - alpha * g[i];
+    x[i] = v > (S)CMF_EPS ? v : (S)CMF_EPS;
+}
+
 // x[i] = a[i] - b[i]   (P = denomW - numW, Q = denomH - numH: the HALS gradients from the MU quantities)
 template <typename S>
 __global__ void sub_kernel(S *x, const S *a, const S *b, int64_t n) {   // x may alias a or b

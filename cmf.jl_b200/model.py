@@ -23,7 +23,7 @@ import warnings
 import numpy as np
 
 from . import _lib
-from ._lib import F32, F64, HALS, MULT, CMFError, check, fptr, julia_array, np_dtype, parse_dtype
+from ._lib import F32, F64, HALS, MULT, PGD, CMFError, check, fptr, julia_array, np_dtype, parse_dtype
 
 # kwargs the reference's methods read (src/algs/alternating.jl:23-31, mult.jl:23,42, hals.jl:31,37,
 # src/model.jl:64,72-73) plus the README-generation spellings (README.md:44-52) and this library's own.
@@ -191,7 +191,18 @@ class HALSUpdate(AbstractCFUpdate):
     _ALG = HALS
 
 
-_ALG_NAMES = {"mult": MultUpdate, ":mult": MultUpdate, "hals": HALSUpdate, ":hals": HALSUpdate}
+class PGDUpdate(AbstractCFUpdate):
+    """src/algs/pgd.jl:112-255 on the GPU for the SquareLoss / NonnegConstraint configuration.  The penalty lists
+    of the reference are given as weights: ``l2W``/``l2H`` = SquarePenalty weight, ``l1W``/``l1H`` = AbsolutePenalty
+    weight; the reference defaults are ``penaltiesW=[SquarePenalty(1)]`` and ``penaltiesH=[]`` (pgd.jl:161,185)."""
+    _ALG = PGD
+
+    def update_motifs(self, data, W, H, l1W=0.0, l2W=1.0, **kwargs):
+        return super().update_motifs(data, W, H, l1W=l1W, l2W=l2W, **kwargs)
+
+
+_ALG_NAMES = {"mult": MultUpdate, ":mult": MultUpdate, "hals": HALSUpdate, ":hals": HALSUpdate,
+              "pgd": PGDUpdate, ":pgd": PGDUpdate}
 
 
 def _resolve_alg(alg):
@@ -200,7 +211,7 @@ def _resolve_alg(alg):
         try:
             return _ALG_NAMES[alg.lower()]
         except KeyError:
-            raise ValueError(f"unknown alg {alg!r}: this path provides 'mult' and 'hals'") from None
+            raise ValueError(f"unknown alg {alg!r}: this path provides 'mult', 'hals' and 'pgd'") from None
     if isinstance(alg, type) and issubclass(alg, AbstractCFUpdate):
         return alg
     raise ValueError(f"alg must be 'mult', 'hals', MultUpdate or HALSUpdate, got {alg!r}")
@@ -335,7 +346,7 @@ def fit_cnmf(data, L=10, K=5, alg=MultUpdate, max_itr=100, max_time=math.inf, **
             rule._h, -1 if unbounded else int(max_itr), float(max_time),
             int(bool(kw.get("eval_mode", False))), int(bool(kw.get("check_convergence", True))),
             int(kw.get("patience", 3)), float(kw.get("tol", 1e-4)),
-            float(kw.get("l1W", 0.0)), float(kw.get("l2W", 0.0)),
+            float(kw.get("l1W", 0.0)), float(kw.get("l2W", 1.0 if rule_cls is PGDUpdate else 0.0)),
             float(kw.get("l1H", 0.0)), float(kw.get("l2H", 0.0)),
             loss_hist.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
             time_hist.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),

@@ -36,7 +36,9 @@ extern "C" {
 typedef struct cmf_ctx *cmf_handle;
 
 enum { CMF_F64 = 0, CMF_F32 = 1 };   /* dtype: arithmetic type of the kernels            */
-enum { CMF_MULT = 0, CMF_HALS = 1 }; /* alg:   MultUpdate (src/algs/mult.jl) / HALSUpdate */
+enum { CMF_MULT = 0, CMF_HALS = 1, CMF_PGD = 2 }; /* alg: MultUpdate (src/algs/mult.jl) / HALSUpdate (hals.jl) /
+                                                      PGDUpdate (pgd.jl: SquareLoss, Nonneg projection,
+                                                      l2 = SquarePenalty weight, l1 = AbsolutePenalty weight) */
 enum {
     CMF_OK = 0,
     CMF_ERR_ARG = 1,   /* bad dimensions / null pointer / wrong state                  */
@@ -55,7 +57,7 @@ int cmf_create(cmf_handle *out, int64_t N, int64_t T, int64_t K, int64_t L, int 
 
 /* Same, for one time-shard [t_begin, t_end) of a T_global-column problem (no reference
  * counterpart: the reference is single-process).  Needs t_end - t_begin >= L-1.
- * HALS is single-shard only in this version (CMF_ERR_UNSUPPORTED otherwise). */
+ * HALS and PGD are single-shard only in this version (CMF_ERR_UNSUPPORTED otherwise). */
 int cmf_create_shard(cmf_handle *out, int64_t N, int64_t T_global, int64_t t_begin, int64_t t_end,
                      int64_t K, int64_t L, int dtype, int alg, int device);
 
@@ -109,9 +111,9 @@ int cmf_get_factors(cmf_handle h, void *W_out, void *H_out);
 
 /* ---- the update rule (single shard) --------------------------------------------------- */
 
-/* update_motifs!(rule, data, W, H; l1W, l2W)      src/algs/mult.jl:23-39, hals.jl:31-34 */
+/* update_motifs!(rule, data, W, H; l1W, l2W)      src/algs/mult.jl:23-39, hals.jl:31-34, pgd.jl:158-178 */
 int cmf_update_motifs(cmf_handle h, double l1W, double l2W);
-/* loss = update_feature_maps!(rule, data, W, H; l1H, l2H)   mult.jl:42-58, hals.jl:37-42 */
+/* loss = update_feature_maps!(rule, data, W, H; l1H, l2H)   mult.jl:42-58, hals.jl:37-42, pgd.jl:181-203 */
 int cmf_update_feature_maps(cmf_handle h, double l1H, double l2H, double *loss_out);
 /* compute_loss(data, W, H)                         src/common.jl:54-55 */
 int cmf_loss(cmf_handle h, double *loss_out);

@@ -247,6 +247,49 @@ class HALSUpdate:
 
 
 # --------------------------------------------------------------------------------------
+# Projected gradient descent  (src/algs/pgd.jl)  -- SquareLoss, Square/Absolute penalties,
+# NonnegConstraint: the configuration the reference's own callers use (test/test.jl:28,
+# figures/thesis/*.jl) minus the masked / absolute losses.
+# --------------------------------------------------------------------------------------
+class PGDUpdate:
+    """src/algs/pgd.jl:112-155.  Penalties are given as weights: ``l2W`` = SquarePenalty weight on W
+    (reference default ``penaltiesW=[SquarePenalty(1)]``, pgd.jl:161), ``l1W`` = AbsolutePenalty weight,
+    likewise ``l1H``/``l2H`` (reference default ``penaltiesH=[]``, pgd.jl:185)."""
+
+    def __init__(self, data, W, H):
+        self.datanorm = float(np.linalg.norm(data))
+        self.est = tensor_conv(W, H)
+        self.stepW = 5.0          # pgd.jl:147-148
+        self.stepH = 5.0
+        self.cur_loss = self.datanorm   # pgd.jl:149 (sic: the norm, not its square)
+        self.step_incr, self.step_decr = 1.05, 0.70
+
+    def _pgd(self, x, grad_fn, step, data, W, H, l1, l2):
+        """pgd.jl:224-255."""
+        gest = 2.0 * (self.est - data)                    # SquareLoss gradient, pgd.jl:30-32
+        g = grad_fn(gest)
+        g = g + 2.0 * l2 * x + l1 * np.sign(x)            # SquarePenalty :77-79, AbsolutePenalty :86-88
+        alpha = step / (np.linalg.norm(g) + EPSILON)      # :236
+        x -= alpha * g                                    # :239
+        np.maximum(x, EPSILON, out=x)                     # NonnegConstraint :93-95
+        self.est = tensor_conv(W, H)                      # :244
+        loss = float(np.linalg.norm(data - self.est) ** 2)   # SquareLoss eval :33-35
+        step *= self.step_incr if loss < self.cur_loss else self.step_decr   # :247-251
+        self.cur_loss = loss
+        return step
+
+    def update_motifs(self, data, W, H, l1W=0.0, l2W=1.0, **_):
+        """pgd.jl:158-178; gradient pgd.jl:206-214."""
+        L = W.shape[2]
+        self.stepW = self._pgd(W, lambda ge: corr_w(H, ge, L), self.stepW, data, W, H, l1W, l2W)
+
+    def update_feature_maps(self, data, W, H, l1H=0.0, l2H=0.0, **_):
+        """pgd.jl:181-203; gradient pgd.jl:218-221."""
+        self.stepH = self._pgd(H, lambda ge: tensor_transconv(W, ge), self.stepH, data, W, H, l1H, l2H)
+        return float(np.sqrt(self.cur_loss / self.datanorm ** 2))
+
+
+# --------------------------------------------------------------------------------------
 # Alternating driver and public entry  (src/algs/alternating.jl, src/model.jl)
 # --------------------------------------------------------------------------------------
 class CNMFResults:
@@ -286,7 +329,7 @@ def fit(rule, data, W_init, H_init, max_itr=100, max_time=np.inf, *, verbose=Fal
     return CNMFResults(data, W, H, time_hist, loss_hist)
 
 
-_ALGS = {"mult": MultUpdate, "hals": HALSUpdate}
+_ALGS = {"mult": MultUpdate, "hals": HALSUpdate, "pgd": PGDUpdate}
 
 
 def fit_cnmf(data, L=10, K=5, alg="mult", max_itr=100, max_time=np.inf, seed=None,

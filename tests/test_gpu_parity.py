@@ -294,3 +294,35 @@ def test_adjointness_at_medium_size_fp32(cmf):
     b = np.vdot(H, cmf.tensor_transconv(W, X, "f32").astype(np.float64))
     c = np.vdot(W, cmf.corr_w(H, X, L, "f32").astype(np.float64))
     assert abs(a - b) < 1e-5 * abs(a) and abs(a - c) < 1e-5 * abs(a)
+
+
+@pytest.mark.parametrize("reg", [{}, dict(l1W=0.05, l2W=0.3, l1H=0.02, l2H=0.1)])
+def test_pgd_fp64_matches_oracle(cmf, orc, reg):
+    # PGDUpdate (src/algs/pgd.jl) behind the same contractions
+    X, W0, H0 = _config1(orc, N=120, T=600)
+    ref = orc.po.fit(orc.po.PGDUpdate(X, W0, H0), X, W0, H0, 40, check_convergence=False, **reg)
+    r = cmf.fit_cnmf(X, L=10, K=5, alg="pgd", max_itr=40, W_init=W0, H_init=H0, check_convergence=False,
+                     layout="KNL", **reg)
+    assert np.allclose(r.loss_hist, ref.loss_hist, rtol=F64_RTOL)
+    assert np.allclose(r.W, ref.W, rtol=1e-8, atol=1e-12) and np.allclose(r.H, ref.H, rtol=1e-8, atol=1e-12)
+    rule = cmf.PGDUpdate(X, W0.copy(), H0.copy())                     # rule-level interface, reference defaults
+    ro = orc.po.PGDUpdate(X, W0, H0)
+    Wg, Hg, Wo, Ho = W0.copy(), H0.copy(), W0.copy(), H0.copy()
+    for _ in range(3):
+        rule.update_motifs(X, Wg, Hg)
+        ro.update_motifs(X, Wo, Ho)
+        assert np.allclose(Wg, Wo, rtol=F64_RTOL)
+        assert abs(rule.update_feature_maps(X, Wg, Hg) - ro.update_feature_maps(X, Wo, Ho)) < 1e-10
+    rule.close()
+
+
+def test_pgd_fp32_engines_loss_within_1e4(cmf, orc):
+    N, T, K, L = 256, 4096, 8, 10
+    X, _, _ = orc.po.synthetic_sequences(K=4, N=N, L=L, T=T, rng=np.random.default_rng(1234))
+    W0, H0 = orc.po.init_rand(X, L, K, np.random.default_rng(0))
+    ref = orc.po.fit(orc.po.PGDUpdate(X, W0, H0), X, W0, H0, 25, check_convergence=False)
+    for engine in (0, 1):
+        r = cmf.fit_cnmf(X, L=L, K=K, alg="pgd", max_itr=25, W_init=W0, H_init=H0, check_convergence=False,
+                         dtype="f32", engine=engine, layout="KNL")
+        rel = np.abs(np.asarray(r.loss_hist) - np.asarray(ref.loss_hist)) / np.asarray(ref.loss_hist)
+        assert rel.max() < F32_LOSS_RTOL, (engine, rel.max())

@@ -179,3 +179,34 @@ def test_golden_fixtures(name):
     assert np.allclose(r.loss_hist, g["loss_hist"], rtol=1e-11)
     assert np.allclose(r.W, g["W"], rtol=1e-9, atol=1e-12)
     assert np.allclose(r.H, g["H"], rtol=1e-9, atol=1e-12)
+
+
+def test_pgd_gradients_are_the_derivatives_of_the_square_loss():
+    # pgd.jl:206-221: dW = corr(H, 2(est - X)), dH = transconv(W, 2(est - X)); checked by central differences
+    N, T, K, L = 6, 17, 2, 4
+    W, H, X = _rand(N, T, K, L, seed=12)
+    f = lambda W_, H_: float(np.sum((po.tensor_conv(W_, H_) - X) ** 2))
+    ge = 2.0 * (po.tensor_conv(W, H) - X)
+    gW, gH = po.corr_w(H, ge, L), po.tensor_transconv(W, ge)
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        k, n, l, t = rng.integers(K), rng.integers(N), rng.integers(L), rng.integers(T)
+        e = 1e-6
+        Wp, Wm = W.copy(), W.copy()
+        Wp[k, n, l] += e
+        Wm[k, n, l] -= e
+        assert abs((f(Wp, H) - f(Wm, H)) / (2 * e) - gW[k, n, l]) < 1e-6 * max(1.0, abs(gW[k, n, l]))
+        Hp, Hm = H.copy(), H.copy()
+        Hp[k, t] += e
+        Hm[k, t] -= e
+        assert abs((f(W, Hp) - f(W, Hm)) / (2 * e) - gH[k, t]) < 1e-6 * max(1.0, abs(gH[k, t]))
+
+
+def test_pgd_driver_semantics():
+    data, _, _ = po.synthetic_sequences(K=2, N=20, L=4, T=80, rng=np.random.default_rng(1))
+    W0, H0 = po.init_rand(data, 4, 2, np.random.default_rng(0))
+    rule = po.PGDUpdate(data, W0, H0)
+    assert rule.stepW == 5.0 and rule.cur_loss == np.linalg.norm(data)      # pgd.jl:147-149
+    r = po.fit(rule, data, W0, H0, 25, check_convergence=False)
+    assert len(r.loss_hist) == 26 and r.loss_hist[-1] < r.loss_hist[0]
+    assert np.all(r.W >= po.EPSILON) and np.all(r.H >= po.EPSILON)          # NonnegConstraint floor
