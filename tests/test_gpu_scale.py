@@ -1,0 +1,119 @@
+"""Full-size GPU checks on BASELINE.json's fp32 configurations through size-independent properties
+(the oracle cannot run at these sizes): adjointness of the three tensor-core contractions, agreement
+of the two independent loss evaluations (direct conv + residual pass vs algebraic expansion),
+MU monotonicity, and sharding invariance.  Data and inits come from the device generators."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+CONFIG3 = dict(N=1024, T=1 << 20, K=20, L=50)      # BASELINE.json configs[2]
+CONFIG4 = dict(N=4096, T=1 << 22, K=64, L=100)     # BASELINE.json configs[3] (the benchmark workload)
+
+
+@pytest.fixture(scope="module")
+def cmf():
+    import __graft_entry__ as ge
+
+    ge.build()
+    import cmf_jl_b200
+
+    return cmf_jl_b200
+
+
+def _make(cmf, cfg, t0=0, t1=None):
+    N, T, K, L = cfg["N"], cfg["T"], cfg["K"], cfg["L"]
+    s = cmf.DeviceShard(N, T, t0, T if t1 is None else t1, K, L, dtype="f32", device=0)
+    s.synth_data(1234, K, L, 0.05, 0.1)
+    s.init_rand(0)
+    return s
+
+
+def _properties(cmf, cfg, iters):
+    import torch
+
+    s = _make(cmf, cfg)
+    f = cmf.ShardedMultFit(s)
+    f.setup_data_norm()
+    f.rescale_init()
+    assert s.get_engine() == 1                      # tcgen05 engine selected by default at these sizes
+    a = s.data_sumsq()
+    # direct loss (TC_CONV) before anything else
+    ss_direct = s.loss_partial()
+    # adjointness on the SAME (W, H): <W, corr(H,X)> == <X, conv(W,H)> == (||X||^2 + ||conv||^2 - ||conv - X||^2)/2
+    # is checked through the two loss paths below; here: numW (TC_CORR) and numH (TC_TRANS) pair up with the
+    # factors they were computed from
+    Wj, Hj = s.get_factors()
+    s.w_partials()                                  # numW = corr(H, X)      (TC_CORR)
+    numW = s.exchange[0].double().cpu().numpy().reshape(cfg["L"], cfg["K"], cfg["N"]).transpose(1, 2, 0)
+    s.h_update(0.0, 0.0)                            # numH = transconv(W, X) (TC_TRANS) with the same W; then H moves
+    numH = s.exchange[2].double().cpu().numpy().reshape(cfg["T"], cfg["K"]).T
+    torch.cuda.synchronize()
+    lhs, rhs = float(np.vdot(Wj, numW)), float(np.vdot(Hj, numH))
+    assert abs(lhs - rhs) < 2e-5 * abs(lhs), (lhs, rhs)
+    s.set_loss_mode(1)
+    ss_exp = s.loss_partial()                       # ||X||^2 - 2<numH,H'> + <WW', H'tH't'>   (new H')
+    s.set_loss_mode(0)
+    ss_dir2 = s.loss_partial()                      # sum (conv(W,H') - X)^2                     (TC_CONV)
+    assert abs(ss_exp - ss_dir2) < 2e-5 * ss_dir2, (ss_exp, ss_dir2)
+    assert 0 < ss_dir2 < a and ss_dir2 <= ss_direct * (1 + 1e-6)      # one H update does not increase the loss
+    # MU monotonicity over full iterations, both loss modes interleaved
+    hist = [math.sqrt(ss_dir2 / a)]
+    for it in range(iters):
+        s.set_loss_mode(it % 2)
+        hist.append(f.iterate())
+    assert all(b <= x * (1 + 1e-5) for x, b in zip(hist[:-1], hist[1:])), hist
+    s.close()
+    return hist
+
+
+def test_config3_full_size_properties(cmf):
+    _properties(cmf, CONFIG3, 3)
+
+
+def test_config3_sharding_invariance(cmf):
+    import torch
+
+    def run(world):
+        plan = cmf.ShardPlan(CONFIG3["T"], world, CONFIG3["L"])
+        shards = [_make(cmf, CONFIG3, a, b) for a, b in plan.ranges]
+        ss = sum(s.data_sumsq() for s in shards)
+        dot = sum(s.init_scale_partials()[0] for s in shards)
+        nrm = sum(s.init_scale_partials()[1] for s in shards)
+        for s in shards:
+            s.set_data_norm(math.sqrt(ss))
+            s.scale_factors(math.sqrt(abs(dot / nrm)))
+        hist = []
+        for _ in range(2):
+            for s in shards:
+                s.w_partials()
+            for which in (0, 1):
+                tot = sum(s.exchange[which].clone() for s in shards)
+                for s in shards:
+                    s.exchange[which].copy_(tot)
+            for s in shards:
+                s.w_apply(0.0, 0.0)
+                s.h_update(0.0, 0.0)
+            for x, y in zip(shards[:-1], shards[1:]):
+                y.recv_left.copy_(x.send_right)
+                x.recv_right.copy_(y.send_left)
+            hist.append(math.sqrt(sum(s.loss_partial() for s in shards) / ss))
+        torch.cuda.synchronize()
+        for s in shards:
+            s.close()
+        return np.asarray(hist)
+
+    a, b = run(1), run(4)
+    assert np.allclose(a, b, rtol=2e-6), (a, b)
+
+
+def test_config4_full_size_properties(cmf):
+    import torch
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 150 * 2 ** 30:
+        pytest.skip("needs ~140 GiB of HBM")
+    hist = _properties(cmf, CONFIG4, 2)
+    assert 0.3 < hist[-1] < 0.5
