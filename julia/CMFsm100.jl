@@ -13,7 +13,7 @@ import Random
 
 const LIB = get(ENV, "LIBCMF_SM100", "libcmf_sm100")
 const CMF_F64, CMF_F32 = Cint(0), Cint(1)
-const CMF_MULT, CMF_HALS = Cint(0), Cint(1)
+const CMF_MULT, CMF_HALS, CMF_PGD = Cint(0), Cint(1), Cint(2)
 
 struct CMFError <: Exception
     code::Cint
@@ -58,8 +58,10 @@ mutable struct SM100Update{ALG} <: AbstractCFUpdate
 end
 const SM100MultUpdate = SM100Update{:mult}
 const SM100HALSUpdate = SM100Update{:hals}
+const SM100PGDUpdate = SM100Update{:pgd}    # src/algs/pgd.jl, SquareLoss; l2W/l1W = Square/Absolute penalty weights
 alg_code(::Type{SM100Update{:mult}}) = CMF_MULT
 alg_code(::Type{SM100Update{:hals}}) = CMF_HALS
+alg_code(::Type{SM100Update{:pgd}}) = CMF_PGD
 
 """`Rule(data, W, H)` -- src/model.jl:79, src/algs/mult.jl:11-20, src/algs/hals.jl:18-28."""
 function (::Type{R})(data::Matrix{T}, W::Array{T,3}, H::Matrix{T}; sync_host=true, device=0) where {R<:SM100Update,T<:Union{Float32,Float64}}
@@ -98,7 +100,7 @@ struct CNMF_results   # src/model.jl:11-17
     data; W; H; time_hist; loss_hist
 end
 
-const ALGS = Dict(:mult => SM100MultUpdate, :hals => SM100HALSUpdate)
+const ALGS = Dict(:mult => SM100MultUpdate, :hals => SM100HALSUpdate, :pgd => SM100PGDUpdate)
 
 """src/model.jl:113-125 (kept in Julia so the random stream is the reference's own)."""
 function init_rand(data, L, K, tensor_conv)
@@ -149,7 +151,7 @@ function fit_cnmf_sm100(data::Matrix{T}; L::Integer=10, K::Integer=5, alg=:mult,
          Ptr{Cdouble}, Ptr{Cdouble}, Int64, Ref{Int64}, Ref{Cint}),
         rule.h.ptr, isfinite(max_itr) ? Int(max_itr) : -1, Float64(max_time),
         get(kw, :eval_mode, false), get(kw, :check_convergence, true), get(kw, :patience, 3), get(kw, :tol, 1e-4),
-        get(kw, :l1W, 0), get(kw, :l2W, 0), get(kw, :l1H, 0), get(kw, :l2H, 0),
+        get(kw, :l1W, 0), get(kw, :l2W, R === SM100PGDUpdate ? 1 : 0), get(kw, :l1H, 0), get(kw, :l2H, 0),   # pgd.jl:161 default SquarePenalty(1)
         loss_hist, time_hist, cap, n, early))
     early[] != 0 && println("Converged early.")                 # alternating.jl:64
     W = similar(W0); H = similar(H0)
