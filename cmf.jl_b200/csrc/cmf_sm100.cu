@@ -207,7 +207,7 @@ template <typename S>
 struct Ctx : cmf_ctx {
     TcState tcs;
     DevBuf<S> X, Hbuf, Wi, Wtmp, numW, denW, GS, Cf, numH, denH, tailC;
-    DevBuf<int> progress;
+    DevBuf<int> progress, lockstep;
     int hals_grid = 0;
     DevBuf<double> exch1, corr_part, loss_part, scal;
     S *H = nullptr;  // owned column 0 inside Hbuf
@@ -396,9 +396,25 @@ struct Ctx : cmf_ctx {
             q.tiles_m = tcs.tiles_m; q.tiles_n = tcs.tiles_n; q.split_len = tcs.split_len; q.tau_hi = Tl + (L - 1);
             q.units = tcs.tiles_m * tcs.tiles_n * tcs.nsplit;
             q.part = corr_part.p;
+            { const char *e = getenv("CMF_CORR_ORDER"); q.corr_order = e ? atoi(e) : 0; }
+            {
+                const char *e = getenv("CMF_LOCKSTEP");            // k-block window; 0 disables (diagnostics)
+                const int w = e ? atoi(e) : 256;
+                if (w > 0) {
+                    if (lockstep.n == 0) lockstep.alloc(1024);
+                    CK(cudaMemsetAsync(lockstep.p, 0, lockstep.n * sizeof(int), stream));
+                    q.lockstep = lockstep.p; q.lockstep_window = w;
+                }
+            }
             const unsigned grid = (unsigned)std::min<int64_t>(q.units, tcs.num_sms);
             prof_begin(PROF_CORR);
-            tc::tc_kernel<tc::TC_CORR><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tcs.mHm[0], tcs.mHm[1], tcs.mXmn[0], tcs.mXmn[1], q);
+            if (q.lockstep != nullptr) {
+                // CTAs wait on one another inside this launch: co-residency must be guaranteed
+                void *args[] = {&tcs.mHm[0], &tcs.mHm[1], &tcs.mXmn[0], &tcs.mXmn[1], &q};
+                CK(cudaLaunchCooperativeKernel((void *)tc::tc_kernel<tc::TC_CORR>, dim3(grid), dim3(tc::THREADS), args, tc::SMEM_BYTES, stream));
+            } else {
+                tc::tc_kernel<tc::TC_CORR><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tcs.mHm[0], tcs.mHm[1], tcs.mXmn[0], tcs.mXmn[1], q);
+            }
             prof_end();
             post_launch();
             const int64_t n = KL() * N;

@@ -51,6 +51,9 @@ struct Params {
     int64_t own;               // owned columns per t tile = BN - (G-1)
     // CORR
     int64_t split_len;         // t columns per split (multiple of BK)
+    int corr_order;            // 0: j tiles fastest (CTAs share the X tile), 1: n tiles fastest (CTAs share the H window)
+    int *lockstep;             // CORR: per-CTA k-block counters (zeroed before the launch) or nullptr
+    int lockstep_window;       // CORR: a CTA may run at most this many k-blocks ahead of the slowest CTA
     int64_t tau_hi;            // valid X columns [0, tau_hi)
     // dims
     int64_t N, K, L, Tl;
@@ -214,16 +217,32 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
         // ================================================================ TMA producer
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
+            int kcount = 0;      // CORR lock-step: k-blocks issued by this CTA so far
             for (int64_t unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
                 int64_t mt = 0, nt = 0;
                 if (MODE == TC_CONV) { nt = unit % p.tiles_n; mt = unit / p.tiles_n; }          // nt: n tile, mt: t tile
                 if (MODE == TC_PLAIN) { nt = unit % p.tiles_n; mt = unit / p.tiles_n; }         // nt: column tile, mt: row tile
-                if (MODE == TC_CORR) { const int64_t r = unit % (p.tiles_m * p.tiles_n); mt = r % p.tiles_m; nt = r / p.tiles_m; }   // j tiles fastest: concurrent CTAs share the X tile
+                if (MODE == TC_CORR) { const int64_t r = unit % (p.tiles_m * p.tiles_n); if (p.corr_order == 0) { mt = r % p.tiles_m; nt = r / p.tiles_m; } else { nt = r % p.tiles_n; mt = r / p.tiles_n; } }
                 const int64_t nseg = n_segments(unit);
                 for (int64_t seg = 0; seg < nseg; ++seg) {
                     int64_t kb0, kbn;
                     segment_kb(unit, seg, kb0, kbn);
                     for (int64_t kb = kb0; kb < kb0 + kbn; ++kb) {
+                        if (MODE == TC_CORR && p.lockstep != nullptr) {
+                            // The ~50 CTAs that share an X tile must stay close in time or the tile falls out of L2 and is
+                            // re-read from HBM (measured: 19x the algorithmic traffic without this).  Every 64 k-blocks each
+                            // CTA publishes its progress and waits while it is more than lockstep_window ahead of the slowest.
+                            if ((kcount & 63) == 0) {
+                                atomicExch(p.lockstep + blockIdx.x, kcount);
+                                for (;;) {
+                                    int mn = 0x7fffffff;
+                                    for (unsigned i = 0; i < gridDim.x; ++i) mn = min(mn, __ldcg(p.lockstep + i));
+                                    if (kcount <= mn + p.lockstep_window) break;
+                                    __nanosleep(200);
+                                }
+                            }
+                            ++kcount;
+                        }
                         mbar_wait(&empty_bar[s], ph ^ 1);
                         unsigned char *st = smem + (size_t)s * STAGE_BYTES;
                         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
@@ -260,6 +279,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                     }
                 }
             }
+            if (MODE == TC_CORR && p.lockstep != nullptr) atomicExch(p.lockstep + blockIdx.x, 0x7fffffff);   // finished: never the slowest
         }
     } else if (warp == 1) {
         // ================================================================ MMA issuer
@@ -324,7 +344,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
         for (int64_t unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
             int64_t mt = 0, nt = 0, sp = 0;
             if (MODE == TC_CONV || MODE == TC_PLAIN) { nt = unit % p.tiles_n; mt = unit / p.tiles_n; }
-            if (MODE == TC_CORR) { sp = unit / (p.tiles_m * p.tiles_n); const int64_t r = unit % (p.tiles_m * p.tiles_n); mt = r % p.tiles_m; nt = r / p.tiles_m; }
+            if (MODE == TC_CORR) { sp = unit / (p.tiles_m * p.tiles_n); const int64_t r = unit % (p.tiles_m * p.tiles_n); if (p.corr_order == 0) { mt = r % p.tiles_m; nt = r / p.tiles_m; } else { nt = r % p.tiles_n; mt = r / p.tiles_n; } }
             const int64_t nseg = n_segments(unit);
             for (int64_t seg = 0; seg < nseg; ++seg) {
                 int64_t kb0, kbn;
@@ -411,16 +431,29 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
 #pragma unroll
                         for (int c = 0; c < 16; ++c) stg[lane][c] = racc[cc + c];
                         __syncwarp();
+                        // 16 (row, column) pairs per lane, 8 at a time with all loads in flight before the adds
+                        // (the partial buffer is not cache resident: a dependent load per element costs ~1 us each)
 #pragma unroll 1
-                        for (int it = 0; it < 16; ++it) {
-                            const int r = it * 2 + (lane >> 4), c = lane & 15;
-                            const int64_t j = mt * BM + quarter * 32 + r;
-                            const int64_t lp = j >> p.Kp_log2, k = j & (p.Kp - 1);   // Kp is a power of two
-                            const int64_t n = nt * BN + col0 + cc + c;
-                            if (lp < p.L && k < p.K && n < p.N) {
-                                double *d = pbase + ((p.L - 1 - lp) * p.K + k) * p.N + n;
+                        for (int it0 = 0; it0 < 16; it0 += 8) {
+                            double *dp[8];
+                            double old[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                const int r = (it0 + u) * 2 + (lane >> 4), c = lane & 15;
+                                const int64_t j = mt * BM + quarter * 32 + r;
+                                const int64_t lp = j >> p.Kp_log2, k = j & (p.Kp - 1);   // Kp is a power of two
+                                const int64_t n = nt * BN + col0 + cc + c;
+                                dp[u] = (lp < p.L && k < p.K && n < p.N) ? pbase + ((p.L - 1 - lp) * p.K + k) * p.N + n : nullptr;
+                            }
+                            if (seg != 0) {
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) old[u] = dp[u] ? __ldcg(dp[u]) : 0.0;
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                const int r = (it0 + u) * 2 + (lane >> 4), c = lane & 15;
                                 const double x = (double)stg[r][c];
-                                *d = (seg == 0) ? x : (*d + x);
+                                if (dp[u]) *dp[u] = (seg == 0) ? x : (old[u] + x);
                             }
                         }
                         __syncwarp();
