@@ -318,9 +318,17 @@ def run_ours(args, cfg, name):
     Fc_rank = Fc / world
     achieved_tf = Fc_rank / (per_launch_ms * 1e-3) / 1e12
     contr_share = sum(v[0] for v in prof.values()) / (ms_per_step * args.steps) if ms > 0 else None
+    # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from one `ncu --set full` capture of this very
+    # workload (profiles/r1_ncu_full_corr_c4_lockstep.md); only known for the 1-GPU c4 correlation launch
+    traffic, traffic_note = None, "no ncu capture for this workload / kernel"
+    if name == "c4" and world == 1 and dom == "corr":
+        traffic = 128.9e9
+        traffic_note = ("ncu --set full, c4, 1 GPU, per launch: 113.9 GB read + 15.1 GB written vs 68.7 GB algorithmic "
+                        "(X hi/lo planes once); profiles/r1_ncu_full_corr_c4_lockstep.md")
     roofline = {
         "bound": "tensor", "kernel": dom, "achieved": achieved_tf, "peak": pk["tensor"], "unit": "TFLOP/s",
-        "frac": achieved_tf / pk["tensor"], "traffic": None, "peak_source": f"{pk['src']} bf16 sustained",
+        "frac": achieved_tf / pk["tensor"], "traffic": traffic, "traffic_note": traffic_note,
+        "peak_source": f"{pk['src']} bf16 sustained",
         "flops_per_launch": Fc_rank, "ms_per_launch": per_launch_ms,
         "executed": {"tflops": 3.0 * achieved_tf if engine == 1 else achieved_tf,
                      "frac": (3.0 * achieved_tf if engine == 1 else achieved_tf) / pk["tensor"],

@@ -487,8 +487,22 @@ struct Ctx : cmf_ctx {
             q.units = cdiv(Tl, q.own);
             q.out = numH.p;
             const unsigned grid = (unsigned)std::min<int64_t>(q.units, tcs.num_sms);
+            {
+                const char *e = getenv("CMF_LOCKSTEP_TRANS");      // k-block window; 0 (default) disables
+                const int w = e ? atoi(e) : 0;
+                if (w > 0 && q.units >= (int64_t)grid) {
+                    if (lockstep.n == 0) lockstep.alloc(1024);
+                    CK(cudaMemsetAsync(lockstep.p, 0, lockstep.n * sizeof(int), stream));
+                    q.lockstep = lockstep.p; q.lockstep_window = w;
+                }
+            }
             prof_begin(PROF_TRANSCONV);
-            tc::tc_kernel<tc::TC_TRANS><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tcs.mWu[0], tcs.mWu[1], tcs.mXk[0], tcs.mXk[1], q);
+            if (q.lockstep != nullptr) {
+                void *args[] = {&tcs.mWu[0], &tcs.mWu[1], &tcs.mXk[0], &tcs.mXk[1], &q};
+                CK(cudaLaunchCooperativeKernel((void *)tc::tc_kernel<tc::TC_TRANS>, dim3(grid), dim3(tc::THREADS), args, tc::SMEM_BYTES, stream));
+            } else {
+                tc::tc_kernel<tc::TC_TRANS><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tcs.mWu[0], tcs.mWu[1], tcs.mXk[0], tcs.mXk[1], q);
+            }
             prof_end();
             post_launch();
         }

@@ -52,8 +52,8 @@ struct Params {
     // CORR
     int64_t split_len;         // t columns per split (multiple of BK)
     int corr_order;            // 0: j tiles fastest (CTAs share the X tile), 1: n tiles fastest (CTAs share the H window)
-    int *lockstep;             // CORR: per-CTA k-block counters (zeroed before the launch) or nullptr
-    int lockstep_window;       // CORR: a CTA may run at most this many k-blocks ahead of the slowest CTA
+    int *lockstep;             // CORR/TRANS: per-CTA k-block counters (zeroed before the launch) or nullptr
+    int lockstep_window;       // a CTA may run at most this many k-blocks ahead of the slowest CTA
     int64_t tau_hi;            // valid X columns [0, tau_hi)
     // dims
     int64_t N, K, L, Tl;
@@ -228,7 +228,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                     int64_t kb0, kbn;
                     segment_kb(unit, seg, kb0, kbn);
                     for (int64_t kb = kb0; kb < kb0 + kbn; ++kb) {
-                        if (MODE == TC_CORR && p.lockstep != nullptr) {
+                        if ((MODE == TC_CORR || MODE == TC_TRANS) && p.lockstep != nullptr) {
                             // The ~50 CTAs that share an X tile must stay close in time or the tile falls out of L2 and is
                             // re-read from HBM (measured: 19x the algorithmic traffic without this).  Every 64 k-blocks each
                             // CTA publishes its progress and waits while it is more than lockstep_window ahead of the slowest.
@@ -279,7 +279,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                     }
                 }
             }
-            if (MODE == TC_CORR && p.lockstep != nullptr) atomicExch(p.lockstep + blockIdx.x, 0x7fffffff);   // finished: never the slowest
+            if ((MODE == TC_CORR || MODE == TC_TRANS) && p.lockstep != nullptr) atomicExch(p.lockstep + blockIdx.x, 0x7fffffff);   // finished: never the slowest
         }
     } else if (warp == 1) {
         // ================================================================ MMA issuer
