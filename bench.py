@@ -359,7 +359,7 @@ def run_ours(args, cfg, name):
                    "seeds": {"data": SEED_DATA, "init": SEED_INIT}, "p_h": P_H, "noise": NOISE,
                    "engine": "tcgen05 split-bf16 (3 MMAs per product, fp32 accumulate)" if engine == 1 else "SIMT fp32",
                    "loss": ("algebraic expansion ||X||^2 - 2<numH,H> + <WW',HtHt'> (exact identity, falls back to the direct "
-                            "pass below 20% loss)" if args.loss_mode == 1 else "direct conv + residual pass")},
+                            "pass below 25% loss)" if args.loss_mode == 1 else "direct conv + residual pass")},
         "value_direct_loss": value_direct,
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_hbm": hbm, "cpu_baseline": cpu,
         "clocks": clocks, "loss": {"initial": loss0, "final": losses[-1] if losses else None},

@@ -357,6 +357,7 @@ struct Ctx : cmf_ctx {
         q.N = N; q.K = K; q.L = L; q.Tl = Tl; q.G = tcs.G; q.Kp = tcs.Kp;
         q.Kp_log2 = 0;
         while ((1 << q.Kp_log2) < tcs.Kp) ++q.Kp_log2;
+        { const char *e = getenv("CMF_PROMO"); q.promo = e ? std::max(1, atoi(e)) : tc::PROMO; }
         return q;
     }
 
@@ -1206,9 +1207,9 @@ int cmf_fit(cmf_handle h, int64_t max_itr, double max_time, int eval_mode, int c
             time_hist[n] = time_hist[n - 1] + dur;
             loss_hist[n] = loss;
             ++n;
-            // the expansion cancels like 1/loss^2: its error is ~1.6e-6/loss^2 relative (measured), so below 20%
+            // the expansion cancels like 1/loss^2: its error is ~2e-6/loss^2 relative (measured), so below 25%
             // relative loss fall back to the direct residual pass (keeps the loss within 1e-4 of the reference)
-            if (h->loss_mode == 1 && !(loss > 0.2)) h->loss_mode = 0;
+            if (h->loss_mode == 1 && !(loss > 0.25)) h->loss_mode = 0;
             if (check_convergence && converged(loss_hist, n, patience, tol)) {   // alternating.jl:63-66
                 if (converged_early) *converged_early = 1;
                 break;

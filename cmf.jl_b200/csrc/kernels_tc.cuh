@@ -34,7 +34,7 @@ constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;   // 48 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
 constexpr int EPI_WARPS = 8;                         // epilogue / promotion warps (2 per TMEM lane quarter)
 constexpr int THREADS = 128 + 32 * EPI_WARPS;        // warpgroup 0: warp 0 TMA, warp 1 MMA + TMEM alloc (2,3 idle); warpgroups 1-2: epilogue
-constexpr int PROMO = 4;                             // k-blocks accumulated in TMEM before promotion to registers
+constexpr int PROMO = 8;                             // k-blocks accumulated in TMEM before promotion to registers
 constexpr int FLUSH_T = 65536;                       // TC_CORR: columns of t accumulated in fp32 registers (RN) before the fp64 flush
 
 enum Mode { TC_CONV = 0, TC_TRANS = 1, TC_CORR = 2, TC_PLAIN = 3 };
@@ -51,6 +51,7 @@ struct Params {
     int64_t own;               // owned columns per t tile = BN - (G-1)
     // CORR
     int64_t split_len;         // t columns per split (multiple of BK)
+    int promo;                 // k-blocks accumulated in TMEM before promotion to registers (PROMO by default)
     int corr_order;            // 0: j tiles fastest (CTAs share the X tile), 1: n tiles fastest (CTAs share the H window)
     int *lockstep;             // CORR/TRANS: per-CTA k-block counters (zeroed before the launch) or nullptr
     int lockstep_window;       // a CTA may run at most this many k-blocks ahead of the slowest CTA
@@ -292,8 +293,8 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                 for (int64_t seg = 0; seg < nseg; ++seg) {
                     int64_t kb0, kbn;
                     segment_kb(unit, seg, kb0, kbn);
-                    for (int64_t c0 = 0; c0 < kbn; c0 += PROMO, ++q) {
-                        const int64_t cn = min((int64_t)PROMO, kbn - c0);
+                    for (int64_t c0 = 0; c0 < kbn; c0 += p.promo, ++q) {
+                        const int64_t cn = min((int64_t)p.promo, kbn - c0);
                         const int acc = (int)(q & 1);
                         mbar_wait(&tmem_empty[acc], (uint32_t)((q >> 1) & 1) ^ 1);
                         tc_fence_after();
@@ -352,7 +353,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
 #pragma unroll
                 for (int c = 0; c < BN / 2; ++c) racc[c] = 0.f;
                 // ---- promotion: racc += TMEM partial, every PROMO k-blocks
-                for (int64_t c0 = 0; c0 < kbn; c0 += PROMO, ++q) {
+                for (int64_t c0 = 0; c0 < kbn; c0 += p.promo, ++q) {
                     const int acc = (int)(q & 1);
                     mbar_wait(&tmem_full[acc], (uint32_t)((q >> 1) & 1));
                     tc_fence_after();

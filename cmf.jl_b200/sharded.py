@@ -288,7 +288,7 @@ class ShardedMultFit:
         s.h_update(l1H, l2H)                     # owned columns of H
         self.exchange_halos()                    # L-1 columns each way
         loss = self.loss()                       # all-reduce of one double
-        if getattr(s, "loss_mode", 0) == 1 and not loss > 0.2:
+        if getattr(s, "loss_mode", 0) == 1 and not loss > 0.25:
             s.set_loss_mode(0)                   # the expansion cancels like 1/loss^2 (same rule on every rank)
         return loss
 

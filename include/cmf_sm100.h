@@ -175,7 +175,7 @@ int cmf_set_engine(cmf_handle h, int engine);
  * ||conv(W,H)-X||^2 = ||X||^2 - 2<transconv(W,X),H> + <W W', Htilde Htilde'> on the numH and W W' that the
  * H update leaves resident plus the Gram of the new H, which the next cmf_w_partials reuses (a third of the
  * contraction work is saved; the halos must not change between cmf_loss_partial and cmf_w_partials).  The
- * identity cancels like 1/loss^2, (measured error ~1.6e-6/loss^2 relative), so callers switch back to 0 when the relative loss drops below 20%
+ * identity cancels like 1/loss^2, (measured error ~2e-6/loss^2 relative), so callers switch back to 0 when the relative loss drops below 25%
  * (cmf_fit and the sharded host loop do). */
 int cmf_set_loss_mode(cmf_handle h, int mode);
 /* The engine currently selected (0 / 1). */
