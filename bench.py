@@ -269,8 +269,7 @@ def run_ours(args, cfg, name):
         Xh = host.numpy().T                       # N x cols, Fortran-ordered view of the pinned buffer
         shard.get_data(Xh, with_halo=True)
         Wh, Hh = shard.get_factors()
-        W0 = np.asfortranarray(Wh, dtype=np.float32)
-        H0 = np.asfortranarray(Hh, dtype=np.float32)
+        W0, H0 = Wh, Hh                           # float32, Fortran-ordered (what a Julia caller holds)
         shard.close()
         del shard, fitter, Wh, Hh
         torch.cuda.empty_cache()
@@ -385,7 +384,7 @@ def _set_sharded_factors(shard, fitter, W, H_owned, t0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))

@@ -131,12 +131,12 @@ class AbstractCFUpdate:
         check(_lib.load().cmf_set_factors(self._h, fptr(Wj), fptr(Hj), 0))
 
     def get_factors(self):
-        """(W as K x N x L, H as K x T) float64 numpy arrays read back from the device."""
+        """(W as K x N x L, H as K x T) numpy arrays of the handle dtype read back from the device."""
         dt = np_dtype(self.dtype)
         W = np.empty((self.K, self.N, self.L), dtype=dt, order="F")
         H = np.empty((self.K, self.T), dtype=dt, order="F")
         check(_lib.load().cmf_get_factors(self._h, fptr(W), fptr(H)))
-        return W.astype(np.float64), H.astype(np.float64)
+        return W, H
 
     def loss(self):
         out = ctypes.c_double()

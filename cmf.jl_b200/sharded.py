@@ -174,7 +174,7 @@ class DeviceShard:
         W = np.empty((self.K, self.N, self.L), dtype=dt, order="F")
         H = np.empty((self.K, self.t1 - self.t0), dtype=dt, order="F")
         check(_lib.load().cmf_get_factors(self._h, fptr(W), fptr(H)))
-        return W.astype(np.float64), H.astype(np.float64)
+        return W, H            # handle dtype (no host-side conversion: H is 1 GiB at the benchmark size)
 
     # split-phase steps -------------------------------------------------------------------------
     def w_partials(self):
