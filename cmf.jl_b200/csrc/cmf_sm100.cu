@@ -249,7 +249,7 @@ struct Ctx : cmf_ctx {
             CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
             REQUIRE(coop != 0, "HALS needs cooperative launch support");
             CK(cudaFuncSetAttribute(hals_h_wave_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hals_h_wave_kernel<S>, HW_TC, smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hals_h_wave_kernel<S>, HW_NT, smem));
             hals_grid = (int)std::min<int64_t>(K, (int64_t)per_sm * sms);
             REQUIRE(hals_grid >= 1, "HALS: H sweep kernel does not fit on the device");
             tailC.alloc((size_t)hals_grid * (size_t)(L * L));
@@ -924,7 +924,7 @@ struct Ctx : cmf_ctx {
         int64_t Kk = K, Ll = L, Tt = Tl, ks = s2_ks, ldv = s2_ld;
         S a1 = (S)l1H, a2 = (S)l2H;
         void *args[] = {&cf, &s2, &q, &hh, &dd, &tc_, &pr, &Kk, &Ll, &Tt, &ks, &ldv, &a1, &a2};
-        CK(cudaLaunchCooperativeKernel((void *)hals_h_wave_kernel<S>, dim3((unsigned)hals_grid), dim3(HW_TC), args, smem, stream));
+        CK(cudaLaunchCooperativeKernel((void *)hals_h_wave_kernel<S>, dim3((unsigned)hals_grid), dim3(HW_NT), args, smem, stream));
         post_launch();
         gram_valid = false;
         numH_valid = false;

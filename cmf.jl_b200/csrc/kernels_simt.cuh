@@ -732,6 +732,28 @@ __global__ void __launch_bounds__(256) hals_w_sweep_kernel(const S *__restrict__
         }
 }
 
+// Sequential recurrence of one component over W interior columns (full lag window, no truncation) with the pending
+// corrections of the next W columns held in registers: p[j] is the pending correction of column t + j.  The W steps
+// are fully unrolled, so the rotation of the window is a compile-time renaming and a step costs its dependent chain
+// (load, 3 FMA/MUL, max, sub) plus W independent FMAs.  Every lane of the warp runs the same scalar code (the values
+// are warp-uniform); lane 0 stores.  Requires L - 1 <= W - 1... i.e. L <= W.
+template <typename S, int W>
+__device__ __forceinline__ void hals_recurrence_block(S *hch, S *qeff, S (&p)[W], const S *c /*shared, zero padded to W*/, S c0,
+                                                       S inv, S l1, int i0, int lane) {
+#pragma unroll
+    for (int u = 0; u < W; ++u) {
+        const S h = hch[i0 + u];
+        const S q = qeff[i0 + u] + p[u];
+        S v = (h * c0 - q - l1) * inv;
+        v = v > S(0) ? v : S(0);
+        const S d = v - h;
+        if (lane == 0) { hch[i0 + u] = v; qeff[i0 + u] = d; }
+        p[u] = S(0);                                   // this slot now stands for column t + W
+#pragma unroll
+        for (int j = 1; j < W; ++j) p[(u + j) % W] = fma(d, c[j], p[(u + j) % W]);   // c[j] = C[k,k,j], zero for j >= L
+    }
+}
+
 // H sweep (hals.jl:121-154) as a wavefront over (component k, time chunk c) in ONE cooperative launch.
 //   Q[t][k] = transconv(W, conv(W,H) - X)[k,t] at the start of the sweep (gradient of the H step),
 //   Cf[(d+L-1)][k][k'] interior lag table, S2 = W W' for the truncated tail tables, D[t][k] = Delta H (output).
@@ -743,18 +765,21 @@ __global__ void __launch_bounds__(256) hals_w_sweep_kernel(const S *__restrict__
 // and its own cell c-1; CTA b owns components b, b+grid, ...; progress[k] counts finished cells of k.
 // Every Q element has exactly one reader/writer at a time, so the result is deterministic and identical to
 // the sequential k-outer / t-inner sweep of the reference.
-constexpr int HW_TC = 1024;  // columns per cell = threads per CTA
+constexpr int HW_TC = 1024;  // columns per cell
+constexpr int HW_NT = 512;   // threads per CTA (512 -> 128 registers per thread for the register-window recurrence)
 // earlier components staged per pull step (sized so the transposed Delta window fits shared memory)
 template <typename S> __host__ __device__ constexpr int hw_kb() { return sizeof(S) == 4 ? 32 : 16; }
 // dynamic shared memory of hals_h_wave_kernel in elements of S
 template <typename S>
 inline size_t hals_wave_smem_elems(int64_t L) {
     const size_t WW = HW_TC + 2 * (L - 1);
-    return 2 * HW_TC + (2 * L + 32) + L + (2 * L - 1) * hw_kb<S>() + hw_kb<S>() * ((WW | 1));
+    const size_t QP = ((WW + 3) >> 2) | 1;
+    const size_t dwin = hw_kb<S>() * 4 * QP > (size_t)4 * HW_TC ? hw_kb<S>() * 4 * QP : (size_t)4 * HW_TC;
+    return 2 * HW_TC + (2 * L + 32) + L + 32 + (2 * L - 1) * hw_kb<S>() + dwin;
 }
 
 template <typename S>
-__global__ void __launch_bounds__(HW_TC) hals_h_wave_kernel(const S *__restrict__ Cf, const S *__restrict__ S2,
+__global__ void __launch_bounds__(HW_NT) hals_h_wave_kernel(const S *__restrict__ Cf, const S *__restrict__ S2,
                                                              const S *__restrict__ Q, S *__restrict__ H, S *__restrict__ D,
                                                              S *__restrict__ tailC_all /*[grid][L*L]*/, int *progress /*[K]*/,
                                                              int64_t K, int64_t L, int64_t T, int64_t Ks, int64_t ld,
@@ -764,9 +789,10 @@ __global__ void __launch_bounds__(HW_TC) hals_h_wave_kernel(const S *__restrict_
     S *qeff = reinterpret_cast<S *>(smem_raw);       // [HW_TC]
     S *pend = qeff + HW_TC;                          // ring of RB entries
     S *ckk = pend + (2 * L + 32);                    // Cf[k,k,s], s = 0..L-1
-    S *hch = ckk + L;                                // [HW_TC] H of the current cell
+    S *ckk32 = ckk + L;                              // [32] C[k,k,j] zero padded (register-window recurrence, L <= 32)
+    S *hch = ckk32 + 32;                             // [HW_TC] H of the current cell
     S *Cs = hch + HW_TC;                             // [(2L-1)][HW_KB] lag-table slice of the pull phase
-    S *Dwin = Cs + (2 * L - 1) * HW_KB;              // [HW_KB][WWP]   transposed Delta window of the pull phase
+    S *Dwin = Cs + (2 * L - 1) * HW_KB;              // [HW_KB][4 planes][QP] transposed Delta window of the pull phase
     const int RB = (int)(2 * L + 32);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int64_t nC = (T + HW_TC - 1) / HW_TC;
@@ -776,6 +802,7 @@ __global__ void __launch_bounds__(HW_TC) hals_h_wave_kernel(const S *__restrict_
     for (int64_t k = blockIdx.x; k < K; k += gridDim.x) {
         // per-component tables
         for (int64_t s = tid; s < L; s += nthr) ckk[s] = Cf[((s + L - 1) * K + k) * K + k];
+        if (tid < 32) ckk32[tid] = (tid >= 1 && tid < L) ? Cf[((tid + L - 1) * K + k) * K + k] : S(0);
         // tailC[w][s] = C_w[k,k,s] = sum_{l<w, l-s>=0} S2[(l,k)][(l-s,k)],  w = 1..L-1, s = 0..L-1
         for (int64_t idx = tid; idx < L * L; idx += nthr) {
             const int64_t w = idx / L, s = idx % L;
@@ -785,6 +812,10 @@ __global__ void __launch_bounds__(HW_TC) hals_h_wave_kernel(const S *__restrict_
         }
         for (int i = tid; i < RB; i += nthr) pend[i] = S(0);
         __syncthreads();
+        S Pw[32];                             // register window of pending corrections (warp 0, L <= 32)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) Pw[j] = S(0);
+        bool ring_mode = false;               // true once the window lives in the shared ring (tail / partial blocks / L > 32)
 
         for (int64_t c = 0; c < nC; ++c) {
             const int64_t t0 = c * HW_TC;
@@ -796,12 +827,19 @@ __global__ void __launch_bounds__(HW_TC) hals_h_wave_kernel(const S *__restrict_
             }
             __syncthreads();
             __threadfence();
-            // ---- pull: corrections from all earlier components, 32 components at a time through shared memory
-            //      (D window transposed so lanes read consecutive t; lag-table slice broadcast)
+            // ---- pull: corrections from all earlier components, HW_KB components at a time through shared memory.
+            //      Register tiling: thread (cg, kq) owns the 4 consecutive columns 4*cg .. 4*cg+3 and a quarter of the
+            //      staged components; along the lag loop the 4 Delta values slide through registers, so each step costs
+            //      one new Delta load + one (broadcast) table load for 4 FMAs.  The Delta window is stored transposed and
+            //      split into 4 planes (index i -> plane i&3, slot i>>2) so that lanes read consecutive words.
             {
-                const int64_t tp = t0 + tid;
-                const int WW = HW_TC + 2 * (int)(L - 1), WWP = WW | 1;
-                S acc = (tp < T) ? Q[tp * K + k] : S(0);
+                const int WW = HW_TC + 2 * (int)(L - 1);
+                const int QP = ((WW + 3) >> 2) | 1;            // slots per plane (odd)
+                const int WWQ = 4 * QP;                        // words per staged component
+                const int cg = tid & (HW_TC / 4 - 1), kq = tid >> 8;       // column group, component half
+                constexpr int NKQ = HW_NT / (HW_TC / 4);                   // 2 groups of components per staged block
+                constexpr int KQ = HW_KB / NKQ;
+                S a4[4] = {S(0), S(0), S(0), S(0)};
                 for (int64_t kp0 = 0; kp0 < k; kp0 += HW_KB) {
                     const int kb = (int)((k - kp0 < HW_KB) ? k - kp0 : HW_KB);
                     __syncthreads();
@@ -810,7 +848,7 @@ __global__ void __launch_bounds__(HW_TC) hals_h_wave_kernel(const S *__restrict_
                         const int64_t t = t0 - (L - 1) + i;
                         S v = S(0);
                         if (kk < kb && t >= 0 && t < Tint) v = __ldcg(D + t * K + kp0 + kk);   // tail columns: slow path below
-                        Dwin[kk * WWP + i] = v;
+                        Dwin[kk * WWQ + (i & 3) * QP + (i >> 2)] = v;
                     }
                     for (int idx = tid; idx < (2 * L - 1) * HW_KB; idx += nthr) {
                         const int kk = idx % HW_KB;
@@ -818,50 +856,96 @@ __global__ void __launch_bounds__(HW_TC) hals_h_wave_kernel(const S *__restrict_
                         Cs[idx] = (kk < kb) ? Cf[(j * K + kp0 + kk) * K + k] : S(0);
                     }
                     __syncthreads();
-                    for (int64_t j = 0; j < 2 * L - 1; ++j) {
-                        const int i = tid + 2 * (int)(L - 1) - (int)j;     // window index of t = tp - dd, dd = j - (L-1)
-                        const S *cr = Cs + j * HW_KB;
-                        S a = S(0);
-#pragma unroll 8
-                        for (int kk = 0; kk < HW_KB; ++kk) a = fma(Dwin[kk * WWP + i], cr[kk], a);
-                        acc += a;
-                    }
-                }
-                // truncated tail columns t >= Tint (only the last chunks see them): C_w from S2 on the fly
-                if (tp < T && tp + (L - 1) >= Tint) {
-                    double accd = 0.0;
-                    const int64_t ta = (tp - (L - 1) > Tint) ? tp - (L - 1) : Tint;
-                    const int64_t tb = tp + (L - 1) < T - 1 ? tp + (L - 1) : T - 1;
-                    for (int64_t t = (ta > 0 ? ta : 0); t <= tb; ++t) {
-                        const int64_t dd = tp - t;
-                        const int64_t w = T - t;    // C_w[k',k,dd] = sum_{l<w, 0<=l-dd<L} S2[(l,k')][(l-dd,k)]
-                        for (int64_t kp = 0; kp < k; ++kp) {
-                            const S d = __ldcg(D + t * K + kp);
-                            if (d == S(0)) continue;
-                            double cw = 0.0;
-                            for (int64_t l = (dd > 0 ? dd : 0); l < w && l - dd < L; ++l)
-                                cw += (double)S2[(l * Ks + kp) * ld + (l - dd) * Ks + k];
-                            accd += (double)d * cw;
+                    for (int kk = kq * KQ; kk < kq * KQ + KQ && kk < kb; ++kk) {
+                        const S *dw = Dwin + kk * WWQ;
+                        // window index of column 4*cg + r at lag step j:  i = 4*cg + r + 2(L-1) - j
+                        const int ib = 4 * cg + 2 * (int)(L - 1);
+                        S d0 = dw[(ib & 3) * QP + (ib >> 2)];
+                        S d1 = dw[((ib + 1) & 3) * QP + ((ib + 1) >> 2)];
+                        S d2 = dw[((ib + 2) & 3) * QP + ((ib + 2) >> 2)];
+                        S d3 = dw[((ib + 3) & 3) * QP + ((ib + 3) >> 2)];
+                        for (int j = 0; j < 2 * (int)L - 1; ++j) {
+                            const S cv = Cs[j * HW_KB + kk];
+                            a4[0] = fma(d0, cv, a4[0]);
+                            a4[1] = fma(d1, cv, a4[1]);
+                            a4[2] = fma(d2, cv, a4[2]);
+                            a4[3] = fma(d3, cv, a4[3]);
+                            const int in = ib - j - 1;         // next step's lowest index (>= 0 while j < 2L-2)
+                            d3 = d2; d2 = d1; d1 = d0;
+                            d0 = (in >= 0) ? dw[(in & 3) * QP + (in >> 2)] : S(0);
                         }
                     }
-                    acc += (S)accd;
+                }
+                // reduce the component groups: red[kq][column] (reuses the Delta window space), then add Q
+                __syncthreads();
+                S *red = Dwin;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) red[kq * HW_TC + 4 * cg + r] = a4[r];
+                __syncthreads();
+                for (int col = tid; col < HW_TC; col += nthr) {
+                    const int64_t tp = t0 + col;
+                    S acc = (tp < T) ? Q[tp * K + k] : S(0);
+#pragma unroll
+                    for (int g = 0; g < NKQ; ++g) acc += red[g * HW_TC + col];
+                    qeff[col] = acc;
                 }
                 __syncthreads();
-                qeff[tid] = acc;
+                // truncated tail columns t >= Tint (only the last chunks see them): C_w from S2 on the fly
+                for (int col = tid; col < HW_TC; col += nthr) {
+                    const int64_t tp = t0 + col;
+                    if (tp < T && tp + (L - 1) >= Tint) {
+                        double accd = 0.0;
+                        const int64_t ta = (tp - (L - 1) > Tint) ? tp - (L - 1) : Tint;
+                        const int64_t tb = tp + (L - 1) < T - 1 ? tp + (L - 1) : T - 1;
+                        for (int64_t t = (ta > 0 ? ta : 0); t <= tb; ++t) {
+                            const int64_t dd = tp - t;
+                            const int64_t w = T - t;    // C_w[k',k,dd] = sum_{l<w, 0<=l-dd<L} S2[(l,k')][(l-dd,k)]
+                            for (int64_t kp = 0; kp < k; ++kp) {
+                                const S d = __ldcg(D + t * K + kp);
+                                if (d == S(0)) continue;
+                                double cw = 0.0;
+                                for (int64_t l = (dd > 0 ? dd : 0); l < w && l - dd < L; ++l)
+                                    cw += (double)S2[(l * Ks + kp) * ld + (l - dd) * Ks + k];
+                                accd += (double)d * cw;
+                            }
+                        }
+                        qeff[col] += (S)accd;
+                    }
+                }
             }
             __syncthreads();
             // ---- sweep: the sequential recurrence of component k over this chunk (warp 0), entirely in shared
             //      memory: H of the chunk is prefetched by all threads, results are written back by all threads
-            {
-                const int64_t tp = t0 + tid;
-                hch[tid] = (tp < T) ? H[tp * K + k] : S(0);
+            for (int col = tid; col < HW_TC; col += nthr) {
+                const int64_t tp = t0 + col;
+                hch[col] = (tp < T) ? H[tp * K + k] : S(0);
             }
             __syncthreads();
             if (tid < 32) {
                 const int lane = tid;
                 const int n = (int)((t0 + HW_TC < T) ? HW_TC : T - t0);
-                int slot = (int)(t0 % RB);
-                for (int i = 0; i < n; ++i) {
+                int i = 0;
+                if (L <= 32 && !ring_mode) {
+                    // register-window recurrence over whole blocks of 32 interior columns
+                    const S c0i = ckk[0], inv_i = S(1) / (c0i + (S)CMF_EPS + l2);
+                    while (i + 32 <= n && t0 + i + 32 <= Tint) {
+                        hals_recurrence_block<S, 32>(hch, qeff, Pw, ckk32, c0i, inv_i, l1, i, lane);
+                        i += 32;
+                    }
+                    if (i < n) {
+                        // the rest (truncated tail of the sequence / partial block) runs on the shared ring: hand the window over
+                        int slot0 = (int)((t0 + i) % RB);
+                        if (lane == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) { int ps = slot0 + j; if (ps >= RB) ps -= RB; pend[ps] = Pw[j]; }
+                        }
+                        ring_mode = true;
+                        __syncwarp();
+                    }
+                }
+                {
+                int slot = (int)((t0 + i) % RB);
+                for (; i < n; ++i) {
                     const int64_t t = t0 + i;
                     const int w = (int)((T - t < L) ? (T - t) : L);
                     const S c0 = (w == (int)L) ? ckk[0] : tailC[w * L + 0];
@@ -887,13 +971,14 @@ __global__ void __launch_bounds__(HW_TC) hals_h_wave_kernel(const S *__restrict_
                     if (++slot == RB) slot = 0;
                     __syncwarp();
                 }
+                }
             }
             __syncthreads();
-            {
-                const int64_t tp = t0 + tid;
+            for (int col = tid; col < HW_TC; col += nthr) {
+                const int64_t tp = t0 + col;
                 if (tp < T) {
-                    H[tp * K + k] = hch[tid];
-                    D[tp * K + k] = qeff[tid];
+                    H[tp * K + k] = hch[col];
+                    D[tp * K + k] = qeff[col];
                 }
             }
             __syncthreads();
