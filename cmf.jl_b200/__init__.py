@@ -10,11 +10,12 @@ from .model import (  # noqa: F401
     converged, corr_w, fit, fit_cnmf, init_rand, num_components, num_iter, num_lags, num_units,
     tensor_conv, tensor_transconv,
 )
+from .io import gen_synthetic, load_model, parameter_sweep, save_model  # noqa: F401
 from .sharded import DeviceShard, ShardedMultFit, ShardPlan  # noqa: F401
 
 __all__ = [
     "fit_cnmf", "init_rand", "MultUpdate", "HALSUpdate", "PGDUpdate", "AbstractCFUpdate", "AlternatingOptimizer",
     "fit", "CNMF_results", "converged", "compute_loss", "tensor_conv", "tensor_transconv", "corr_w",
     "num_lags", "num_units", "num_components", "num_iter", "ShardPlan", "DeviceShard",
-    "ShardedMultFit", "CMFError",
+    "ShardedMultFit", "CMFError", "gen_synthetic", "save_model", "load_model", "parameter_sweep",
 ]

@@ -273,11 +273,11 @@ struct Ctx : cmf_ctx {
         if constexpr (!std::is_same<S, float>::value) { return; } else {
             TcState &t = tcs;
             if (K > 128 || N % 8 != 0) return;
-            t.Kp = K <= 16 ? 16 : K <= 32 ? 32 : K <= 64 ? 64 : 128;
-            t.G = 128 / t.Kp;
+            t.Kp = (int)(cdiv(K, 8) * 8);                          // TMA row strides must be multiples of 16 bytes
+            t.G = 128 / t.Kp;                                      // lags per 128-row tile of the transposed conv
             t.KLp = cdiv(L * t.Kp, 64) * 64;
             t.groups = cdiv(L, t.G);
-            t.rows_u = t.groups * 128;
+            t.rows_u = cdiv(L * t.Kp + 128, 128) * 128;             // dense rows l*Kp + k, padded so every 128-row box is in bounds
             const int64_t hal = L - 1;
             t.hrows = Tl + hal;                                   // window rows addressed (X columns incl. right halo)
             cudaDeviceProp prop;
@@ -291,7 +291,7 @@ struct Ctx : cmf_ctx {
             t.Wc_hi.alloc((size_t)(N * t.KLp)); t.Wc_lo.alloc((size_t)(N * t.KLp));
             t.Wu_hi.alloc((size_t)(t.rows_u * N)); t.Wu_lo.alloc((size_t)(t.rows_u * N));
             t.groups_c = cdiv(2 * L - 1, t.G);
-            t.rows_c = t.groups_c * 128;
+            t.rows_c = cdiv((2 * L - 1) * t.Kp + 128, 128) * 128;
             t.Cc_hi.alloc((size_t)(t.rows_c * t.Kp)); t.Cc_lo.alloc((size_t)(t.rows_c * t.Kp));
             t.Gc_hi.alloc((size_t)(KL() * t.KLp)); t.Gc_lo.alloc((size_t)(KL() * t.KLp));
             if (GS.n < (size_t)(t.rows_u * t.rows_u)) GS.alloc((size_t)(t.rows_u * t.rows_u));
@@ -355,8 +355,6 @@ struct Ctx : cmf_ctx {
         tc::Params q;
         memset(&q, 0, sizeof(q));
         q.N = N; q.K = K; q.L = L; q.Tl = Tl; q.G = tcs.G; q.Kp = tcs.Kp;
-        q.Kp_log2 = 0;
-        while ((1 << q.Kp_log2) < tcs.Kp) ++q.Kp_log2;
         { const char *e = getenv("CMF_PROMO"); q.promo = e ? std::max(1, atoi(e)) : tc::PROMO; }
         return q;
     }

@@ -10,7 +10,7 @@
 // One kernel template, three modes (shapes are per CTA tile, M = 128 TMEM lanes, N = 256 columns):
 //   TC_CONV   D[n, t]      = sum_j Wc[n][j] * Hwin[t][j]          j = (L-1-l)*Kp + k   (K-major, SW64)
 //             epilogue: sum (D - X[t][n])^2  -> loss partials        (src/common.jl:24-34,54-59)
-//   TC_TRANS  D[(i,k), c]  = sum_{g} sum_n Wu[(gG+i)*Kp+k][n] * X[t0+c+gG][n]   (K-major, SW64)
+//   TC_TRANS  D[(i,k), c]  = sum_{g} sum_n Wu[(gG+i)*Kp+k][n] * X[t0+c+gG][n]   (K-major, SW64; G = 128/Kp lags per tile)
 //             epilogue: numH[t0+c-i][k] += D[(i,k), c]               (src/common.jl:71-81)
 //   TC_CORR   D[j, n]      = sum_t Hwin[t][j] * X[t][n]             (both MN-major, SW128)
 //             epilogue: every TC_FLUSH_T columns of t, part[(l,k)][n] (+)= D  in double
@@ -47,7 +47,7 @@ struct Params {
     int64_t nkb;            // CONV: k-blocks per tile
     // TRANS
     int64_t groups, nblocks;   // lag groups, n blocks of BK
-    int G, Kp, Kp_log2;        // lags per group (128 / Kp), padded K (power of two)
+    int G, Kp;                 // lags per 128-row group (128 / Kp, rounded down), K padded to a multiple of 8
     int64_t own;               // owned columns per t tile = BN - (G-1)
     // CORR
     int64_t split_len;         // t columns per split (multiple of BK)
@@ -262,7 +262,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                         } else if (MODE == TC_TRANS) {
                             const int64_t nb = kb / p.groups, g = kb % p.groups;   // n-block outer, lag group inner: the X sub-window stays in L2
                             const int32_t c0 = (int32_t)(nb * BK);
-                            const int32_t rowA = (int32_t)(g * BM), rowB = (int32_t)(unit * p.own + g * p.G);
+                            const int32_t rowA = (int32_t)(g * p.G * p.Kp), rowB = (int32_t)(unit * p.own + g * p.G);   // G*Kp <= 128 rows per lag group
                             tma_load_2d(st, &mapA_hi, &full_bar[s], c0, rowA);
                             tma_load_2d(st + A_PLANE, &mapA_lo, &full_bar[s], c0, rowA);
                             tma_load_2d(st + 2 * A_PLANE, &mapB_hi, &full_bar[s], c0, rowB);
@@ -392,7 +392,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                     // one pass per lag of the group, ordered by a named barrier over the epilogue warps, so the
                     // additions into numH happen in a fixed order (deterministic)
                     for (int pass = 0; pass < p.G; ++pass) {
-                        if (i == pass && k < p.K) {
+                        if (i == pass && k < p.K) {      // rows >= G*Kp (i >= G) belong to the next lag group: ignored
 #pragma unroll
                             for (int c = 0; c < BN / 2; ++c) {
                                 const int64_t cc = col0 + c - i;            // owned column index
@@ -442,7 +442,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                             for (int u = 0; u < 8; ++u) {
                                 const int r = (it0 + u) * 2 + (lane >> 4), c = lane & 15;
                                 const int64_t j = mt * BM + quarter * 32 + r;
-                                const int64_t lp = j >> p.Kp_log2, k = j & (p.Kp - 1);   // Kp is a power of two
+                                const int64_t lp = j / p.Kp, k = j - lp * p.Kp;
                                 const int64_t n = nt * BN + col0 + cc + c;
                                 dp[u] = (lp < p.L && k < p.K && n < p.N) ? pbase + ((p.L - 1 - lp) * p.K + k) * p.N + n : nullptr;
                             }

@@ -91,3 +91,17 @@ def test_kwarg_normalisation_and_alg_resolution():
     with pytest.raises(ValueError):
         model._resolve_alg("anls")
     assert model.converged([1, 1, 1, 1], 3, 1e-4) and not model.converged([1, 1, 1], 3, 1e-4)
+
+
+def test_save_load_round_trip(tmp_path):
+    # src/model.jl:149-181 with the real struct fields
+    import cmf_jl_b200 as cmf
+
+    rng = np.random.default_rng(0)
+    r = cmf.CNMF_results(rng.random((4, 9)), rng.random((3, 4, 2)), rng.random((2, 9)), [0.0, 0.1], [0.9, 0.5], "LNK")
+    p = tmp_path / "model.npz"
+    cmf.save_model(r, p)
+    q = cmf.load_model(p)
+    assert np.array_equal(q.W, r.W) and np.array_equal(q.H, r.H) and np.array_equal(q.data, r.data)
+    assert q.loss_hist == r.loss_hist and q.time_hist == r.time_hist and q.layout == "LNK"
+    assert cmf.num_lags(q) == 3 and cmf.num_units(q) == 4 and cmf.num_components(q) == 2 and cmf.num_iter(q) == 2

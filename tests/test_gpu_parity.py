@@ -326,3 +326,15 @@ def test_pgd_fp32_engines_loss_within_1e4(cmf, orc):
                          dtype="f32", engine=engine, layout="KNL")
         rel = np.abs(np.asarray(r.loss_hist) - np.asarray(ref.loss_hist)) / np.asarray(ref.loss_hist)
         assert rel.max() < F32_LOSS_RTOL, (engine, rel.max())
+
+
+def test_gen_synthetic_and_parameter_sweep(cmf):
+    # README.md:14-23: data = CMF.gen_synthetic(N=500, T=2000); fit_cnmf(data; L=10, K=5, alg=:hals)
+    data = cmf.gen_synthetic(N=60, T=300, K=3, L=8, seed=7)
+    assert data.shape == (60, 300) and data.min() >= 0.0 and data.std() > 0
+    assert np.array_equal(data, cmf.gen_synthetic(N=60, T=300, K=3, L=8, seed=7))
+    assert not np.array_equal(data, cmf.gen_synthetic(N=60, T=300, K=3, L=8, seed=8))
+    sweep = cmf.parameter_sweep(data, L_vals=[4, 6], K_vals=[2], alg_vals=["mult", ":hals"], max_itr=5, seed=0)
+    assert set(sweep) == {(4, 2, "mult"), (6, 2, "mult"), (4, 2, ":hals"), (6, 2, ":hals")}
+    for r in sweep.values():
+        assert r.loss_hist[-1] < r.loss_hist[0]
