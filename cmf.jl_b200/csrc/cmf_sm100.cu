@@ -106,7 +106,7 @@ struct cmf_ctx {
     }
     virtual ~cmf_ctx() { prof_clear(); }
     virtual void get_data(void *X_out, int with_halo) = 0;
-    virtual bool tc_available() const = 0;
+    virtual bool tc_available() = 0;
     virtual void set_data(const void *X, int64_t first_col) = 0;
     virtual void synth_data(uint64_t seed, int64_t Kt, int64_t Lt, double p_h, double noise) = 0;
     virtual double data_sumsq() = 0;
@@ -187,7 +187,7 @@ CUtensorMap make_map_mn(void *base, uint64_t rows, uint64_t row_stride, uint64_t
 }
 
 struct TcState {
-    bool ok = false;
+    bool ok = false, tried = false;
     int Kp = 0, G = 0, num_sms = 148;
     int64_t KLp = 0, rows_u = 0, groups = 0, hrows = 0;
     DevBuf<__nv_bfloat16> X_hi, X_lo, Hw_hi, Hw_lo, Hm_hi, Hm_lo, Wc_hi, Wc_lo, Wu_hi, Wu_lo, Cc_hi, Cc_lo;
@@ -261,17 +261,23 @@ struct Ctx : cmf_ctx {
         corr_part.alloc((size_t)std::max<int64_t>((int64_t)nsplit_w * KL() * N, (int64_t)nsplit_g * KL() * K));
         conv_blocks_max = (int)(cdiv(N, BN) * cdiv(Tl + hal, BT));
         loss_part.alloc((size_t)std::max(2 * conv_blocks_max, 4096));
-        tc_setup();
+        // the tensor-core engine is set up right away only where it is the default (big contractions); small problems
+        // build it lazily on cmf_set_engine(h, 1)
+        if (sizeof(S) == 4 && N >= 256 && Tl >= 4096 && K * L >= 256) tc_setup();
         CK(cudaStreamSynchronize(stream));
     }
 
     // ---------------------------------------------------------------- tcgen05 engine (fp32 only)
     bool tc_active() const { return engine == 1 && tcs.ok; }
-    bool tc_available() const override { return tcs.ok; }
+    bool tc_available() override {
+        if (!tcs.ok && !tcs.tried) tc_setup();
+        return tcs.ok;
+    }
 
     void tc_setup() {
         if constexpr (!std::is_same<S, float>::value) { return; } else {
             TcState &t = tcs;
+            t.tried = true;
             if (K > 128 || N % 8 != 0) return;
             t.Kp = (int)(cdiv(K, 8) * 8);                          // TMA row strides must be multiples of 16 bytes
             t.G = 128 / t.Kp;                                      // lags per 128-row tile of the transposed conv
@@ -346,6 +352,7 @@ struct Ctx : cmf_ctx {
             CK(cudaFuncSetAttribute(tc::tc_kernel<tc::TC_CORR>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
             CK(cudaFuncSetAttribute(tc::tc_kernel<tc::TC_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
             t.ok = true;
+            t.x_dirty = t.w_dirty = true;
             // default engine: tensor cores when the contraction is big enough to fill 128x256 tiles
             if (N >= 256 && Tl >= 4096 && K * L >= 256) engine = 1;
         }
