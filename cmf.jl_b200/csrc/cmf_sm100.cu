@@ -363,6 +363,7 @@ struct Ctx : cmf_ctx {
         memset(&q, 0, sizeof(q));
         q.N = N; q.K = K; q.L = L; q.Tl = Tl; q.G = tcs.G; q.Kp = tcs.Kp;
         { const char *e = getenv("CMF_PROMO"); q.promo = e ? std::max(1, atoi(e)) : tc::PROMO; }
+        { const char *e = getenv("CMF_TC_PRODUCTS"); q.nprod = (e && atoi(e) == 2) ? 2 : 3; }   // experiment knob, default 3
         return q;
     }
 

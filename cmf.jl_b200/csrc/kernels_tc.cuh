@@ -51,6 +51,7 @@ struct Params {
     int64_t own;               // owned columns per t tile = BN - (G-1)
     // CORR
     int64_t split_len;         // t columns per split (multiple of BK)
+    int nprod;                 // bf16 products per logical product: 3 (hi*hi + hi*lo + lo*hi, default) or 2 (A operand in single bf16)
     int promo;                 // k-blocks accumulated in TMEM before promotion to registers (PROMO by default)
     int corr_order;            // 0: j tiles fastest (CTAs share the X tile), 1: n tiles fastest (CTAs share the H window)
     int *lockstep;             // CORR/TRANS: per-CTA k-block counters (zeroed before the launch) or nullptr
@@ -246,17 +247,17 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                         }
                         mbar_wait(&empty_bar[s], ph ^ 1);
                         unsigned char *st = smem + (size_t)s * STAGE_BYTES;
-                        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                        mbar_expect_tx(&full_bar[s], p.nprod == 3 ? STAGE_BYTES : STAGE_BYTES - A_PLANE);
                         if (MODE == TC_CONV) {
                             const int32_t j0 = (int32_t)(kb * BK);
                             tma_load_2d(st, &mapA_hi, &full_bar[s], j0, (int32_t)(nt * BM));
-                            tma_load_2d(st + A_PLANE, &mapA_lo, &full_bar[s], j0, (int32_t)(nt * BM));
+                            if (p.nprod == 3) tma_load_2d(st + A_PLANE, &mapA_lo, &full_bar[s], j0, (int32_t)(nt * BM));
                             tma_load_2d(st + 2 * A_PLANE, &mapB_hi, &full_bar[s], j0, (int32_t)(mt * BN));
                             tma_load_2d(st + 2 * A_PLANE + B_PLANE, &mapB_lo, &full_bar[s], j0, (int32_t)(mt * BN));
                         } else if (MODE == TC_PLAIN) {
                             const int32_t k0 = (int32_t)(kb * BK);
                             tma_load_2d(st, &mapA_hi, &full_bar[s], k0, (int32_t)(mt * BM));
-                            tma_load_2d(st + A_PLANE, &mapA_lo, &full_bar[s], k0, (int32_t)(mt * BM));
+                            if (p.nprod == 3) tma_load_2d(st + A_PLANE, &mapA_lo, &full_bar[s], k0, (int32_t)(mt * BM));
                             tma_load_2d(st + 2 * A_PLANE, &mapB_hi, &full_bar[s], k0, (int32_t)(nt * BN));
                             tma_load_2d(st + 2 * A_PLANE + B_PLANE, &mapB_lo, &full_bar[s], k0, (int32_t)(nt * BN));
                         } else if (MODE == TC_TRANS) {
@@ -264,7 +265,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                             const int32_t c0 = (int32_t)(nb * BK);
                             const int32_t rowA = (int32_t)(g * p.G * p.Kp), rowB = (int32_t)(unit * p.own + g * p.G);   // G*Kp <= 128 rows per lag group
                             tma_load_2d(st, &mapA_hi, &full_bar[s], c0, rowA);
-                            tma_load_2d(st + A_PLANE, &mapA_lo, &full_bar[s], c0, rowA);
+                            if (p.nprod == 3) tma_load_2d(st + A_PLANE, &mapA_lo, &full_bar[s], c0, rowA);
                             tma_load_2d(st + 2 * A_PLANE, &mapB_hi, &full_bar[s], c0, rowB);
                             tma_load_2d(st + 2 * A_PLANE + B_PLANE, &mapB_lo, &full_bar[s], c0, rowB);
                         } else {
@@ -272,7 +273,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                             // groups), so one TMA per plane fills all the 4 KB swizzle atoms of the tile
                             const int32_t trow = (int32_t)(kb * BK);
                             tma_load_3d(st, &mapA_hi, &full_bar[s], 0, trow, (int32_t)(mt * 2));
-                            tma_load_3d(st + A_PLANE, &mapA_lo, &full_bar[s], 0, trow, (int32_t)(mt * 2));
+                            if (p.nprod == 3) tma_load_3d(st + A_PLANE, &mapA_lo, &full_bar[s], 0, trow, (int32_t)(mt * 2));
                             tma_load_3d(st + 2 * A_PLANE, &mapB_hi, &full_bar[s], 0, trow, (int32_t)(nt * 4));
                             tma_load_3d(st + 2 * A_PLANE + B_PLANE, &mapB_lo, &full_bar[s], 0, trow, (int32_t)(nt * 4));
                         }
@@ -319,8 +320,12 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                                     dah = make_desc(a_hi + off, 16, 512, 4); dal = make_desc(a_lo + off, 16, 512, 4);
                                     dbh = make_desc(b_hi + off, 16, 512, 4); dbl = make_desc(b_lo + off, 16, 512, 4);
                                 }
-                                tc_mma(d_tmem, dal, dbh, idesc, accumulate);   // lo*hi
-                                tc_mma(d_tmem, dah, dbl, idesc, 1u);           // hi*lo
+                                if (p.nprod == 3) {
+                                    tc_mma(d_tmem, dal, dbh, idesc, accumulate);   // lo*hi
+                                    tc_mma(d_tmem, dah, dbl, idesc, 1u);           // hi*lo
+                                } else {
+                                    tc_mma(d_tmem, dah, dbl, idesc, accumulate);   // hi*lo (A carried in single bf16)
+                                }
                                 tc_mma(d_tmem, dah, dbh, idesc, 1u);           // hi*hi
                                 accumulate = 1u;
                             }
