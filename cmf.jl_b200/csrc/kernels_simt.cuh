@@ -737,8 +737,8 @@ __global__ void __launch_bounds__(256) hals_w_sweep_kernel(const S *__restrict__
 // are fully unrolled, so the rotation of the window is a compile-time renaming and a step costs its dependent chain
 // (load, 3 FMA/MUL, max, sub) plus W independent FMAs.  Every lane of the warp runs the same scalar code (the values
 // are warp-uniform); lane 0 stores.  Requires L - 1 <= W - 1... i.e. L <= W.
-template <typename S, int W>
-__device__ __forceinline__ void hals_recurrence_block(S *hch, S *qeff, S (&p)[W], const S *c /*shared, zero padded to W*/, S c0,
+template <typename S, int W, typename CT>
+__device__ __forceinline__ void hals_recurrence_block(S *hch, S *qeff, S (&p)[W], const CT &c /*C[k,k,j], zero for j >= L*/, S c0,
                                                        S inv, S l1, int i0, int lane) {
 #pragma unroll
     for (int u = 0; u < W; ++u) {
@@ -750,7 +750,7 @@ __device__ __forceinline__ void hals_recurrence_block(S *hch, S *qeff, S (&p)[W]
         if (lane == 0) { hch[i0 + u] = v; qeff[i0 + u] = d; }
         p[u] = S(0);                                   // this slot now stands for column t + W
 #pragma unroll
-        for (int j = 1; j < W; ++j) p[(u + j) % W] = fma(d, c[j], p[(u + j) % W]);   // c[j] = C[k,k,j], zero for j >= L
+        for (int j = 1; j < W; ++j) p[(u + j) % W] = fma(d, c[j], p[(u + j) % W]);
     }
 }
 
@@ -813,8 +813,13 @@ __global__ void __launch_bounds__(HW_NT) hals_h_wave_kernel(const S *__restrict_
         for (int i = tid; i < RB; i += nthr) pend[i] = S(0);
         __syncthreads();
         S Pw[32];                             // register window of pending corrections (warp 0, L <= 32)
+        S creg[sizeof(S) == 4 ? 32 : 1];      // C[k,k,j] in registers (fp32; 128 registers per thread at 512 threads)
 #pragma unroll
         for (int j = 0; j < 32; ++j) Pw[j] = S(0);
+        if (sizeof(S) == 4) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) creg[j % (sizeof(S) == 4 ? 32 : 1)] = ckk32[j];
+        }
         bool ring_mode = false;               // true once the window lives in the shared ring (tail / partial blocks / L > 32)
 
         for (int64_t c = 0; c < nC; ++c) {
@@ -929,7 +934,8 @@ __global__ void __launch_bounds__(HW_NT) hals_h_wave_kernel(const S *__restrict_
                     // register-window recurrence over whole blocks of 32 interior columns
                     const S c0i = ckk[0], inv_i = S(1) / (c0i + (S)CMF_EPS + l2);
                     while (i + 32 <= n && t0 + i + 32 <= Tint) {
-                        hals_recurrence_block<S, 32>(hch, qeff, Pw, ckk32, c0i, inv_i, l1, i, lane);
+                        if (sizeof(S) == 4) hals_recurrence_block<S, 32>(hch, qeff, Pw, creg, c0i, inv_i, l1, i, lane);   // table in registers
+                        else hals_recurrence_block<S, 32>(hch, qeff, Pw, ckk32, c0i, inv_i, l1, i, lane);                  // fp64: table in shared memory
                         i += 32;
                     }
                     if (i < n) {
