@@ -254,26 +254,36 @@ class HALSUpdate:
 class PGDUpdate:
     """src/algs/pgd.jl:112-155.  Penalties are given as weights: ``l2W`` = SquarePenalty weight on W
     (reference default ``penaltiesW=[SquarePenalty(1)]``, pgd.jl:161), ``l1W`` = AbsolutePenalty weight,
-    likewise ``l1H``/``l2H`` (reference default ``penaltiesH=[]``, pgd.jl:185)."""
+    likewise ``l1H``/``l2H`` (reference default ``penaltiesH=[]``, pgd.jl:185).  ``loss_func`` is "square"
+    (SquareLoss, pgd.jl:28-35) or "absolute" (AbsoluteLoss, :38-45); ``mask`` (N x T) wraps it in a MaskedLoss
+    (:59-70: the gradient is multiplied by the mask, the loss is evaluated on mask.*data and mask.*est)."""
 
-    def __init__(self, data, W, H):
+    def __init__(self, data, W, H, loss_func="square", mask=None):
         self.datanorm = float(np.linalg.norm(data))
         self.est = tensor_conv(W, H)
         self.stepW = 5.0          # pgd.jl:147-148
         self.stepH = 5.0
         self.cur_loss = self.datanorm   # pgd.jl:149 (sic: the norm, not its square)
         self.step_incr, self.step_decr = 1.05, 0.70
+        self.loss_func, self.mask = loss_func, mask
+
+    def _loss_grad(self, data):
+        g = 2.0 * (self.est - data) if self.loss_func == "square" else np.sign(self.est - data)   # :30-32 / :40-42
+        return g if self.mask is None else g * self.mask                                           # :63-66
+
+    def _loss_eval(self, data):
+        b, e = (data, self.est) if self.mask is None else (self.mask * data, self.mask * self.est)  # :67-69
+        return float(np.linalg.norm(b - e) ** 2) if self.loss_func == "square" else float(np.sum(np.abs(b - e)))
 
     def _pgd(self, x, grad_fn, step, data, W, H, l1, l2):
         """pgd.jl:224-255."""
-        gest = 2.0 * (self.est - data)                    # SquareLoss gradient, pgd.jl:30-32
-        g = grad_fn(gest)
+        g = grad_fn(self._loss_grad(data))
         g = g + 2.0 * l2 * x + l1 * np.sign(x)            # SquarePenalty :77-79, AbsolutePenalty :86-88
         alpha = step / (np.linalg.norm(g) + EPSILON)      # :236
         x -= alpha * g                                    # :239
         np.maximum(x, EPSILON, out=x)                     # NonnegConstraint :93-95
         self.est = tensor_conv(W, H)                      # :244
-        loss = float(np.linalg.norm(data - self.est) ** 2)   # SquareLoss eval :33-35
+        loss = self._loss_eval(data)                      # :245
         step *= self.step_incr if loss < self.cur_loss else self.step_decr   # :247-251
         self.cur_loss = loss
         return step
