@@ -194,6 +194,8 @@ def run_ours(args, cfg, name):
     plan = cmf.ShardPlan(T, world, L)
     t0, t1 = plan.ranges[rank]
     shard = cmf.DeviceShard(N, T, t0, t1, K, L, dtype="f32", device=local_rank)
+    if args.engine is not None:
+        shard.set_engine(args.engine)
     shard.set_loss_mode(args.loss_mode)
     fitter = cmf.ShardedMultFit(shard, rank, world, dist)
 
@@ -277,6 +279,8 @@ def run_ours(args, cfg, name):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         sh2 = cmf.DeviceShard(N, T, t0, t1, K, L, dtype="f32", device=local_rank)
+        if args.engine is not None:
+            sh2.set_engine(args.engine)
         sh2.set_loss_mode(args.loss_mode)
         f2 = cmf.ShardedMultFit(sh2, rank, world, dist)
         sh2.set_data(Xh, t0)                      # H2D of this rank's columns from pinned host memory
@@ -391,6 +395,8 @@ def main():
     ap.add_argument("--T", type=int, default=None, help="override T (development only; reported in config.workload)")
     ap.add_argument("--loss-mode", type=int, default=1, choices=[0, 1],
                     help="1: loss by the algebraic expansion on resident numH / W W' (default); 0: direct residual pass")
+    ap.add_argument("--engine", type=int, default=None, choices=[0, 1, 2],
+                    help="contraction engine (default: the library's choice): 0 SIMT, 1 tcgen05 time domain, 2 tcgen05 frequency domain")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -12,6 +12,7 @@ SOURCES = [os.path.join(HERE, "csrc", "cmf_sm100.cu")]
 DEPS = SOURCES + [
     os.path.join(HERE, "csrc", "kernels_simt.cuh"),
     os.path.join(HERE, "csrc", "kernels_tc.cuh"),
+    os.path.join(HERE, "csrc", "kernels_fd.cuh"),
     os.path.join(ROOT, "include", "cmf_sm100.h"),
 ]
 

@@ -19,6 +19,7 @@
 
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_fd.cuh"
 
 namespace {
 
@@ -107,6 +108,7 @@ struct cmf_ctx {
     virtual ~cmf_ctx() { prof_clear(); }
     virtual void get_data(void *X_out, int with_halo) = 0;
     virtual bool tc_available() = 0;
+    virtual bool fd_available() = 0;
     virtual void set_data(const void *X, int64_t first_col) = 0;
     virtual void synth_data(uint64_t seed, int64_t Kt, int64_t Lt, double p_h, double noise) = 0;
     virtual double data_sumsq() = 0;
@@ -203,9 +205,22 @@ struct TcState {
     bool x_dirty = true, w_dirty = true;
 };
 
+// frequency-domain engine state (kernels_fd.cuh): spectrum of X (built once per data set) and the per-iteration spectra
+struct FdState {
+    bool ok = false, tried = false;
+    int B = 0, logB = 0, V = 0, F = 0;
+    int64_t nblk = 0, nblkp = 0;          // overlap-save blocks covering the owned columns; padded to a multiple of 16
+    DevBuf<__nv_bfloat16> Xf_hi, Xf_lo, Ah_hi, Ah_lo, Aw_hi, Aw_lo;
+    DevBuf<float> Of, Df;
+    CUtensorMap mXfK[2], mXfMN[2], mAw[2], mAh[2];
+    bool x_dirty = true, w_dirty = true;
+    std::string why;                      // reason the engine is unavailable
+};
+
 template <typename S>
 struct Ctx : cmf_ctx {
     TcState tcs;
+    FdState fds;
     DevBuf<S> X, Hbuf, Wi, Wtmp, numW, denW, GS, Cf, numH, denH, tailC;
     DevBuf<int> progress, lockstep;
     int hals_grid = 0;
@@ -268,7 +283,132 @@ struct Ctx : cmf_ctx {
     }
 
     // ---------------------------------------------------------------- tcgen05 engine (fp32 only)
-    bool tc_active() const { return engine == 1 && tcs.ok; }
+    bool tc_active() const { return engine >= 1 && tcs.ok; }
+    bool fd_active() const { return engine == 2 && tcs.ok && fds.ok; }
+    bool fd_available() override {
+        if (!tc_available()) return false;
+        if (!fds.ok && !fds.tried) fd_setup();
+        if (fds.ok) { tcs.X_hi.free(); tcs.X_lo.free(); tcs.x_dirty = true; }   // the two engines never hold both copies of X
+        return fds.ok;
+    }
+    void mark_w_dirty() { tcs.w_dirty = true; fds.w_dirty = true; }
+
+    // ---------------------------------------------------------------- frequency-domain engine (fp32, K <= 64, L <= 256)
+    void fd_setup() {
+        if constexpr (!std::is_same<S, float>::value) { return; } else {
+            FdState &f = fds;
+            f.tried = true;
+            if (!tcs.ok) { f.why = "needs the tcgen05 engine"; return; }
+            if (K > fd::KQ || L > 256 || N < 16) { f.why = "needs K <= 64, L <= 256, N >= 16"; return; }
+            int B = 64, logB = 6;
+            while (B < 4 * L) { B *= 2; ++logB; }
+            if (const char *e = getenv("CMF_FD_B")) {
+                const int want = atoi(e);
+                if (want >= 2 * L && want >= 64 && want <= 1024 && (want & (want - 1)) == 0) { B = want; logB = 0; while ((1 << logB) < B) ++logB; }
+            }
+            f.B = B; f.logB = logB; f.V = B - (int)L + 1; f.F = B / 2 + 1;
+            f.nblk = cdiv(Tl, f.V);
+            f.nblkp = cdiv(f.nblk, 16) * 16;
+            const size_t xf = (size_t)f.F * (size_t)f.nblkp * 2 * (size_t)N + 64;
+            const size_t ah = (size_t)f.F * (size_t)f.nblkp * 2 * fd::MROWS + 64;
+            const size_t aw = (size_t)f.F * fd::MROWS * 2 * (size_t)N + 64;
+            const size_t of = (size_t)f.F * (size_t)f.nblkp * fd::MROWS, df = (size_t)f.F * fd::MROWS * (size_t)N;
+            const size_t need = 4 * (xf + ah + aw) + 4 * (of + df);
+            tcs.X_hi.free(); tcs.X_lo.free(); tcs.x_dirty = true;
+            size_t free_b = 0, total_b = 0;
+            CK(cudaMemGetInfo(&free_b, &total_b));
+            if (need + ((size_t)1 << 30) > free_b) { f.why = "not enough device memory for the spectrum of X"; return; }
+            f.Xf_hi.alloc(xf); f.Xf_lo.alloc(xf);
+            f.Ah_hi.alloc(ah); f.Ah_lo.alloc(ah);
+            f.Aw_hi.alloc(aw); f.Aw_lo.alloc(aw);
+            f.Of.alloc(of); f.Df.alloc(df);
+            __nv_bfloat16 *xs[2] = {f.Xf_hi.p, f.Xf_lo.p}, *as[2] = {f.Ah_hi.p, f.Ah_lo.p}, *ws[2] = {f.Aw_hi.p, f.Aw_lo.p};
+            const uint64_t rows = (uint64_t)f.F * (uint64_t)f.nblkp;
+            for (int i = 0; i < 2; ++i) {
+                f.mXfK[i] = make_map_2d(xs[i], (uint64_t)(2 * N), rows, (uint64_t)N * 4, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
+                f.mXfMN[i] = make_map_mn(xs[i], rows * 2, (uint64_t)N * 2, (uint64_t)cdiv(N, 64), tc::BK, 4);
+                f.mAw[i] = make_map_2d(ws[i], (uint64_t)(2 * N), (uint64_t)f.F * fd::MROWS, (uint64_t)N * 4, tc::BK, tc::BM, CU_TENSOR_MAP_SWIZZLE_64B);
+                f.mAh[i] = make_map_mn(as[i], rows * 2, (uint64_t)fd::MROWS * 2, 2, tc::BK, 2);
+            }
+            CK(cudaFuncSetAttribute(tc::tc_kernel<tc::TC_FQT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+            CK(cudaFuncSetAttribute(tc::tc_kernel<tc::TC_FQC>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+            const int big = (int)fd_smem(fd_cols_h()), small_ = (int)fd_smem(16);
+            CK(cudaFuncSetAttribute(fd::fft_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_));
+            CK(cudaFuncSetAttribute(fd::fft_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_));
+            CK(cudaFuncSetAttribute(fd::ifft_numW_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_));
+            CK(cudaFuncSetAttribute(fd::fft_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+            CK(cudaFuncSetAttribute(fd::ifft_numH_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+            f.x_dirty = f.w_dirty = true;
+            f.ok = true;
+        }
+    }
+    // component pairs per CTA of the H-side transforms: 32 (all 64 rows) while the tile fits in shared memory
+    int fd_cols_h() const { return fds.B <= 512 ? 32 : 16; }
+    size_t fd_smem(int C) const { return ((size_t)fds.B * (size_t)C + (size_t)fds.B / 2) * sizeof(float2); }
+
+    void fd_build_X() {
+        if constexpr (std::is_same<S, float>::value) {
+            FdState &f = fds;
+            if (!f.x_dirty) return;
+            dim3 grid((unsigned)f.nblkp, (unsigned)cdiv(N, 32));
+            fd::fft_x_kernel<<<grid, fd::NT, fd_smem(16), stream>>>(X.p, f.Xf_hi.p, f.Xf_lo.p, N, Tl + (L - 1), f.B, f.logB, f.V, f.nblkp);
+            post_launch();
+            f.x_dirty = false;
+        }
+    }
+    // numW through the spectrum of X (mult.jl:32)
+    void fd_corr() {
+        if constexpr (std::is_same<S, float>::value) {
+            FdState &f = fds;
+            fd_build_X();
+            const int C = fd_cols_h();
+            fd::fft_h_kernel<<<dim3((unsigned)f.nblkp, (unsigned)(32 / C)), fd::NT, fd_smem(C), stream>>>(
+                H, f.Ah_hi.p, f.Ah_lo.p, K, Tl, f.B, f.logB, f.V, f.nblkp, C);
+            post_launch();
+            tc::Params q = tc_base_params();
+            q.nprod = 3;
+            q.tiles_n = cdiv(N, tc::BN);
+            q.nkb = f.nblkp * 2 / tc::BK;
+            q.units = (int64_t)f.F * q.tiles_n;
+            q.fq_rows = f.nblkp * 2;
+            q.out = f.Df.p; q.Mrows = fd::MROWS; q.Ncols = N; q.ldo = N;
+            const unsigned grid = (unsigned)std::min<int64_t>(q.units, tcs.num_sms);
+            prof_begin(PROF_CORR);
+            tc::tc_kernel<tc::TC_FQC><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(f.mAh[0], f.mAh[1], f.mXfMN[0], f.mXfMN[1], q);
+            prof_end();
+            post_launch();
+            fd::ifft_numW_kernel<<<dim3((unsigned)cdiv(N, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(f.Df.p, numW.p, N, K, L, f.B, f.logB);
+            post_launch();
+        }
+    }
+    // numH through the spectrum of X (mult.jl:47)
+    void fd_transconv() {
+        if constexpr (std::is_same<S, float>::value) {
+            FdState &f = fds;
+            fd_build_X();
+            if (f.w_dirty) {
+                fd::fft_w_kernel<<<dim3((unsigned)cdiv(N, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(Wi.p, f.Aw_hi.p, f.Aw_lo.p, N, K, L, f.B, f.logB);
+                post_launch();
+                f.w_dirty = false;
+            }
+            tc::Params q = tc_base_params();
+            q.nprod = 3;
+            q.tiles_n = cdiv(f.nblkp, tc::BN);
+            q.nkb = cdiv(2 * N, tc::BK);
+            q.units = (int64_t)f.F * q.tiles_n;
+            q.fq_rows = f.nblkp;
+            q.out = f.Of.p;
+            const unsigned grid = (unsigned)std::min<int64_t>(q.units, tcs.num_sms);
+            prof_begin(PROF_TRANSCONV);
+            tc::tc_kernel<tc::TC_FQT><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(f.mAw[0], f.mAw[1], f.mXfK[0], f.mXfK[1], q);
+            prof_end();
+            post_launch();
+            const int C = fd_cols_h();
+            fd::ifft_numH_kernel<<<dim3((unsigned)f.nblk, (unsigned)(32 / C)), fd::NT, fd_smem(C), stream>>>(
+                f.Of.p, numH.p, K, Tl, f.B, f.logB, f.V, f.nblkp, C);
+            post_launch();
+        }
+    }
     bool tc_available() override {
         if (!tcs.ok && !tcs.tried) tc_setup();
         return tcs.ok;
@@ -291,7 +431,6 @@ struct Ctx : cmf_ctx {
             if (prop.major != 10) return;                         // tcgen05 needs sm_100
             t.num_sms = prop.multiProcessorCount;
             const size_t hw_elems = (size_t)((Tl + 2 * hal) * t.Kp + t.KLp + 64);
-            t.X_hi.alloc(X.n + 64); t.X_lo.alloc(X.n + 64);          // +64: the 3-D maps may touch one atom past the last row
             t.Hw_hi.alloc(hw_elems); t.Hw_lo.alloc(hw_elems);
             t.Hm_hi.alloc(hw_elems); t.Hm_lo.alloc(hw_elems);
             t.Wc_hi.alloc((size_t)(N * t.KLp)); t.Wc_lo.alloc((size_t)(N * t.KLp));
@@ -303,15 +442,13 @@ struct Ctx : cmf_ctx {
             if (GS.n < (size_t)(t.rows_u * t.rows_u)) GS.alloc((size_t)(t.rows_u * t.rows_u));
             // tensor maps (index 0 = hi plane, 1 = lo plane)
             __nv_bfloat16 *wc[2] = {t.Wc_hi.p, t.Wc_lo.p}, *hw[2] = {t.Hw_hi.p, t.Hw_lo.p}, *hm[2] = {t.Hm_hi.p, t.Hm_lo.p};
-            __nv_bfloat16 *wu[2] = {t.Wu_hi.p, t.Wu_lo.p}, *xs[2] = {t.X_hi.p, t.X_lo.p};
+            __nv_bfloat16 *wu[2] = {t.Wu_hi.p, t.Wu_lo.p};
             for (int i = 0; i < 2; ++i) {
                 t.mWc[i] = make_map_2d(wc[i], (uint64_t)t.KLp, (uint64_t)N, (uint64_t)t.KLp * 2, tc::BK, tc::BM, CU_TENSOR_MAP_SWIZZLE_64B);
                 // overlapping-row "window" map: row t starts at element t*Kp and is KLp long
                 t.mHw[i] = make_map_2d(hw[i], (uint64_t)t.KLp, (uint64_t)t.hrows, (uint64_t)t.Kp * 2, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
                 t.mHm[i] = make_map_mn(hm[i], (uint64_t)t.hrows, (uint64_t)t.Kp * 2, (uint64_t)(t.KLp / 64), tc::BK, 2);
                 t.mWu[i] = make_map_2d(wu[i], (uint64_t)N, (uint64_t)t.rows_u, (uint64_t)N * 2, tc::BK, tc::BM, CU_TENSOR_MAP_SWIZZLE_64B);
-                t.mXk[i] = make_map_2d(xs[i], (uint64_t)N, (uint64_t)(Tl + hal), (uint64_t)N * 2, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
-                t.mXmn[i] = make_map_mn(xs[i], (uint64_t)(Tl + hal), (uint64_t)N * 2, (uint64_t)cdiv(N, 64), tc::BK, 4);
                 // Gram: "X" = H rows from owned column 0 (owned + right halo), [t][Kp] MN-major
                 t.mHmn[i] = make_map_mn(hw[i] + hal * t.Kp, (uint64_t)(Tl + hal), (uint64_t)t.Kp * 2, (uint64_t)cdiv(t.Kp, 64), tc::BK, 4);
                 // denomH: A = C table rows (d'*Kp + k) x Kp, "X" = H rows from the left halo on, K-major
@@ -367,9 +504,20 @@ struct Ctx : cmf_ctx {
         return q;
     }
 
+    // the time-domain bf16 planes of X are allocated on first use: the frequency-domain engine never needs them
     void tc_split_X() {
         if constexpr (std::is_same<S, float>::value) {
             if (!tcs.ok || !tcs.x_dirty) return;
+            TcState &t = tcs;
+            if (t.X_hi.n == 0) {
+                const int64_t hal = L - 1;
+                t.X_hi.alloc(X.n + 64); t.X_lo.alloc(X.n + 64);      // +64: the 3-D maps may touch one atom past the last row
+                __nv_bfloat16 *xs[2] = {t.X_hi.p, t.X_lo.p};
+                for (int i = 0; i < 2; ++i) {
+                    t.mXk[i] = make_map_2d(xs[i], (uint64_t)N, (uint64_t)(Tl + hal), (uint64_t)N * 2, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
+                    t.mXmn[i] = make_map_mn(xs[i], (uint64_t)(Tl + hal), (uint64_t)N * 2, (uint64_t)cdiv(N, 64), tc::BK, 4);
+                }
+            }
             tc::split_plain_kernel<<<(unsigned)cdiv((int64_t)X.n, 256), 256, 0, stream>>>(X.p, tcs.X_hi.p, tcs.X_lo.p, (int64_t)X.n);
             post_launch();
             tcs.x_dirty = false;
@@ -397,6 +545,7 @@ struct Ctx : cmf_ctx {
     // numW via tensor cores (mult.jl:32)
     void tc_corr() {
         if constexpr (std::is_same<S, float>::value) {
+            if (fd_active()) { fd_corr(); return; }
             tc_split_X();
             tc_split_H(true);
             tc::Params q = tc_base_params();
@@ -487,6 +636,7 @@ struct Ctx : cmf_ctx {
     // numH via tensor cores (mult.jl:47)
     void tc_transconv() {
         if constexpr (std::is_same<S, float>::value) {
+            if (fd_active()) { fd_transconv(); return; }
             tc_split_X();
             tc_split_W();
             tc::Params q = tc_base_params();
@@ -677,6 +827,7 @@ struct Ctx : cmf_ctx {
     }
     void finish_data() {
         tcs.x_dirty = true;
+        fds.x_dirty = true;
         numH_valid = false;
         data_sumsq_local = data_sumsq();
         data_norm = std::sqrt(data_sumsq_local);
@@ -720,7 +871,7 @@ struct Ctx : cmf_ctx {
         CK(cudaMemcpyAsync(H + (lo - t0) * K, src, (size_t)((hi - lo) * K) * sizeof(S), cudaMemcpyHostToDevice, stream));
         CK(cudaStreamSynchronize(stream));
         have_factors = true;
-        tcs.w_dirty = true;
+        mark_w_dirty();
         numH_valid = false;
         gram_valid = false;
         pgd_stepW = pgd_stepH = 5.0;            // a new rule instance (pgd.jl:147-149)
@@ -739,7 +890,7 @@ struct Ctx : cmf_ctx {
         post_launch();
         CK(cudaStreamSynchronize(stream));
         have_factors = true;
-        tcs.w_dirty = true;
+        mark_w_dirty();
         numH_valid = false;
         gram_valid = false;
     }
@@ -762,7 +913,7 @@ struct Ctx : cmf_ctx {
         post_launch();
         scale_kernel<S><<<(unsigned)cdiv((int64_t)Hbuf.n, 256), 256, 0, stream>>>(Hbuf.p, (S)s, (int64_t)Hbuf.n);
         post_launch();
-        tcs.w_dirty = true;
+        mark_w_dirty();
         numH_valid = false;
         gram_valid = false;
     }
@@ -813,7 +964,7 @@ struct Ctx : cmf_ctx {
             launch_gemm<false>(GS.p, Wi.p, denW.p, KL(), N, KL(), KL(), N, N);   // denomW = G * Wi (mult.jl:28,33)
         }
         launch_mu(Wi.p, numW.p, denW.p, l1W, l2W, KL() * N);                  // mult.jl:37-38
-        tcs.w_dirty = true;
+        mark_w_dirty();
         numH_valid = false;
     }
 
@@ -897,7 +1048,7 @@ struct Ctx : cmf_ctx {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)N, 256, smem, stream>>>(GS.p, numW.p, Wi.p, K, L, N, (S)l1W, (S)l2W);   // hals.jl:90-112
         post_launch();
-        tcs.w_dirty = true;
+        mark_w_dirty();
         numH_valid = false;
     }
 
@@ -959,7 +1110,7 @@ struct Ctx : cmf_ctx {
         pgd_grad_kernel<S><<<(unsigned)cdiv(KL() * N, 256), 256, 0, stream>>>(denW.p, denW.p, numW.p, Wi.p, (S)l1W, (S)l2W, KL() * N);
         post_launch();
         pgd_step(Wi.p, denW.p, KL() * N, pgd_stepW);
-        tcs.w_dirty = true;
+        mark_w_dirty();
         numH_valid = false;
         pgd_adapt(loss_partial(), pgd_stepW);                                           // pgd.jl:244-252
     }
@@ -1294,8 +1445,11 @@ int cmf_set_stream(cmf_handle h, void *stream) {
 int cmf_set_engine(cmf_handle h, int engine) {
     return guarded([&] {
         REQUIRE(h, "null handle");
-        REQUIRE(engine == 0 || engine == 1, "engine must be 0 (SIMT) or 1 (tcgen05)");
-        if (engine == 1 && !h->tc_available())
+        REQUIRE(engine >= 0 && engine <= 2, "engine must be 0 (SIMT), 1 (tcgen05, time domain) or 2 (tcgen05, frequency domain)");
+        use(h);
+        if (engine == 2 && !h->fd_available())
+            throw CmfError(CMF_ERR_UNSUPPORTED, "the frequency-domain engine needs an fp32 handle with K <= 64, L <= 256, N % 8 == 0 on sm_100 and room for the spectrum of X");
+        if (engine >= 1 && !h->tc_available())
             throw CmfError(CMF_ERR_UNSUPPORTED, "tcgen05 engine needs an fp32 MultUpdate handle with K <= 128 and N % 8 == 0 on sm_100");
         h->engine = engine;
     });

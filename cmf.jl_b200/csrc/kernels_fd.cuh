@@ -1,0 +1,235 @@
+// Frequency-domain engine: the two data-sized contractions of the fit path,
+//   numH[k,t]   = sum_l sum_n W[k,n,l] X[n,t+l]      (src/common.jl:71-81, called at src/algs/mult.jl:47)
+//   numW[k,n,l] = sum_t H[k,t] X[n,t+l]              (src/algs/mult.jl:31-34)
+// are correlations along t, so in overlap-save blocks of length B (hop V = B-L+1) they become, per frequency f, one
+// small complex matrix product over the spectrum of X:
+//   numH^[k,b,f] = sum_n conj(W^[k,n,f]) X^[n,b,f]          numW^[k,n,f] = sum_b conj(Hz^[k,b,f]) X^[n,b,f]
+// (Hz = the V owned columns of block b, zero padded to B).  That cuts 2NKLT flops to ~8NKT(B/V) and makes the path
+// HBM-bound on the spectrum of X, which is constant over the fit and computed once (the circular-convolution idea of
+// src/common.jl:36-50, made exact by overlap-save).  The complex products run as real GEMMs on the tcgen05 kernel
+// (kernels_tc.cuh, modes TC_FQT / TC_FQC) with split-bf16 operands; this file holds the SIMT FFT kernels around them.
+//
+// Layouts (bf16 hi/lo planes unless noted; c = 0 real part, 1 imaginary part; rows m = k real, m = 64 + k imaginary):
+//   Xf [f][b][c][n]          B operand of both products (K-major for TC_FQT, MN-major for TC_FQC)
+//   Aw [f][m][c][n]          conj(W^) as the real 128 x 2N matrix [[Wr, Wi], [-Wi, Wr]]          (A of TC_FQT)
+//   Ah [f][b][c][m]          conj(Hz^) as the real 2nblk x 128 matrix, rows (b,c): [Hr | -Hi], [Hi | Hr]  (A of TC_FQC)
+//   Of [f][b][m]   fp32      numH^ (output of TC_FQT)
+//   Df [f][m][n]   fp32      numW^ (output of TC_FQC)
+//
+// FFT: in-place radix-2 decimation-in-frequency in shared memory over a tile d[B][C] of C independent complex columns
+// (column index fastest: conflict-free), output in bit-reversed order.  Two real sequences ride in one complex transform
+// (z = a + i b; A[f] = (Z[f] + conj(Z[B-f]))/2, B[f] = (Z[f] - conj(Z[B-f]))/(2i)), forward and inverse.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cmf {
+namespace fd {
+
+constexpr int NT = 256;      // threads per CTA
+constexpr int MROWS = 128;   // rows of the A operands / outputs per frequency (2 x 64 components)
+constexpr int KQ = 64;       // row offset of the imaginary parts
+
+__device__ __forceinline__ void make_twiddles(float2 *tw, int B) {
+    for (int m = threadIdx.x; m < B / 2; m += NT) {
+        float s, c;
+        sincospif(-2.0f * (float)m / (float)B, &s, &c);   // exp(-2 pi i m / B)
+        tw[m] = make_float2(c, s);
+    }
+}
+
+__device__ __forceinline__ int rev(int x, int logB) { return (int)(__brev((unsigned)x) >> (32 - logB)); }
+
+// log2(B) butterfly passes over d[B][C]; X[f] ends up in row rev(f).  INV uses the conjugate twiddles (no scaling).
+template <bool INV>
+__device__ __forceinline__ void fft_passes(float2 *d, const float2 *tw, int B, int logB, int C) {
+    const int c = threadIdx.x % C, j0 = threadIdx.x / C, jstep = NT / C;
+    for (int s = 0; s < logB; ++s) {
+        const int half = B >> (s + 1);
+        for (int j = j0; j < B / 2; j += jstep) {
+            const int pos = j & (half - 1), g = j >> (logB - 1 - s);
+            const int i0 = g * 2 * half + pos, i1 = i0 + half;
+            const float2 a = d[i0 * C + c], b = d[i1 * C + c];
+            float2 w = tw[pos << s];
+            if (INV) w.y = -w.y;
+            d[i0 * C + c] = make_float2(a.x + b.x, a.y + b.y);
+            const float tx = a.x - b.x, ty = a.y - b.y;
+            d[i1 * C + c] = make_float2(tx * w.x - ty * w.y, tx * w.y + ty * w.x);
+        }
+        __syncthreads();
+    }
+}
+
+// spectra of the two real sequences packed in one complex transform: A = (ar, ai), B = (br, bi) at frequency f
+__device__ __forceinline__ void unpack_pair(const float2 *d, int f, int B, int logB, int C, int p, float &ar, float &ai, float &br,
+                                            float &bi) {
+    const float2 z = d[rev(f, logB) * C + p], y = d[rev((B - f) & (B - 1), logB) * C + p];
+    ar = 0.5f * (z.x + y.x); ai = 0.5f * (z.y - y.y);
+    br = 0.5f * (z.y + y.y); bi = -0.5f * (z.x - y.x);
+}
+
+// the inverse of unpack_pair: rows f and B-f of Z = A + iB from the half spectra A = (re.x, im.x), B = (re.y, im.y)
+__device__ __forceinline__ void pack_pair(float2 *d, int f, int B, int C, int p, float2 re, float2 im) {
+    if (f == 0 || f == B / 2) im = make_float2(0.f, 0.f);          // real sequences: these bins are real
+    d[f * C + p] = make_float2(re.x - im.y, im.x + re.y);
+    if (f > 0 && f < B / 2) d[(B - f) * C + p] = make_float2(re.x + im.y, re.y - im.x);
+}
+
+__device__ __forceinline__ void store_split2(__nv_bfloat16 *hi, __nv_bfloat16 *lo, int64_t idx, float a, float b) {
+    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+    const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah)), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+    __nv_bfloat162 h, l;
+    h.x = ah; h.y = bh; l.x = al; l.y = bl;
+    *reinterpret_cast<__nv_bfloat162 *>(hi + idx) = h;
+    *reinterpret_cast<__nv_bfloat162 *>(lo + idx) = l;
+}
+
+// X[t][N] fp32 (xcols rows) -> Xf.  grid (nblkp, ceil(N/32)); 16 complex columns = 32 units per CTA.
+__global__ void __launch_bounds__(NT)
+fft_x_kernel(const float *__restrict__ X, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int64_t N, int64_t xcols,
+             int B, int logB, int V, int64_t nblkp) {
+    extern __shared__ float2 fd_smem[];
+    constexpr int C = 16;
+    float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;
+    const int64_t b = blockIdx.x;
+    const int p = threadIdx.x % C;
+    const int64_t n = (int64_t)blockIdx.y * 32 + 2 * p;
+    make_twiddles(tw, B);
+    for (int i = threadIdx.x / C; i < B; i += NT / C) {
+        const int64_t t = b * V + i;
+        float2 v = make_float2(0.f, 0.f);
+        if (t < xcols && n < N) v = *reinterpret_cast<const float2 *>(X + t * N + n);
+        d[i * C + p] = v;
+    }
+    __syncthreads();
+    fft_passes<false>(d, tw, B, logB, C);
+    if (n >= N) return;
+    for (int f = threadIdx.x / C; f <= B / 2; f += NT / C) {
+        float ar, ai, br, bi;
+        unpack_pair(d, f, B, logB, C, p, ar, ai, br, bi);
+        const int64_t r = ((int64_t)f * nblkp + b) * 2;
+        store_split2(hi, lo, r * N + n, ar, br);
+        store_split2(hi, lo, (r + 1) * N + n, ai, bi);
+    }
+}
+
+// H[t][K] fp32 (owned column 0 first; only the V owned columns of each block, zero padded) -> Ah.
+// grid (nblkp, 32 / C); C complex columns = 2C components per CTA.
+__global__ void __launch_bounds__(NT)
+fft_h_kernel(const float *__restrict__ H, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int64_t K, int64_t Tl,
+             int B, int logB, int V, int64_t nblkp, int C) {
+    extern __shared__ float2 fd_smem[];
+    float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;
+    const int64_t b = blockIdx.x;
+    const int p = threadIdx.x % C;
+    const int k = 2 * ((int)blockIdx.y * C + p);
+    make_twiddles(tw, B);
+    for (int i = threadIdx.x / C; i < B; i += NT / C) {
+        const int64_t t = b * V + i;
+        float2 v = make_float2(0.f, 0.f);
+        if (i < V && t < Tl) {
+            if (k < K) v.x = H[t * K + k];
+            if (k + 1 < K) v.y = H[t * K + k + 1];
+        }
+        d[i * C + p] = v;
+    }
+    __syncthreads();
+    fft_passes<false>(d, tw, B, logB, C);
+    for (int f = threadIdx.x / C; f <= B / 2; f += NT / C) {
+        float ar, ai, br, bi;
+        unpack_pair(d, f, B, logB, C, p, ar, ai, br, bi);
+        const int64_t r = (((int64_t)f * nblkp + b) * 2) * MROWS;
+        store_split2(hi, lo, r + k, ar, br);                       // row (b, re): [ Hr | -Hi ]
+        store_split2(hi, lo, r + KQ + k, -ai, -bi);
+        store_split2(hi, lo, r + MROWS + k, ai, bi);               // row (b, im): [ Hi |  Hr ]
+        store_split2(hi, lo, r + MROWS + KQ + k, ar, br);
+    }
+}
+
+// Wi[(l*K+k)][N] fp32 -> Aw.  grid (ceil(N/32), K).
+__global__ void __launch_bounds__(NT)
+fft_w_kernel(const float *__restrict__ Wi, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int64_t N, int64_t K,
+             int64_t L, int B, int logB) {
+    extern __shared__ float2 fd_smem[];
+    constexpr int C = 16;
+    float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;
+    const int64_t k = blockIdx.y;
+    const int p = threadIdx.x % C;
+    const int64_t n = (int64_t)blockIdx.x * 32 + 2 * p;
+    make_twiddles(tw, B);
+    for (int i = threadIdx.x / C; i < B; i += NT / C) {
+        float2 v = make_float2(0.f, 0.f);
+        if (i < L && n < N) v = *reinterpret_cast<const float2 *>(Wi + ((int64_t)i * K + k) * N + n);
+        d[i * C + p] = v;
+    }
+    __syncthreads();
+    fft_passes<false>(d, tw, B, logB, C);
+    if (n >= N) return;
+    for (int f = threadIdx.x / C; f <= B / 2; f += NT / C) {
+        float ar, ai, br, bi;
+        unpack_pair(d, f, B, logB, C, p, ar, ai, br, bi);
+        const int64_t re = ((int64_t)f * MROWS + k) * 2 * N, im = ((int64_t)f * MROWS + KQ + k) * 2 * N;
+        store_split2(hi, lo, re + n, ar, br);                      // row k:      [  Wr | Wi ]
+        store_split2(hi, lo, re + N + n, ai, bi);
+        store_split2(hi, lo, im + n, -ai, -bi);                    // row 64 + k: [ -Wi | Wr ]
+        store_split2(hi, lo, im + N + n, ar, br);
+    }
+}
+
+// Of[f][b][m] fp32 -> numH[t][K] (owned columns; V valid outputs per block).  grid (nblk, 32 / C).
+__global__ void __launch_bounds__(NT)
+ifft_numH_kernel(const float *__restrict__ Of, float *__restrict__ numH, int64_t K, int64_t Tl, int B, int logB, int V,
+                 int64_t nblkp, int C) {
+    extern __shared__ float2 fd_smem[];
+    float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;
+    const int64_t b = blockIdx.x;
+    const int p = threadIdx.x % C;
+    const int k = 2 * ((int)blockIdx.y * C + p);
+    make_twiddles(tw, B);
+    for (int f = threadIdx.x / C; f <= B / 2; f += NT / C) {
+        const float *o = Of + ((int64_t)f * nblkp + b) * MROWS;
+        pack_pair(d, f, B, C, p, *reinterpret_cast<const float2 *>(o + k), *reinterpret_cast<const float2 *>(o + KQ + k));
+    }
+    __syncthreads();
+    fft_passes<true>(d, tw, B, logB, C);
+    const float sc = 1.0f / (float)B;
+    for (int i = threadIdx.x / C; i < V; i += NT / C) {
+        const int64_t t = b * V + i;
+        if (t >= Tl) break;
+        const float2 z = d[rev(i, logB) * C + p];
+        if (k < K) numH[t * K + k] = z.x * sc;
+        if (k + 1 < K) numH[t * K + k + 1] = z.y * sc;
+    }
+}
+
+// Df[f][m][n] fp32 -> numW[(l*K+k)][N], l < L.  grid (ceil(N/32), K).
+__global__ void __launch_bounds__(NT)
+ifft_numW_kernel(const float *__restrict__ Df, float *__restrict__ numW, int64_t N, int64_t K, int64_t L, int B, int logB) {
+    extern __shared__ float2 fd_smem[];
+    constexpr int C = 16;
+    float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;
+    const int64_t k = blockIdx.y;
+    const int p = threadIdx.x % C;
+    const int64_t n = (int64_t)blockIdx.x * 32 + 2 * p;
+    make_twiddles(tw, B);
+    for (int f = threadIdx.x / C; f <= B / 2; f += NT / C) {
+        float2 re = make_float2(0.f, 0.f), im = re;
+        if (n < N) {
+            re = *reinterpret_cast<const float2 *>(Df + ((int64_t)f * MROWS + k) * N + n);
+            im = *reinterpret_cast<const float2 *>(Df + ((int64_t)f * MROWS + KQ + k) * N + n);
+        }
+        pack_pair(d, f, B, C, p, re, im);
+    }
+    __syncthreads();
+    fft_passes<true>(d, tw, B, logB, C);
+    if (n >= N) return;
+    const float sc = 1.0f / (float)B;
+    for (int l = threadIdx.x / C; l < L; l += NT / C) {
+        const float2 z = d[rev(l, logB) * C + p];
+        *reinterpret_cast<float2 *>(numW + ((int64_t)l * K + k) * N + n) = make_float2(z.x * sc, z.y * sc);
+    }
+}
+
+}  // namespace fd
+}  // namespace cmf

@@ -17,6 +17,9 @@
 //                                                                      (src/algs/mult.jl:31-34)
 //   TC_PLAIN  D[m, n]      = sum_k A[m][k] * B[n][k]                (K-major, SW64)  plain GEMM for the two small
 //             epilogue: outp[m*ldo + n] = D                          T-independent products G*W and W*W'
+// and the two per-frequency products of the frequency-domain engine (kernels_fd.cuh), one unit = (frequency f, column tile):
+//   TC_FQT    D[m, b]      = sum_(c,n) Aw[f][m][(c,n)] * Xf[f][b][(c,n)]   (K-major, SW64)   numH^ -> Of[f][b][m]
+//   TC_FQC    D[m, n]      = sum_(b,c) Ah[f][(b,c)][m] * Xf[f][(b,c)][n]   (MN-major, SW128) numW^ -> Df[f][m][n]
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -37,7 +40,7 @@ constexpr int THREADS = 128 + 32 * EPI_WARPS;        // warpgroup 0: warp 0 TMA,
 constexpr int PROMO = 8;                             // k-blocks accumulated in TMEM before promotion to registers
 constexpr int FLUSH_T = 65536;                       // TC_CORR: columns of t accumulated in fp32 registers (RN) before the fp64 flush
 
-enum Mode { TC_CONV = 0, TC_TRANS = 1, TC_CORR = 2, TC_PLAIN = 3 };
+enum Mode { TC_CONV = 0, TC_TRANS = 1, TC_CORR = 2, TC_PLAIN = 3, TC_FQT = 4, TC_FQC = 5 };
 
 struct Params {
     // work decomposition
@@ -65,6 +68,7 @@ struct Params {
     float *out;                // TRANS: numH [t][K];  PLAIN: output matrix
     int64_t Mrows, Ncols, ldo; // PLAIN: output bounds and row stride
     double *part;              // CORR: [split][L*K*N]
+    int64_t fq_rows;           // FQT / FQC: rows of the B map per frequency (nblk resp. 2*nblk)
 };
 
 // ---------------------------------------------------------------------------------- PTX wrappers
@@ -170,7 +174,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ float stage_s[(MODE == TC_CORR || MODE == TC_PLAIN) ? EPI_WARPS : 1][32][17];   // write-out staging
+    __shared__ float stage_s[(MODE == TC_CORR || MODE == TC_PLAIN || MODE == TC_FQC) ? EPI_WARPS : 1][32][17];   // write-out staging
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -200,7 +204,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
         return c > 0 ? c : 1;
     };
     auto segment_kb = [&](int64_t unit, int64_t seg, int64_t &kb0, int64_t &kbn) {
-        if (MODE == TC_CONV || MODE == TC_PLAIN) { kb0 = 0; kbn = p.nkb; }
+        if (MODE == TC_CONV || MODE == TC_PLAIN || MODE == TC_FQT || MODE == TC_FQC) { kb0 = 0; kbn = p.nkb; }
         else if (MODE == TC_TRANS) { kb0 = 0; kbn = p.groups * p.nblocks; }
         else {
             const int64_t sp = unit / (p.tiles_m * p.tiles_n);
@@ -224,6 +228,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                 int64_t mt = 0, nt = 0;
                 if (MODE == TC_CONV) { nt = unit % p.tiles_n; mt = unit / p.tiles_n; }          // nt: n tile, mt: t tile
                 if (MODE == TC_PLAIN) { nt = unit % p.tiles_n; mt = unit / p.tiles_n; }         // nt: column tile, mt: row tile
+                if (MODE == TC_FQT || MODE == TC_FQC) { nt = unit % p.tiles_n; mt = unit / p.tiles_n; }   // nt: column tile, mt: frequency
                 if (MODE == TC_CORR) { const int64_t r = unit % (p.tiles_m * p.tiles_n); if (p.corr_order == 0) { mt = r % p.tiles_m; nt = r / p.tiles_m; } else { nt = r % p.tiles_n; mt = r / p.tiles_n; } }
                 const int64_t nseg = n_segments(unit);
                 for (int64_t seg = 0; seg < nseg; ++seg) {
@@ -268,6 +273,19 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                             if (p.nprod == 3) tma_load_2d(st + A_PLANE, &mapA_lo, &full_bar[s], c0, rowA);
                             tma_load_2d(st + 2 * A_PLANE, &mapB_hi, &full_bar[s], c0, rowB);
                             tma_load_2d(st + 2 * A_PLANE + B_PLANE, &mapB_lo, &full_bar[s], c0, rowB);
+                        } else if (MODE == TC_FQT) {
+                            const int32_t k0 = (int32_t)(kb * BK);
+                            const int32_t rowB = (int32_t)(mt * p.fq_rows + nt * BN);
+                            tma_load_2d(st, &mapA_hi, &full_bar[s], k0, (int32_t)(mt * BM));
+                            tma_load_2d(st + A_PLANE, &mapA_lo, &full_bar[s], k0, (int32_t)(mt * BM));
+                            tma_load_2d(st + 2 * A_PLANE, &mapB_hi, &full_bar[s], k0, rowB);
+                            tma_load_2d(st + 2 * A_PLANE + B_PLANE, &mapB_lo, &full_bar[s], k0, rowB);
+                        } else if (MODE == TC_FQC) {
+                            const int32_t trow = (int32_t)(mt * p.fq_rows + kb * BK);
+                            tma_load_3d(st, &mapA_hi, &full_bar[s], 0, trow, 0);
+                            tma_load_3d(st + A_PLANE, &mapA_lo, &full_bar[s], 0, trow, 0);
+                            tma_load_3d(st + 2 * A_PLANE, &mapB_hi, &full_bar[s], 0, trow, (int32_t)(nt * 4));
+                            tma_load_3d(st + 2 * A_PLANE + B_PLANE, &mapB_lo, &full_bar[s], 0, trow, (int32_t)(nt * 4));
                         } else {
                             // MN-major operands come through 3-D maps (64 contiguous elements, t rows, 64-element
                             // groups), so one TMA per plane fills all the 4 KB swizzle atoms of the tile
@@ -286,7 +304,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
     } else if (warp == 1) {
         // ================================================================ MMA issuer
         if (lane == 0) {
-            constexpr uint32_t idesc = (MODE == TC_CORR) ? make_idesc(1, 1) : make_idesc(0, 0);
+            constexpr uint32_t idesc = (MODE == TC_CORR || MODE == TC_FQC) ? make_idesc(1, 1) : make_idesc(0, 0);
             int s = 0; uint32_t ph = 0;
             int64_t q = 0;   // promotion-chunk counter (TMEM double buffer)
             for (int64_t unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
@@ -309,7 +327,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
 #pragma unroll
                             for (int ks = 0; ks < BK / 16; ++ks) {
                                 uint64_t dah, dal, dbh, dbl;
-                                if (MODE == TC_CORR) {
+                                if (MODE == TC_CORR || MODE == TC_FQC) {
                                     // MN-major SW128: LBO = 4096 B between 64-element MN groups, SBO = 1024 B between 8-row K groups
                                     const uint32_t off = (uint32_t)ks * 2048u;
                                     dah = make_desc(a_hi + off, 4096, 1024, 2); dal = make_desc(a_lo + off, 4096, 1024, 2);
@@ -349,7 +367,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
         float racc[BN / 2];
         for (int64_t unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
             int64_t mt = 0, nt = 0, sp = 0;
-            if (MODE == TC_CONV || MODE == TC_PLAIN) { nt = unit % p.tiles_n; mt = unit / p.tiles_n; }
+            if (MODE == TC_CONV || MODE == TC_PLAIN || MODE == TC_FQT || MODE == TC_FQC) { nt = unit % p.tiles_n; mt = unit / p.tiles_n; }
             if (MODE == TC_CORR) { sp = unit / (p.tiles_m * p.tiles_n); const int64_t r = unit % (p.tiles_m * p.tiles_n); if (p.corr_order == 0) { mt = r % p.tiles_m; nt = r / p.tiles_m; } else { nt = r % p.tiles_n; mt = r / p.tiles_n; } }
             const int64_t nseg = n_segments(unit);
             for (int64_t seg = 0; seg < nseg; ++seg) {
@@ -410,9 +428,19 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                         }
                         if (p.G > 1) asm volatile("bar.sync 1, 256;" ::: "memory");
                     }
-                } else if (MODE == TC_PLAIN) {
-                    // fp32 store through the per-warp staging tile (coalesced 64-byte row segments)
+                } else if (MODE == TC_FQT) {
+                    // Of[f][b][m]: lanes hold consecutive rows m, so every column is one coalesced 128-byte store
+                    const int64_t b0 = nt * BN + col0;
+                    float *o = p.out + (mt * p.fq_rows + b0) * BM + row;
+#pragma unroll
+                    for (int c = 0; c < BN / 2; ++c)
+                        if (b0 + c < p.fq_rows) o[(int64_t)c * BM] = racc[c];
+                } else if (MODE == TC_PLAIN || MODE == TC_FQC) {
+                    // fp32 store through the per-warp staging tile (coalesced 64-byte row segments);
+                    // FQC: one 128-row output matrix per frequency, Df[f][m][n]
                     float(*stg)[17] = stage_s[warp - 4];
+                    const int64_t mrow0 = (MODE == TC_FQC) ? 0 : mt * BM;
+                    float *outp = p.out + ((MODE == TC_FQC) ? mt * BM * p.ldo : 0);
 #pragma unroll
                     for (int cc = 0; cc < BN / 2; cc += 16) {
 #pragma unroll
@@ -421,9 +449,9 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
 #pragma unroll 1
                         for (int it = 0; it < 16; ++it) {
                             const int r = it * 2 + (lane >> 4), c = lane & 15;
-                            const int64_t m = mt * BM + quarter * 32 + r;
+                            const int64_t m = mrow0 + quarter * 32 + r;
                             const int64_t n = nt * BN + col0 + cc + c;
-                            if (m < p.Mrows && n < p.Ncols) p.out[m * p.ldo + n] = stg[r][c];
+                            if (m < p.Mrows && n < p.Ncols) outp[m * p.ldo + n] = stg[r][c];
                         }
                         __syncwarp();
                     }
