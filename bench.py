@@ -321,26 +321,44 @@ def run_ours(args, cfg, name):
     Fc_rank = Fc / world
     achieved_tf = Fc_rank / (per_launch_ms * 1e-3) / 1e12
     contr_share = sum(v[0] for v in prof.values()) / (ms_per_step * args.steps) if ms > 0 else None
-    # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from one `ncu --set full` capture of this very
-    # workload (profiles/r1_ncu_full_corr_c4_lockstep.md); only known for the 1-GPU c4 correlation launch
-    traffic, traffic_note = None, "no ncu capture for this workload / kernel"
-    if name == "c4" and world == 1 and dom == "corr":
-        traffic = 128.9e9
-        traffic_note = ("ncu --set full, c4, 1 GPU, per launch: 113.9 GB read + 15.1 GB written vs 68.7 GB algorithmic "
-                        "(X hi/lo planes once); profiles/r1_ncu_full_corr_c4_lockstep.md")
-    roofline = {
-        "bound": "tensor", "kernel": dom, "achieved": achieved_tf, "peak": pk["tensor"], "unit": "TFLOP/s",
-        "frac": achieved_tf / pk["tensor"], "traffic": traffic, "traffic_note": traffic_note,
-        "peak_source": f"{pk['src']} bf16 sustained",
-        "flops_per_launch": Fc_rank, "ms_per_launch": per_launch_ms,
-        "executed": {"tflops": 3.0 * achieved_tf if engine == 1 else achieved_tf,
-                     "frac": (3.0 * achieved_tf if engine == 1 else achieved_tf) / pk["tensor"],
-                     "note": "bf16 tensor FLOPs actually issued: every fp32 product is 3 bf16 MMAs (hi*hi + hi*lo + lo*hi)"},
-        "note": "arithmetic intensity K*L/2 = %d FLOP/B >> machine balance: the contraction is tensor/FMA bound, "
-                "not HBM bound (SURVEY.md section 8d); algorithmic FLOPs 2*N*K*(L*T - L(L-1)/2) per contraction launch" % (K * L // 2),
-        "kernel_ms": {k: {"total_ms": v[0], "launches": v[1]} for k, v in prof.items()},
-        "contraction_share_of_step": contr_share,
-    }
+    Tl = t1 - t0
+    if engine == 2:
+        # frequency-domain engine: the dominant kernel streams the spectrum of X once per launch and is HBM-bound.
+        # Algorithmic bytes per launch (one contraction): X once + the small operand + the output,
+        # in fp32; the bytes actually moved are the bf16 hi/lo spectrum planes (B/V * (B/2+1)/(B/2) ~ 1.25x of X).
+        Bfft = 64
+        while Bfft < 4 * L:
+            Bfft *= 2
+        V, F = Bfft - L + 1, Bfft // 2 + 1
+        nblkp = -(-(-(-Tl // V)) // 16) * 16
+        alg_bytes = 4.0 * (N * Tl + K * Tl + K * N * L)
+        moved_bytes = 4.0 * F * nblkp * 2 * N
+        exec_flops = 3.0 * 2.0 * 128 * (2 * N) * nblkp * F
+        achieved_gbs = alg_bytes / (per_launch_ms * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture of this workload
+        traffic, traffic_note = None, "no ncu capture for this workload / kernel"
+        if name == "c4" and world == 1 and dom in NCU_TRAFFIC_C4_FD:
+            traffic, traffic_note = NCU_TRAFFIC_C4_FD[dom]
+        roofline = {
+            "bound": "hbm", "kernel": dom + (" (TC_FQT: per-frequency conj(W^) X^)" if dom == "transconv" else " (TC_FQC: per-frequency conj(H^) X^)"),
+            "achieved": achieved_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved_gbs / pk["hbm"],
+            "traffic": traffic, "traffic_note": traffic_note, "peak_source": f"{pk['src']} HBM copy bandwidth",
+            "bytes_per_launch": alg_bytes, "ms_per_launch": per_launch_ms,
+            "moved": {"bytes_per_launch": moved_bytes, "gbs": moved_bytes / (per_launch_ms * 1e-3) / 1e9,
+                      "frac": moved_bytes / (per_launch_ms * 1e-3) / 1e9 / pk["hbm"],
+                      "note": "size of the spectrum planes the kernel streams (block length %d, hop %d, %d blocks)" % (Bfft, V, nblkp)},
+            "tensor": {"executed_tflops": exec_flops / (per_launch_ms * 1e-3) / 1e12,
+                       "frac": exec_flops / (per_launch_ms * 1e-3) / 1e12 / pk["tensor"],
+                       "equivalent_time_domain_tflops": achieved_tf,
+                       "note": "bf16 MMAs issued (3 per product) vs sustained bf16 peak; 'equivalent' = the time-domain "
+                               "2*N*K*L*T FLOPs this launch replaces"},
+            "note": "overlap-save spectrum of X (constant over the fit) turns the shifted contraction into one 128 x 2N (resp. "
+                    "2nblk) real GEMM per frequency: ~8.5 instead of 2*L flops per element of X, so HBM binds",
+            "kernel_ms": {k: {"total_ms": v[0], "launches": v[1]} for k, v in prof.items()},
+            "contraction_share_of_step": contr_share,
+        }
+    else:
+        roofline = _tensor_roofline(name, world, dom, engine, achieved_tf, pk, Fc_rank, per_launch_ms, K, L, prof, contr_share)
     B = bytes_iteration(N, T, K, L) / world
     hbm = {"achieved": B / (ms_per_step * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
            "frac": B / (ms_per_step * 1e-3) / 1e9 / pk["hbm"],
@@ -360,7 +378,9 @@ def run_ours(args, cfg, name):
         "config": {"workload": f"{name}: MU N={N} T={T} K={K} L={L}", "alg": "mult", "parallelism": f"T-shard x{world}",
                    "l2": "inputs (X = %.1f GiB per GPU) exceed the 126 MB L2" % (4.0 * N * (t1 - t0) / 2 ** 30),
                    "seeds": {"data": SEED_DATA, "init": SEED_INIT}, "p_h": P_H, "noise": NOISE,
-                   "engine": "tcgen05 split-bf16 (3 MMAs per product, fp32 accumulate)" if engine == 1 else "SIMT fp32",
+                   "engine": {0: "SIMT fp32", 1: "tcgen05 split-bf16, time domain (3 MMAs per product, fp32 accumulate)",
+                              2: "tcgen05 split-bf16, frequency domain (overlap-save spectrum of X, SIMT FFTs, per-frequency "
+                                 "complex products with 3 MMAs per product)"}[engine],
                    "loss": ("algebraic expansion ||X||^2 - 2<numH,H> + <WW',HtHt'> (exact identity, falls back to the direct "
                             "pass below 25% loss)" if args.loss_mode == 1 else "direct conv + residual pass")},
         "value_direct_loss": value_direct,
@@ -370,6 +390,33 @@ def run_ours(args, cfg, name):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _tensor_roofline(name, world, dom, engine, achieved_tf, pk, Fc_rank, per_launch_ms, K, L, prof, contr_share):
+    # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from one `ncu --set full` capture of this very
+    # workload (profiles/r1_ncu_full_corr_c4_lockstep.md); only known for the 1-GPU c4 correlation launch
+    traffic, traffic_note = None, "no ncu capture for this workload / kernel"
+    if name == "c4" and world == 1 and dom == "corr":
+        traffic = 128.9e9
+        traffic_note = ("ncu --set full, c4, 1 GPU, per launch: 113.9 GB read + 15.1 GB written vs 68.7 GB algorithmic "
+                        "(X hi/lo planes once); profiles/r1_ncu_full_corr_c4_lockstep.md")
+    return {
+        "bound": "tensor", "kernel": dom, "achieved": achieved_tf, "peak": pk["tensor"], "unit": "TFLOP/s",
+        "frac": achieved_tf / pk["tensor"], "traffic": traffic, "traffic_note": traffic_note,
+        "peak_source": f"{pk['src']} bf16 sustained",
+        "flops_per_launch": Fc_rank, "ms_per_launch": per_launch_ms,
+        "executed": {"tflops": 3.0 * achieved_tf if engine == 1 else achieved_tf,
+                     "frac": (3.0 * achieved_tf if engine == 1 else achieved_tf) / pk["tensor"],
+                     "note": "bf16 tensor FLOPs actually issued: every fp32 product is 3 bf16 MMAs (hi*hi + hi*lo + lo*hi)"},
+        "note": "arithmetic intensity K*L/2 = %d FLOP/B >> machine balance: the contraction is tensor/FMA bound, "
+                "not HBM bound (SURVEY.md section 8d); algorithmic FLOPs 2*N*K*(L*T - L(L-1)/2) per contraction launch" % (K * L // 2),
+        "kernel_ms": {k: {"total_ms": v[0], "launches": v[1]} for k, v in prof.items()},
+        "contraction_share_of_step": contr_share,
+    }
+
+
+# per-launch DRAM traffic of the frequency-domain kernels at c4 on one GPU, from `ncu --set full` (profiles/); filled per round
+NCU_TRAFFIC_C4_FD = {}
 
 
 def _set_sharded_factors(shard, fitter, W, H_owned, t0):

@@ -48,6 +48,9 @@ template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
     void alloc(size_t count) {
         free();
         n = count;
@@ -109,6 +112,7 @@ struct cmf_ctx {
     virtual void get_data(void *X_out, int with_halo) = 0;
     virtual bool tc_available() = 0;
     virtual bool fd_available() = 0;
+    virtual void fd_release() = 0;
     virtual void set_data(const void *X, int64_t first_col) = 0;
     virtual void synth_data(uint64_t seed, int64_t Kt, int64_t Lt, double p_h, double noise) = 0;
     virtual double data_sumsq() = 0;
@@ -215,6 +219,11 @@ struct FdState {
     CUtensorMap mXfK[2], mXfMN[2], mAw[2], mAh[2];
     bool x_dirty = true, w_dirty = true;
     std::string why;                      // reason the engine is unavailable
+    void release() {
+        Xf_hi.free(); Xf_lo.free(); Ah_hi.free(); Ah_lo.free(); Aw_hi.free(); Aw_lo.free(); Of.free(); Df.free();
+        ok = tried = false;
+        x_dirty = w_dirty = true;
+    }
 };
 
 template <typename S>
@@ -278,7 +287,16 @@ struct Ctx : cmf_ctx {
         loss_part.alloc((size_t)std::max(2 * conv_blocks_max, 4096));
         // the tensor-core engine is set up right away only where it is the default (big contractions); small problems
         // build it lazily on cmf_set_engine(h, 1)
-        if (sizeof(S) == 4 && N >= 256 && Tl >= 4096 && K * L >= 256) tc_setup();
+        if (sizeof(S) == 4 && N >= 256 && Tl >= 4096 && K * L >= 256) {
+            tc_setup();
+            // frequency-domain engine by default where it wins: enough lags that 2*L direct flops per element exceed the
+            // ~8.5 of the per-frequency products, and room for the spectrum of X (CMF_ENGINE_DEFAULT=1 keeps engine 1)
+            const char *e = getenv("CMF_ENGINE_DEFAULT");
+            if (tcs.ok && engine == 1 && L >= 8 && K <= fd::KQ && !(e && atoi(e) == 1)) {
+                fd_setup();
+                if (fds.ok) engine = 2;
+            }
+        }
         CK(cudaStreamSynchronize(stream));
     }
 
@@ -291,6 +309,7 @@ struct Ctx : cmf_ctx {
         if (fds.ok) { tcs.X_hi.free(); tcs.X_lo.free(); tcs.x_dirty = true; }   // the two engines never hold both copies of X
         return fds.ok;
     }
+    void fd_release() override { fds.release(); }
     void mark_w_dirty() { tcs.w_dirty = true; fds.w_dirty = true; }
 
     // ---------------------------------------------------------------- frequency-domain engine (fp32, K <= 64, L <= 256)
@@ -1449,6 +1468,7 @@ int cmf_set_engine(cmf_handle h, int engine) {
         use(h);
         if (engine == 2 && !h->fd_available())
             throw CmfError(CMF_ERR_UNSUPPORTED, "the frequency-domain engine needs an fp32 handle with K <= 64, L <= 256, N % 8 == 0 on sm_100 and room for the spectrum of X");
+        if (engine < 2) h->fd_release();               // the spectrum of X and the time-domain planes never coexist
         if (engine >= 1 && !h->tc_available())
             throw CmfError(CMF_ERR_UNSUPPORTED, "tcgen05 engine needs an fp32 MultUpdate handle with K <= 128 and N % 8 == 0 on sm_100");
         h->engine = engine;

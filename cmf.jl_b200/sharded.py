@@ -100,7 +100,8 @@ class DeviceShard:
         self.send_left, self.send_right, self.recv_left, self.recv_right = v
 
     def set_engine(self, engine):
-        """0 = SIMT kernels, 1 = tcgen05 tensor-core kernels (raises if the handle cannot use them)."""
+        """0 = SIMT kernels, 1 = tcgen05 kernels in the time domain, 2 = frequency-domain engine (spectrum of X +
+        per-frequency tcgen05 products); raises if the handle cannot use the engine."""
         check(_lib.load().cmf_set_engine(self._h, int(engine)))
 
     def set_loss_mode(self, mode):

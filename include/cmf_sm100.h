@@ -167,8 +167,13 @@ int cmf_set_stream(cmf_handle h, void *stream);
  * `which` (0 = conv/residual/loss, 1 = transposed conv for numH, 2 = correlation for numW). */
 int cmf_profile(cmf_handle h, int enable);
 int cmf_profile_read(cmf_handle h, int which, double *ms_total, int64_t *count);
-/* Selects the contraction engine: 0 = SIMT kernels (fp64 and fp32), 1 = tcgen05 tensor-core
- * kernels (fp32 data, split-bf16 operands) where available.  Default: best available. */
+/* Selects the contraction engine: 0 = SIMT kernels (fp64 and fp32); 1 = tcgen05 tensor-core kernels in the
+ * time domain (fp32 data, split-bf16 operands, K <= 128, N % 8 == 0); 2 = frequency-domain engine: numW
+ * (mult.jl:32) and numH (mult.jl:47) through the overlap-save spectrum of X (computed once per data set, the
+ * circular-convolution idea of src/common.jl:36-50 made exact) with the per-frequency complex products on
+ * tcgen05 -- HBM-bound instead of tensor-bound (fp32, K <= 64, L <= 256, room for ~1.25x the size of X in
+ * bf16 hi/lo planes; the time-domain planes of engine 1 are released).  Returns CMF_ERR_UNSUPPORTED when the
+ * handle cannot use the engine.  Default: best available (2 for large problems with L >= 8, else 1, else 0). */
 int cmf_set_engine(cmf_handle h, int engine);
 /* How the tcgen05 engine evaluates the loss inside the iteration (mult.jl:55-57): 0 = direct fused
  * conv + residual pass (default; always used by the SIMT/fp64 engines), 1 = the exact identity
@@ -178,7 +183,7 @@ int cmf_set_engine(cmf_handle h, int engine);
  * identity cancels like 1/loss^2, (measured error ~2e-6/loss^2 relative), so callers switch back to 0 when the relative loss drops below 25%
  * (cmf_fit and the sharded host loop do). */
 int cmf_set_loss_mode(cmf_handle h, int mode);
-/* The engine currently selected (0 / 1). */
+/* The engine currently selected (0 / 1 / 2). */
 int cmf_get_engine(cmf_handle h, int *engine_out);
 
 /* ---- primitives (tests; one-shot, host in / host out) ----------------------------------- */

@@ -38,7 +38,7 @@ def _properties(cmf, cfg, iters):
     f = cmf.ShardedMultFit(s)
     f.setup_data_norm()
     f.rescale_init()
-    assert s.get_engine() == 1                      # tcgen05 engine selected by default at these sizes
+    assert s.get_engine() == 2                      # frequency-domain tcgen05 engine selected by default at these sizes
     a = s.data_sumsq()
     # direct loss (TC_CONV) before anything else
     ss_direct = s.loss_partial()
@@ -106,7 +106,7 @@ def test_config3_sharding_invariance(cmf):
         return np.asarray(hist)
 
     a, b = run(1), run(4)
-    assert np.allclose(a, b, rtol=2e-6), (a, b)
+    assert np.allclose(a, b, rtol=1e-5), (a, b)       # shards cut the overlap-save blocks differently: rounding differs
 
 
 def test_config4_full_size_properties(cmf):
