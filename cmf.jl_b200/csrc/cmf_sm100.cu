@@ -214,15 +214,16 @@ struct FdState {
     bool ok = false, tried = false;
     int B = 0, logB = 0, V = 0, F = 0;
     int64_t nblk = 0, nblkp = 0;          // overlap-save blocks covering the owned columns; padded to a multiple of 16
-    DevBuf<__nv_bfloat16> Xf_hi, Xf_lo, Ah_hi, Ah_lo, Aw_hi, Aw_lo;
-    DevBuf<float> Of, Df;
-    CUtensorMap mXfK[2], mXfMN[2], mAw[2], mAh[2];
-    bool x_dirty = true, w_dirty = true;
+    DevBuf<__nv_bfloat16> Xf_hi, Xf_lo, Ah_hi, Ah_lo, Aw_hi, Aw_lo, Hf_hi, Hf_lo;
+    DevBuf<float> Of, Df, Gf;
+    CUtensorMap mXfK[2], mXfMN[2], mAw[2], mAh[2], mHfMN[2];
+    bool x_dirty = true, w_dirty = true, h_dirty = true;   // h_dirty: Ah does not hold the spectrum of the current H
     std::string why;                      // reason the engine is unavailable
     void release() {
         Xf_hi.free(); Xf_lo.free(); Ah_hi.free(); Ah_lo.free(); Aw_hi.free(); Aw_lo.free(); Of.free(); Df.free();
+        Hf_hi.free(); Hf_lo.free(); Gf.free();
         ok = tried = false;
-        x_dirty = w_dirty = true;
+        x_dirty = w_dirty = h_dirty = true;
     }
 };
 
@@ -332,7 +333,8 @@ struct Ctx : cmf_ctx {
             const size_t ah = (size_t)f.F * (size_t)f.nblkp * 2 * fd::MROWS + 64;
             const size_t aw = (size_t)f.F * fd::MROWS * 2 * (size_t)N + 64;
             const size_t of = (size_t)f.F * (size_t)f.nblkp * fd::MROWS, df = (size_t)f.F * fd::MROWS * (size_t)N;
-            const size_t need = 4 * (xf + ah + aw) + 4 * (of + df);
+            const size_t hf = (size_t)f.F * (size_t)f.nblkp * 2 * fd::KQ + 256, gf = (size_t)f.F * fd::MROWS * fd::KQ;
+            const size_t need = 4 * (xf + ah + aw + hf) + 4 * (of + df + gf);
             tcs.X_hi.free(); tcs.X_lo.free(); tcs.x_dirty = true;
             size_t free_b = 0, total_b = 0;
             CK(cudaMemGetInfo(&free_b, &total_b));
@@ -341,6 +343,7 @@ struct Ctx : cmf_ctx {
             f.Ah_hi.alloc(ah); f.Ah_lo.alloc(ah);
             f.Aw_hi.alloc(aw); f.Aw_lo.alloc(aw);
             f.Of.alloc(of); f.Df.alloc(df);
+            f.Hf_hi.alloc(hf); f.Hf_lo.alloc(hf); f.Gf.alloc(gf);
             __nv_bfloat16 *xs[2] = {f.Xf_hi.p, f.Xf_lo.p}, *as[2] = {f.Ah_hi.p, f.Ah_lo.p}, *ws[2] = {f.Aw_hi.p, f.Aw_lo.p};
             const uint64_t rows = (uint64_t)f.F * (uint64_t)f.nblkp;
             for (int i = 0; i < 2; ++i) {
@@ -348,21 +351,23 @@ struct Ctx : cmf_ctx {
                 f.mXfMN[i] = make_map_mn(xs[i], rows * 2, (uint64_t)N * 2, (uint64_t)cdiv(N, 64), tc::BK, 4);
                 f.mAw[i] = make_map_2d(ws[i], (uint64_t)(2 * N), (uint64_t)f.F * fd::MROWS, (uint64_t)N * 4, tc::BK, tc::BM, CU_TENSOR_MAP_SWIZZLE_64B);
                 f.mAh[i] = make_map_mn(as[i], rows * 2, (uint64_t)fd::MROWS * 2, 2, tc::BK, 2);
+                f.mHfMN[i] = make_map_mn(i == 0 ? f.Hf_hi.p : f.Hf_lo.p, rows * 2, (uint64_t)fd::KQ * 2, 1, tc::BK, 4);
             }
             CK(cudaFuncSetAttribute(tc::tc_kernel<tc::TC_FQT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
             CK(cudaFuncSetAttribute(tc::tc_kernel<tc::TC_FQC>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
             const int big = (int)fd_smem(fd_cols_h()), small_ = (int)fd_smem(16);
             CK(cudaFuncSetAttribute(fd::fft_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_));
             CK(cudaFuncSetAttribute(fd::fft_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_));
-            CK(cudaFuncSetAttribute(fd::ifft_numW_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_));
+            CK(cudaFuncSetAttribute(fd::ifft_numW_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_));
+            CK(cudaFuncSetAttribute(fd::ifft_numW_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_));
             CK(cudaFuncSetAttribute(fd::fft_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
             CK(cudaFuncSetAttribute(fd::ifft_numH_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-            f.x_dirty = f.w_dirty = true;
+            f.x_dirty = f.w_dirty = f.h_dirty = true;
             f.ok = true;
         }
     }
     // component pairs per CTA of the H-side transforms: 32 (all 64 rows) while the tile fits in shared memory
-    int fd_cols_h() const { return fds.B <= 512 ? 32 : 16; }
+    int fd_cols_h() const { return 16; }
     size_t fd_smem(int C) const { return ((size_t)fds.B * (size_t)C + (size_t)fds.B / 2) * sizeof(float2); }
 
     void fd_build_X() {
@@ -380,10 +385,7 @@ struct Ctx : cmf_ctx {
         if constexpr (std::is_same<S, float>::value) {
             FdState &f = fds;
             fd_build_X();
-            const int C = fd_cols_h();
-            fd::fft_h_kernel<<<dim3((unsigned)f.nblkp, (unsigned)(32 / C)), fd::NT, fd_smem(C), stream>>>(
-                H, f.Ah_hi.p, f.Ah_lo.p, K, Tl, f.B, f.logB, f.V, f.nblkp, C);
-            post_launch();
+            fd_spectrum_H();
             tc::Params q = tc_base_params();
             q.nprod = 3;
             q.tiles_n = cdiv(N, tc::BN);
@@ -396,7 +398,42 @@ struct Ctx : cmf_ctx {
             tc::tc_kernel<tc::TC_FQC><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(f.mAh[0], f.mAh[1], f.mXfMN[0], f.mXfMN[1], q);
             prof_end();
             post_launch();
-            fd::ifft_numW_kernel<<<dim3((unsigned)cdiv(N, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(f.Df.p, numW.p, N, K, L, f.B, f.logB);
+            fd::ifft_numW_kernel<float><<<dim3((unsigned)cdiv(N, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(f.Df.p, numW.p, N, N, K, L, f.B, f.logB);
+            post_launch();
+        }
+    }
+    // Ah = spectrum of the owned columns of the current H, block by block (shared by numW and the Gram partial)
+    void fd_spectrum_H() {
+        if constexpr (std::is_same<S, float>::value) {
+            FdState &f = fds;
+            if (!f.h_dirty) return;
+            const int C = fd_cols_h();
+            fd::fft_h_kernel<<<dim3((unsigned)f.nblkp, (unsigned)(32 / C)), fd::NT, fd_smem(C), stream>>>(
+                H, f.Ah_hi.p, f.Ah_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V, f.nblkp, C, 0);
+            post_launch();
+            f.h_dirty = false;
+        }
+    }
+    // Gram partial Rg[d][k][k'] = sum_u H[u][k] H[u+d][k'] through the spectrum of H (u owned, u+d into the right halo)
+    void fd_gram() {
+        if constexpr (std::is_same<S, float>::value) {
+            FdState &f = fds;
+            fd_spectrum_H();
+            const int C = fd_cols_h();
+            fd::fft_h_kernel<<<dim3((unsigned)f.nblkp, (unsigned)(32 / C)), fd::NT, fd_smem(C), stream>>>(
+                H, f.Hf_hi.p, f.Hf_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V, f.nblkp, C, 1);
+            post_launch();
+            tc::Params q = tc_base_params();
+            q.nprod = 3;
+            q.tiles_n = 1;
+            q.nkb = f.nblkp * 2 / tc::BK;
+            q.units = (int64_t)f.F;
+            q.fq_rows = f.nblkp * 2;
+            q.out = f.Gf.p; q.Mrows = fd::MROWS; q.Ncols = K; q.ldo = fd::KQ;
+            const unsigned grid = (unsigned)std::min<int64_t>(q.units, tcs.num_sms);
+            tc::tc_kernel<tc::TC_FQC><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(f.mAh[0], f.mAh[1], f.mHfMN[0], f.mHfMN[1], q);
+            post_launch();
+            fd::ifft_numW_kernel<double><<<dim3((unsigned)cdiv(K, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(f.Gf.p, exch1.p, K, fd::KQ, K, L, f.B, f.logB);
             post_launch();
         }
     }
@@ -892,7 +929,7 @@ struct Ctx : cmf_ctx {
         have_factors = true;
         mark_w_dirty();
         numH_valid = false;
-        gram_valid = false;
+        gram_valid = false; fds.h_dirty = true;
         pgd_stepW = pgd_stepH = 5.0;            // a new rule instance (pgd.jl:147-149)
         pgd_cur_loss = data_norm;
     }
@@ -911,7 +948,7 @@ struct Ctx : cmf_ctx {
         have_factors = true;
         mark_w_dirty();
         numH_valid = false;
-        gram_valid = false;
+        gram_valid = false; fds.h_dirty = true;
     }
 
     void init_scale_partials(double out[2]) override {
@@ -934,7 +971,7 @@ struct Ctx : cmf_ctx {
         post_launch();
         mark_w_dirty();
         numH_valid = false;
-        gram_valid = false;
+        gram_valid = false; fds.h_dirty = true;
     }
 
     void get_factors(void *Wo, void *Ho) override {
@@ -960,7 +997,8 @@ struct Ctx : cmf_ctx {
     }
 
     void gram_partial() {
-        if (tc_active()) { tc_split_H(true); tc_split_H(false); tc_gram(); }
+        if (fd_active()) fd_gram();
+        else if (tc_active()) { tc_split_H(true); tc_split_H(false); tc_gram(); }
         else launch_corr(H, K, K, Tl + (L - 1), nsplit_g, split_g, nullptr, exch1.p);
         if (L > 1) {
             h_tail_kernel<S><<<(unsigned)cdiv((L - 1) * K, 256), 256, 0, stream>>>(H, exch1.p + L * K * K, K, L, Tl, is_last ? 1 : 0);
@@ -1003,6 +1041,25 @@ struct Ctx : cmf_ctx {
         post_launch();
     }
 
+    // truncated tail of denomH (the last L-1 columns, mult.jl:44,48 with the conv cut at T) from S2 = W W' in GS
+    DevBuf<double> tail_part;
+    void launch_denomH_tail() {
+        const int nb = (int)cdiv((2 * L - 1) * K, 256);
+        const size_t smem = (size_t)8 * (size_t)(L - 1) * sizeof(double);
+        if (getenv("CMF_TAIL_DIRECT") || smem > 48 * 1024) {          // literal form (kept for A/B and very long lags)
+            dim3 grid((unsigned)(L - 1), (unsigned)K);
+            denomH_tail_kernel<S><<<grid, 256, 0, stream>>>(GS.p, H, denH.p, K, L, Tl, -(L - 1), s2_ks, s2_ld);
+            post_launch();
+            return;
+        }
+        const size_t need = (size_t)nb * (size_t)(L - 1) * (size_t)K;
+        if (tail_part.n < need) tail_part.alloc(need);
+        denomH_tail_prefix_kernel<S><<<dim3((unsigned)nb, (unsigned)K), 256, smem, stream>>>(GS.p, H, tail_part.p, K, L, Tl, -(L - 1), s2_ks, s2_ld);
+        post_launch();
+        denomH_tail_reduce_kernel<S><<<(unsigned)cdiv((L - 1) * K, 256), 256, 0, stream>>>(tail_part.p, denH.p, K, L, Tl, nb);
+        post_launch();
+    }
+
     void h_update(double l1H, double l2H) override {
         REQUIRE(have_data && have_factors, "update: data and factors must be set first");
         if (tc_active()) tc_transconv();
@@ -1012,13 +1069,11 @@ struct Ctx : cmf_ctx {
         if (tc_active()) { tc_split_H(false); tc_denomH(); }
         else launch_transconv(Cf.p, Hbuf.p, denH.p, K, K, 2 * L - 1, K, Tl, Tl + 2 * (L - 1));
         if (is_last && L > 1) {
-            dim3 grid((unsigned)(L - 1), (unsigned)K);
-            denomH_tail_kernel<S><<<grid, 256, 0, stream>>>(GS.p, H, denH.p, K, L, Tl, -(L - 1), s2_ks, s2_ld);
-            post_launch();
+            launch_denomH_tail();
         }
         launch_mu(H, numH.p, denH.p, l1H, l2H, Tl * K);                       // mult.jl:51-52
         numH_valid = (alg == CMF_MULT);
-        gram_valid = false;
+        gram_valid = false; fds.h_dirty = true;
     }
 
     double loss_partial() override {
@@ -1085,9 +1140,7 @@ struct Ctx : cmf_ctx {
         if (tc_active()) { tc_split_H(false); tc_denomH(); }
         else launch_transconv(Cf.p, Hbuf.p, denH.p, K, K, 2 * L - 1, K, Tl, Tl + 2 * (L - 1));
         if (L > 1) {
-            dim3 grid((unsigned)(L - 1), (unsigned)K);
-            denomH_tail_kernel<S><<<grid, 256, 0, stream>>>(GS.p, H, denH.p, K, L, Tl, -(L - 1), s2_ks, s2_ld);
-            post_launch();
+            launch_denomH_tail();
         }
         sub_kernel<S><<<(unsigned)cdiv(Tl * K, 256), 256, 0, stream>>>(numH.p, denH.p, numH.p, Tl * K);        // Q
         post_launch();
@@ -1102,7 +1155,7 @@ struct Ctx : cmf_ctx {
         void *args[] = {&cf, &s2, &q, &hh, &dd, &tc_, &pr, &Kk, &Ll, &Tt, &ks, &ldv, &a1, &a2};
         CK(cudaLaunchCooperativeKernel((void *)hals_h_wave_kernel<S>, dim3((unsigned)hals_grid), dim3(HW_NT), args, smem, stream));
         post_launch();
-        gram_valid = false;
+        gram_valid = false; fds.h_dirty = true;
         numH_valid = false;
         return loss_partial();                                                // hals.jl:41
     }
@@ -1142,14 +1195,12 @@ struct Ctx : cmf_ctx {
         if (tc_active()) { tc_split_H(false); tc_denomH(); }
         else launch_transconv(Cf.p, Hbuf.p, denH.p, K, K, 2 * L - 1, K, Tl, Tl + 2 * (L - 1));
         if (L > 1) {
-            dim3 grid((unsigned)(L - 1), (unsigned)K);
-            denomH_tail_kernel<S><<<grid, 256, 0, stream>>>(GS.p, H, denH.p, K, L, Tl, -(L - 1), s2_ks, s2_ld);
-            post_launch();
+            launch_denomH_tail();
         }
         pgd_grad_kernel<S><<<(unsigned)cdiv(Tl * K, 256), 256, 0, stream>>>(denH.p, denH.p, numH.p, H, (S)l1H, (S)l2H, Tl * K);
         post_launch();
         pgd_step(H, denH.p, Tl * K, pgd_stepH);
-        gram_valid = false;
+        gram_valid = false; fds.h_dirty = true;
         numH_valid = true;                                                              // W unchanged: the expansion loss may reuse numH / W W'
         pgd_adapt(loss_partial(), pgd_stepH);
         return pgd_cur_loss;                                                            // caller: sqrt(cur_loss / datanorm^2), pgd.jl:202

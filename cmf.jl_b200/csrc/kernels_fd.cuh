@@ -15,6 +15,10 @@
 //   Ah [f][b][c][m]          conj(Hz^) as the real 2nblk x 128 matrix, rows (b,c): [Hr | -Hi], [Hi | Hr]  (A of TC_FQC)
 //   Of [f][b][m]   fp32      numH^ (output of TC_FQT)
 //   Df [f][m][n]   fp32      numW^ (output of TC_FQC)
+// The Gram cross-correlation of H (Rg[d][k][k'] = sum_u H[k,u] H[k',u+d], the Toeplitz part of Htilde Htilde', mult.jl:28,33)
+// is the same product with the spectrum of H itself as the B operand:
+//   Hf [f][b][c][k']         full blocks of H (owned columns + right halo), 64 columns per row    (B of TC_FQC)
+//   Gf [f][m][k']  fp32      Rg^ (output of TC_FQC)
 //
 // FFT: in-place radix-2 decimation-in-frequency in shared memory over a tile d[B][C] of C independent complex columns
 // (column index fastest: conflict-free), output in bit-reversed order.  Two real sequences ride in one complex transform
@@ -114,11 +118,12 @@ fft_x_kernel(const float *__restrict__ X, __nv_bfloat16 *__restrict__ hi, __nv_b
     }
 }
 
-// H[t][K] fp32 (owned column 0 first; only the V owned columns of each block, zero padded) -> Ah.
+// H[t][K] fp32 (owned column 0 first).  full == 0: only the V owned columns of each block, zero padded -> Ah;
+// full != 0: whole blocks over the hcols = Tl + L-1 columns present (owned + right halo) -> Hf.
 // grid (nblkp, 32 / C); C complex columns = 2C components per CTA.
 __global__ void __launch_bounds__(NT)
 fft_h_kernel(const float *__restrict__ H, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int64_t K, int64_t Tl,
-             int B, int logB, int V, int64_t nblkp, int C) {
+             int64_t hcols, int B, int logB, int V, int64_t nblkp, int C, int full) {
     extern __shared__ float2 fd_smem[];
     float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;
     const int64_t b = blockIdx.x;
@@ -128,7 +133,7 @@ fft_h_kernel(const float *__restrict__ H, __nv_bfloat16 *__restrict__ hi, __nv_b
     for (int i = threadIdx.x / C; i < B; i += NT / C) {
         const int64_t t = b * V + i;
         float2 v = make_float2(0.f, 0.f);
-        if (i < V && t < Tl) {
+        if (full ? (t < hcols) : (i < V && t < Tl)) {
             if (k < K) v.x = H[t * K + k];
             if (k + 1 < K) v.y = H[t * K + k + 1];
         }
@@ -139,6 +144,12 @@ fft_h_kernel(const float *__restrict__ H, __nv_bfloat16 *__restrict__ hi, __nv_b
     for (int f = threadIdx.x / C; f <= B / 2; f += NT / C) {
         float ar, ai, br, bi;
         unpack_pair(d, f, B, logB, C, p, ar, ai, br, bi);
+        if (full) {
+            const int64_t r = (((int64_t)f * nblkp + b) * 2) * KQ;
+            store_split2(hi, lo, r + k, ar, br);
+            store_split2(hi, lo, r + KQ + k, ai, bi);
+            continue;
+        }
         const int64_t r = (((int64_t)f * nblkp + b) * 2) * MROWS;
         store_split2(hi, lo, r + k, ar, br);                       // row (b, re): [ Hr | -Hi ]
         store_split2(hi, lo, r + KQ + k, -ai, -bi);
@@ -203,9 +214,11 @@ ifft_numH_kernel(const float *__restrict__ Of, float *__restrict__ numH, int64_t
     }
 }
 
-// Df[f][m][n] fp32 -> numW[(l*K+k)][N], l < L.  grid (ceil(N/32), K).
+// Df[f][m][n] fp32 (row stride ldi) -> out[(l*K+k)*N + n], l < L.  grid (ceil(N/32), K).
+// OutT = float: numW (N even, paired stores);  OutT = double: the Gram partial Rg[d][k][k'] with N = K.
+template <typename OutT>
 __global__ void __launch_bounds__(NT)
-ifft_numW_kernel(const float *__restrict__ Df, float *__restrict__ numW, int64_t N, int64_t K, int64_t L, int B, int logB) {
+ifft_numW_kernel(const float *__restrict__ Df, OutT *__restrict__ out, int64_t N, int64_t ldi, int64_t K, int64_t L, int B, int logB) {
     extern __shared__ float2 fd_smem[];
     constexpr int C = 16;
     float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;
@@ -216,8 +229,8 @@ ifft_numW_kernel(const float *__restrict__ Df, float *__restrict__ numW, int64_t
     for (int f = threadIdx.x / C; f <= B / 2; f += NT / C) {
         float2 re = make_float2(0.f, 0.f), im = re;
         if (n < N) {
-            re = *reinterpret_cast<const float2 *>(Df + ((int64_t)f * MROWS + k) * N + n);
-            im = *reinterpret_cast<const float2 *>(Df + ((int64_t)f * MROWS + KQ + k) * N + n);
+            re = *reinterpret_cast<const float2 *>(Df + ((int64_t)f * MROWS + k) * ldi + n);
+            im = *reinterpret_cast<const float2 *>(Df + ((int64_t)f * MROWS + KQ + k) * ldi + n);
         }
         pack_pair(d, f, B, C, p, re, im);
     }
@@ -227,7 +240,13 @@ ifft_numW_kernel(const float *__restrict__ Df, float *__restrict__ numW, int64_t
     const float sc = 1.0f / (float)B;
     for (int l = threadIdx.x / C; l < L; l += NT / C) {
         const float2 z = d[rev(l, logB) * C + p];
-        *reinterpret_cast<float2 *>(numW + ((int64_t)l * K + k) * N + n) = make_float2(z.x * sc, z.y * sc);
+        OutT *o = out + ((int64_t)l * K + k) * N + n;
+        if (sizeof(OutT) == 4) {
+            *reinterpret_cast<float2 *>(o) = make_float2(z.x * sc, z.y * sc);
+        } else {
+            o[0] = (OutT)(z.x * sc);
+            if (n + 1 < N) o[1] = (OutT)(z.y * sc);
+        }
     }
 }
 

@@ -577,6 +577,54 @@ __global__ void __launch_bounds__(256) denomH_tail_kernel(const S *__restrict__ 
     if (threadIdx.x == 0) den[t * K + k] = (S)s;
 }
 
+// The same tail in prefix form, each element of S2 read once: thread (d, k') keeps the truncated table entry
+//   C_w[d][k][k'] = sum_{l<w, 0<=l-d<L} S2[(l,k)][(l-d,k')]        (w = 1 .. L-1, one more lag l = w-1 per step)
+// in a register while w grows, and den[Tl-w][k] = sum_{d,k'} C_w[d][k][k'] H[Tl-w+d][k'].  Warp sums go to shared
+// memory, block sums to part[block][c][k] (c = L-1-w, the tail column index); denomH_tail_reduce_kernel adds the blocks
+// in order (deterministic).  grid (ceil((2L-1)K / 256), K), dynamic smem 8*(L-1) doubles.
+template <typename S>
+__global__ void __launch_bounds__(256) denomH_tail_prefix_kernel(const S *__restrict__ S2, const S *__restrict__ H,
+                                                                  double *__restrict__ part, int64_t K, int64_t L, int64_t Tl,
+                                                                  int64_t h_lo, int64_t Ks, int64_t ld) {
+    extern __shared__ double tail_sm[];                 // [8 warps][L-1]
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t k = blockIdx.y;
+    const bool live = e < (2 * L - 1) * K;
+    const int64_t dq = live ? e / K : 0, kp = live ? e - dq * K : 0;
+    const int64_t d = dq - (L - 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Lm = (int)(L - 1);
+    S pre = S(0);
+    for (int w = 1; w <= Lm; ++w) {
+        const int64_t l = w - 1, lp = l - d;
+        if (live && lp >= 0 && lp < L) pre += S2[(l * Ks + k) * ld + lp * Ks + kp];
+        const int64_t u = Tl - w + d;
+        double v = 0.0;
+        if (live && pre != S(0) && u >= h_lo) v = (double)(pre * H[u * K + kp]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) tail_sm[warp * Lm + (w - 1)] = v;
+    }
+    __syncthreads();
+    for (int w = threadIdx.x + 1; w <= Lm; w += blockDim.x) {
+        double s = 0.0;
+        for (int q = 0; q < 8; ++q) s += tail_sm[q * Lm + (w - 1)];
+        part[((int64_t)blockIdx.x * Lm + (Lm - w)) * K + k] = s;
+    }
+}
+
+template <typename S>
+__global__ void denomH_tail_reduce_kernel(const double *__restrict__ part, S *__restrict__ den, int64_t K, int64_t L, int64_t Tl,
+                                          int nblocks) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // c * K + k
+    if (i >= (L - 1) * K) return;
+    const int64_t c = i / K, k = i - c * K, t = Tl - (L - 1) + c;
+    if (t < 0) return;
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += part[(int64_t)b * (L - 1) * K + i];
+    den[t * K + k] = (S)s;
+}
+
 // ------------------------------------------------------------------------------------------
 // element-wise pieces
 // ------------------------------------------------------------------------------------------

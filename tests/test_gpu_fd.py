@@ -64,6 +64,11 @@ def test_fd_contractions_match_oracle(cmf, orc, dims):
     torch.cuda.synchronize()
     numW = s.exchange[0].cpu().numpy().reshape(L, K, N).transpose(1, 2, 0)
     assert _scale_err(numW, orc.co.corr_w(H, X, L)) < 3e-5
+    # Gram partial Rg[d][k][k'] through the spectrum of H
+    from oracle import restructured as rs
+
+    Rg = s.exchange[1].cpu().numpy()[: L * K * K].reshape(L, K, K).transpose(1, 2, 0)
+    assert _scale_err(Rg, rs.gram_R(H, L)) < 3e-5
     s.h_update(0.0, 0.0)
     torch.cuda.synchronize()
     numH = s.exchange[2].cpu().numpy().reshape(T, K).T
