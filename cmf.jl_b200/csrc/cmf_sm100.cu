@@ -214,14 +214,16 @@ struct FdState {
     bool ok = false, tried = false;
     int B = 0, logB = 0, V = 0, F = 0;
     int64_t nblk = 0, nblkp = 0;          // overlap-save blocks covering the owned columns; padded to a multiple of 16
-    DevBuf<__nv_bfloat16> Xf_hi, Xf_lo, Ah_hi, Ah_lo, Aw_hi, Aw_lo, Hf_hi, Hf_lo;
+    int V2 = 0;                           // hop of the denomH blocking (2L-1 lags): B - 2L + 2
+    int64_t nblk2 = 0;
+    DevBuf<__nv_bfloat16> Xf_hi, Xf_lo, Ah_hi, Ah_lo, Aw_hi, Aw_lo, Hf_hi, Hf_lo, Ac_hi, Ac_lo;
     DevBuf<float> Of, Df, Gf;
-    CUtensorMap mXfK[2], mXfMN[2], mAw[2], mAh[2], mHfMN[2];
+    CUtensorMap mXfK[2], mXfMN[2], mAw[2], mAh[2], mHfMN[2], mAc[2], mHf2K[2];
     bool x_dirty = true, w_dirty = true, h_dirty = true;   // h_dirty: Ah does not hold the spectrum of the current H
     std::string why;                      // reason the engine is unavailable
     void release() {
         Xf_hi.free(); Xf_lo.free(); Ah_hi.free(); Ah_lo.free(); Aw_hi.free(); Aw_lo.free(); Of.free(); Df.free();
-        Hf_hi.free(); Hf_lo.free(); Gf.free();
+        Hf_hi.free(); Hf_lo.free(); Gf.free(); Ac_hi.free(); Ac_lo.free();
         ok = tried = false;
         x_dirty = w_dirty = h_dirty = true;
     }
@@ -324,7 +326,7 @@ struct Ctx : cmf_ctx {
             while (B < 4 * L) { B *= 2; ++logB; }
             if (const char *e = getenv("CMF_FD_B")) {
                 const int want = atoi(e);
-                if (want >= 2 * L && want >= 64 && want <= 1024 && (want & (want - 1)) == 0) { B = want; logB = 0; while ((1 << logB) < B) ++logB; }
+                if (want >= 4 * L && want >= 64 && want <= 1024 && (want & (want - 1)) == 0) { B = want; logB = 0; while ((1 << logB) < B) ++logB; }
             }
             f.B = B; f.logB = logB; f.V = B - (int)L + 1; f.F = B / 2 + 1;
             f.nblk = cdiv(Tl, f.V);
@@ -332,9 +334,13 @@ struct Ctx : cmf_ctx {
             const size_t xf = (size_t)f.F * (size_t)f.nblkp * 2 * (size_t)N + 64;
             const size_t ah = (size_t)f.F * (size_t)f.nblkp * 2 * fd::MROWS + 64;
             const size_t aw = (size_t)f.F * fd::MROWS * 2 * (size_t)N + 64;
-            const size_t of = (size_t)f.F * (size_t)f.nblkp * fd::MROWS, df = (size_t)f.F * fd::MROWS * (size_t)N;
-            const size_t hf = (size_t)f.F * (size_t)f.nblkp * 2 * fd::KQ + 256, gf = (size_t)f.F * fd::MROWS * fd::KQ;
-            const size_t need = 4 * (xf + ah + aw + hf) + 4 * (of + df + gf);
+            f.V2 = B - 2 * (int)L + 2;
+            f.nblk2 = cdiv(Tl, f.V2);
+            const size_t of = (size_t)f.F * (size_t)std::max(f.nblkp, f.nblk2) * fd::MROWS, df = (size_t)f.F * fd::MROWS * (size_t)N;
+            // Hf serves the Gram partial (nblkp blocks) and, later on the same stream, denomH (nblk2 blocks)
+            const size_t hf = (size_t)f.F * (size_t)std::max(f.nblkp, f.nblk2) * 2 * fd::KQ + 256, gf = (size_t)f.F * fd::MROWS * fd::KQ;
+            const size_t ac = (size_t)f.F * fd::MROWS * fd::MROWS;
+            const size_t need = 4 * (xf + ah + aw + hf + ac) + 4 * (of + df + gf);
             tcs.X_hi.free(); tcs.X_lo.free(); tcs.x_dirty = true;
             size_t free_b = 0, total_b = 0;
             CK(cudaMemGetInfo(&free_b, &total_b));
@@ -344,6 +350,7 @@ struct Ctx : cmf_ctx {
             f.Aw_hi.alloc(aw); f.Aw_lo.alloc(aw);
             f.Of.alloc(of); f.Df.alloc(df);
             f.Hf_hi.alloc(hf); f.Hf_lo.alloc(hf); f.Gf.alloc(gf);
+            f.Ac_hi.alloc(ac); f.Ac_lo.alloc(ac);
             __nv_bfloat16 *xs[2] = {f.Xf_hi.p, f.Xf_lo.p}, *as[2] = {f.Ah_hi.p, f.Ah_lo.p}, *ws[2] = {f.Aw_hi.p, f.Aw_lo.p};
             const uint64_t rows = (uint64_t)f.F * (uint64_t)f.nblkp;
             for (int i = 0; i < 2; ++i) {
@@ -352,6 +359,8 @@ struct Ctx : cmf_ctx {
                 f.mAw[i] = make_map_2d(ws[i], (uint64_t)(2 * N), (uint64_t)f.F * fd::MROWS, (uint64_t)N * 4, tc::BK, tc::BM, CU_TENSOR_MAP_SWIZZLE_64B);
                 f.mAh[i] = make_map_mn(as[i], rows * 2, (uint64_t)fd::MROWS * 2, 2, tc::BK, 2);
                 f.mHfMN[i] = make_map_mn(i == 0 ? f.Hf_hi.p : f.Hf_lo.p, rows * 2, (uint64_t)fd::KQ * 2, 1, tc::BK, 4);
+                f.mAc[i] = make_map_2d(i == 0 ? f.Ac_hi.p : f.Ac_lo.p, fd::MROWS, (uint64_t)f.F * fd::MROWS, (uint64_t)fd::MROWS * 2, tc::BK, tc::BM, CU_TENSOR_MAP_SWIZZLE_64B);
+                f.mHf2K[i] = make_map_2d(i == 0 ? f.Hf_hi.p : f.Hf_lo.p, fd::MROWS, (uint64_t)f.F * (uint64_t)f.nblk2, (uint64_t)fd::MROWS * 2, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
             }
             CK(cudaFuncSetAttribute(tc::tc_kernel<tc::TC_FQT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
             CK(cudaFuncSetAttribute(tc::tc_kernel<tc::TC_FQC>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
@@ -402,6 +411,33 @@ struct Ctx : cmf_ctx {
             post_launch();
         }
     }
+    // denomH = C (*) H through the spectrum of H (mult.jl:44,48): the numH product with the lag table in place of W and
+    // H (both halos) in place of X; needs lag_tables() done.  The last L-1 columns are overwritten by the truncated tail.
+    void fd_denomH() {
+        if constexpr (std::is_same<S, float>::value) {
+            FdState &f = fds;
+            fd::fft_w_kernel<<<dim3((unsigned)cdiv(K, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(
+                Cf.p, f.Ac_hi.p, f.Ac_lo.p, K, K, 2 * L - 1, f.B, f.logB, fd::MROWS, fd::KQ);
+            post_launch();
+            const int C = fd_cols_h();
+            fd::fft_h_kernel<<<dim3((unsigned)f.nblk2, (unsigned)(32 / C)), fd::NT, fd_smem(C), stream>>>(
+                H, f.Hf_hi.p, f.Hf_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V2, f.nblk2, C, 1, -(L - 1));
+            post_launch();
+            tc::Params q = tc_base_params();
+            q.nprod = 3;
+            q.tiles_n = cdiv(f.nblk2, tc::BN);
+            q.nkb = fd::MROWS / tc::BK;
+            q.units = (int64_t)f.F * q.tiles_n;
+            q.fq_rows = f.nblk2;
+            q.out = f.Of.p;
+            const unsigned grid = (unsigned)std::min<int64_t>(q.units, tcs.num_sms);
+            tc::tc_kernel<tc::TC_FQT><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(f.mAc[0], f.mAc[1], f.mHf2K[0], f.mHf2K[1], q);
+            post_launch();
+            fd::ifft_numH_kernel<<<dim3((unsigned)f.nblk2, (unsigned)(32 / C)), fd::NT, fd_smem(C), stream>>>(
+                f.Of.p, denH.p, K, Tl, f.B, f.logB, f.V2, f.nblk2, C);
+            post_launch();
+        }
+    }
     // Ah = spectrum of the owned columns of the current H, block by block (shared by numW and the Gram partial)
     void fd_spectrum_H() {
         if constexpr (std::is_same<S, float>::value) {
@@ -409,7 +445,7 @@ struct Ctx : cmf_ctx {
             if (!f.h_dirty) return;
             const int C = fd_cols_h();
             fd::fft_h_kernel<<<dim3((unsigned)f.nblkp, (unsigned)(32 / C)), fd::NT, fd_smem(C), stream>>>(
-                H, f.Ah_hi.p, f.Ah_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V, f.nblkp, C, 0);
+                H, f.Ah_hi.p, f.Ah_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V, f.nblkp, C, 0, 0);
             post_launch();
             f.h_dirty = false;
         }
@@ -421,7 +457,7 @@ struct Ctx : cmf_ctx {
             fd_spectrum_H();
             const int C = fd_cols_h();
             fd::fft_h_kernel<<<dim3((unsigned)f.nblkp, (unsigned)(32 / C)), fd::NT, fd_smem(C), stream>>>(
-                H, f.Hf_hi.p, f.Hf_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V, f.nblkp, C, 1);
+                H, f.Hf_hi.p, f.Hf_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V, f.nblkp, C, 1, 0);
             post_launch();
             tc::Params q = tc_base_params();
             q.nprod = 3;
@@ -443,7 +479,7 @@ struct Ctx : cmf_ctx {
             FdState &f = fds;
             fd_build_X();
             if (f.w_dirty) {
-                fd::fft_w_kernel<<<dim3((unsigned)cdiv(N, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(Wi.p, f.Aw_hi.p, f.Aw_lo.p, N, K, L, f.B, f.logB);
+                fd::fft_w_kernel<<<dim3((unsigned)cdiv(N, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(Wi.p, f.Aw_hi.p, f.Aw_lo.p, N, K, L, f.B, f.logB, 2 * N, N);
                 post_launch();
                 f.w_dirty = false;
             }
@@ -1066,7 +1102,8 @@ struct Ctx : cmf_ctx {
         else launch_transconv(Wi.p, X.p, numH.p, N, K, L, N, Tl, Tl + (L - 1));    // numH (mult.jl:47)
         lag_tables();
         // denomH = C (*) H on all owned columns (mult.jl:44,48), then the truncated tail
-        if (tc_active()) { tc_split_H(false); tc_denomH(); }
+        if (fd_active()) fd_denomH();
+        else if (tc_active()) { tc_split_H(false); tc_denomH(); }
         else launch_transconv(Cf.p, Hbuf.p, denH.p, K, K, 2 * L - 1, K, Tl, Tl + 2 * (L - 1));
         if (is_last && L > 1) {
             launch_denomH_tail();
@@ -1137,7 +1174,8 @@ struct Ctx : cmf_ctx {
         if (tc_active()) tc_transconv();
         else launch_transconv(Wi.p, X.p, numH.p, N, K, L, N, Tl, Tl + (L - 1));
         lag_tables();
-        if (tc_active()) { tc_split_H(false); tc_denomH(); }
+        if (fd_active()) fd_denomH();
+        else if (tc_active()) { tc_split_H(false); tc_denomH(); }
         else launch_transconv(Cf.p, Hbuf.p, denH.p, K, K, 2 * L - 1, K, Tl, Tl + 2 * (L - 1));
         if (L > 1) {
             launch_denomH_tail();
@@ -1192,7 +1230,8 @@ struct Ctx : cmf_ctx {
         if (tc_active()) tc_transconv();
         else launch_transconv(Wi.p, X.p, numH.p, N, K, L, N, Tl, Tl + (L - 1));
         lag_tables();
-        if (tc_active()) { tc_split_H(false); tc_denomH(); }
+        if (fd_active()) fd_denomH();
+        else if (tc_active()) { tc_split_H(false); tc_denomH(); }
         else launch_transconv(Cf.p, Hbuf.p, denH.p, K, K, 2 * L - 1, K, Tl, Tl + 2 * (L - 1));
         if (L > 1) {
             launch_denomH_tail();

@@ -19,6 +19,10 @@
 // is the same product with the spectrum of H itself as the B operand:
 //   Hf [f][b][c][k']         full blocks of H (owned columns + right halo), 64 columns per row    (B of TC_FQC)
 //   Gf [f][m][k']  fp32      Rg^ (output of TC_FQC)
+// and denomH = C (*) H (mult.jl:44,48 in Gram form: 2L-1 lags of the K x K table C over H with both halos) is the numH
+// product with N -> K: blocks of hop V2 = B-2L+2 starting L-1 columns early,
+//   Ac [f][m][c][k']         conj(C^) as the real 128 x 128 matrix                                 (A of TC_FQT)
+//   Hf [f][b][c][k']         full blocks of H (same layout as above, other blocking)               (B of TC_FQT)
 //
 // FFT: in-place radix-2 decimation-in-frequency in shared memory over a tile d[B][C] of C independent complex columns
 // (column index fastest: conflict-free), output in bit-reversed order.  Two real sequences ride in one complex transform
@@ -118,12 +122,13 @@ fft_x_kernel(const float *__restrict__ X, __nv_bfloat16 *__restrict__ hi, __nv_b
     }
 }
 
-// H[t][K] fp32 (owned column 0 first).  full == 0: only the V owned columns of each block, zero padded -> Ah;
-// full != 0: whole blocks over the hcols = Tl + L-1 columns present (owned + right halo) -> Hf.
+// H[t][K] fp32 (owned column 0 first; block b starts at column b*V + t_off, t_off <= 0 reaches into the left halo).
+// full == 0: only the V owned columns of each block, zero padded -> Ah;
+// full != 0: whole blocks over the columns present, t < hcols = Tl + L-1 (owned + right halo) -> Hf.
 // grid (nblkp, 32 / C); C complex columns = 2C components per CTA.
 __global__ void __launch_bounds__(NT)
 fft_h_kernel(const float *__restrict__ H, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int64_t K, int64_t Tl,
-             int64_t hcols, int B, int logB, int V, int64_t nblkp, int C, int full) {
+             int64_t hcols, int B, int logB, int V, int64_t nblkp, int C, int full, int64_t t_off) {
     extern __shared__ float2 fd_smem[];
     float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;
     const int64_t b = blockIdx.x;
@@ -131,7 +136,7 @@ fft_h_kernel(const float *__restrict__ H, __nv_bfloat16 *__restrict__ hi, __nv_b
     const int k = 2 * ((int)blockIdx.y * C + p);
     make_twiddles(tw, B);
     for (int i = threadIdx.x / C; i < B; i += NT / C) {
-        const int64_t t = b * V + i;
+        const int64_t t = b * V + t_off + i;
         float2 v = make_float2(0.f, 0.f);
         if (full ? (t < hcols) : (i < V && t < Tl)) {
             if (k < K) v.x = H[t * K + k];
@@ -158,10 +163,11 @@ fft_h_kernel(const float *__restrict__ H, __nv_bfloat16 *__restrict__ hi, __nv_b
     }
 }
 
-// Wi[(l*K+k)][N] fp32 -> Aw.  grid (ceil(N/32), K).
+// Wi[(l*K+k)][N] fp32 -> Aw (rows of ldw elements, imaginary block at column coff: 2N / N for W; 128 / 64 for the
+// K x K lag table C with N = K and L = 2L-1 lags -> Ac).  grid (ceil(N/32), K).
 __global__ void __launch_bounds__(NT)
 fft_w_kernel(const float *__restrict__ Wi, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int64_t N, int64_t K,
-             int64_t L, int B, int logB) {
+             int64_t L, int B, int logB, int64_t ldw, int64_t coff) {
     extern __shared__ float2 fd_smem[];
     constexpr int C = 16;
     float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;
@@ -171,7 +177,11 @@ fft_w_kernel(const float *__restrict__ Wi, __nv_bfloat16 *__restrict__ hi, __nv_
     make_twiddles(tw, B);
     for (int i = threadIdx.x / C; i < B; i += NT / C) {
         float2 v = make_float2(0.f, 0.f);
-        if (i < L && n < N) v = *reinterpret_cast<const float2 *>(Wi + ((int64_t)i * K + k) * N + n);
+        if (i < L && n < N) {
+            const float *src = Wi + ((int64_t)i * K + k) * N + n;
+            if ((N & 1) == 0) v = *reinterpret_cast<const float2 *>(src);
+            else { v.x = src[0]; if (n + 1 < N) v.y = src[1]; }
+        }
         d[i * C + p] = v;
     }
     __syncthreads();
@@ -180,11 +190,11 @@ fft_w_kernel(const float *__restrict__ Wi, __nv_bfloat16 *__restrict__ hi, __nv_
     for (int f = threadIdx.x / C; f <= B / 2; f += NT / C) {
         float ar, ai, br, bi;
         unpack_pair(d, f, B, logB, C, p, ar, ai, br, bi);
-        const int64_t re = ((int64_t)f * MROWS + k) * 2 * N, im = ((int64_t)f * MROWS + KQ + k) * 2 * N;
+        const int64_t re = ((int64_t)f * MROWS + k) * ldw, im = ((int64_t)f * MROWS + KQ + k) * ldw;
         store_split2(hi, lo, re + n, ar, br);                      // row k:      [  Wr | Wi ]
-        store_split2(hi, lo, re + N + n, ai, bi);
+        store_split2(hi, lo, re + coff + n, ai, bi);
         store_split2(hi, lo, im + n, -ai, -bi);                    // row 64 + k: [ -Wi | Wr ]
-        store_split2(hi, lo, im + N + n, ar, br);
+        store_split2(hi, lo, im + coff + n, ar, br);
     }
 }
 

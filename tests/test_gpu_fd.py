@@ -73,6 +73,9 @@ def test_fd_contractions_match_oracle(cmf, orc, dims):
     torch.cuda.synchronize()
     numH = s.exchange[2].cpu().numpy().reshape(T, K).T
     assert _scale_err(numH, orc.co.tensor_transconv(W, X)) < 3e-5
+    # denomH = C (*) H through the spectrum of H + truncated tail
+    denH = s.exchange[3].cpu().numpy().reshape(T, K).T
+    assert _scale_err(denH, orc.co.tensor_transconv(W, orc.co.tensor_conv(W, H))) < 3e-5
     # new data on the same handle: the spectrum of X is rebuilt
     X2 = np.random.default_rng(7).random((N, T))
     s.set_data(X2, 0)
