@@ -270,14 +270,28 @@ def run_ours(args, cfg, name):
         host = torch.empty((hi - t0, N), dtype=torch.float32, pin_memory=True)   # [t][n] == Julia N x cols
         Xh = host.numpy().T                       # N x cols, Fortran-ordered view of the pinned buffer
         shard.get_data(Xh, with_halo=True)
-        Wh, Hh = shard.get_factors()
-        W0, H0 = Wh, Hh                           # float32, Fortran-ordered (what a Julia caller holds)
+        # the caller's factors, also in pinned host memory: W (K x N x L) and H over this rank's columns + halos (the halo
+        # columns are filled by exchange, not uploaded), Fortran-ordered float32 (what a Julia caller holds)
+        lo_h, hi_h = max(t0 - (L - 1), 0), min(t1 + (L - 1), T)
+        w_pin = torch.empty((L, N, K), dtype=torch.float32, pin_memory=True)
+        h_pin = torch.zeros((hi_h - lo_h, K), dtype=torch.float32, pin_memory=True)
+        W0, Hbuf = w_pin.numpy().T, h_pin.numpy().T          # K x N x L and K x cols, Fortran-ordered views
+        shard.get_factors(out=(W0, Hbuf[:, t0 - lo_h : t0 - lo_h + (t1 - t0)]))
+        we_pin = torch.empty((L, N, K), dtype=torch.float32, pin_memory=True)
+        he_pin = torch.empty((t1 - t0, K), dtype=torch.float32, pin_memory=True)
+        We, He = we_pin.numpy().T, he_pin.numpy().T
         shard.close()
-        del shard, fitter, Wh, Hh
+        del shard, fitter
         torch.cuda.empty_cache()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        marks = [time.perf_counter()]
+
+        def mark():
+            torch.cuda.synchronize()
+            marks.append(time.perf_counter())
+
         sh2 = cmf.DeviceShard(N, T, t0, t1, K, L, dtype="f32", device=local_rank)
         if args.engine is not None:
             sh2.set_engine(args.engine)
@@ -285,12 +299,17 @@ def run_ours(args, cfg, name):
         f2 = cmf.ShardedMultFit(sh2, rank, world, dist)
         sh2.set_data(Xh, t0)                      # H2D of this rank's columns from pinned host memory
         f2.setup_data_norm()
+        mark()
         # factors: host W (replicated) and this rank's columns of H (+ halos are exchanged, not uploaded)
-        _set_sharded_factors(sh2, f2, W0, H0, t0)
+        sh2.set_factors(W0, Hbuf, lo_h)
+        f2.exchange_halos()
         el = [f2.loss()]
+        mark()
         for _ in range(args.steps):
             el.append(f2.iterate())               # each iteration reads its loss back (8 bytes D2H)
-        We, He = sh2.get_factors()                # D2H of the result
+        mark()
+        sh2.get_factors(out=(We, He))             # D2H of the result into pinned host memory
+        mark()
         e1.record()
         barrier()
         ems = e0.elapsed_time(e1)
@@ -298,13 +317,15 @@ def run_ours(args, cfg, name):
             t = torch.tensor([ems], dtype=torch.float64, device=f"cuda:{local_rank}")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t.item())
-        h2d = (Xh.nbytes + W0.size * 4 + H0.size * 4) * world / args.steps
+        h2d = (Xh.nbytes + W0.size * 4 + Hbuf.size * 4) * world / args.steps
         d2h = ((We.size + He.size) * 4 * world + 8 * (args.steps + 1)) / args.steps
         e2e = {"value": args.steps / (ems / 1e3), "unit": "iterations/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "iterations": args.steps,
                "note": "fit through the public API from pinned host buffers: one upload of X/W/H, K iterations "
                        "each reading its loss back, one download of W/H; bytes are totals divided by K",
-               "final_loss": el[-1]}
+               "final_loss": el[-1],
+               "phases_s": dict(zip(("create+upload_X+norm", "upload_factors+first_loss", "iterations", "download_W_H"),
+                                    [round(y - x, 4) for x, y in zip(marks[:-1], marks[1:])]))}
         sh2.close()
 
     if rank != 0:
@@ -390,6 +411,33 @@ def run_ours(args, cfg, name):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _tensor_roofline(name, world, dom, engine, achieved_tf, pk, Fc_rank, per_launch_ms, K, L, prof, contr_share):
+    # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from one `ncu --set full` capture of this very
+    # workload (profiles/r1_ncu_full_corr_c4_lockstep.md); only known for the 1-GPU c4 correlation launch
+    traffic, traffic_note = None, "no ncu capture for this workload / kernel"
+    if name == "c4" and world == 1 and dom == "corr":
+        traffic = 128.9e9
+        traffic_note = ("ncu --set full, c4, 1 GPU, per launch: 113.9 GB read + 15.1 GB written vs 68.7 GB algorithmic "
+                        "(X hi/lo planes once); profiles/r1_ncu_full_corr_c4_lockstep.md")
+    return {
+        "bound": "tensor", "kernel": dom, "achieved": achieved_tf, "peak": pk["tensor"], "unit": "TFLOP/s",
+        "frac": achieved_tf / pk["tensor"], "traffic": traffic, "traffic_note": traffic_note,
+        "peak_source": f"{pk['src']} bf16 sustained",
+        "flops_per_launch": Fc_rank, "ms_per_launch": per_launch_ms,
+        "executed": {"tflops": 3.0 * achieved_tf if engine == 1 else achieved_tf,
+                     "frac": (3.0 * achieved_tf if engine == 1 else achieved_tf) / pk["tensor"],
+                     "note": "bf16 tensor FLOPs actually issued: every fp32 product is 3 bf16 MMAs (hi*hi + hi*lo + lo*hi)"},
+        "note": "arithmetic intensity K*L/2 = %d FLOP/B >> machine balance: the contraction is tensor/FMA bound, "
+                "not HBM bound (SURVEY.md section 8d); algorithmic FLOPs 2*N*K*(L*T - L(L-1)/2) per contraction launch" % (K * L // 2),
+        "kernel_ms": {k: {"total_ms": v[0], "launches": v[1]} for k, v in prof.items()},
+        "contraction_share_of_step": contr_share,
+    }
+
+
+# per-launch DRAM traffic of the frequency-domain kernels at c4 on one GPU, from `ncu --set full` (profiles/); filled per round
+NCU_TRAFFIC_C4_FD = {}
 
 
 def _tensor_roofline(name, world, dom, engine, achieved_tf, pk, Fc_rank, per_launch_ms, K, L, prof, contr_share):

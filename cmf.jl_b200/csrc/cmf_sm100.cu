@@ -1115,7 +1115,12 @@ struct Ctx : cmf_ctx {
 
     double loss_partial() override {
         REQUIRE(have_data && have_factors, "loss: data and factors must be set first");
-        if (loss_mode == 1 && tc_active() && numH_valid) return loss_partial_expansion();
+        if (loss_mode == 1 && tc_active()) {
+            // frequency-domain engine: numH and W W' are cheap, so the expansion also serves calls that find them stale
+            // (the loss at the initial factors, after a W-only step, after the HALS sweep overwrote numH)
+            if (!numH_valid && fd_active()) { tc_transconv(); lag_tables(); numH_valid = true; }
+            if (numH_valid) return loss_partial_expansion();
+        }
         int64_t nb = conv_nblocks(0, Tl);
         if (tc_active()) nb = tc_conv_loss();
         else launch_conv(Wi.p, H, K, L, -(L - 1), Tl + (L - 1), 0, Tl, 4, nullptr, loss_part.p);  // mult.jl:55-57

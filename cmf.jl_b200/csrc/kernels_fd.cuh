@@ -24,8 +24,8 @@
 //   Ac [f][m][c][k']         conj(C^) as the real 128 x 128 matrix                                 (A of TC_FQT)
 //   Hf [f][b][c][k']         full blocks of H (same layout as above, other blocking)               (B of TC_FQT)
 //
-// FFT: in-place radix-2 decimation-in-frequency in shared memory over a tile d[B][C] of C independent complex columns
-// (column index fastest: conflict-free), output in bit-reversed order.  Two real sequences ride in one complex transform
+// FFT: in-place radix-2 decimation-in-frequency (two stages fused per pass) in shared memory over a tile d[B][C] of C
+// independent complex columns (column index fastest: conflict-free), output in bit-reversed order.  Two real sequences ride in one complex transform
 // (z = a + i b; A[f] = (Z[f] + conj(Z[B-f]))/2, B[f] = (Z[f] - conj(Z[B-f]))/(2i)), forward and inverse.
 #pragma once
 #include <cuda_bf16.h>
@@ -49,21 +49,39 @@ __device__ __forceinline__ void make_twiddles(float2 *tw, int B) {
 
 __device__ __forceinline__ int rev(int x, int logB) { return (int)(__brev((unsigned)x) >> (32 - logB)); }
 
-// log2(B) butterfly passes over d[B][C]; X[f] ends up in row rev(f).  INV uses the conjugate twiddles (no scaling).
+// log2(B) radix-2 decimation-in-frequency stages over d[B][C], two stages fused per pass (four rows in registers, the
+// second twiddle of the first stage is the first times -+i): half the shared-memory traffic and barriers of plain
+// radix-2, same bit-reversed output order (X[f] ends up in row rev(f)).  INV uses the conjugate twiddles (no scaling).
+__device__ __forceinline__ float2 cmul(float2 a, float2 w) { return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
+
 template <bool INV>
 __device__ __forceinline__ void fft_passes(float2 *d, const float2 *tw, int B, int logB, int C) {
     const int c = threadIdx.x % C, j0 = threadIdx.x / C, jstep = NT / C;
-    for (int s = 0; s < logB; ++s) {
-        const int half = B >> (s + 1);
+    int s = 0;
+    for (; s + 1 < logB; s += 2) {
+        const int n = B >> s, q = n >> 2, lq = logB - s - 2;      // block size of the first stage, its quarter
+        for (int j = j0; j < B / 4; j += jstep) {
+            const int pos = j & (q - 1), g = j >> lq;
+            float2 *r0 = d + (size_t)(g * n + pos) * C + c, *r1 = r0 + (size_t)q * C, *r2 = r1 + (size_t)q * C, *r3 = r2 + (size_t)q * C;
+            const float2 a0 = *r0, a1 = *r1, a2 = *r2, a3 = *r3;
+            float2 w1 = tw[pos << s], w2 = tw[pos << (s + 1)];
+            if (INV) { w1.y = -w1.y; w2.y = -w2.y; }
+            const float2 b0 = make_float2(a0.x + a2.x, a0.y + a2.y), b2 = cmul(make_float2(a0.x - a2.x, a0.y - a2.y), w1);
+            const float2 b1 = make_float2(a1.x + a3.x, a1.y + a3.y), uw = cmul(make_float2(a1.x - a3.x, a1.y - a3.y), w1);
+            const float2 b3 = INV ? make_float2(-uw.y, uw.x) : make_float2(uw.y, -uw.x);
+            *r0 = make_float2(b0.x + b1.x, b0.y + b1.y);
+            *r1 = cmul(make_float2(b0.x - b1.x, b0.y - b1.y), w2);
+            *r2 = make_float2(b2.x + b3.x, b2.y + b3.y);
+            *r3 = cmul(make_float2(b2.x - b3.x, b2.y - b3.y), w2);
+        }
+        __syncthreads();
+    }
+    if (s < logB) {                                               // odd log2(B): last stage, distance 1, twiddle 1
         for (int j = j0; j < B / 2; j += jstep) {
-            const int pos = j & (half - 1), g = j >> (logB - 1 - s);
-            const int i0 = g * 2 * half + pos, i1 = i0 + half;
-            const float2 a = d[i0 * C + c], b = d[i1 * C + c];
-            float2 w = tw[pos << s];
-            if (INV) w.y = -w.y;
-            d[i0 * C + c] = make_float2(a.x + b.x, a.y + b.y);
-            const float tx = a.x - b.x, ty = a.y - b.y;
-            d[i1 * C + c] = make_float2(tx * w.x - ty * w.y, tx * w.y + ty * w.x);
+            float2 *r0 = d + (size_t)(2 * j) * C + c, *r1 = r0 + C;
+            const float2 a = *r0, b = *r1;
+            *r0 = make_float2(a.x + b.x, a.y + b.y);
+            *r1 = make_float2(a.x - b.x, a.y - b.y);
         }
         __syncthreads();
     }

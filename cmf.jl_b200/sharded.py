@@ -170,10 +170,18 @@ class DeviceShard:
     def scale_factors(self, s):
         check(_lib.load().cmf_scale_factors(self._h, float(s)))
 
-    def get_factors(self):
+    def get_factors(self, out=None):
+        """W (K x N x L) and the owned columns of H (K x Tl), Fortran order, handle dtype.  ``out=(W, H)`` downloads
+        into caller-owned arrays of that shape/order/dtype (e.g. views of pinned buffers)."""
         dt = np_dtype(self.dtype)
-        W = np.empty((self.K, self.N, self.L), dtype=dt, order="F")
-        H = np.empty((self.K, self.t1 - self.t0), dtype=dt, order="F")
+        if out is not None:
+            W, H = out
+            for a, shp in ((W, (self.K, self.N, self.L)), (H, (self.K, self.t1 - self.t0))):
+                if a.shape != shp or a.dtype != dt or not a.flags.f_contiguous:
+                    raise ValueError("get_factors(out=...): need Fortran-ordered arrays of the handle dtype, shapes K x N x L and K x Tl")
+        else:
+            W = np.empty((self.K, self.N, self.L), dtype=dt, order="F")
+            H = np.empty((self.K, self.t1 - self.t0), dtype=dt, order="F")
         check(_lib.load().cmf_get_factors(self._h, fptr(W), fptr(H)))
         return W, H            # handle dtype (no host-side conversion: H is 1 GiB at the benchmark size)
 

@@ -1,4 +1,4 @@
-"""CPU emulation of the frequency-domain contraction path (DESIGN.md section 4.4): does it hold the fp32 parity bar?
+"""CPU emulation of the frequency-domain contraction path (DESIGN.md section 4.3): does it hold the fp32 parity bar?
 
 MU on the fp64 oracle's data and inits, with numW (mult.jl:32) and numH (mult.jl:47) computed the way the device does:
 overlap-save blocks of length B (hop V = B-L+1), fp32 FFT, spectra split into bf16 hi/lo planes, three products

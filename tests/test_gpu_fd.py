@@ -172,10 +172,12 @@ def test_fd_other_rules_match_oracle(cmf, orc, alg, iters):
     else:
         reg = {}
         ref = orc.po.fit(orc.po.PGDUpdate(X, W0, H0), X, W0, H0, iters, check_convergence=False)
-    r = cmf.fit_cnmf(X, L=L, K=K, alg=alg, max_itr=iters, W_init=W0, H_init=H0, check_convergence=False,
-                     dtype="f32", engine=2, layout="KNL", **reg)
-    rel = np.abs(np.asarray(r.loss_hist) - np.asarray(ref.loss_hist)) / np.asarray(ref.loss_hist)
-    assert rel.max() < 1e-4, rel
+    for loss_mode in (0, 1):      # 1: every loss (incl. the initial one and those after W-only steps) by the expansion
+        r = cmf.fit_cnmf(X, L=L, K=K, alg=alg, max_itr=iters, W_init=W0, H_init=H0, check_convergence=False,
+                         dtype="f32", engine=2, loss_mode=loss_mode, layout="KNL", **reg)
+        rel = np.abs(np.asarray(r.loss_hist) - np.asarray(ref.loss_hist)) / np.asarray(ref.loss_hist)
+        print(alg, "loss_mode", loss_mode, "max rel loss err", rel.max())
+        assert rel.max() < 1e-4, (loss_mode, rel)
 
 
 def test_fd_unsupported_shapes_fail_loudly(cmf):
