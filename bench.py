@@ -181,6 +181,9 @@ def run_ours(args, cfg, name):
         ge.build()
     dist = None
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -437,47 +440,12 @@ def _tensor_roofline(name, world, dom, engine, achieved_tf, pk, Fc_rank, per_lau
 
 
 # per-launch DRAM traffic of the frequency-domain kernels at c4 on one GPU, from `ncu --set full` (profiles/); filled per round
-NCU_TRAFFIC_C4_FD = {}
-
-
-def _tensor_roofline(name, world, dom, engine, achieved_tf, pk, Fc_rank, per_launch_ms, K, L, prof, contr_share):
-    # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from one `ncu --set full` capture of this very
-    # workload (profiles/r1_ncu_full_corr_c4_lockstep.md); only known for the 1-GPU c4 correlation launch
-    traffic, traffic_note = None, "no ncu capture for this workload / kernel"
-    if name == "c4" and world == 1 and dom == "corr":
-        traffic = 128.9e9
-        traffic_note = ("ncu --set full, c4, 1 GPU, per launch: 113.9 GB read + 15.1 GB written vs 68.7 GB algorithmic "
-                        "(X hi/lo planes once); profiles/r1_ncu_full_corr_c4_lockstep.md")
-    return {
-        "bound": "tensor", "kernel": dom, "achieved": achieved_tf, "peak": pk["tensor"], "unit": "TFLOP/s",
-        "frac": achieved_tf / pk["tensor"], "traffic": traffic, "traffic_note": traffic_note,
-        "peak_source": f"{pk['src']} bf16 sustained",
-        "flops_per_launch": Fc_rank, "ms_per_launch": per_launch_ms,
-        "executed": {"tflops": 3.0 * achieved_tf if engine == 1 else achieved_tf,
-                     "frac": (3.0 * achieved_tf if engine == 1 else achieved_tf) / pk["tensor"],
-                     "note": "bf16 tensor FLOPs actually issued: every fp32 product is 3 bf16 MMAs (hi*hi + hi*lo + lo*hi)"},
-        "note": "arithmetic intensity K*L/2 = %d FLOP/B >> machine balance: the contraction is tensor/FMA bound, "
-                "not HBM bound (SURVEY.md section 8d); algorithmic FLOPs 2*N*K*(L*T - L(L-1)/2) per contraction launch" % (K * L // 2),
-        "kernel_ms": {k: {"total_ms": v[0], "launches": v[1]} for k, v in prof.items()},
-        "contraction_share_of_step": contr_share,
-    }
-
-
-# per-launch DRAM traffic of the frequency-domain kernels at c4 on one GPU, from `ncu --set full` (profiles/); filled per round
-NCU_TRAFFIC_C4_FD = {}
-
-
-def _set_sharded_factors(shard, fitter, W, H_owned, t0):
-    """Uploads W and this rank's owned H columns, then fills the halos by exchange."""
-    import numpy as np
-
-    L, K = shard.L, shard.K
-    lo = max(t0 - (L - 1), 0)
-    hi = min(shard.t1 + (L - 1), shard.T)
-    buf = np.zeros((K, hi - lo), dtype=H_owned.dtype, order="F")
-    buf[:, t0 - lo : t0 - lo + H_owned.shape[1]] = H_owned
-    shard.set_factors(W, buf, lo)
-    fitter.exchange_halos()
+NCU_TRAFFIC_C4_FD = {
+    "transconv": (89.76e9, "ncu --set full, c4, 1 GPU, per launch: 88.42 GB read + 1.34 GB written vs 85.56 GB of spectrum planes + 1.08 GB "
+                           "operand that must be read and 69.9 GB algorithmic; profiles/r1_ncu_full_fd_kernels.md"),
+    "corr": (90.11e9, "ncu --set full, c4, 1 GPU, per launch: 89.57 GB read + 0.54 GB written vs 85.56 GB of spectrum planes + 2.67 GB "
+                      "operand that must be read and 69.9 GB algorithmic; profiles/r1_ncu_full_fd_kernels.md"),
+}
 
 
 def main():

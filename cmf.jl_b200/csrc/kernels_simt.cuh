@@ -532,6 +532,31 @@ __global__ void s2_dot_G_kernel(const S *__restrict__ S2, int64_t Ks, int64_t ld
     if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
 
+// The same sum walked along the block diagonals of G: thread (d, k, k') visits (l, l') = (d+s, s) (d >= 0) or (s, s-d) (d < 0),
+// where the Toeplitz part is constant and the tail grows by one product per step,
+//   tail(l+1, l'+1) = tail(l, l') + Ht[L-2-l][k] Ht[L-2-l'][k'],
+// so every element of S2 is read once and the (K L)^2 L tail work becomes (K L)^2.  grid-stride over (2L-1) K K diagonals.
+template <typename S>
+__global__ void s2_dot_G_diag_kernel(const S *__restrict__ S2, int64_t Ks, int64_t ld, const double *__restrict__ Rg,
+                                     const double *__restrict__ Ht, int64_t K, int64_t L, double *__restrict__ partial) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    const int64_t total = (2 * L - 1) * K * K;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t kp = e % K, k = (e / K) % K, d = e / (K * K) - (L - 1);
+        const double r = (d >= 0) ? Rg[(d * K + k) * K + kp] : Rg[((-d) * K + kp) * K + k];
+        const int64_t steps = L - (d >= 0 ? d : -d);
+        int64_t l = d >= 0 ? d : 0, lp = d >= 0 ? 0 : -d;
+        double tail = 0.0;
+        for (int64_t s_ = 0; s_ < steps; ++s_, ++l, ++lp) {
+            acc += (r - tail) * (double)S2[(l * Ks + k) * ld + lp * Ks + kp];
+            if (s_ + 1 < steps) tail += Ht[(L - 2 - l) * K + k] * Ht[(L - 2 - lp) * K + kp];
+        }
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
 // Cf[(d+L-1)][k][k'] = sum_{l, 0<=l-d<L} S2[(l,k)][(l-d,k')]      (S2 = W W' over the unfolded rows)
 // S2 is addressed as S2[(l*Ks + k) * ld + (l'*Ks + k')]: (Ks, ld) = (K, K*L) for the SIMT product and
 // (Kp, rows_u) for the tensor-core product over the padded rows.

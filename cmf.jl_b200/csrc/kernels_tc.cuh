@@ -578,6 +578,26 @@ __global__ void build_G_split_kernel(const double *__restrict__ Rg, const double
     hi[idx] = h; lo[idx] = l_;
 }
 
+// The same planes written along the block diagonals (see s2_dot_G_diag_kernel): thread (d, k, k') walks (l, l') with the
+// Toeplitz part constant and the tail updated by one product per step.  The zero padding of Gc is never touched.
+__global__ void build_G_split_diag_kernel(const double *__restrict__ Rg, const double *__restrict__ Ht, __nv_bfloat16 *__restrict__ hi,
+                                          __nv_bfloat16 *__restrict__ lo, int64_t K, int64_t L, int Kp, int64_t KLp) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (2 * L - 1) * K * K) return;
+    const int64_t kp = e % K, k = (e / K) % K, d = e / (K * K) - (L - 1);
+    const double r = (d >= 0) ? Rg[(d * K + k) * K + kp] : Rg[((-d) * K + kp) * K + k];
+    const int64_t steps = L - (d >= 0 ? d : -d);
+    int64_t l = d >= 0 ? d : 0, lp = d >= 0 ? 0 : -d;
+    double tail = 0.0;
+    for (int64_t s_ = 0; s_ < steps; ++s_, ++l, ++lp) {
+        const int64_t idx = (l * K + k) * KLp + (L - 1 - lp) * Kp + kp;
+        __nv_bfloat16 h, l_;
+        split_bf16((float)(r - tail), h, l_);
+        hi[idx] = h; lo[idx] = l_;
+        if (s_ + 1 < steps) tail += Ht[(L - 2 - l) * K + k] * Ht[(L - 2 - lp) * K + kp];
+    }
+}
+
 // Cf[(d')][k][k'] fp32 ((2L-1) x K x K) -> Cc[(d'*Kp + k)][Kp] hi/lo (rows_c rows, zero padded)  [denomH A operand]
 __global__ void split_C_kernel(const float *__restrict__ Cf, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo,
                                int64_t K, int64_t D, int Kp, int64_t rows_c) {
