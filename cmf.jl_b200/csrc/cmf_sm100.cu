@@ -376,7 +376,13 @@ struct Ctx : cmf_ctx {
         }
     }
     // component pairs per CTA of the H-side transforms: 32 (all 64 rows) while the tile fits in shared memory
-    int fd_cols_h() const { return 16; }
+    int fd_cols_h() const {
+        if (const char *e = getenv("CMF_FD_COLS")) {
+            const int c = atoi(e);
+            if ((c == 8 || c == 16 || c == 32) && (size_t)fds.B * (size_t)c * sizeof(float2) <= 160 * 1024) return c;
+        }
+        return 16;
+    }
     size_t fd_smem(int C) const { return ((size_t)fds.B * (size_t)C + (size_t)fds.B / 2) * sizeof(float2); }
 
     void fd_build_X() {

@@ -171,3 +171,70 @@ def hals_iteration_gram(data, W, H, l1W=0.0, l2W=0.0, l1H=0.0, l2H=0.0):
     H = hals_H_sweep_gram(R, W, H, l1H, l2H)
     R = tensor_conv(W, H) - data
     return W, H, float(np.linalg.norm(R) / np.linalg.norm(data))
+
+
+# ---------------------------------------------------------------------------- frequency-domain (overlap-save) forms
+# The algebra of the device's frequency-domain engine (kernels_fd.cuh) in float64 NumPy: blocks
+# of length B with hop V = B-L+1 (numH, numW, Gram) or V2 = B-2L+2 (denomH), per-frequency products with the conjugate
+# spectrum of the small operand, inverse transform, keep the valid samples.  tests/test_oracle.py proves each one equal
+# to the literal restatement, which pins the block/mask/offset conventions the CUDA kernels follow.
+def _blocks(A, B, hop, nblk, start=0):
+    """A[:, start + b*hop + i] for b < nblk, i < B, zero outside A's columns -> rows x nblk x B."""
+    rows, T = A.shape
+    idx = start + (np.arange(nblk) * hop)[:, None] + np.arange(B)[None, :]
+    ok = (idx >= 0) & (idx < T)
+    return np.where(ok[None], A[:, np.clip(idx, 0, T - 1)], 0.0)
+
+
+def fd_block_length(L):
+    B = 64
+    while B < 4 * L:
+        B *= 2
+    return B
+
+
+def numH_overlap_save(W, X, B=None):
+    """transconv(W, X) (common.jl:71-81): numH^[k,b,f] = sum_n conj(W^[k,n,f]) X^[n,b,f], first V samples of each block."""
+    K, N, L = W.shape
+    T = X.shape[1]
+    B = B or fd_block_length(L)
+    V = B - L + 1
+    nblk = -(-T // V)
+    Xf = np.fft.rfft(_blocks(X, B, V, nblk), axis=2)                 # N x nblk x F
+    Wf = np.fft.rfft(W, n=B, axis=2)                                  # K x N x F
+    out = np.fft.irfft(np.einsum("knf,nbf->kbf", Wf.conj(), Xf), n=B, axis=2)[:, :, :V]
+    return out.reshape(K, -1)[:, :T]
+
+
+def numW_overlap_save(H, X, L, B=None):
+    """corr_w(H, X) (mult.jl:31-34): numW^[k,n,f] = sum_b conj(Hz^[k,b,f]) X^[n,b,f] with Hz the V owned columns of block b
+    zero padded to B; first L lags."""
+    K, T = H.shape
+    B = B or fd_block_length(L)
+    V = B - L + 1
+    nblk = -(-T // V)
+    Xf = np.fft.rfft(_blocks(X, B, V, nblk), axis=2)
+    Hz = _blocks(H, B, V, nblk)
+    Hz[:, :, V:] = 0.0
+    Hf = np.fft.rfft(Hz, axis=2)                                      # K x nblk x F
+    return np.fft.irfft(np.einsum("kbf,nbf->knf", Hf.conj(), Xf), n=B, axis=2)[:, :, :L]
+
+
+def gram_overlap_save(H, L, B=None):
+    """gram_R(H, L): the numW form with the full blocks of H itself in place of X."""
+    return numW_overlap_save(H, H, L, B)                               # R[k, k', d]
+
+
+def denomH_interior_overlap_save(W, H, B=None):
+    """C (*) H with the interior lag table (all columns; the last L-1 are only valid where the conv is not truncated):
+    2L-1 lags d' = d + L-1 over blocks of hop V2 = B-2L+2 that start L-1 columns early."""
+    K, N, L = W.shape
+    T = H.shape[1]
+    B = B or fd_block_length(L)
+    V2 = B - 2 * L + 2
+    nblk = -(-T // V2)
+    C = Cw_tables(W)[L - 1]                                            # K x K x (2L-1): C[k, k', d + L-1]
+    Cf = np.fft.rfft(C, n=B, axis=2)
+    Hf = np.fft.rfft(_blocks(H, B, V2, nblk, start=-(L - 1)), axis=2)  # K x nblk x F
+    out = np.fft.irfft(np.einsum("kjf,jbf->kbf", Cf.conj(), Hf), n=B, axis=2)[:, :, :V2]
+    return out.reshape(K, -1)[:, :T]

@@ -210,3 +210,22 @@ def test_pgd_driver_semantics():
     r = po.fit(rule, data, W0, H0, 25, check_convergence=False)
     assert len(r.loss_hist) == 26 and r.loss_hist[-1] < r.loss_hist[0]
     assert np.all(r.W >= po.EPSILON) and np.all(r.H >= po.EPSILON)          # NonnegConstraint floor
+
+
+# ---------------------------------------------------------------------------------------------
+# frequency-domain (overlap-save) forms of the device engine == the literal restatement
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dims", [(13, 300, 3, 5), (8, 157, 4, 16), (6, 90, 2, 1), (5, 700, 3, 30)])
+def test_overlap_save_forms_equal_literal(dims):
+    from oracle import restructured as rs
+
+    N, T, K, L = dims
+    rng = np.random.default_rng(sum(dims))
+    W, H, X = rng.random((K, N, L)), rng.random((K, T)), rng.random((N, T))
+    for B in (None, 2 * rs.fd_block_length(L)):
+        assert np.allclose(rs.numH_overlap_save(W, X, B), po.tensor_transconv(W, X), rtol=1e-10, atol=1e-10)
+        assert np.allclose(rs.numW_overlap_save(H, X, L, B), po.corr_w(H, X, L), rtol=1e-10, atol=1e-10)
+        assert np.allclose(rs.gram_overlap_save(H, L, B), rs.gram_R(H, L), rtol=1e-10, atol=1e-10)
+        lit = rs.denomH_gram(W, H)
+        fd = rs.denomH_interior_overlap_save(W, H, B)
+        assert np.allclose(fd[:, : T - (L - 1)], lit[:, : T - (L - 1)], rtol=1e-10, atol=1e-10)
