@@ -624,7 +624,7 @@ struct Ctx : cmf_ctx {
     void tc_split_W() {
         if constexpr (std::is_same<S, float>::value) {
             if (!tcs.w_dirty) return;
-            tc::split_W_kernel<<<(unsigned)cdiv(L * tcs.Kp * N, 256), 256, 0, stream>>>(
+            tc::split_W_kernel<<<dim3((unsigned)cdiv(N, 32), (unsigned)cdiv(tcs.Kp, 32), (unsigned)L), dim3(32, 8), 0, stream>>>(
                 Wi.p, tcs.Wc_hi.p, tcs.Wc_lo.p, tcs.Wu_hi.p, tcs.Wu_lo.p, N, K, L, tcs.Kp, tcs.KLp);
             post_launch();
             tcs.w_dirty = false;

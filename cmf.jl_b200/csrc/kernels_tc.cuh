@@ -538,21 +538,37 @@ __global__ void split_H_kernel(const float *__restrict__ Hbuf, __nv_bfloat16 *__
 
 // Wi[(l*K+k)][N] fp32 ->  Wc[n][j], j = (L-1-l)*Kp + k  (row length KLp, zero padded)   [conv A operand]
 //                    and  Wu[(l*Kp+k)][N]               (rows_u rows, zero padded)      [transconv A operand]
+// One CTA per (32 units n, 32 components k, lag l): Wu is written as read (coalesced along n), Wc goes through a
+// shared-memory transpose so that its rows are written 32 components (64 bytes) at a time.
+// grid (ceil(N/32), ceil(Kp/32), L), block (32, 8).
 __global__ void split_W_kernel(const float *__restrict__ Wi, __nv_bfloat16 *__restrict__ wc_hi, __nv_bfloat16 *__restrict__ wc_lo,
                                __nv_bfloat16 *__restrict__ wu_hi, __nv_bfloat16 *__restrict__ wu_lo, int64_t N, int64_t K,
                                int64_t L, int Kp, int64_t KLp) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= L * Kp * N) return;
-    const int64_t n = idx % N;
-    const int64_t r = idx / N;
-    const int64_t l = r / Kp;
-    const int k = (int)(r % Kp);
-    const float v = (k < K) ? Wi[(l * K + k) * N + n] : 0.f;
-    __nv_bfloat16 h, lo_;
-    split_bf16(v, h, lo_);
-    wu_hi[idx] = h; wu_lo[idx] = lo_;
-    const int64_t j = (L - 1 - l) * Kp + k;
-    wc_hi[n * KLp + j] = h; wc_lo[n * KLp + j] = lo_;
+    __shared__ float tile[32][33];
+    const int64_t l = blockIdx.z;
+    const int64_t n0 = (int64_t)blockIdx.x * 32, k0 = (int64_t)blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int64_t k = k0 + r, n = n0 + threadIdx.x;
+        float v = 0.f;
+        if (k < Kp && n < N) {
+            if (k < K) v = Wi[(l * K + k) * N + n];
+            __nv_bfloat16 h, lo_;
+            split_bf16(v, h, lo_);
+            const int64_t idx = (l * Kp + k) * N + n;
+            wu_hi[idx] = h; wu_lo[idx] = lo_;
+        }
+        tile[r][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int64_t n = n0 + r, k = k0 + threadIdx.x;
+        if (n < N && k < Kp) {
+            __nv_bfloat16 h, lo_;
+            split_bf16(tile[threadIdx.x][r], h, lo_);
+            const int64_t j = (L - 1 - l) * Kp + k;
+            wc_hi[n * KLp + j] = h; wc_lo[n * KLp + j] = lo_;
+        }
+    }
 }
 
 // G = Htilde Htilde' (see build_G_kernel) written as bf16 hi/lo planes Gc[j][jj]: rows j = l*K + k (Wi order),
