@@ -50,6 +50,7 @@ SIGNATURES = {
     "cmf_set_engine": [_h, _int],
     "cmf_get_engine": [_h, _c.POINTER(_int)],
     "cmf_set_loss_mode": [_h, _int],
+    "cmf_get_loss_mode": [_h, _c.POINTER(_int)],
     "cmf_profile": [_h, _int],
     "cmf_profile_read": [_h, _int, _c.POINTER(_dbl), _c.POINTER(_i64)],
     "cmf_tensor_conv": [_i64, _i64, _i64, _i64, _int, _vp, _vp, _vp],

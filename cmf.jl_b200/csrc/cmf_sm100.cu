@@ -82,6 +82,7 @@ struct cmf_ctx {
     double data_norm = 0.0;
     double data_sumsq_local = 0.0;   // ||X_owned||^2 of this shard
     int loss_mode = 0;               // 0 = direct residual pass, 1 = algebraic expansion when its inputs are resident
+    bool loss_mode_explicit = false; // set by cmf_set_loss_mode: engine changes then leave the mode alone
     double pgd_stepW = 5.0, pgd_stepH = 5.0, pgd_cur_loss = 0.0;   // PGDUpdate state (pgd.jl:147-151)
     bool numH_valid = false;         // numH buffer == transconv(current W, X) and GS == W W' of the current W
     bool gram_valid = false;         // exchange buffer 1 holds the local Gram/tail partial of the current H
@@ -297,7 +298,8 @@ struct Ctx : cmf_ctx {
             const char *e = getenv("CMF_ENGINE_DEFAULT");
             if (tcs.ok && engine == 1 && L >= 8 && K <= fd::KQ && !(e && atoi(e) == 1)) {
                 fd_setup();
-                if (fds.ok) engine = 2;
+                // with this engine the expansion loss is the default too: the direct pass would cost 10x the iteration
+                if (fds.ok) { engine = 2; loss_mode = 1; }
             }
         }
         CK(cudaStreamSynchronize(stream));
@@ -1351,6 +1353,17 @@ void use(cmf_handle h) {
     CK(cudaSetDevice(h->device));
 }
 
+// The expansion loss cancels like 1/loss^2 (error ~2e-6/loss^2 relative, measured): at or below 25 % relative loss
+// (or when the expansion went negative) switch the handle back to the direct residual pass and re-evaluate with it.
+double guarded_loss(cmf_handle h, double sumsq) {
+    double loss = std::sqrt(sumsq) / h->data_norm;
+    if (h->loss_mode == 1 && !(loss > 0.25)) {
+        h->loss_mode = 0;
+        loss = std::sqrt(h->loss_partial()) / h->data_norm;
+    }
+    return loss;
+}
+
 // src/model.jl:91-107
 bool converged(const double *loss_hist, int64_t n, int patience, double tol) {
     if (n <= patience) return false;
@@ -1435,13 +1448,13 @@ int cmf_update_feature_maps(cmf_handle h, double l1H, double l2H, double *loss_o
         use(h);
         double loss;
         if (h->alg == CMF_HALS) {
-            loss = std::sqrt(h->hals_update_feature_maps(l1H, l2H)) / h->data_norm;
+            loss = guarded_loss(h, h->hals_update_feature_maps(l1H, l2H));
         } else if (h->alg == CMF_PGD) {
             loss = std::sqrt(h->pgd_update_feature_maps(l1H, l2H)) / h->data_norm;
         } else {
             REQUIRE(h->is_first && h->is_last, "sharded handles use the split-phase calls");
             h->h_update(l1H, l2H);
-            loss = std::sqrt(h->loss_partial()) / h->data_norm;
+            loss = guarded_loss(h, h->loss_partial());
         }
         if (loss_out) *loss_out = loss;
     });
@@ -1452,7 +1465,7 @@ int cmf_loss(cmf_handle h, double *loss_out) {
         use(h);
         REQUIRE(loss_out, "null output");
         REQUIRE(h->is_first && h->is_last, "sharded handles use cmf_loss_partial");
-        *loss_out = std::sqrt(h->loss_partial()) / h->data_norm;
+        *loss_out = guarded_loss(h, h->loss_partial());
     });
 }
 
@@ -1467,7 +1480,7 @@ int cmf_fit(cmf_handle h, int64_t max_itr, double max_time, int eval_mode, int c
         REQUIRE(h->is_first && h->is_last, "cmf_fit drives a single shard; sharded fits use the split-phase calls");
         if (converged_early) *converged_early = 0;
         int64_t n = 0;
-        loss_hist[n] = std::sqrt(h->loss_partial()) / h->data_norm;   // alternating.jl:37
+        loss_hist[n] = guarded_loss(h, h->loss_partial());   // alternating.jl:37
         time_hist[n] = 0.0;
         ++n;
         int64_t itr = 1;
@@ -1478,22 +1491,20 @@ int cmf_fit(cmf_handle h, int64_t max_itr, double max_time, int eval_mode, int c
             double loss;
             if (h->alg == CMF_HALS) {
                 if (!eval_mode) h->hals_update_motifs(l1W, l2W);
-                loss = std::sqrt(h->hals_update_feature_maps(l1H, l2H)) / h->data_norm;
+                loss = guarded_loss(h, h->hals_update_feature_maps(l1H, l2H));
             } else if (h->alg == CMF_PGD) {
                 if (!eval_mode) h->pgd_update_motifs(l1W, l2W);
                 loss = std::sqrt(h->pgd_update_feature_maps(l1H, l2H)) / h->data_norm;
+                if (h->loss_mode == 1 && !(loss > 0.25)) h->loss_mode = 0;   // PGD adapts its step on this value: no re-evaluation
             } else {
                 if (!eval_mode) { h->w_partials(); h->w_apply(l1W, l2W); }
                 h->h_update(l1H, l2H);
-                loss = std::sqrt(h->loss_partial()) / h->data_norm;
+                loss = guarded_loss(h, h->loss_partial());
             }
             const double dur = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
             time_hist[n] = time_hist[n - 1] + dur;
             loss_hist[n] = loss;
             ++n;
-            // the expansion cancels like 1/loss^2: its error is ~2e-6/loss^2 relative (measured), so below 25%
-            // relative loss fall back to the direct residual pass (keeps the loss within 1e-4 of the reference)
-            if (h->loss_mode == 1 && !(loss > 0.25)) h->loss_mode = 0;
             if (check_convergence && converged(loss_hist, n, patience, tol)) {   // alternating.jl:63-66
                 if (converged_early) *converged_early = 1;
                 break;
@@ -1580,6 +1591,7 @@ int cmf_set_engine(cmf_handle h, int engine) {
         if (engine >= 1 && !h->tc_available())
             throw CmfError(CMF_ERR_UNSUPPORTED, "tcgen05 engine needs an fp32 MultUpdate handle with K <= 128 and N % 8 == 0 on sm_100");
         h->engine = engine;
+        if (!h->loss_mode_explicit) h->loss_mode = (engine == 2) ? 1 : 0;   // the expansion is the default of engine 2 only
     });
 }
 
@@ -1588,7 +1600,11 @@ int cmf_set_loss_mode(cmf_handle h, int mode) {
         REQUIRE(h, "null handle");
         REQUIRE(mode == 0 || mode == 1, "loss mode must be 0 (direct) or 1 (expansion)");
         h->loss_mode = mode;
+        h->loss_mode_explicit = true;
     });
+}
+int cmf_get_loss_mode(cmf_handle h, int *mode_out) {
+    return guarded([&] { REQUIRE(h && mode_out, "null argument"); *mode_out = h->loss_mode; });
 }
 int cmf_get_engine(cmf_handle h, int *engine_out) {
     return guarded([&] { REQUIRE(h && engine_out, "null argument"); *engine_out = h->engine; });

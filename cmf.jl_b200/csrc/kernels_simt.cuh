@@ -846,8 +846,8 @@ template <typename S> __host__ __device__ constexpr int hw_kb() { return sizeof(
 template <typename S>
 inline size_t hals_wave_smem_elems(int64_t L) {
     const size_t WW = HW_TC + 2 * (L - 1);
-    const size_t QP = ((WW + 3) >> 2) | 1;
-    const size_t dwin = hw_kb<S>() * 4 * QP > (size_t)4 * HW_TC ? hw_kb<S>() * 4 * QP : (size_t)4 * HW_TC;
+    const size_t QP = ((WW + 7) >> 3) | 1;
+    const size_t dwin = hw_kb<S>() * 8 * QP > (size_t)4 * HW_TC ? hw_kb<S>() * 8 * QP : (size_t)4 * HW_TC;
     return 2 * HW_TC + (2 * L + 32) + L + 32 + (2 * L - 1) * hw_kb<S>() + dwin;
 }
 
@@ -865,7 +865,7 @@ __global__ void __launch_bounds__(HW_NT) hals_h_wave_kernel(const S *__restrict_
     S *ckk32 = ckk + L;                              // [32] C[k,k,j] zero padded (register-window recurrence, L <= 32)
     S *hch = ckk32 + 32;                             // [HW_TC] H of the current cell
     S *Cs = hch + HW_TC;                             // [(2L-1)][HW_KB] lag-table slice of the pull phase
-    S *Dwin = Cs + (2 * L - 1) * HW_KB;              // [HW_KB][4 planes][QP] transposed Delta window of the pull phase
+    S *Dwin = Cs + (2 * L - 1) * HW_KB;              // [HW_KB][8 planes][QP] transposed Delta window of the pull phase
     const int RB = (int)(2 * L + 32);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int64_t nC = (T + HW_TC - 1) / HW_TC;
@@ -906,18 +906,20 @@ __global__ void __launch_bounds__(HW_NT) hals_h_wave_kernel(const S *__restrict_
             __syncthreads();
             __threadfence();
             // ---- pull: corrections from all earlier components, HW_KB components at a time through shared memory.
-            //      Register tiling: thread (cg, kq) owns the 4 consecutive columns 4*cg .. 4*cg+3 and a quarter of the
-            //      staged components; along the lag loop the 4 Delta values slide through registers, so each step costs
-            //      one new Delta load + one (broadcast) table load for 4 FMAs.  The Delta window is stored transposed and
-            //      split into 4 planes (index i -> plane i&3, slot i>>2) so that lanes read consecutive words.
+            //      Register tiling: thread (cg, kq) owns the 8 consecutive columns 8*cg .. 8*cg+7 and a quarter of the
+            //      staged components; along the lag loop the 8 Delta values slide through registers, so each step costs
+            //      one new Delta load + one (broadcast) table load for 8 FMAs.  The Delta window is stored transposed and
+            //      split into 8 planes (index i -> plane i&7, slot i>>3) so that lanes read consecutive words.
             {
                 const int WW = HW_TC + 2 * (int)(L - 1);
-                const int QP = ((WW + 3) >> 2) | 1;            // slots per plane (odd)
-                const int WWQ = 4 * QP;                        // words per staged component
-                const int cg = tid & (HW_TC / 4 - 1), kq = tid >> 8;       // column group, component half
-                constexpr int NKQ = HW_NT / (HW_TC / 4);                   // 2 groups of components per staged block
+                const int QP = ((WW + 7) >> 3) | 1;            // slots per plane (odd)
+                const int WWQ = 8 * QP;                        // words per staged component
+                const int cg = tid & (HW_TC / 8 - 1), kq = tid >> 7;       // column group, component quarter
+                constexpr int NKQ = HW_NT / (HW_TC / 8);                   // 4 groups of components per staged block
                 constexpr int KQ = HW_KB / NKQ;
-                S a4[4] = {S(0), S(0), S(0), S(0)};
+                S a8[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) a8[r] = S(0);
                 for (int64_t kp0 = 0; kp0 < k; kp0 += HW_KB) {
                     const int kb = (int)((k - kp0 < HW_KB) ? k - kp0 : HW_KB);
                     __syncthreads();
@@ -926,7 +928,7 @@ __global__ void __launch_bounds__(HW_NT) hals_h_wave_kernel(const S *__restrict_
                         const int64_t t = t0 - (L - 1) + i;
                         S v = S(0);
                         if (kk < kb && t >= 0 && t < Tint) v = __ldcg(D + t * K + kp0 + kk);   // tail columns: slow path below
-                        Dwin[kk * WWQ + (i & 3) * QP + (i >> 2)] = v;
+                        Dwin[kk * WWQ + (i & 7) * QP + (i >> 3)] = v;
                     }
                     for (int idx = tid; idx < (2 * L - 1) * HW_KB; idx += nthr) {
                         const int kk = idx % HW_KB;
@@ -936,21 +938,19 @@ __global__ void __launch_bounds__(HW_NT) hals_h_wave_kernel(const S *__restrict_
                     __syncthreads();
                     for (int kk = kq * KQ; kk < kq * KQ + KQ && kk < kb; ++kk) {
                         const S *dw = Dwin + kk * WWQ;
-                        // window index of column 4*cg + r at lag step j:  i = 4*cg + r + 2(L-1) - j
-                        const int ib = 4 * cg + 2 * (int)(L - 1);
-                        S d0 = dw[(ib & 3) * QP + (ib >> 2)];
-                        S d1 = dw[((ib + 1) & 3) * QP + ((ib + 1) >> 2)];
-                        S d2 = dw[((ib + 2) & 3) * QP + ((ib + 2) >> 2)];
-                        S d3 = dw[((ib + 3) & 3) * QP + ((ib + 3) >> 2)];
+                        // window index of column 8*cg + r at lag step j:  i = 8*cg + r + 2(L-1) - j
+                        const int ib = 8 * cg + 2 * (int)(L - 1);
+                        S dv[8];
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) dv[r] = dw[((ib + r) & 7) * QP + ((ib + r) >> 3)];
                         for (int j = 0; j < 2 * (int)L - 1; ++j) {
                             const S cv = Cs[j * HW_KB + kk];
-                            a4[0] = fma(d0, cv, a4[0]);
-                            a4[1] = fma(d1, cv, a4[1]);
-                            a4[2] = fma(d2, cv, a4[2]);
-                            a4[3] = fma(d3, cv, a4[3]);
+#pragma unroll
+                            for (int r = 0; r < 8; ++r) a8[r] = fma(dv[r], cv, a8[r]);
                             const int in = ib - j - 1;         // next step's lowest index (>= 0 while j < 2L-2)
-                            d3 = d2; d2 = d1; d1 = d0;
-                            d0 = (in >= 0) ? dw[(in & 3) * QP + (in >> 2)] : S(0);
+#pragma unroll
+                            for (int r = 7; r > 0; --r) dv[r] = dv[r - 1];
+                            dv[0] = (in >= 0) ? dw[(in & 7) * QP + (in >> 3)] : S(0);
                         }
                     }
                 }
@@ -958,7 +958,7 @@ __global__ void __launch_bounds__(HW_NT) hals_h_wave_kernel(const S *__restrict_
                 __syncthreads();
                 S *red = Dwin;
 #pragma unroll
-                for (int r = 0; r < 4; ++r) red[kq * HW_TC + 4 * cg + r] = a4[r];
+                for (int r = 0; r < 8; ++r) red[kq * HW_TC + 8 * cg + r] = a8[r];
                 __syncthreads();
                 for (int col = tid; col < HW_TC; col += nthr) {
                     const int64_t tp = t0 + col;

@@ -107,7 +107,12 @@ class DeviceShard:
     def set_loss_mode(self, mode):
         """0 = direct residual pass, 1 = algebraic expansion on resident numH / C (tcgen05 engine only)."""
         check(_lib.load().cmf_set_loss_mode(self._h, int(mode)))
-        self.loss_mode = int(mode)
+
+    @property
+    def loss_mode(self):
+        out = ctypes.c_int(0)
+        check(_lib.load().cmf_get_loss_mode(self._h, ctypes.byref(out)))
+        return out.value
 
     def get_engine(self):
         out = ctypes.c_int()

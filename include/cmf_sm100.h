@@ -183,6 +183,10 @@ int cmf_set_engine(cmf_handle h, int engine);
  * identity cancels like 1/loss^2, (measured error ~2e-6/loss^2 relative), so callers switch back to 0 when the relative loss drops below 25%
  * (cmf_fit and the sharded host loop do). */
 int cmf_set_loss_mode(cmf_handle h, int mode);
+/* The loss mode currently in force (handles that select the frequency-domain engine by themselves start with 1; the
+ * single-shard calls cmf_loss / cmf_update_feature_maps / cmf_fit drop back to 0 and re-evaluate with the direct pass the
+ * first time the relative loss is <= 25%; sharded callers apply the same rule to the all-reduced loss). */
+int cmf_get_loss_mode(cmf_handle h, int *mode_out);
 /* The engine currently selected (0 / 1 / 2). */
 int cmf_get_engine(cmf_handle h, int *engine_out);
 

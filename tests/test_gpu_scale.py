@@ -39,8 +39,10 @@ def _properties(cmf, cfg, iters):
     f.setup_data_norm()
     f.rescale_init()
     assert s.get_engine() == 2                      # frequency-domain tcgen05 engine selected by default at these sizes
+    assert s.loss_mode == 1                         # ... and with it the expansion loss
     a = s.data_sumsq()
     # direct loss (TC_CONV) before anything else
+    s.set_loss_mode(0)
     ss_direct = s.loss_partial()
     # adjointness on the SAME (W, H): <W, corr(H,X)> == <X, conv(W,H)> == (||X||^2 + ||conv||^2 - ||conv - X||^2)/2
     # is checked through the two loss paths below; here: numW (TC_CORR) and numH (TC_TRANS) pair up with the
