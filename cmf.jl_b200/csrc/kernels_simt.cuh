@@ -805,26 +805,33 @@ __global__ void __launch_bounds__(256) hals_w_sweep_kernel(const S *__restrict__
         }
 }
 
-// Sequential recurrence of one component over W interior columns (full lag window, no truncation) with the pending
+// Sequential recurrence of one component over W = 32 interior columns (full lag window, no truncation) with the pending
 // corrections of the next W columns held in registers: p[j] is the pending correction of column t + j.  The W steps
-// are fully unrolled, so the rotation of the window is a compile-time renaming and a step costs its dependent chain
-// (load, 3 FMA/MUL, max, sub) plus W independent FMAs.  Every lane of the warp runs the same scalar code (the values
-// are warp-uniform); lane 0 stores.  Requires L - 1 <= W - 1... i.e. L <= W.
+// are fully unrolled, so the rotation of the window is a compile-time renaming.  Lane u holds h and q of column i0 + u
+// (one coalesced shared load per block) and receives that column's result; the per-column values are broadcast by
+// shuffles that do not depend on the recurrence, so a step costs its dependent chain (add, 2 FMA/MUL, max, sub) plus W
+// independent FMAs, with no shared-memory access inside the chain.  Every lane runs the same scalar code (the values
+// are warp-uniform).  Requires L <= W.
 template <typename S, int W, typename CT>
 __device__ __forceinline__ void hals_recurrence_block(S *hch, S *qeff, S (&p)[W], const CT &c /*C[k,k,j], zero for j >= L*/, S c0,
                                                        S inv, S l1, int i0, int lane) {
+    static_assert(W == 32, "one column per lane");
+    const S hl = hch[i0 + lane], ql = qeff[i0 + lane];
+    S vout = S(0), dout = S(0);
 #pragma unroll
     for (int u = 0; u < W; ++u) {
-        const S h = hch[i0 + u];
-        const S q = qeff[i0 + u] + p[u];
+        const S h = __shfl_sync(0xffffffffu, hl, u);
+        const S q = __shfl_sync(0xffffffffu, ql, u) + p[u];
         S v = (h * c0 - q - l1) * inv;
         v = v > S(0) ? v : S(0);
         const S d = v - h;
-        if (lane == 0) { hch[i0 + u] = v; qeff[i0 + u] = d; }
+        if (lane == u) { vout = v; dout = d; }
         p[u] = S(0);                                   // this slot now stands for column t + W
 #pragma unroll
         for (int j = 1; j < W; ++j) p[(u + j) % W] = fma(d, c[j], p[(u + j) % W]);
     }
+    hch[i0 + lane] = vout;
+    qeff[i0 + lane] = dout;                            // Delta H of the block (qeff is dead now)
 }
 
 // H sweep (hals.jl:121-154) as a wavefront over (component k, time chunk c) in ONE cooperative launch.
@@ -923,12 +930,24 @@ __global__ void __launch_bounds__(HW_NT) hals_h_wave_kernel(const S *__restrict_
                 for (int64_t kp0 = 0; kp0 < k; kp0 += HW_KB) {
                     const int kb = (int)((k - kp0 < HW_KB) ? k - kp0 : HW_KB);
                     __syncthreads();
-                    for (int idx = tid; idx < WW * HW_KB; idx += nthr) {
-                        const int kk = idx % HW_KB, i = idx / HW_KB;
-                        const int64_t t = t0 - (L - 1) + i;
-                        S v = S(0);
-                        if (kk < kb && t >= 0 && t < Tint) v = __ldcg(D + t * K + kp0 + kk);   // tail columns: slow path below
-                        Dwin[kk * WWQ + (i & 7) * QP + (i >> 3)] = v;
+                    // 8 loads in flight per thread: Delta comes from L2 (written by other SMs), a dependent load per
+                    // element would expose its latency 68 times per staged block
+                    for (int base = tid; base < WW * HW_KB; base += nthr * 8) {
+                        S v8[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int idx = base + u * nthr;
+                            const int kk = idx % HW_KB, i = idx / HW_KB;
+                            const int64_t t = t0 - (L - 1) + i;
+                            v8[u] = S(0);
+                            if (idx < WW * HW_KB && kk < kb && t >= 0 && t < Tint) v8[u] = __ldcg(D + t * K + kp0 + kk);   // tail columns: slow path below
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int idx = base + u * nthr;
+                            const int kk = idx % HW_KB, i = idx / HW_KB;
+                            if (idx < WW * HW_KB) Dwin[kk * WWQ + (i & 7) * QP + (i >> 3)] = v8[u];
+                        }
                     }
                     for (int idx = tid; idx < (2 * L - 1) * HW_KB; idx += nthr) {
                         const int kk = idx % HW_KB;
