@@ -236,6 +236,7 @@ struct Ctx : cmf_ctx {
     FdState fds;
     DevBuf<S> X, Hbuf, Wi, Wtmp, numW, denW, GS, Cf, numH, denH, tailC;
     DevBuf<int> progress, lockstep;
+    DevBuf<S> tailCt;                  // HALS H sweep: truncated lag tables of all component pairs
     int hals_grid = 0;
     DevBuf<double> exch1, corr_part, loss_part, scal;
     S *H = nullptr;  // owned column 0 inside Hbuf
@@ -1210,7 +1211,20 @@ struct Ctx : cmf_ctx {
         int *pr = progress.p;
         int64_t Kk = K, Ll = L, Tt = Tl, ks = s2_ks, ldv = s2_ld;
         S a1 = (S)l1H, a2 = (S)l2H;
-        void *args[] = {&cf, &s2, &q, &hh, &dd, &tc_, &pr, &Kk, &Ll, &Tt, &ks, &ldv, &a1, &a2};
+        int dbg = getenv("CMF_HALS_DEBUG") ? atoi(getenv("CMF_HALS_DEBUG")) : 0;   // 1: phase clocks of the last component; 2 / 4: timing runs without the pull / recurrence
+        // truncated lag tables of all component pairs for the pull over the last L-1 columns (skipped when they would not fit: the
+        // kernel then forms them on the fly)
+        const S *ct = nullptr;
+        {
+            const size_t need = (size_t)(L - 1) * (size_t)(2 * L - 1) * (size_t)(K * K);
+            if (L > 1 && need * sizeof(S) <= ((size_t)1 << 30) && !getenv("CMF_HALS_TAIL_DIRECT")) {
+                if (tailCt.n < need) tailCt.alloc(need);
+                hals_tail_table_kernel<S><<<(unsigned)cdiv((2 * L - 1) * K * K, 256), 256, 0, stream>>>(GS.p, tailCt.p, K, L, s2_ks, s2_ld);
+                post_launch();
+                ct = tailCt.p;
+            }
+        }
+        void *args[] = {&cf, &s2, &q, &hh, &dd, &tc_, &pr, &Kk, &Ll, &Tt, &ks, &ldv, &a1, &a2, &dbg, &ct};
         CK(cudaLaunchCooperativeKernel((void *)hals_h_wave_kernel<S>, dim3((unsigned)hals_grid), dim3(HW_NT), args, smem, stream));
         post_launch();
         gram_valid = false; fds.h_dirty = true;

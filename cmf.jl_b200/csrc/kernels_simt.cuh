@@ -834,6 +834,22 @@ __device__ __forceinline__ void hals_recurrence_block(S *hch, S *qeff, S (&p)[W]
     qeff[i0 + lane] = dout;                            // Delta H of the block (qeff is dead now)
 }
 
+// Truncated lag tables of the H sweep for every pair of components (the sweep's pull over the last L-1 columns):
+//   Ct[w-1][dd+L-1][k][k'] = C_w[k',k,dd] = sum_{l<w, 0<=l-dd<L} S2[(l,k')][(l-dd,k)],   w = 1..L-1
+// one thread per (dd, k, k') walks w with a running sum (each element of S2 is read once per table it enters).
+template <typename S>
+__global__ void hals_tail_table_kernel(const S *__restrict__ S2, S *__restrict__ Ct, int64_t K, int64_t L, int64_t Ks, int64_t ld) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (2 * L - 1) * K * K) return;
+    const int64_t kp = e % K, k = (e / K) % K, dq = e / (K * K), dd = dq - (L - 1);
+    double pre = 0.0;
+    for (int64_t w = 1; w < L; ++w) {
+        const int64_t l = w - 1, lp = l - dd;
+        if (lp >= 0 && lp < L) pre += (double)S2[(l * Ks + kp) * ld + lp * Ks + k];
+        Ct[(((w - 1) * (2 * L - 1) + dq) * K + k) * K + kp] = (S)pre;
+    }
+}
+
 // H sweep (hals.jl:121-154) as a wavefront over (component k, time chunk c) in ONE cooperative launch.
 //   Q[t][k] = transconv(W, conv(W,H) - X)[k,t] at the start of the sweep (gradient of the H step),
 //   Cf[(d+L-1)][k][k'] interior lag table, S2 = W W' for the truncated tail tables, D[t][k] = Delta H (output).
@@ -855,7 +871,7 @@ inline size_t hals_wave_smem_elems(int64_t L) {
     const size_t WW = HW_TC + 2 * (L - 1);
     const size_t QP = ((WW + 7) >> 3) | 1;
     const size_t dwin = hw_kb<S>() * 8 * QP > (size_t)4 * HW_TC ? hw_kb<S>() * 8 * QP : (size_t)4 * HW_TC;
-    return 2 * HW_TC + (2 * L + 32) + L + 32 + (2 * L - 1) * hw_kb<S>() + dwin;
+    return 2 * HW_TC + (2 * L + 32) + L + 32 + (2 * L + 6) * hw_kb<S>() + dwin;
 }
 
 template <typename S>
@@ -863,8 +879,13 @@ __global__ void __launch_bounds__(HW_NT) hals_h_wave_kernel(const S *__restrict_
                                                              const S *__restrict__ Q, S *__restrict__ H, S *__restrict__ D,
                                                              S *__restrict__ tailC_all /*[grid][L*L]*/, int *progress /*[K]*/,
                                                              int64_t K, int64_t L, int64_t T, int64_t Ks, int64_t ld,
-                                                             S l1, S l2) {
+                                                             S l1, S l2, int debug, const S *__restrict__ Ct /*tail tables or nullptr*/) {
     constexpr int HW_KB = hw_kb<S>();
+    // optional phase clocks of the last component (CMF_HALS_DEBUG): cycles of thread 0 between marks, barrier waits included
+    __shared__ long long dbg_acc[8];
+    __shared__ long long dbg_t;
+#define HW_MARK(i) do { if ((debug & 1) && threadIdx.x == 0) { const long long now_ = clock64(); dbg_acc[i] += now_ - dbg_t; dbg_t = now_; } } while (0)
+    if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) dbg_acc[i] = 0; dbg_t = clock64(); }
     extern __shared__ __align__(16) unsigned char smem_raw[];
     S *qeff = reinterpret_cast<S *>(smem_raw);       // [HW_TC]
     S *pend = qeff + HW_TC;                          // ring of RB entries
@@ -872,7 +893,7 @@ __global__ void __launch_bounds__(HW_NT) hals_h_wave_kernel(const S *__restrict_
     S *ckk32 = ckk + L;                              // [32] C[k,k,j] zero padded (register-window recurrence, L <= 32)
     S *hch = ckk32 + 32;                             // [HW_TC] H of the current cell
     S *Cs = hch + HW_TC;                             // [(2L-1)][HW_KB] lag-table slice of the pull phase
-    S *Dwin = Cs + (2 * L - 1) * HW_KB;              // [HW_KB][8 planes][QP] transposed Delta window of the pull phase
+    S *Dwin = Cs + (2 * L + 6) * HW_KB;              // [HW_KB][8 planes][QP] transposed Delta window of the pull phase (Cs: lag rows padded to a multiple of 8)
     const int RB = (int)(2 * L + 32);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int64_t nC = (T + HW_TC - 1) / HW_TC;
@@ -902,6 +923,7 @@ __global__ void __launch_bounds__(HW_NT) hals_h_wave_kernel(const S *__restrict_
         }
         bool ring_mode = false;               // true once the window lives in the shared ring (tail / partial blocks / L > 32)
 
+        if ((debug & 1) && tid == 0) { for (int i = 0; i < 8; ++i) dbg_acc[i] = 0; dbg_t = clock64(); }
         for (int64_t c = 0; c < nC; ++c) {
             const int64_t t0 = c * HW_TC;
             // ---- wait: component k-1 must have finished cell min(c+1, nC-1)
@@ -912,6 +934,7 @@ __global__ void __launch_bounds__(HW_NT) hals_h_wave_kernel(const S *__restrict_
             }
             __syncthreads();
             __threadfence();
+            HW_MARK(0);
             // ---- pull: corrections from all earlier components, HW_KB components at a time through shared memory.
             //      Register tiling: thread (cg, kq) owns the 8 consecutive columns 8*cg .. 8*cg+7 and a quarter of the
             //      staged components; along the lag loop the 8 Delta values slide through registers, so each step costs
@@ -927,11 +950,39 @@ __global__ void __launch_bounds__(HW_NT) hals_h_wave_kernel(const S *__restrict_
                 S a8[8];
 #pragma unroll
                 for (int r = 0; r < 8; ++r) a8[r] = S(0);
-                for (int64_t kp0 = 0; kp0 < k; kp0 += HW_KB) {
+                for (int64_t kp0 = 0; kp0 < ((debug & 2) ? 0 : k); kp0 += HW_KB) {   // debug bit 1: timing without the pull (wrong results)
                     const int kb = (int)((k - kp0 < HW_KB) ? k - kp0 : HW_KB);
                     __syncthreads();
                     // 8 loads in flight per thread: Delta comes from L2 (written by other SMs), a dependent load per
                     // element would expose its latency 68 times per staged block
+                    if (sizeof(S) == 4 && (K & 3) == 0) {
+                        // 128-bit loads: 4 staged components per load (kp0 is a multiple of HW_KB, rows of Delta are K long)
+                        constexpr int KB4 = HW_KB / 4;
+                        for (int base = tid; base < WW * KB4; base += nthr * 4) {
+                            float4 v4[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int idx = base + u * nthr;
+                                const int k4 = (idx % KB4) * 4, i = idx / KB4;
+                                const int64_t t = t0 - (L - 1) + i;
+                                v4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (idx < WW * KB4 && k4 < kb && t >= 0 && t < Tint)
+                                    v4[u] = __ldcg(reinterpret_cast<const float4 *>(D + t * K + kp0 + k4));
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int idx = base + u * nthr;
+                                const int k4 = (idx % KB4) * 4, i = idx / KB4;
+                                if (idx < WW * KB4) {
+                                    const int ad = (i & 7) * QP + (i >> 3);
+                                    Dwin[(k4 + 0) * WWQ + ad] = (S)((k4 + 0 < kb) ? v4[u].x : 0.f);
+                                    Dwin[(k4 + 1) * WWQ + ad] = (S)((k4 + 1 < kb) ? v4[u].y : 0.f);
+                                    Dwin[(k4 + 2) * WWQ + ad] = (S)((k4 + 2 < kb) ? v4[u].z : 0.f);
+                                    Dwin[(k4 + 3) * WWQ + ad] = (S)((k4 + 3 < kb) ? v4[u].w : 0.f);
+                                }
+                            }
+                        }
+                    } else
                     for (int base = tid; base < WW * HW_KB; base += nthr * 8) {
                         S v8[8];
 #pragma unroll
@@ -949,29 +1000,50 @@ __global__ void __launch_bounds__(HW_NT) hals_h_wave_kernel(const S *__restrict_
                             if (idx < WW * HW_KB) Dwin[kk * WWQ + (i & 7) * QP + (i >> 3)] = v8[u];
                         }
                     }
-                    for (int idx = tid; idx < (2 * L - 1) * HW_KB; idx += nthr) {
+                    const int nlp = (2 * (int)L - 1 + 7) & ~7;                 // lag rows padded with zeros to a multiple of 8
+                    for (int idx = tid; idx < nlp * HW_KB; idx += nthr) {
                         const int kk = idx % HW_KB;
                         const int64_t j = idx / HW_KB;
-                        Cs[idx] = (kk < kb) ? Cf[(j * K + kp0 + kk) * K + k] : S(0);
+                        Cs[idx] = (kk < kb && j < 2 * L - 1) ? Cf[(j * K + kp0 + kk) * K + k] : S(0);
                     }
                     __syncthreads();
-                    for (int kk = kq * KQ; kk < kq * KQ + KQ && kk < kb; ++kk) {
-                        const S *dw = Dwin + kk * WWQ;
-                        // window index of column 8*cg + r at lag step j:  i = 8*cg + r + 2(L-1) - j
+                    HW_MARK(1);
+                    // two staged components per pass (they share the index arithmetic); the window of 8 Delta values per
+                    // component is a circular register file whose rotation is compile-time: the lag loop is unrolled by 8,
+                    // slot (r - jj) & 7 holds window index ib + r - j at step j = j0 + jj, and step jj refills slot -jj.
+                    for (int kk = kq * KQ; kk < kq * KQ + KQ && kk < kb; kk += 2) {
+                        const bool two = kk + 1 < kb;
+                        const S *dwa = Dwin + kk * WWQ, *dwb = two ? dwa + WWQ : dwa;
                         const int ib = 8 * cg + 2 * (int)(L - 1);
-                        S dv[8];
+                        const int nl = 2 * (int)L - 1;
+                        S da[8], db[8];
+                        da[0] = S(0); db[0] = S(0);
 #pragma unroll
-                        for (int r = 0; r < 8; ++r) dv[r] = dw[((ib + r) & 7) * QP + ((ib + r) >> 3)];
-                        for (int j = 0; j < 2 * (int)L - 1; ++j) {
-                            const S cv = Cs[j * HW_KB + kk];
+                        for (int o = 1; o < 8; ++o) {
+                            const int ad = ((ib + o) & 7) * QP + ((ib + o) >> 3);
+                            da[o] = dwa[ad]; db[o] = dwb[ad];
+                        }
+                        // the padded lag rows of Cs are zero, so whole groups of 8 steps run without a branch (window
+                        // indices below 0 are clamped: their table entries are zero)
+                        const int kkb = two ? kk + 1 : kk;
+                        const S cbs = two ? S(1) : S(0);
+                        for (int j0 = 0; j0 < nl; j0 += 8) {
 #pragma unroll
-                            for (int r = 0; r < 8; ++r) a8[r] = fma(dv[r], cv, a8[r]);
-                            const int in = ib - j - 1;         // next step's lowest index (>= 0 while j < 2L-2)
+                            for (int jj = 0; jj < 8; ++jj) {
+                                const int j = j0 + jj;
+                                const int in = max(ib - j, 0);         // window index entering at this step (column r = 0)
+                                const int ad = (in & 7) * QP + (in >> 3);
+                                da[(8 - jj) & 7] = dwa[ad]; db[(8 - jj) & 7] = dwb[ad];
+                                const S ca = Cs[j * HW_KB + kk], cb = Cs[j * HW_KB + kkb] * cbs;
 #pragma unroll
-                            for (int r = 7; r > 0; --r) dv[r] = dv[r - 1];
-                            dv[0] = (in >= 0) ? dw[(in & 7) * QP + (in >> 3)] : S(0);
+                                for (int r = 0; r < 8; ++r) {
+                                    a8[r] = fma(da[(r - jj + 8) & 7], ca, a8[r]);
+                                    a8[r] = fma(db[(r - jj + 8) & 7], cb, a8[r]);
+                                }
+                            }
                         }
                     }
+                    HW_MARK(2);
                 }
                 // reduce the component groups: red[kq][column] (reuses the Delta window space), then add Q
                 __syncthreads();
@@ -987,7 +1059,43 @@ __global__ void __launch_bounds__(HW_NT) hals_h_wave_kernel(const S *__restrict_
                     qeff[col] = acc;
                 }
                 __syncthreads();
-                // truncated tail columns t >= Tint (only the last chunks see them): C_w from S2 on the fly
+                // truncated tail columns t >= Tint (only the last chunks see them): the tables C_w[k',k,dd] come precomputed
+                // (hals_tail_table_kernel) as Ct[w-1][dd+L-1][k][k']; work item = (column, block of earlier components),
+                // block sums go through shared memory and are added in a fixed order (deterministic)
+                if (Ct != nullptr) {
+                    if (k > 0 && t0 + HW_TC + (L - 1) > Tint) {
+                        const int64_t c_lo = (t0 > Tint - (L - 1)) ? t0 : Tint - (L - 1);
+                        const int64_t c_hi = (t0 + HW_TC < T) ? t0 + HW_TC : T;
+                        const int ncol = (int)(c_hi - c_lo);
+                        const int CH = (int)((k + 15) / 16 > 16 ? (k + 15) / 16 : 16);
+                        const int nch = (int)((k + CH - 1) / CH);
+                        S *part = Dwin;                            // [nch][HW_TC], nch <= 16
+                        if (ncol > 0) {
+                            for (int it = tid; it < ncol * nch; it += nthr) {
+                                const int ci = it % ncol, ch = it / ncol;
+                                const int64_t tp = c_lo + ci;
+                                int64_t ta = (tp - (L - 1) > Tint) ? tp - (L - 1) : Tint;
+                                if (ta < 0) ta = 0;
+                                const int64_t tb = tp + (L - 1) < T - 1 ? tp + (L - 1) : T - 1;
+                                const int64_t kp_lo = (int64_t)ch * CH, kp_hi = (kp_lo + CH < k) ? kp_lo + CH : k;
+                                double accd = 0.0;
+                                for (int64_t t = ta; t <= tb; ++t) {
+                                    const int64_t dd = tp - t, w = T - t;
+                                    const S *ct = Ct + ((((w - 1) * (2 * L - 1) + (dd + L - 1)) * K + k) * K);
+                                    const S *dr = D + t * K;
+                                    for (int64_t kp = kp_lo; kp < kp_hi; ++kp) accd += (double)__ldcg(dr + kp) * (double)ct[kp];
+                                }
+                                part[ch * HW_TC + ci] = (S)accd;
+                            }
+                            __syncthreads();
+                            for (int ci = tid; ci < ncol; ci += nthr) {
+                                double sacc = 0.0;
+                                for (int ch = 0; ch < nch; ++ch) sacc += (double)part[ch * HW_TC + ci];
+                                qeff[(int)(c_lo - t0) + ci] += (S)sacc;
+                            }
+                        }
+                    }
+                } else
                 for (int col = tid; col < HW_TC; col += nthr) {
                     const int64_t tp = t0 + col;
                     if (tp < T && tp + (L - 1) >= Tint) {
@@ -1011,6 +1119,7 @@ __global__ void __launch_bounds__(HW_NT) hals_h_wave_kernel(const S *__restrict_
                 }
             }
             __syncthreads();
+            HW_MARK(3);
             // ---- sweep: the sequential recurrence of component k over this chunk (warp 0), entirely in shared
             //      memory: H of the chunk is prefetched by all threads, results are written back by all threads
             for (int col = tid; col < HW_TC; col += nthr) {
@@ -1018,7 +1127,8 @@ __global__ void __launch_bounds__(HW_NT) hals_h_wave_kernel(const S *__restrict_
                 hch[col] = (tp < T) ? H[tp * K + k] : S(0);
             }
             __syncthreads();
-            if (tid < 32) {
+            HW_MARK(4);
+            if (tid < 32 && !(debug & 4)) {   // debug bit 2: timing without the recurrence (wrong results)
                 const int lane = tid;
                 const int n = (int)((t0 + HW_TC < T) ? HW_TC : T - t0);
                 int i = 0;
@@ -1072,6 +1182,7 @@ __global__ void __launch_bounds__(HW_NT) hals_h_wave_kernel(const S *__restrict_
                 }
             }
             __syncthreads();
+            HW_MARK(5);
             for (int col = tid; col < HW_TC; col += nthr) {
                 const int64_t tp = t0 + col;
                 if (tp < T) {
@@ -1084,10 +1195,17 @@ __global__ void __launch_bounds__(HW_NT) hals_h_wave_kernel(const S *__restrict_
             __threadfence();
             __syncthreads();
             if (tid == 0) atomicExch(progress + k, (int)(c + 1));
+            HW_MARK(6);
         }
+        if ((debug & 1) && tid == 0 && k == K - 1)
+            printf("hals_h_wave component %lld, %lld cells, kcycles per cell: wait %.1f  stage %.1f  pull %.1f  reduce+Q %.1f  loadH %.1f  recurrence %.1f  writeback+publish %.1f\n",
+                   (long long)k, (long long)nC, dbg_acc[0] / 1e3 / nC, dbg_acc[1] / 1e3 / nC, dbg_acc[2] / 1e3 / nC, dbg_acc[3] / 1e3 / nC,
+                   dbg_acc[4] / 1e3 / nC, dbg_acc[5] / 1e3 / nC, dbg_acc[6] / 1e3 / nC);
         __syncthreads();
     }
 }
+
+#undef HW_MARK
 
 // Projected gradient descent pieces (src/algs/pgd.jl:224-255, SquareLoss):
 //   g = 2*(den - num) + 2*l2*x + l1*sign(x)      gradient of ||conv - X||^2 plus Square/Absolute penalties (:30-32,:77-88)
