@@ -218,13 +218,17 @@ struct FdState {
     int V2 = 0;                           // hop of the denomH blocking (2L-1 lags): B - 2L + 2
     int64_t nblk2 = 0;
     DevBuf<__nv_bfloat16> Xf_hi, Xf_lo, Ah_hi, Ah_lo, Aw_hi, Aw_lo, Hf_hi, Hf_lo, Ac_hi, Ac_lo;
-    DevBuf<float> Of, Df, Gf;
-    CUtensorMap mXfK[2], mXfMN[2], mAw[2], mAh[2], mHfMN[2], mAc[2], mHf2K[2];
+    DevBuf<float> Of, Df, Gf, Yf;
+    DevBuf<__nv_bfloat16> Awm_hi, Awm_lo; // direct loss pass: spectrum of W as the A operand of TC_FQX (allocated on first use)
+    int64_t nbc = 0;                      // blocks per chunk of the direct loss pass (Yf holds F x nbc x 2 x N floats)
+    bool wx_dirty = true;
+    CUtensorMap mXfK[2], mXfMN[2], mAw[2], mAh[2], mHfMN[2], mAc[2], mHf2K[2], mAwm[2], mHcK[2];
     bool x_dirty = true, w_dirty = true, h_dirty = true;   // h_dirty: Ah does not hold the spectrum of the current H
     std::string why;                      // reason the engine is unavailable
     void release() {
         Xf_hi.free(); Xf_lo.free(); Ah_hi.free(); Ah_lo.free(); Aw_hi.free(); Aw_lo.free(); Of.free(); Df.free();
         Hf_hi.free(); Hf_lo.free(); Gf.free(); Ac_hi.free(); Ac_lo.free();
+        Yf.free(); Awm_hi.free(); Awm_lo.free(); nbc = 0; wx_dirty = true;
         ok = tried = false;
         x_dirty = w_dirty = h_dirty = true;
     }
@@ -316,7 +320,7 @@ struct Ctx : cmf_ctx {
         return fds.ok;
     }
     void fd_release() override { fds.release(); }
-    void mark_w_dirty() { tcs.w_dirty = true; fds.w_dirty = true; }
+    void mark_w_dirty() { tcs.w_dirty = true; fds.w_dirty = true; fds.wx_dirty = true; }
 
     // ---------------------------------------------------------------- frequency-domain engine (fp32, K <= 64, L <= 256)
     void fd_setup() {
@@ -367,8 +371,11 @@ struct Ctx : cmf_ctx {
             }
             CK(cudaFuncSetAttribute(tc::tc_kernel<tc::TC_FQT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
             CK(cudaFuncSetAttribute(tc::tc_kernel<tc::TC_FQC>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+            CK(cudaFuncSetAttribute(tc::tc_kernel<tc::TC_FQX>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+
             const int big = (int)fd_smem(fd_cols_h()), small_ = (int)fd_smem(16);
             CK(cudaFuncSetAttribute(fd::fft_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_));
+            CK(cudaFuncSetAttribute(fd::ifft_resid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_));
             CK(cudaFuncSetAttribute(fd::fft_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_));
             CK(cudaFuncSetAttribute(fd::ifft_numW_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_));
             CK(cudaFuncSetAttribute(fd::ifft_numW_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_));
@@ -426,7 +433,7 @@ struct Ctx : cmf_ctx {
         if constexpr (std::is_same<S, float>::value) {
             FdState &f = fds;
             fd::fft_w_kernel<<<dim3((unsigned)cdiv(K, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(
-                Cf.p, f.Ac_hi.p, f.Ac_lo.p, K, K, 2 * L - 1, f.B, f.logB, fd::MROWS, fd::KQ);
+                Cf.p, f.Ac_hi.p, f.Ac_lo.p, K, K, 2 * L - 1, f.B, f.logB, fd::MROWS, fd::KQ, 0);
             post_launch();
             const int C = fd_cols_h();
             fd::fft_h_kernel<<<dim3((unsigned)f.nblk2, (unsigned)(32 / C)), fd::NT, fd_smem(C), stream>>>(
@@ -446,6 +453,66 @@ struct Ctx : cmf_ctx {
                 f.Of.p, denH.p, K, Tl, f.B, f.logB, f.V2, f.nblk2, C);
             post_launch();
         }
+    }
+    // sum of squared residuals (mult.jl:55-57) through the frequency domain: Xhat^ = W^ H^ per frequency for a chunk of
+    // blocks (TC_FQX), inverse transform, subtract X, sum of squares (ifft_resid_kernel); returns the number of partials.
+    // ~5x cheaper than the time-domain TC_CONV pass at c4, and free of the cancellation of the expansion.
+    int64_t fd_conv_loss() {
+        if constexpr (std::is_same<S, float>::value) {
+            FdState &f = fds;
+            const int64_t ntile32 = cdiv(N, 32);
+            if (f.Awm_hi.n == 0) {
+                const size_t aw = (size_t)f.F * 2 * fd::MROWS * (size_t)N + 64;
+                size_t free_b = 0, total_b = 0;
+                CK(cudaMemGetInfo(&free_b, &total_b));
+                const size_t per_block = (size_t)f.F * 2 * (size_t)N * sizeof(float);          // Yf bytes per block
+                REQUIRE(free_b > 4 * aw + 256 * per_block + ((size_t)1 << 29), "not enough device memory for the frequency-domain loss pass");
+                size_t budget = std::min<size_t>((free_b - 4 * aw - ((size_t)1 << 29)) / 2, (size_t)12 << 30);
+                int64_t nbc = (int64_t)(budget / per_block) / tc::BN * tc::BN;
+                nbc = std::max<int64_t>(tc::BN, std::min<int64_t>(nbc, cdiv(f.nblk, tc::BN) * tc::BN));
+                if (const char *e = getenv("CMF_FD_NBC")) { const int64_t v = atoll(e); if (v >= tc::BN && v % tc::BN == 0 && v < nbc) nbc = v; }   // tests: force several chunks
+                f.nbc = nbc;
+                f.Awm_hi.alloc(aw); f.Awm_lo.alloc(aw);
+                f.Yf.alloc((size_t)f.F * (size_t)nbc * 2 * (size_t)N);
+                for (int i = 0; i < 2; ++i) {
+                    f.mAwm[i] = make_map_mn(i == 0 ? f.Awm_hi.p : f.Awm_lo.p, (uint64_t)f.F * 2 * fd::MROWS, (uint64_t)N * 2, (uint64_t)cdiv(N, 64), tc::BK, 2);
+                    f.mHcK[i] = make_map_2d(i == 0 ? f.Hf_hi.p : f.Hf_lo.p, fd::MROWS, (uint64_t)f.F * (uint64_t)f.nblk, (uint64_t)fd::MROWS * 2, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
+                }
+                f.wx_dirty = true;
+            }
+            const size_t need_lp = (size_t)(f.nblk * ntile32);
+            if (loss_part.n < need_lp) loss_part.alloc(std::max<size_t>(need_lp, 4096));
+            if (f.wx_dirty) {
+                fd::fft_w_kernel<<<dim3((unsigned)cdiv(N, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(Wi.p, f.Awm_hi.p, f.Awm_lo.p, N, K, L, f.B, f.logB, 2 * N, N, 1);
+                post_launch();
+                f.wx_dirty = false;
+            }
+            const int C = fd_cols_h();
+            fd::fft_h_kernel<<<dim3((unsigned)f.nblk, (unsigned)(32 / C)), fd::NT, fd_smem(C), stream>>>(
+                H, f.Hf_hi.p, f.Hf_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V, f.nblk, C, 1, -(L - 1));
+            post_launch();
+            prof_begin(PROF_CONV);
+            for (int64_t b0 = 0; b0 < f.nblk; b0 += f.nbc) {
+                const int64_t cur = std::min(f.nbc, f.nblk - b0);
+                tc::Params q = tc_base_params();
+                q.nprod = 3;
+                q.tiles_n = cdiv(cur, tc::BN);
+                q.tiles_m = cdiv(N, tc::BM);
+                q.nkb = fd::MROWS / tc::BK;
+                q.units = (int64_t)f.F * 2 * q.tiles_m * q.tiles_n;
+                q.fq_rows = f.nblk; q.b_off = b0; q.nbc = cur;
+                q.out = f.Yf.p;
+                const unsigned grid = (unsigned)std::min<int64_t>(q.units, tcs.num_sms);
+                tc::tc_kernel<tc::TC_FQX><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(f.mAwm[0], f.mAwm[1], f.mHcK[0], f.mHcK[1], q);
+                post_launch();
+                fd::ifft_resid_kernel<<<dim3((unsigned)cur, (unsigned)ntile32), fd::NT, fd_smem(16), stream>>>(
+                    f.Yf.p, X.p, loss_part.p + b0 * ntile32, N, Tl, L, f.B, f.logB, f.V, cur, b0);
+                post_launch();
+            }
+            prof_end();
+            return f.nblk * ntile32;
+        }
+        return 0;
     }
     // Ah = spectrum of the owned columns of the current H, block by block (shared by numW and the Gram partial)
     void fd_spectrum_H() {
@@ -488,7 +555,7 @@ struct Ctx : cmf_ctx {
             FdState &f = fds;
             fd_build_X();
             if (f.w_dirty) {
-                fd::fft_w_kernel<<<dim3((unsigned)cdiv(N, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(Wi.p, f.Aw_hi.p, f.Aw_lo.p, N, K, L, f.B, f.logB, 2 * N, N);
+                fd::fft_w_kernel<<<dim3((unsigned)cdiv(N, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(Wi.p, f.Aw_hi.p, f.Aw_lo.p, N, K, L, f.B, f.logB, 2 * N, N, 0);
                 post_launch();
                 f.w_dirty = false;
             }
@@ -1135,7 +1202,8 @@ struct Ctx : cmf_ctx {
             if (numH_valid) return loss_partial_expansion();
         }
         int64_t nb = conv_nblocks(0, Tl);
-        if (tc_active()) nb = tc_conv_loss();
+        if (fd_active() && !getenv("CMF_FD_LOSS_TC")) nb = fd_conv_loss();
+        else if (tc_active()) nb = tc_conv_loss();
         else launch_conv(Wi.p, H, K, L, -(L - 1), Tl + (L - 1), 0, Tl, 4, nullptr, loss_part.p);  // mult.jl:55-57
         reduce_scalar(loss_part.p, nb, scal.p);
         return fetch_scalar(scal.p);

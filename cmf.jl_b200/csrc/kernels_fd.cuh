@@ -23,6 +23,10 @@
 // product with N -> K: blocks of hop V2 = B-2L+2 starting L-1 columns early,
 //   Ac [f][m][c][k']         conj(C^) as the real 128 x 128 matrix                                 (A of TC_FQT)
 //   Hf [f][b][c][k']         full blocks of H (same layout as above, other blocking)               (B of TC_FQT)
+// The direct loss ||conv(W,H) - X||^2 (mult.jl:55-57) goes the other way: Xhat^[n,b,f] = sum_k W^[k,n,f] H^[k,b,f] over full
+// blocks of H that start L-1 columns early (hop V), inverse transform, the last V samples of a block are exact:
+//   Awm[f][co][c][k][n]      W^ as the real matrices [Wr | -Wi] (co = re) and [Wi | Wr] (co = im), n contiguous (A of TC_FQX)
+//   Yf [f][b][co][n] fp32    Xhat^ for a chunk of blocks (output of TC_FQX) -> ifft_resid_kernel subtracts X and sums squares
 //
 // FFT: in-place radix-2 decimation-in-frequency (two stages fused per pass) in shared memory over a tile d[B][C] of C
 // independent complex columns (column index fastest: conflict-free), output in bit-reversed order.  Two real sequences ride in one complex transform
@@ -185,7 +189,7 @@ fft_h_kernel(const float *__restrict__ H, __nv_bfloat16 *__restrict__ hi, __nv_b
 // K x K lag table C with N = K and L = 2L-1 lags -> Ac).  grid (ceil(N/32), K).
 __global__ void __launch_bounds__(NT)
 fft_w_kernel(const float *__restrict__ Wi, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int64_t N, int64_t K,
-             int64_t L, int B, int logB, int64_t ldw, int64_t coff) {
+             int64_t L, int B, int logB, int64_t ldw, int64_t coff, int xmode) {
     extern __shared__ float2 fd_smem[];
     constexpr int C = 16;
     float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;
@@ -208,6 +212,14 @@ fft_w_kernel(const float *__restrict__ Wi, __nv_bfloat16 *__restrict__ hi, __nv_
     for (int f = threadIdx.x / C; f <= B / 2; f += NT / C) {
         float ar, ai, br, bi;
         unpack_pair(d, f, B, logB, C, p, ar, ai, br, bi);
+        if (xmode) {                                               // Awm[f][co][c][k][n]: re = [Wr | -Wi], im = [Wi | Wr]
+            const int64_t r0 = (((int64_t)f * 2 + 0) * MROWS + k) * N + n, r1 = (((int64_t)f * 2 + 1) * MROWS + k) * N + n;
+            store_split2(hi, lo, r0, ar, br);
+            store_split2(hi, lo, r0 + KQ * N, -ai, -bi);
+            store_split2(hi, lo, r1, ai, bi);
+            store_split2(hi, lo, r1 + KQ * N, ar, br);
+            continue;
+        }
         const int64_t re = ((int64_t)f * MROWS + k) * ldw, im = ((int64_t)f * MROWS + KQ + k) * ldw;
         store_split2(hi, lo, re + n, ar, br);                      // row k:      [  Wr | Wi ]
         store_split2(hi, lo, re + coff + n, ai, bi);
@@ -239,6 +251,60 @@ ifft_numH_kernel(const float *__restrict__ Of, float *__restrict__ numH, int64_t
         const float2 z = d[rev(i, logB) * C + p];
         if (k < K) numH[t * K + k] = z.x * sc;
         if (k + 1 < K) numH[t * K + k + 1] = z.y * sc;
+    }
+}
+
+// Yf[f][bc][co][n] fp32 (a chunk of nbc blocks starting at block b0) -> partial[bc * gridDim.y + blockIdx.y] =
+// sum over the V exact samples of the block and the CTA's 32 units of (Xhat - X)^2.  Block b covers the columns
+// [b*V - (L-1), b*V - (L-1) + B) of H, so sample i >= L-1 of the inverse transform is Xhat at t = b*V + i - (L-1).
+// grid (nbc, ceil(N/32)).
+__global__ void __launch_bounds__(NT)
+ifft_resid_kernel(const float *__restrict__ Yf, const float *__restrict__ X, double *__restrict__ partial, int64_t N, int64_t Tl,
+                  int64_t L, int B, int logB, int V, int64_t nbc, int64_t b0) {
+    extern __shared__ float2 fd_smem[];
+    __shared__ double red[NT / 32];
+    constexpr int C = 16;
+    float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;
+    const int64_t bc = blockIdx.x;
+    const int p = threadIdx.x % C;
+    const int64_t n = (int64_t)blockIdx.y * 32 + 2 * p;
+    make_twiddles(tw, B);
+    for (int f = threadIdx.x / C; f <= B / 2; f += NT / C) {
+        float2 re = make_float2(0.f, 0.f), im = re;
+        if (n < N) {
+            const float *y = Yf + (((int64_t)f * nbc + bc) * 2) * N + n;
+            re = *reinterpret_cast<const float2 *>(y);
+            im = *reinterpret_cast<const float2 *>(y + N);
+        }
+        pack_pair(d, f, B, C, p, re, im);
+    }
+    __syncthreads();
+    fft_passes<true>(d, tw, B, logB, C);
+    const float sc = 1.0f / (float)B;
+    float acc = 0.f;
+    double accd = 0.0;
+    if (n < N) {
+        int cnt = 0;
+        for (int i = (int)(L - 1) + threadIdx.x / C; i < B; i += NT / C) {
+            const int64_t t = (b0 + bc) * V + (i - (L - 1));
+            if (t >= Tl) break;
+            const float2 z = d[rev(i, logB) * C + p];
+            const float2 x = *reinterpret_cast<const float2 *>(X + t * N + n);
+            const float r0 = z.x * sc - x.x, r1 = z.y * sc - x.y;
+            acc = fmaf(r0, r0, acc);
+            acc = fmaf(r1, r1, acc);
+            if (++cnt == 8) { accd += (double)acc; acc = 0.f; cnt = 0; }
+        }
+    }
+    accd += (double)acc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) accd += __shfl_xor_sync(0xffffffffu, accd, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = accd;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < NT / 32; ++w) s += red[w];
+        partial[bc * gridDim.y + blockIdx.y] = s;
     }
 }
 

@@ -20,6 +20,8 @@
 // and the two per-frequency products of the frequency-domain engine (kernels_fd.cuh), one unit = (frequency f, column tile):
 //   TC_FQT    D[m, b]      = sum_(c,n) Aw[f][m][(c,n)] * Xf[f][b][(c,n)]   (K-major, SW64)   numH^ -> Of[f][b][m]
 //   TC_FQC    D[m, n]      = sum_(b,c) Ah[f][(b,c)][m] * Xf[f][(b,c)][n]   (MN-major, SW128) numW^ -> Df[f][m][n]
+//   TC_FQX    D[n, b]      = sum_(c,k) Awm[f][co][(c,k)][n] * Hc[f][b][(c,k)]  (A MN-major SW128, B K-major SW64)
+//             one unit = (f, co = re/im, tile of 128 units n, tile of 256 blocks): Xhat^ -> Yf[f][b][co][n]   (loss pass)
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -40,7 +42,7 @@ constexpr int THREADS = 128 + 32 * EPI_WARPS;        // warpgroup 0: warp 0 TMA,
 constexpr int PROMO = 8;                             // k-blocks accumulated in TMEM before promotion to registers
 constexpr int FLUSH_T = 65536;                       // TC_CORR: columns of t accumulated in fp32 registers (RN) before the fp64 flush
 
-enum Mode { TC_CONV = 0, TC_TRANS = 1, TC_CORR = 2, TC_PLAIN = 3, TC_FQT = 4, TC_FQC = 5 };
+enum Mode { TC_CONV = 0, TC_TRANS = 1, TC_CORR = 2, TC_PLAIN = 3, TC_FQT = 4, TC_FQC = 5, TC_FQX = 6 };
 
 struct Params {
     // work decomposition
@@ -68,7 +70,8 @@ struct Params {
     float *out;                // TRANS: numH [t][K];  PLAIN: output matrix
     int64_t Mrows, Ncols, ldo; // PLAIN: output bounds and row stride
     double *part;              // CORR: [split][L*K*N]
-    int64_t fq_rows;           // FQT / FQC: rows of the B map per frequency (nblk resp. 2*nblk)
+    int64_t fq_rows;           // FQT / FQC / FQX: rows of the B map per frequency (nblk resp. 2*nblk)
+    int64_t b_off, nbc;        // FQX: first block and number of blocks of the chunk this launch covers
 };
 
 // ---------------------------------------------------------------------------------- PTX wrappers
@@ -204,7 +207,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
         return c > 0 ? c : 1;
     };
     auto segment_kb = [&](int64_t unit, int64_t seg, int64_t &kb0, int64_t &kbn) {
-        if (MODE == TC_CONV || MODE == TC_PLAIN || MODE == TC_FQT || MODE == TC_FQC) { kb0 = 0; kbn = p.nkb; }
+        if (MODE == TC_CONV || MODE == TC_PLAIN || MODE == TC_FQT || MODE == TC_FQC || MODE == TC_FQX) { kb0 = 0; kbn = p.nkb; }
         else if (MODE == TC_TRANS) { kb0 = 0; kbn = p.groups * p.nblocks; }
         else {
             const int64_t sp = unit / (p.tiles_m * p.tiles_n);
@@ -280,6 +283,15 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                             tma_load_2d(st + A_PLANE, &mapA_lo, &full_bar[s], k0, (int32_t)(mt * BM));
                             tma_load_2d(st + 2 * A_PLANE, &mapB_hi, &full_bar[s], k0, rowB);
                             tma_load_2d(st + 2 * A_PLANE + B_PLANE, &mapB_lo, &full_bar[s], k0, rowB);
+                        } else if (MODE == TC_FQX) {
+                            // unit = ((f*2 + co) * tiles_m + n tile) * tiles_n + block tile
+                            const int64_t bt = unit % p.tiles_n, r1 = unit / p.tiles_n, ntile = r1 % p.tiles_m, fc = r1 / p.tiles_m;
+                            const int32_t trow = (int32_t)(fc * BM + kb * BK);                       // Awm rows ((f*2+co)*128 + (c,k))
+                            const int32_t rowB = (int32_t)((fc >> 1) * p.fq_rows + p.b_off + bt * BN);
+                            tma_load_3d(st, &mapA_hi, &full_bar[s], 0, trow, (int32_t)(ntile * 2));
+                            tma_load_3d(st + A_PLANE, &mapA_lo, &full_bar[s], 0, trow, (int32_t)(ntile * 2));
+                            tma_load_2d(st + 2 * A_PLANE, &mapB_hi, &full_bar[s], (int32_t)(kb * BK), rowB);
+                            tma_load_2d(st + 2 * A_PLANE + B_PLANE, &mapB_lo, &full_bar[s], (int32_t)(kb * BK), rowB);
                         } else if (MODE == TC_FQC) {
                             const int32_t trow = (int32_t)(mt * p.fq_rows + kb * BK);
                             tma_load_3d(st, &mapA_hi, &full_bar[s], 0, trow, 0);
@@ -304,7 +316,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
     } else if (warp == 1) {
         // ================================================================ MMA issuer
         if (lane == 0) {
-            constexpr uint32_t idesc = (MODE == TC_CORR || MODE == TC_FQC) ? make_idesc(1, 1) : make_idesc(0, 0);
+            constexpr uint32_t idesc = (MODE == TC_CORR || MODE == TC_FQC) ? make_idesc(1, 1) : (MODE == TC_FQX) ? make_idesc(1, 0) : make_idesc(0, 0);
             int s = 0; uint32_t ph = 0;
             int64_t q = 0;   // promotion-chunk counter (TMEM double buffer)
             for (int64_t unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
@@ -332,6 +344,11 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                                     const uint32_t off = (uint32_t)ks * 2048u;
                                     dah = make_desc(a_hi + off, 4096, 1024, 2); dal = make_desc(a_lo + off, 4096, 1024, 2);
                                     dbh = make_desc(b_hi + off, 4096, 1024, 2); dbl = make_desc(b_lo + off, 4096, 1024, 2);
+                                } else if (MODE == TC_FQX) {
+                                    // A MN-major SW128 (as above), B K-major SW64 (as below)
+                                    const uint32_t offa = (uint32_t)ks * 2048u, offb = (uint32_t)ks * 32u;
+                                    dah = make_desc(a_hi + offa, 4096, 1024, 2); dal = make_desc(a_lo + offa, 4096, 1024, 2);
+                                    dbh = make_desc(b_hi + offb, 16, 512, 4); dbl = make_desc(b_lo + offb, 16, 512, 4);
                                 } else {
                                     // K-major SW64: 64-byte rows, SBO = 512 B between 8-row groups, +32 B per 16-element K step
                                     const uint32_t off = (uint32_t)ks * 32u;
@@ -427,6 +444,16 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                             }
                         }
                         if (p.G > 1) asm volatile("bar.sync 1, 256;" ::: "memory");
+                    }
+                } else if (MODE == TC_FQX) {
+                    // Yf[f][b][co][n] (blocks numbered inside the chunk): lanes hold consecutive units n -> coalesced rows
+                    const int64_t bt = unit % p.tiles_n, r1 = unit / p.tiles_n, ntile = r1 % p.tiles_m, fc = r1 / p.tiles_m;
+                    const int64_t b0 = bt * BN + col0, n = ntile * BM + row;
+                    float *o = p.out + (((fc >> 1) * p.nbc + b0) * 2 + (fc & 1)) * p.N + n;
+                    if (n < p.N) {
+#pragma unroll
+                        for (int c = 0; c < BN / 2; ++c)
+                            if (b0 + c < p.nbc) o[(int64_t)c * 2 * p.N] = racc[c];
                     }
                 } else if (MODE == TC_FQT) {
                     // Of[f][b][m]: lanes hold consecutive rows m, so every column is one coalesced 128-byte store

@@ -60,6 +60,11 @@ def test_fd_contractions_match_oracle(cmf, orc, dims):
     s.set_data(X, 0)
     s.set_factors(W, H, 0)
     s.set_data_norm(1.0)
+    # direct loss pass through the frequency domain (TC_FQX + inverse FFT + residual)
+    s.set_loss_mode(0)
+    ref_ss = float(np.sum((orc.co.tensor_conv(W, H) - X) ** 2))
+    got_ss = s.loss_partial()
+    assert abs(got_ss - ref_ss) < 2e-5 * ref_ss, (got_ss, ref_ss)
     s.w_partials()
     torch.cuda.synchronize()
     numW = s.exchange[0].cpu().numpy().reshape(L, K, N).transpose(1, 2, 0)
@@ -178,6 +183,22 @@ def test_fd_other_rules_match_oracle(cmf, orc, alg, iters):
         rel = np.abs(np.asarray(r.loss_hist) - np.asarray(ref.loss_hist)) / np.asarray(ref.loss_hist)
         print(alg, "loss_mode", loss_mode, "max rel loss err", rel.max())
         assert rel.max() < 1e-4, (loss_mode, rel)
+
+
+def test_fd_loss_pass_in_chunks(cmf, orc, monkeypatch):
+    # the direct loss pass works through the blocks in chunks (Yf holds the spectrum of Xhat for one chunk): force 2 chunks
+    monkeypatch.setenv("CMF_FD_NBC", "256")
+    N, T, K, L = 64, 20000, 4, 5                       # block length 64, hop 60 -> 334 blocks
+    W, H, X = _rand(N, T, K, L, seed=11)
+    s = cmf.DeviceShard(N, T, 0, T, K, L, dtype="f32", device=0)
+    s.set_engine(2)
+    s.set_loss_mode(0)
+    s.set_data(X, 0)
+    s.set_factors(W, H, 0)
+    ref_ss = float(np.sum((orc.co.tensor_conv(W, H) - X) ** 2))
+    got_ss = s.loss_partial()
+    assert abs(got_ss - ref_ss) < 2e-5 * ref_ss, (got_ss, ref_ss)
+    s.close()
 
 
 def test_fd_unsupported_shapes_fail_loudly(cmf):
