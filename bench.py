@@ -187,8 +187,18 @@ def run_ours(args, cfg, name):
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-        dist.barrier()
+        # NCCL prints its version banner to stdout while the communicator is set up: point fd 1 at stderr for that part
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     torch.cuda.set_device(local_rank)
     import cmf_jl_b200 as cmf
 
