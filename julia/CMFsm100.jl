@@ -133,7 +133,8 @@ function fit_cnmf_sm100(data::Matrix{T}; L::Integer=10, K::Integer=5, alg=:mult,
     for (a, b) in ((:l1_W, :l1W), (:l2_W, :l2W), (:l1_H, :l1H), (:l2_H, :l2H), (:initW, :W_init), (:initH, :H_init))
         haskey(kw, a) && (kw[b] = pop!(kw, a))
     end
-    known = (:l1W, :l2W, :l1H, :l2H, :seed, :W_init, :H_init, :check_convergence, :patience, :eval_mode, :tol, :verbose)
+    known = (:l1W, :l2W, :l1H, :l2H, :seed, :W_init, :H_init, :check_convergence, :patience, :eval_mode, :tol, :verbose,
+             :engine, :loss_mode)      # sm100 extras: contraction engine 0/1/2 and loss evaluation 0/1 (include/cmf_sm100.h)
     for k in keys(kw)
         k in known || @warn "fit_cnmf_sm100: unknown keyword $k ignored (CMF.jl ignores it silently)"
     end
@@ -143,6 +144,8 @@ function fit_cnmf_sm100(data::Matrix{T}; L::Integer=10, K::Integer=5, alg=:mult,
     W0 = convert(Array{T,3}, get(kw, :W_init, W0)); H0 = convert(Matrix{T}, get(kw, :H_init, H0))   # model.jl:72-73
     R = alg isa Symbol ? ALGS[alg] : alg
     rule = R(data, W0, H0; sync_host=false)                      # model.jl:79
+    haskey(kw, :engine) && check(ccall((:cmf_set_engine, LIB), Cint, (Ptr{Cvoid}, Cint), rule.h.ptr, kw[:engine]))
+    haskey(kw, :loss_mode) && check(ccall((:cmf_set_loss_mode, LIB), Cint, (Ptr{Cvoid}, Cint), rule.h.ptr, kw[:loss_mode]))
     cap = isfinite(max_itr) ? Int(max_itr) + 1 : 1_000_001
     loss_hist = zeros(Cdouble, cap); time_hist = zeros(Cdouble, cap)
     n = Ref{Int64}(0); early = Ref{Cint}(0)
