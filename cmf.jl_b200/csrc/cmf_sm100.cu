@@ -215,6 +215,7 @@ struct FdState {
     bool ok = false, tried = false;
     int B = 0, logB = 0, V = 0, F = 0;
     int64_t nblk = 0, nblkp = 0;          // overlap-save blocks covering the owned columns; padded to a multiple of 16
+    int Kq = 64, MR = 128;                // components padded to Kq = 64 or 128; MR = 2 Kq rows (real | imaginary) per frequency
     int V2 = 0;                           // hop of the denomH blocking (2L-1 lags): B - 2L + 2
     int64_t nblk2 = 0;
     DevBuf<__nv_bfloat16> Xf_hi, Xf_lo, Ah_hi, Ah_lo, Aw_hi, Aw_lo, Hf_hi, Hf_lo, Ac_hi, Ac_lo;
@@ -301,7 +302,7 @@ struct Ctx : cmf_ctx {
             // frequency-domain engine by default where it wins: enough lags that 2*L direct flops per element exceed the
             // ~8.5 of the per-frequency products, and room for the spectrum of X (CMF_ENGINE_DEFAULT=1 keeps engine 1)
             const char *e = getenv("CMF_ENGINE_DEFAULT");
-            if (tcs.ok && engine == 1 && L >= 8 && K <= fd::KQ && !(e && atoi(e) == 1)) {
+            if (tcs.ok && engine == 1 && L >= 8 && K <= fd::KQ_MAX && !(e && atoi(e) == 1)) {
                 fd_setup();
                 // with this engine the expansion loss is the default too: the direct pass would cost 10x the iteration
                 if (fds.ok) { engine = 2; loss_mode = 1; }
@@ -328,7 +329,9 @@ struct Ctx : cmf_ctx {
             FdState &f = fds;
             f.tried = true;
             if (!tcs.ok) { f.why = "needs the tcgen05 engine"; return; }
-            if (K > fd::KQ || L > 256 || N < 16) { f.why = "needs K <= 64, L <= 256, N >= 16"; return; }
+            if (K > fd::KQ_MAX || L > 256 || N < 16) { f.why = "needs K <= 128, L <= 256, N >= 16"; return; }
+            f.Kq = (K <= 64) ? 64 : 128;
+            f.MR = 2 * f.Kq;
             int B = 64, logB = 6;
             while (B < 4 * L) { B *= 2; ++logB; }
             if (const char *e = getenv("CMF_FD_B")) {
@@ -339,14 +342,14 @@ struct Ctx : cmf_ctx {
             f.nblk = cdiv(Tl, f.V);
             f.nblkp = cdiv(f.nblk, 16) * 16;
             const size_t xf = (size_t)f.F * (size_t)f.nblkp * 2 * (size_t)N + 64;
-            const size_t ah = (size_t)f.F * (size_t)f.nblkp * 2 * fd::MROWS + 64;
-            const size_t aw = (size_t)f.F * fd::MROWS * 2 * (size_t)N + 64;
+            const size_t ah = (size_t)f.F * (size_t)f.nblkp * 2 * f.MR + 64;
+            const size_t aw = (size_t)f.F * f.MR * 2 * (size_t)N + 64;
             f.V2 = B - 2 * (int)L + 2;
             f.nblk2 = cdiv(Tl, f.V2);
-            const size_t of = (size_t)f.F * (size_t)std::max(f.nblkp, f.nblk2) * fd::MROWS, df = (size_t)f.F * fd::MROWS * (size_t)N;
+            const size_t of = (size_t)f.F * (size_t)std::max(f.nblkp, f.nblk2) * f.MR, df = (size_t)f.F * f.MR * (size_t)N;
             // Hf serves the Gram partial (nblkp blocks) and, later on the same stream, denomH (nblk2 blocks)
-            const size_t hf = (size_t)f.F * (size_t)std::max(f.nblkp, f.nblk2) * 2 * fd::KQ + 256, gf = (size_t)f.F * fd::MROWS * fd::KQ;
-            const size_t ac = (size_t)f.F * fd::MROWS * fd::MROWS;
+            const size_t hf = (size_t)f.F * (size_t)std::max(f.nblkp, f.nblk2) * 2 * f.Kq + 256, gf = (size_t)f.F * f.MR * f.Kq;
+            const size_t ac = (size_t)f.F * f.MR * f.MR;
             const size_t need = 4 * (xf + ah + aw + hf + ac) + 4 * (of + df + gf);
             tcs.X_hi.free(); tcs.X_lo.free(); tcs.x_dirty = true;
             size_t free_b = 0, total_b = 0;
@@ -363,11 +366,11 @@ struct Ctx : cmf_ctx {
             for (int i = 0; i < 2; ++i) {
                 f.mXfK[i] = make_map_2d(xs[i], (uint64_t)(2 * N), rows, (uint64_t)N * 4, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
                 f.mXfMN[i] = make_map_mn(xs[i], rows * 2, (uint64_t)N * 2, (uint64_t)cdiv(N, 64), tc::BK, 4);
-                f.mAw[i] = make_map_2d(ws[i], (uint64_t)(2 * N), (uint64_t)f.F * fd::MROWS, (uint64_t)N * 4, tc::BK, tc::BM, CU_TENSOR_MAP_SWIZZLE_64B);
-                f.mAh[i] = make_map_mn(as[i], rows * 2, (uint64_t)fd::MROWS * 2, 2, tc::BK, 2);
-                f.mHfMN[i] = make_map_mn(i == 0 ? f.Hf_hi.p : f.Hf_lo.p, rows * 2, (uint64_t)fd::KQ * 2, 1, tc::BK, 4);
-                f.mAc[i] = make_map_2d(i == 0 ? f.Ac_hi.p : f.Ac_lo.p, fd::MROWS, (uint64_t)f.F * fd::MROWS, (uint64_t)fd::MROWS * 2, tc::BK, tc::BM, CU_TENSOR_MAP_SWIZZLE_64B);
-                f.mHf2K[i] = make_map_2d(i == 0 ? f.Hf_hi.p : f.Hf_lo.p, fd::MROWS, (uint64_t)f.F * (uint64_t)f.nblk2, (uint64_t)fd::MROWS * 2, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
+                f.mAw[i] = make_map_2d(ws[i], (uint64_t)(2 * N), (uint64_t)f.F * f.MR, (uint64_t)N * 4, tc::BK, tc::BM, CU_TENSOR_MAP_SWIZZLE_64B);
+                f.mAh[i] = make_map_mn(as[i], rows * 2, (uint64_t)f.MR * 2, (uint64_t)(f.MR / 64), tc::BK, 2);
+                f.mHfMN[i] = make_map_mn(i == 0 ? f.Hf_hi.p : f.Hf_lo.p, rows * 2, (uint64_t)f.Kq * 2, (uint64_t)(f.Kq / 64), tc::BK, 4);
+                f.mAc[i] = make_map_2d(i == 0 ? f.Ac_hi.p : f.Ac_lo.p, f.MR, (uint64_t)f.F * f.MR, (uint64_t)f.MR * 2, tc::BK, tc::BM, CU_TENSOR_MAP_SWIZZLE_64B);
+                f.mHf2K[i] = make_map_2d(i == 0 ? f.Hf_hi.p : f.Hf_lo.p, f.MR, (uint64_t)f.F * (uint64_t)f.nblk2, (uint64_t)f.MR * 2, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
             }
             CK(cudaFuncSetAttribute(tc::tc_kernel<tc::TC_FQT>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
             CK(cudaFuncSetAttribute(tc::tc_kernel<tc::TC_FQC>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
@@ -415,15 +418,15 @@ struct Ctx : cmf_ctx {
             q.nprod = 3;
             q.tiles_n = cdiv(N, tc::BN);
             q.nkb = f.nblkp * 2 / tc::BK;
-            q.units = (int64_t)f.F * q.tiles_n;
+            q.MR = f.MR; q.mtiles = f.MR / tc::BM; q.units = (int64_t)f.F * q.tiles_n * q.mtiles;
             q.fq_rows = f.nblkp * 2;
-            q.out = f.Df.p; q.Mrows = fd::MROWS; q.Ncols = N; q.ldo = N;
+            q.out = f.Df.p; q.Mrows = f.MR; q.Ncols = N; q.ldo = N;
             const unsigned grid = (unsigned)std::min<int64_t>(q.units, tcs.num_sms);
             prof_begin(PROF_CORR);
             tc::tc_kernel<tc::TC_FQC><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(f.mAh[0], f.mAh[1], f.mXfMN[0], f.mXfMN[1], q);
             prof_end();
             post_launch();
-            fd::ifft_numW_kernel<float><<<dim3((unsigned)cdiv(N, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(f.Df.p, numW.p, N, N, K, L, f.B, f.logB);
+            fd::ifft_numW_kernel<float><<<dim3((unsigned)cdiv(N, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(f.Df.p, numW.p, N, N, K, L, f.B, f.logB, f.Kq);
             post_launch();
         }
     }
@@ -433,24 +436,24 @@ struct Ctx : cmf_ctx {
         if constexpr (std::is_same<S, float>::value) {
             FdState &f = fds;
             fd::fft_w_kernel<<<dim3((unsigned)cdiv(K, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(
-                Cf.p, f.Ac_hi.p, f.Ac_lo.p, K, K, 2 * L - 1, f.B, f.logB, fd::MROWS, fd::KQ, 0);
+                Cf.p, f.Ac_hi.p, f.Ac_lo.p, K, K, 2 * L - 1, f.B, f.logB, f.MR, f.Kq, 0, f.Kq);
             post_launch();
             const int C = fd_cols_h();
-            fd::fft_h_kernel<<<dim3((unsigned)f.nblk2, (unsigned)(32 / C)), fd::NT, fd_smem(C), stream>>>(
-                H, f.Hf_hi.p, f.Hf_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V2, f.nblk2, C, 1, -(L - 1));
+            fd::fft_h_kernel<<<dim3((unsigned)f.nblk2, (unsigned)(f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
+                H, f.Hf_hi.p, f.Hf_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V2, f.nblk2, C, 1, -(L - 1), f.Kq);
             post_launch();
             tc::Params q = tc_base_params();
             q.nprod = 3;
             q.tiles_n = cdiv(f.nblk2, tc::BN);
-            q.nkb = fd::MROWS / tc::BK;
-            q.units = (int64_t)f.F * q.tiles_n;
+            q.nkb = f.MR / tc::BK;
+            q.MR = f.MR; q.mtiles = f.MR / tc::BM; q.units = (int64_t)f.F * q.tiles_n * q.mtiles;
             q.fq_rows = f.nblk2;
             q.out = f.Of.p;
             const unsigned grid = (unsigned)std::min<int64_t>(q.units, tcs.num_sms);
             tc::tc_kernel<tc::TC_FQT><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(f.mAc[0], f.mAc[1], f.mHf2K[0], f.mHf2K[1], q);
             post_launch();
-            fd::ifft_numH_kernel<<<dim3((unsigned)f.nblk2, (unsigned)(32 / C)), fd::NT, fd_smem(C), stream>>>(
-                f.Of.p, denH.p, K, Tl, f.B, f.logB, f.V2, f.nblk2, C);
+            fd::ifft_numH_kernel<<<dim3((unsigned)f.nblk2, (unsigned)(f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
+                f.Of.p, denH.p, K, Tl, f.B, f.logB, f.V2, f.nblk2, C, f.Kq);
             post_launch();
         }
     }
@@ -462,7 +465,7 @@ struct Ctx : cmf_ctx {
             FdState &f = fds;
             const int64_t ntile32 = cdiv(N, 32);
             if (f.Awm_hi.n == 0) {
-                const size_t aw = (size_t)f.F * 2 * fd::MROWS * (size_t)N + 64;
+                const size_t aw = (size_t)f.F * 2 * f.MR * (size_t)N + 64;
                 size_t free_b = 0, total_b = 0;
                 CK(cudaMemGetInfo(&free_b, &total_b));
                 const size_t per_block = (size_t)f.F * 2 * (size_t)N * sizeof(float);          // Yf bytes per block
@@ -475,21 +478,21 @@ struct Ctx : cmf_ctx {
                 f.Awm_hi.alloc(aw); f.Awm_lo.alloc(aw);
                 f.Yf.alloc((size_t)f.F * (size_t)nbc * 2 * (size_t)N);
                 for (int i = 0; i < 2; ++i) {
-                    f.mAwm[i] = make_map_mn(i == 0 ? f.Awm_hi.p : f.Awm_lo.p, (uint64_t)f.F * 2 * fd::MROWS, (uint64_t)N * 2, (uint64_t)cdiv(N, 64), tc::BK, 2);
-                    f.mHcK[i] = make_map_2d(i == 0 ? f.Hf_hi.p : f.Hf_lo.p, fd::MROWS, (uint64_t)f.F * (uint64_t)f.nblk, (uint64_t)fd::MROWS * 2, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
+                    f.mAwm[i] = make_map_mn(i == 0 ? f.Awm_hi.p : f.Awm_lo.p, (uint64_t)f.F * 2 * f.MR, (uint64_t)N * 2, (uint64_t)cdiv(N, 64), tc::BK, 2);
+                    f.mHcK[i] = make_map_2d(i == 0 ? f.Hf_hi.p : f.Hf_lo.p, f.MR, (uint64_t)f.F * (uint64_t)f.nblk, (uint64_t)f.MR * 2, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
                 }
                 f.wx_dirty = true;
             }
             const size_t need_lp = (size_t)(f.nblk * ntile32);
             if (loss_part.n < need_lp) loss_part.alloc(std::max<size_t>(need_lp, 4096));
             if (f.wx_dirty) {
-                fd::fft_w_kernel<<<dim3((unsigned)cdiv(N, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(Wi.p, f.Awm_hi.p, f.Awm_lo.p, N, K, L, f.B, f.logB, 2 * N, N, 1);
+                fd::fft_w_kernel<<<dim3((unsigned)cdiv(N, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(Wi.p, f.Awm_hi.p, f.Awm_lo.p, N, K, L, f.B, f.logB, 2 * N, N, 1, f.Kq);
                 post_launch();
                 f.wx_dirty = false;
             }
             const int C = fd_cols_h();
-            fd::fft_h_kernel<<<dim3((unsigned)f.nblk, (unsigned)(32 / C)), fd::NT, fd_smem(C), stream>>>(
-                H, f.Hf_hi.p, f.Hf_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V, f.nblk, C, 1, -(L - 1));
+            fd::fft_h_kernel<<<dim3((unsigned)f.nblk, (unsigned)(f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
+                H, f.Hf_hi.p, f.Hf_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V, f.nblk, C, 1, -(L - 1), f.Kq);
             post_launch();
             prof_begin(PROF_CONV);
             for (int64_t b0 = 0; b0 < f.nblk; b0 += f.nbc) {
@@ -498,8 +501,8 @@ struct Ctx : cmf_ctx {
                 q.nprod = 3;
                 q.tiles_n = cdiv(cur, tc::BN);
                 q.tiles_m = cdiv(N, tc::BM);
-                q.nkb = fd::MROWS / tc::BK;
-                q.units = (int64_t)f.F * 2 * q.tiles_m * q.tiles_n;
+                q.nkb = f.MR / tc::BK;
+                q.MR = f.MR; q.mtiles = 1; q.units = (int64_t)f.F * 2 * q.tiles_m * q.tiles_n;
                 q.fq_rows = f.nblk; q.b_off = b0; q.nbc = cur;
                 q.out = f.Yf.p;
                 const unsigned grid = (unsigned)std::min<int64_t>(q.units, tcs.num_sms);
@@ -520,8 +523,8 @@ struct Ctx : cmf_ctx {
             FdState &f = fds;
             if (!f.h_dirty) return;
             const int C = fd_cols_h();
-            fd::fft_h_kernel<<<dim3((unsigned)f.nblkp, (unsigned)(32 / C)), fd::NT, fd_smem(C), stream>>>(
-                H, f.Ah_hi.p, f.Ah_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V, f.nblkp, C, 0, 0);
+            fd::fft_h_kernel<<<dim3((unsigned)f.nblkp, (unsigned)(f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
+                H, f.Ah_hi.p, f.Ah_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V, f.nblkp, C, 0, 0, f.Kq);
             post_launch();
             f.h_dirty = false;
         }
@@ -532,20 +535,20 @@ struct Ctx : cmf_ctx {
             FdState &f = fds;
             fd_spectrum_H();
             const int C = fd_cols_h();
-            fd::fft_h_kernel<<<dim3((unsigned)f.nblkp, (unsigned)(32 / C)), fd::NT, fd_smem(C), stream>>>(
-                H, f.Hf_hi.p, f.Hf_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V, f.nblkp, C, 1, 0);
+            fd::fft_h_kernel<<<dim3((unsigned)f.nblkp, (unsigned)(f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
+                H, f.Hf_hi.p, f.Hf_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V, f.nblkp, C, 1, 0, f.Kq);
             post_launch();
             tc::Params q = tc_base_params();
             q.nprod = 3;
             q.tiles_n = 1;
             q.nkb = f.nblkp * 2 / tc::BK;
-            q.units = (int64_t)f.F;
+            q.MR = f.MR; q.mtiles = f.MR / tc::BM; q.units = (int64_t)f.F * q.mtiles;
             q.fq_rows = f.nblkp * 2;
-            q.out = f.Gf.p; q.Mrows = fd::MROWS; q.Ncols = K; q.ldo = fd::KQ;
+            q.out = f.Gf.p; q.Mrows = f.MR; q.Ncols = K; q.ldo = f.Kq;
             const unsigned grid = (unsigned)std::min<int64_t>(q.units, tcs.num_sms);
             tc::tc_kernel<tc::TC_FQC><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(f.mAh[0], f.mAh[1], f.mHfMN[0], f.mHfMN[1], q);
             post_launch();
-            fd::ifft_numW_kernel<double><<<dim3((unsigned)cdiv(K, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(f.Gf.p, exch1.p, K, fd::KQ, K, L, f.B, f.logB);
+            fd::ifft_numW_kernel<double><<<dim3((unsigned)cdiv(K, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(f.Gf.p, exch1.p, K, f.Kq, K, L, f.B, f.logB, f.Kq);
             post_launch();
         }
     }
@@ -555,7 +558,7 @@ struct Ctx : cmf_ctx {
             FdState &f = fds;
             fd_build_X();
             if (f.w_dirty) {
-                fd::fft_w_kernel<<<dim3((unsigned)cdiv(N, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(Wi.p, f.Aw_hi.p, f.Aw_lo.p, N, K, L, f.B, f.logB, 2 * N, N, 0);
+                fd::fft_w_kernel<<<dim3((unsigned)cdiv(N, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(Wi.p, f.Aw_hi.p, f.Aw_lo.p, N, K, L, f.B, f.logB, 2 * N, N, 0, f.Kq);
                 post_launch();
                 f.w_dirty = false;
             }
@@ -563,7 +566,7 @@ struct Ctx : cmf_ctx {
             q.nprod = 3;
             q.tiles_n = cdiv(f.nblkp, tc::BN);
             q.nkb = cdiv(2 * N, tc::BK);
-            q.units = (int64_t)f.F * q.tiles_n;
+            q.MR = f.MR; q.mtiles = f.MR / tc::BM; q.units = (int64_t)f.F * q.tiles_n * q.mtiles;
             q.fq_rows = f.nblkp;
             q.out = f.Of.p;
             const unsigned grid = (unsigned)std::min<int64_t>(q.units, tcs.num_sms);
@@ -572,8 +575,8 @@ struct Ctx : cmf_ctx {
             prof_end();
             post_launch();
             const int C = fd_cols_h();
-            fd::ifft_numH_kernel<<<dim3((unsigned)f.nblk, (unsigned)(32 / C)), fd::NT, fd_smem(C), stream>>>(
-                f.Of.p, numH.p, K, Tl, f.B, f.logB, f.V, f.nblkp, C);
+            fd::ifft_numH_kernel<<<dim3((unsigned)f.nblk, (unsigned)(f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
+                f.Of.p, numH.p, K, Tl, f.B, f.logB, f.V, f.nblkp, C, f.Kq);
             post_launch();
         }
     }
@@ -1668,7 +1671,7 @@ int cmf_set_engine(cmf_handle h, int engine) {
         REQUIRE(engine >= 0 && engine <= 2, "engine must be 0 (SIMT), 1 (tcgen05, time domain) or 2 (tcgen05, frequency domain)");
         use(h);
         if (engine == 2 && !h->fd_available())
-            throw CmfError(CMF_ERR_UNSUPPORTED, "the frequency-domain engine needs an fp32 handle with K <= 64, L <= 256, N % 8 == 0 on sm_100 and room for the spectrum of X");
+            throw CmfError(CMF_ERR_UNSUPPORTED, "the frequency-domain engine needs an fp32 handle with K <= 128, L <= 256, N % 8 == 0 on sm_100 and room for the spectrum of X");
         if (engine < 2) h->fd_release();               // the spectrum of X and the time-domain planes never coexist
         if (engine >= 1 && !h->tc_available())
             throw CmfError(CMF_ERR_UNSUPPORTED, "tcgen05 engine needs an fp32 MultUpdate handle with K <= 128 and N % 8 == 0 on sm_100");

@@ -9,7 +9,7 @@
 // src/common.jl:36-50, made exact by overlap-save).  The complex products run as real GEMMs on the tcgen05 kernel
 // (kernels_tc.cuh, modes TC_FQT / TC_FQC) with split-bf16 operands; this file holds the SIMT FFT kernels around them.
 //
-// Layouts (bf16 hi/lo planes unless noted; c = 0 real part, 1 imaginary part; rows m = k real, m = 64 + k imaginary):
+// Layouts (bf16 hi/lo planes unless noted; c = 0 real part, 1 imaginary part; rows m = k real, m = Kq + k imaginary, Kq = 64 or 128):
 //   Xf [f][b][c][n]          B operand of both products (K-major for TC_FQT, MN-major for TC_FQC)
 //   Aw [f][m][c][n]          conj(W^) as the real 128 x 2N matrix [[Wr, Wi], [-Wi, Wr]]          (A of TC_FQT)
 //   Ah [f][b][c][m]          conj(Hz^) as the real 2nblk x 128 matrix, rows (b,c): [Hr | -Hi], [Hi | Hr]  (A of TC_FQC)
@@ -40,8 +40,8 @@ namespace cmf {
 namespace fd {
 
 constexpr int NT = 512;      // threads per CTA (A/B at c4: 256 -> 49, 512 -> 44, 1024 -> 50 ms per iteration)
-constexpr int MROWS = 128;   // rows of the A operands / outputs per frequency (2 x 64 components)
-constexpr int KQ = 64;       // row offset of the imaginary parts
+constexpr int KQ_MAX = 128;  // components are padded to Kq = 64 or 128 rows; the A operands / outputs have MROWS = 2 Kq rows per
+                             // frequency (m = k real part, m = Kq + k imaginary part), i.e. one or two 128-row tensor-core tiles
 
 __device__ __forceinline__ void make_twiddles(float2 *tw, int B) {
     for (int m = threadIdx.x; m < B / 2; m += NT) {
@@ -150,7 +150,8 @@ fft_x_kernel(const float *__restrict__ X, __nv_bfloat16 *__restrict__ hi, __nv_b
 // grid (nblkp, 32 / C); C complex columns = 2C components per CTA.
 __global__ void __launch_bounds__(NT)
 fft_h_kernel(const float *__restrict__ H, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int64_t K, int64_t Tl,
-             int64_t hcols, int B, int logB, int V, int64_t nblkp, int C, int full, int64_t t_off) {
+             int64_t hcols, int B, int logB, int V, int64_t nblkp, int C, int full, int64_t t_off, int kq) {
+    const int64_t KQ = kq, MROWS = 2 * kq;
     extern __shared__ float2 fd_smem[];
     float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;
     const int64_t b = blockIdx.x;
@@ -189,7 +190,8 @@ fft_h_kernel(const float *__restrict__ H, __nv_bfloat16 *__restrict__ hi, __nv_b
 // K x K lag table C with N = K and L = 2L-1 lags -> Ac).  grid (ceil(N/32), K).
 __global__ void __launch_bounds__(NT)
 fft_w_kernel(const float *__restrict__ Wi, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int64_t N, int64_t K,
-             int64_t L, int B, int logB, int64_t ldw, int64_t coff, int xmode) {
+             int64_t L, int B, int logB, int64_t ldw, int64_t coff, int xmode, int kq) {
+    const int64_t KQ = kq, MROWS = 2 * kq;
     extern __shared__ float2 fd_smem[];
     constexpr int C = 16;
     float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;
@@ -231,7 +233,8 @@ fft_w_kernel(const float *__restrict__ Wi, __nv_bfloat16 *__restrict__ hi, __nv_
 // Of[f][b][m] fp32 -> numH[t][K] (owned columns; V valid outputs per block).  grid (nblk, 32 / C).
 __global__ void __launch_bounds__(NT)
 ifft_numH_kernel(const float *__restrict__ Of, float *__restrict__ numH, int64_t K, int64_t Tl, int B, int logB, int V,
-                 int64_t nblkp, int C) {
+                 int64_t nblkp, int C, int kq) {
+    const int64_t KQ = kq, MROWS = 2 * kq;
     extern __shared__ float2 fd_smem[];
     float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;
     const int64_t b = blockIdx.x;
@@ -312,7 +315,9 @@ ifft_resid_kernel(const float *__restrict__ Yf, const float *__restrict__ X, dou
 // OutT = float: numW (N even, paired stores);  OutT = double: the Gram partial Rg[d][k][k'] with N = K.
 template <typename OutT>
 __global__ void __launch_bounds__(NT)
-ifft_numW_kernel(const float *__restrict__ Df, OutT *__restrict__ out, int64_t N, int64_t ldi, int64_t K, int64_t L, int B, int logB) {
+ifft_numW_kernel(const float *__restrict__ Df, OutT *__restrict__ out, int64_t N, int64_t ldi, int64_t K, int64_t L, int B, int logB,
+                 int kq) {
+    const int64_t KQ = kq, MROWS = 2 * kq;
     extern __shared__ float2 fd_smem[];
     constexpr int C = 16;
     float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;

@@ -72,6 +72,8 @@ struct Params {
     double *part;              // CORR: [split][L*K*N]
     int64_t fq_rows;           // FQT / FQC / FQX: rows of the B map per frequency (nblk resp. 2*nblk)
     int64_t b_off, nbc;        // FQX: first block and number of blocks of the chunk this launch covers
+    int64_t MR;                // FQT / FQC / FQX: rows per frequency of the A operand / output (2 Kq = 128 or 256)
+    int mtiles;                // FQT / FQC: 128-row tiles per frequency (MR / 128); the tiles of one column tile are adjacent units
 };
 
 // ---------------------------------------------------------------------------------- PTX wrappers
@@ -231,7 +233,8 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                 int64_t mt = 0, nt = 0;
                 if (MODE == TC_CONV) { nt = unit % p.tiles_n; mt = unit / p.tiles_n; }          // nt: n tile, mt: t tile
                 if (MODE == TC_PLAIN) { nt = unit % p.tiles_n; mt = unit / p.tiles_n; }         // nt: column tile, mt: row tile
-                if (MODE == TC_FQT || MODE == TC_FQC) { nt = unit % p.tiles_n; mt = unit / p.tiles_n; }   // nt: column tile, mt: frequency
+                int64_t fq_m = 0;                                                                        // FQT / FQC: 128-row tile of the frequency
+                if (MODE == TC_FQT || MODE == TC_FQC) { fq_m = unit % p.mtiles; const int64_t r = unit / p.mtiles; nt = r % p.tiles_n; mt = r / p.tiles_n; }   // nt: column tile, mt: frequency
                 if (MODE == TC_CORR) { const int64_t r = unit % (p.tiles_m * p.tiles_n); if (p.corr_order == 0) { mt = r % p.tiles_m; nt = r / p.tiles_m; } else { nt = r % p.tiles_n; mt = r / p.tiles_n; } }
                 const int64_t nseg = n_segments(unit);
                 for (int64_t seg = 0; seg < nseg; ++seg) {
@@ -279,14 +282,15 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                         } else if (MODE == TC_FQT) {
                             const int32_t k0 = (int32_t)(kb * BK);
                             const int32_t rowB = (int32_t)(mt * p.fq_rows + nt * BN);
-                            tma_load_2d(st, &mapA_hi, &full_bar[s], k0, (int32_t)(mt * BM));
-                            tma_load_2d(st + A_PLANE, &mapA_lo, &full_bar[s], k0, (int32_t)(mt * BM));
+                            const int32_t rowA = (int32_t)(mt * p.MR + fq_m * BM);
+                            tma_load_2d(st, &mapA_hi, &full_bar[s], k0, rowA);
+                            tma_load_2d(st + A_PLANE, &mapA_lo, &full_bar[s], k0, rowA);
                             tma_load_2d(st + 2 * A_PLANE, &mapB_hi, &full_bar[s], k0, rowB);
                             tma_load_2d(st + 2 * A_PLANE + B_PLANE, &mapB_lo, &full_bar[s], k0, rowB);
                         } else if (MODE == TC_FQX) {
                             // unit = ((f*2 + co) * tiles_m + n tile) * tiles_n + block tile
                             const int64_t bt = unit % p.tiles_n, r1 = unit / p.tiles_n, ntile = r1 % p.tiles_m, fc = r1 / p.tiles_m;
-                            const int32_t trow = (int32_t)(fc * BM + kb * BK);                       // Awm rows ((f*2+co)*128 + (c,k))
+                            const int32_t trow = (int32_t)(fc * p.MR + kb * BK);                     // Awm rows ((f*2+co)*MR + (c,k))
                             const int32_t rowB = (int32_t)((fc >> 1) * p.fq_rows + p.b_off + bt * BN);
                             tma_load_3d(st, &mapA_hi, &full_bar[s], 0, trow, (int32_t)(ntile * 2));
                             tma_load_3d(st + A_PLANE, &mapA_lo, &full_bar[s], 0, trow, (int32_t)(ntile * 2));
@@ -294,8 +298,8 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                             tma_load_2d(st + 2 * A_PLANE + B_PLANE, &mapB_lo, &full_bar[s], (int32_t)(kb * BK), rowB);
                         } else if (MODE == TC_FQC) {
                             const int32_t trow = (int32_t)(mt * p.fq_rows + kb * BK);
-                            tma_load_3d(st, &mapA_hi, &full_bar[s], 0, trow, 0);
-                            tma_load_3d(st + A_PLANE, &mapA_lo, &full_bar[s], 0, trow, 0);
+                            tma_load_3d(st, &mapA_hi, &full_bar[s], 0, trow, (int32_t)(fq_m * 2));
+                            tma_load_3d(st + A_PLANE, &mapA_lo, &full_bar[s], 0, trow, (int32_t)(fq_m * 2));
                             tma_load_3d(st + 2 * A_PLANE, &mapB_hi, &full_bar[s], 0, trow, (int32_t)(nt * 4));
                             tma_load_3d(st + 2 * A_PLANE + B_PLANE, &mapB_lo, &full_bar[s], 0, trow, (int32_t)(nt * 4));
                         } else {
@@ -384,7 +388,9 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
         float racc[BN / 2];
         for (int64_t unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
             int64_t mt = 0, nt = 0, sp = 0;
-            if (MODE == TC_CONV || MODE == TC_PLAIN || MODE == TC_FQT || MODE == TC_FQC) { nt = unit % p.tiles_n; mt = unit / p.tiles_n; }
+            int64_t fq_m = 0;
+            if (MODE == TC_CONV || MODE == TC_PLAIN) { nt = unit % p.tiles_n; mt = unit / p.tiles_n; }
+            if (MODE == TC_FQT || MODE == TC_FQC) { fq_m = unit % p.mtiles; const int64_t r = unit / p.mtiles; nt = r % p.tiles_n; mt = r / p.tiles_n; }
             if (MODE == TC_CORR) { sp = unit / (p.tiles_m * p.tiles_n); const int64_t r = unit % (p.tiles_m * p.tiles_n); if (p.corr_order == 0) { mt = r % p.tiles_m; nt = r / p.tiles_m; } else { nt = r % p.tiles_n; mt = r / p.tiles_n; } }
             const int64_t nseg = n_segments(unit);
             for (int64_t seg = 0; seg < nseg; ++seg) {
@@ -458,16 +464,16 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                 } else if (MODE == TC_FQT) {
                     // Of[f][b][m]: lanes hold consecutive rows m, so every column is one coalesced 128-byte store
                     const int64_t b0 = nt * BN + col0;
-                    float *o = p.out + (mt * p.fq_rows + b0) * BM + row;
+                    float *o = p.out + (mt * p.fq_rows + b0) * p.MR + fq_m * BM + row;
 #pragma unroll
                     for (int c = 0; c < BN / 2; ++c)
-                        if (b0 + c < p.fq_rows) o[(int64_t)c * BM] = racc[c];
+                        if (b0 + c < p.fq_rows) o[(int64_t)c * p.MR] = racc[c];
                 } else if (MODE == TC_PLAIN || MODE == TC_FQC) {
                     // fp32 store through the per-warp staging tile (coalesced 64-byte row segments);
                     // FQC: one 128-row output matrix per frequency, Df[f][m][n]
                     float(*stg)[17] = stage_s[warp - 4];
-                    const int64_t mrow0 = (MODE == TC_FQC) ? 0 : mt * BM;
-                    float *outp = p.out + ((MODE == TC_FQC) ? mt * BM * p.ldo : 0);
+                    const int64_t mrow0 = (MODE == TC_FQC) ? fq_m * BM : mt * BM;
+                    float *outp = p.out + ((MODE == TC_FQC) ? mt * p.MR * p.ldo : 0);
 #pragma unroll
                     for (int cc = 0; cc < BN / 2; cc += 16) {
 #pragma unroll

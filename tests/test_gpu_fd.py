@@ -45,7 +45,9 @@ def _scale_err(a, b):
 # (N, T, K, L): block lengths 64..512, odd K, ragged N (not a multiple of 32/64/256) and T, L = 1, small T,
 # one block only, many column tiles of blocks (T / V > 256)
 FD_DIMS = [(256, 5000, 16, 12), (264, 3001, 21, 7), (384, 9000, 64, 20), (512, 40000, 8, 33), (128, 3000, 5, 1),
-           (256, 6000, 10, 100), (136, 400, 3, 30), (64, 20000, 4, 5)]
+           (256, 6000, 10, 100), (136, 400, 3, 30), (64, 20000, 4, 5),
+           # more than 64 components: two 128-row tiles per frequency (Kq = 128)
+           (128, 20000, 128, 3), (256, 6000, 100, 12), (136, 3000, 65, 9)]
 
 
 @pytest.mark.parametrize("dims", FD_DIMS)
@@ -185,6 +187,26 @@ def test_fd_other_rules_match_oracle(cmf, orc, alg, iters):
         assert rel.max() < 1e-4, (loss_mode, rel)
 
 
+def test_fd_fit_many_components(cmf, orc):
+    # K > 64: every product runs on two 128-row tiles per frequency; MU with both loss modes and HALS
+    N, T, K, L = 128, 3000, 80, 6
+    X, _, _ = orc.po.synthetic_sequences(K=6, N=N, L=L, T=T, rng=np.random.default_rng(1234))
+    W0, H0 = orc.po.init_rand(X, L, K, np.random.default_rng(0))
+    ref = orc.co.fit(orc.co.MultUpdate, X, W0, H0, 30, check_convergence=False)
+    for loss_mode in (0, 1):
+        r = cmf.fit_cnmf(X, L=L, K=K, alg="mult", max_itr=30, W_init=W0, H_init=H0, check_convergence=False,
+                         dtype="f32", engine=2, loss_mode=loss_mode, layout="KNL")
+        rel = np.abs(np.asarray(r.loss_hist) - np.asarray(ref.loss_hist)) / np.asarray(ref.loss_hist)
+        print("K=80 mult loss_mode", loss_mode, "max rel loss err", rel.max())
+        assert rel.max() < 1e-4, (loss_mode, rel.max())
+    refh = orc.co.fit(orc.co.HALSUpdate, X, W0, H0, 6, check_convergence=False, l1H=0.05, l2W=0.1)
+    rh = cmf.fit_cnmf(X, L=L, K=K, alg="hals", max_itr=6, W_init=W0, H_init=H0, check_convergence=False,
+                      dtype="f32", engine=2, layout="KNL", l1H=0.05, l2W=0.1)
+    rel = np.abs(np.asarray(rh.loss_hist) - np.asarray(refh.loss_hist)) / np.asarray(refh.loss_hist)
+    print("K=80 hals max rel loss err", rel.max())
+    assert rel.max() < 1e-4, rel
+
+
 def test_fd_loss_pass_in_chunks(cmf, orc, monkeypatch):
     # the direct loss pass works through the blocks in chunks (Yf holds the spectrum of Xhat for one chunk): force 2 chunks
     monkeypatch.setenv("CMF_FD_NBC", "256")
@@ -202,7 +224,7 @@ def test_fd_loss_pass_in_chunks(cmf, orc, monkeypatch):
 
 
 def test_fd_unsupported_shapes_fail_loudly(cmf):
-    s = cmf.DeviceShard(128, 20000, 0, 20000, 128, 3, dtype="f32", device=0)   # K > 64
+    s = cmf.DeviceShard(128, 20000, 0, 20000, 130, 3, dtype="f32", device=0)   # K > 128
     with pytest.raises(Exception):
         s.set_engine(2)
     s.close()
