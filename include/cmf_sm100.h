@@ -171,7 +171,7 @@ int cmf_profile_read(cmf_handle h, int which, double *ms_total, int64_t *count);
  * time domain (fp32 data, split-bf16 operands, K <= 128, N % 8 == 0); 2 = frequency-domain engine: numW
  * (mult.jl:32) and numH (mult.jl:47) through the overlap-save spectrum of X (computed once per data set, the
  * circular-convolution idea of src/common.jl:36-50 made exact) with the per-frequency complex products on
- * tcgen05 -- HBM-bound instead of tensor-bound (fp32, K <= 64, L <= 256, room for ~1.25x the size of X in
+ * tcgen05 -- HBM-bound instead of tensor-bound (fp32, K <= 128, L <= 256, room for ~1.25x the size of X in
  * bf16 hi/lo planes; the time-domain planes of engine 1 are released).  Returns CMF_ERR_UNSUPPORTED when the
  * handle cannot use the engine.  Default: best available (2 for large problems with L >= 8, else 1, else 0). */
 int cmf_set_engine(cmf_handle h, int engine);
