@@ -238,3 +238,18 @@ def denomH_interior_overlap_save(W, H, B=None):
     Hf = np.fft.rfft(_blocks(H, B, V2, nblk, start=-(L - 1)), axis=2)  # K x nblk x F
     out = np.fft.irfft(np.einsum("kjf,jbf->kbf", Cf.conj(), Hf), n=B, axis=2)[:, :, :V2]
     return out.reshape(K, -1)[:, :T]
+
+
+def conv_overlap_save(W, H, B=None):
+    """tensor_conv(W, H) (common.jl:24-34), the way the device's direct loss pass forms it: Xhat^[n,b,f] = sum_k W^[k,n,f]
+    H^[k,b,f] over full blocks of H that start L-1 columns early (hop V = B-L+1, zero history before column 0); the last V
+    samples of each inverse transform are exact."""
+    K, N, L = W.shape
+    T = H.shape[1]
+    B = B or fd_block_length(L)
+    V = B - L + 1
+    nblk = -(-T // V)
+    Hf = np.fft.rfft(_blocks(H, B, V, nblk, start=-(L - 1)), axis=2)   # K x nblk x F
+    Wf = np.fft.rfft(W, n=B, axis=2)                                    # K x N x F
+    y = np.fft.irfft(np.einsum("knf,kbf->nbf", Wf, Hf), n=B, axis=2)[:, :, L - 1:]
+    return y.reshape(N, -1)[:, :T]

@@ -229,3 +229,4 @@ def test_overlap_save_forms_equal_literal(dims):
         lit = rs.denomH_gram(W, H)
         fd = rs.denomH_interior_overlap_save(W, H, B)
         assert np.allclose(fd[:, : T - (L - 1)], lit[:, : T - (L - 1)], rtol=1e-10, atol=1e-10)
+        assert np.allclose(rs.conv_overlap_save(W, H, B), po.tensor_conv(W, H), rtol=1e-10, atol=1e-10)
