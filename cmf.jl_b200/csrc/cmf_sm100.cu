@@ -242,7 +242,7 @@ struct Ctx : cmf_ctx {
     DevBuf<S> X, Hbuf, Wi, Wtmp, numW, denW, GS, Cf, numH, denH, tailC;
     DevBuf<int> progress, lockstep;
     DevBuf<S> tailCt;                  // HALS H sweep: truncated lag tables of all component pairs
-    int hals_grid = 0;
+    int hals_grid = 0, hals_grid_ovl = -1;
     DevBuf<double> exch1, corr_part, loss_part, scal;
     S *H = nullptr;  // owned column 0 inside Hbuf
     int nsplit_w = 1, nsplit_g = 1;
@@ -1296,6 +1296,29 @@ struct Ctx : cmf_ctx {
             }
         }
         void *args[] = {&cf, &s2, &q, &hh, &dd, &tc_, &pr, &Kk, &Ll, &Tt, &ks, &ldv, &a1, &a2, &dbg, &ct};
+        // fp32: the recurrence of cell c overlaps the staging and pull of cell c+1 (hals_h_wave_ovl_kernel, bit-identical results);
+        // CMF_HALS_OVERLAP=0 or any debug mode selects the plain kernel
+        bool ovl = false;
+        if constexpr (std::is_same<S, float>::value) {
+            const char *e = getenv("CMF_HALS_OVERLAP");
+            ovl = dbg == 0 && !(e && atoi(e) == 0);
+            if (ovl) {
+                const size_t smem_o = smem + (size_t)2 * HW_TC * sizeof(S);
+                if (hals_grid_ovl < 0) {
+                    int per_sm = 0, sms = 0;
+                    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+                    cudaError_t e1 = cudaFuncSetAttribute(hals_h_wave_ovl_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_o);
+                    cudaError_t e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hals_h_wave_ovl_kernel<S>, HW_NT_OVL, smem_o);
+                    hals_grid_ovl = (e1 == cudaSuccess && e2 == cudaSuccess) ? (int)std::min<int64_t>(K, (int64_t)per_sm * sms) : 0;
+                    if (e1 != cudaSuccess || e2 != cudaSuccess) cudaGetLastError();
+                }
+                // same tailC scratch (one L*L table per CTA): the overlapped grid must not exceed the plain one
+                if (hals_grid_ovl >= 1 && hals_grid_ovl <= hals_grid)
+                    CK(cudaLaunchCooperativeKernel((void *)hals_h_wave_ovl_kernel<S>, dim3((unsigned)hals_grid_ovl), dim3(HW_NT_OVL), args, smem_o, stream));
+                else ovl = false;
+            }
+        }
+        if (!ovl)
         CK(cudaLaunchCooperativeKernel((void *)hals_h_wave_kernel<S>, dim3((unsigned)hals_grid), dim3(HW_NT), args, smem, stream));
         post_launch();
         gram_valid = false; fds.h_dirty = true;

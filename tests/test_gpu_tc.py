@@ -181,3 +181,21 @@ def test_hals_wavefront_many_components_fp64(cmf, orc):
                      layout="KNL", l1H=0.05, l2W=0.1)
     assert np.allclose(r.loss_hist, ref.loss_hist, rtol=1e-9)
     assert np.allclose(r.H, ref.H, rtol=1e-8, atol=1e-11) and np.allclose(r.W, ref.W, rtol=1e-8, atol=1e-11)
+
+
+@pytest.mark.parametrize("dims", [(64, 5000, 9, 6), (128, 9000, 40, 32), (32, 3000, 5, 40)])
+def test_hals_overlapped_sweep_is_bit_identical(cmf, orc, dims, monkeypatch):
+    # fp32 handles run the H sweep with the recurrence of cell c overlapped with the pull of cell c+1
+    # (hals_h_wave_ovl_kernel); CMF_HALS_OVERLAP=0 selects the plain wavefront kernel.  Same arithmetic, same order.
+    N, T, K, L = dims
+    W, H, X = _rand(N, T, K, L, seed=sum(dims))
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("CMF_HALS_OVERLAP", flag)
+        r = cmf.fit_cnmf(X, L=L, K=K, alg="hals", max_itr=3, W_init=W, H_init=H, check_convergence=False,
+                         dtype="f32", engine=0, layout="KNL", l1H=0.05, l2W=0.1)
+        out[flag] = r
+    assert np.array_equal(out["0"].H, out["1"].H) and np.array_equal(out["0"].W, out["1"].W)
+    assert np.array_equal(out["0"].loss_hist, out["1"].loss_hist)
+    ref = orc.co.fit(orc.co.HALSUpdate, X, W, H, 3, check_convergence=False, l1H=0.05, l2W=0.1)
+    assert np.allclose(out["1"].loss_hist, ref.loss_hist, rtol=1e-4)
