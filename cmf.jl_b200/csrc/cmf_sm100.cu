@@ -1296,12 +1296,14 @@ struct Ctx : cmf_ctx {
             }
         }
         void *args[] = {&cf, &s2, &q, &hh, &dd, &tc_, &pr, &Kk, &Ll, &Tt, &ks, &ldv, &a1, &a2, &dbg, &ct};
-        // fp32: the recurrence of cell c overlaps the staging and pull of cell c+1 (hals_h_wave_ovl_kernel, bit-identical results);
-        // CMF_HALS_OVERLAP=0 or any debug mode selects the plain kernel
+        // CMF_HALS_OVERLAP=1 (fp32, experimental): the recurrence of cell c runs in its own warp while the other warps stage and
+        // pull cell c+1 (hals_h_wave_ovl_kernel, bit-identical results).  Measured: no gain yet (223.6 vs 219.1 ms per sweep at
+        // config-5 shape, T = 2^20) -- the recurrence warp shares its scheduler with four busy pull warps and slows down by about as
+        // much as the overlap saves; it stays opt-in until the pull team leaves that scheduler free.
         bool ovl = false;
         if constexpr (std::is_same<S, float>::value) {
             const char *e = getenv("CMF_HALS_OVERLAP");
-            ovl = dbg == 0 && !(e && atoi(e) == 0);
+            ovl = dbg == 0 && e && atoi(e) == 1;
             if (ovl) {
                 const size_t smem_o = smem + (size_t)2 * HW_TC * sizeof(S);
                 if (hals_grid_ovl < 0) {

@@ -1207,6 +1207,7 @@ __global__ void __launch_bounds__(HW_NT) hals_h_wave_kernel(const S *__restrict_
 
 #undef HW_MARK
 
+// EXPERIMENTAL (CMF_HALS_OVERLAP=1, off by default: validated bit-identical, but not faster yet -- see cmf_sm100.cu).
 // The same sweep with the recurrence of cell c overlapped with the staging and pull of cell c+1 (fp32 handles): 640 threads,
 // warpgroups 0-3 are the pull team (named barrier 1 over 512 threads), warp 16 is the recurrence warp, the two sides hand the
 // double-buffered (qeff, hch) pair over through the shared counters ready_c / done_c.  Arithmetic and order of every

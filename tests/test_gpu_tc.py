@@ -185,8 +185,8 @@ def test_hals_wavefront_many_components_fp64(cmf, orc):
 
 @pytest.mark.parametrize("dims", [(64, 5000, 9, 6), (128, 9000, 40, 32), (32, 3000, 5, 40)])
 def test_hals_overlapped_sweep_is_bit_identical(cmf, orc, dims, monkeypatch):
-    # fp32 handles run the H sweep with the recurrence of cell c overlapped with the pull of cell c+1
-    # (hals_h_wave_ovl_kernel); CMF_HALS_OVERLAP=0 selects the plain wavefront kernel.  Same arithmetic, same order.
+    # CMF_HALS_OVERLAP=1 runs the H sweep of fp32 handles with the recurrence of cell c overlapped with the pull of cell c+1
+    # (hals_h_wave_ovl_kernel, experimental); the default is the plain wavefront kernel.  Same arithmetic, same order.
     N, T, K, L = dims
     W, H, X = _rand(N, T, K, L, seed=sum(dims))
     out = {}
