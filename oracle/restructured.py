@@ -253,3 +253,35 @@ def conv_overlap_save(W, H, B=None):
     Wf = np.fft.rfft(W, n=B, axis=2)                                    # K x N x F
     y = np.fft.irfft(np.einsum("knf,kbf->nbf", Wf, Hf), n=B, axis=2)[:, :, L - 1:]
     return y.reshape(N, -1)[:, :T]
+
+
+def build_G_from_R(R, H, L):
+    """build_G with the Toeplitz part given (e.g. from gram_overlap_save)."""
+    K, T = H.shape
+    G = np.zeros((L * K, L * K))
+    for l in range(L):
+        for lp in range(L):
+            base = R[:, :, l - lp] if l >= lp else R[:, :, lp - l].T
+            tail = np.zeros((K, K))
+            for i in range(min(l, lp)):
+                tail += np.outer(H[:, T - l + i], H[:, T - lp + i])
+            G[l * K : (l + 1) * K, lp * K : (lp + 1) * K] = base - tail
+    return G
+
+
+def mu_iteration_overlap_save(data, W, H, l1W=0.0, l2W=0.0, l1H=0.0, l2H=0.0, B=None):
+    """One MU iteration exactly as the frequency-domain engine executes it (float64): numW, the Gram of H, numH, denomH and the
+    direct loss all through overlap-save blocks; G*W, the truncated tail of denomH and the ratio updates in the time domain."""
+    K, N, L = W.shape
+    T = H.shape[1]
+    numW = numW_overlap_save(H, data, L, B)
+    G = build_G_from_R(gram_overlap_save(H, L, B), H, L)
+    denW = fold_W(G @ unfold_W(W), K, L)
+    W = np.maximum(W * numW / (denW + l1W + 2 * l2W * W + EPSILON), EPSILON)
+    numH = numH_overlap_save(W, data, B)
+    denH = denomH_interior_overlap_save(W, H, B)
+    if L > 1:
+        denH[:, T - (L - 1):] = denomH_gram(W, H)[:, T - (L - 1):]       # truncated tail (denomH_tail_prefix_kernel)
+    H = np.maximum(H * numH / (denH + l1H + 2 * l2H * H + EPSILON), EPSILON)
+    loss = np.linalg.norm(conv_overlap_save(W, H, B) - data) / np.linalg.norm(data)
+    return W, H, float(loss)

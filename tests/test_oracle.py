@@ -230,3 +230,22 @@ def test_overlap_save_forms_equal_literal(dims):
         fd = rs.denomH_interior_overlap_save(W, H, B)
         assert np.allclose(fd[:, : T - (L - 1)], lit[:, : T - (L - 1)], rtol=1e-10, atol=1e-10)
         assert np.allclose(rs.conv_overlap_save(W, H, B), po.tensor_conv(W, H), rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize("reg", [{}, dict(l1W=0.1, l2W=0.5, l1H=0.1, l2H=0.2)])
+def test_mu_iteration_in_the_frequency_domain_equals_literal(reg):
+    # the whole iteration of the device's frequency-domain engine (all five overlap-save pieces) == src/algs/mult.jl
+    from oracle import restructured as rs
+
+    N, T, K, L = 11, 260, 3, 7
+    X, _, _ = po.synthetic_sequences(K=2, N=N, L=L, T=T, rng=np.random.default_rng(5))
+    W, H = po.init_rand(X, L, K, np.random.default_rng(1))
+    rule = po.MultUpdate(X, W, H)
+    Wl, Hl = W.copy(), H.copy()
+    Wf, Hf = W.copy(), H.copy()
+    for _ in range(4):
+        rule.update_motifs(X, Wl, Hl, **{k: v for k, v in reg.items() if k.endswith("W")})
+        loss_l = rule.update_feature_maps(X, Wl, Hl, **{k: v for k, v in reg.items() if k.endswith("H")})
+        Wf, Hf, loss_f = rs.mu_iteration_overlap_save(X, Wf, Hf, **reg)
+        assert abs(loss_l - loss_f) < 1e-11
+    assert np.allclose(Wl, Wf, rtol=1e-9, atol=1e-13) and np.allclose(Hl, Hf, rtol=1e-9, atol=1e-13)
