@@ -28,6 +28,7 @@ CONFIGS = {
     "c4": dict(N=4096, T=1 << 22, K=64, L=100),
     "c3": dict(N=1024, T=1 << 20, K=20, L=50),
     "c1": dict(N=500, T=2000, K=5, L=10),
+    "c5": dict(N=512, T=1 << 24, K=128, L=32),     # spectrogram-shaped, HALS (--alg hals)
 }
 SEED_DATA, SEED_INIT, P_H, NOISE = 1234, 0, 0.05, 0.1
 
@@ -97,12 +98,27 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's algorithm (oracle port, NumPy/OpenBLAS per-lag GEMMs like src/common.jl)
 # ------------------------------------------------------------------------------------------------
-def cpu_iteration_time(cfg, T_sample, steps, warmup):
+def cpu_iteration_time(cfg, T_sample, steps, warmup, threads=None):
     """Seconds per literal MU iteration (src/algs/mult.jl:23-58) on a T_sample-column slice of the
-    workload (same N, K, L), Float64 like the reference, all host threads OpenBLAS gives us."""
+    workload (same N, K, L), Float64 like the reference, on `threads` BLAS threads (default: every host
+    core, set explicitly -- launchers such as torch.distributed.run export OMP_NUM_THREADS=1)."""
     import numpy as np
+    from threadpoolctl import threadpool_limits
 
     from oracle import cnmf_oracle as po
+
+    with threadpool_limits(limits=threads or host_cores(), user_api="blas"):
+        return _cpu_iteration_time(np, po, cfg, T_sample, steps, warmup)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def _cpu_iteration_time(np, po, cfg, T_sample, steps, warmup):
 
     N, K, L = cfg["N"], cfg["K"], cfg["L"]
     rng = np.random.default_rng(SEED_DATA)
@@ -123,13 +139,35 @@ def cpu_iteration_time(cfg, T_sample, steps, warmup):
     return (time.perf_counter() - t0) / steps
 
 
-def cpu_threads():
-    try:
-        from threadpoolctl import threadpool_info
+def cpu_iteration_time_hals(cfg, T_sample):
+    """Seconds per literal HALS iteration (src/algs/hals.jl:31-154: rank-1 sweeps on a persistent residual) of the plain-C
+    restatement (oracle/cnmf_oracle.c, OpenMP where the reference's BLAS would thread) on a T_sample-column slice."""
+    import numpy as np
 
-        return max([p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"] or [os.cpu_count()])
+    from oracle import c_oracle as co
+
+    N, K, L = cfg["N"], cfg["K"], cfg["L"]
+    rng = np.random.default_rng(SEED_DATA)
+    X = np.asfortranarray(rng.random((N, T_sample)))
+    W = np.asfortranarray(rng.random((K, N, L)))
+    H = np.asfortranarray(rng.random((K, T_sample)))
+    rule = co.HALSUpdate(X, W, H)
+    t0 = time.perf_counter()
+    rule.update_motifs(X, W, H)
+    rule.update_feature_maps(X, W, H)
+    return time.perf_counter() - t0
+
+
+def cpu_threads(threads=None):
+    """BLAS threads actually in use inside a `threadpool_limits(threads or all cores)` region."""
+    try:
+        import numpy  # noqa: F401  (loads the BLAS that threadpoolctl inspects)
+        from threadpoolctl import threadpool_info, threadpool_limits
+
+        with threadpool_limits(limits=threads or host_cores(), user_api="blas"):
+            return max([p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"] or [1])
     except Exception:
-        return os.cpu_count()
+        return 1
 
 
 def cpu_sample_T(cfg):
@@ -149,12 +187,16 @@ def run_reference(args, cfg, name):
     its = 1.0 / (sec * cfg["T"] / Ts)                 # cost is exactly linear in T
     sample = f"literal MU iteration timed on a T={Ts} slice (same N,K,L), extrapolated x{cfg['T'] / Ts:.0f} to T={cfg['T']}"
     cores = cpu_threads()
+    # the reference's own SLURM jobs asked for 2 CPUs (figures/fast_bcd/synthetic_run.sh:7): the same sample on 2 threads
+    sec2 = cpu_iteration_time(cfg, Ts, 1, 1, threads=2)
+    its2 = 1.0 / (sec2 * cfg["T"] / Ts)
     line = {
         "impl": "reference", "metric": "CNMF iterations/sec", "value": its, "unit": "iterations/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / its,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{name}: MU N={cfg['N']} T={cfg['T']} K={cfg['K']} L={cfg['L']}", "alg": "mult"},
-        "cpu_baseline": {"value": its, "unit": "iterations/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": its, "unit": "iterations/s", "cores": cores, "kind": "port", "sample": sample,
+                         "two_threads": {"value": its2, "cores": cpu_threads(2)}},
         "e2e": {"value": its, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "Julia is not installed in this image, so the reference itself cannot run; this is the "
                 "NumPy/OpenBLAS restatement of src/algs/mult.jl (oracle/cnmf_oracle.py), same per-lag GEMM structure",
@@ -205,11 +247,29 @@ def run_ours(args, cfg, name):
     N, T, K, L = cfg["N"], cfg["T"], cfg["K"], cfg["L"]
     plan = cmf.ShardPlan(T, world, L)
     t0, t1 = plan.ranges[rank]
-    shard = cmf.DeviceShard(N, T, t0, t1, K, L, dtype="f32", device=local_rank)
-    if args.engine is not None:
-        shard.set_engine(args.engine)
-    shard.set_loss_mode(args.loss_mode)
-    fitter = cmf.ShardedMultFit(shard, rank, world, dist)
+    # collectives: "lib" = NCCL inside libcmf_sm100 (the reference-facing calls drive all ranks; one process per GPU under
+    # torchrun, the 128-byte NCCL id travels over torch.distributed), "host" = the older split-phase calls with
+    # torch.distributed doing the collectives between them
+    uid = None
+    if world > 1 and args.collectives == "lib":
+        box = [cmf.DeviceShard.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+
+    def make_shard():
+        if world > 1 and args.collectives == "lib":
+            sh = cmf.DeviceShard(N, T, t0, t1, K, L, dtype="f32", device=local_rank, alg=args.alg, comm=(uid, rank, world))
+        else:
+            sh = cmf.DeviceShard(N, T, t0, t1, K, L, dtype="f32", device=local_rank, alg=args.alg)
+        if args.engine is not None:
+            sh.set_engine(args.engine)
+        if args.alg == "mult":
+            sh.set_loss_mode(args.loss_mode)
+        if world > 1 and args.collectives == "host":
+            return sh, cmf.ShardedMultFit(sh, rank, world, dist)
+        return sh, cmf.LibraryFit(sh)
+
+    shard, fitter = make_shard()
 
     def barrier():
         if world > 1:
@@ -257,7 +317,7 @@ def run_ours(args, cfg, name):
 
     # secondary: the same iteration with the loss evaluated by the direct conv + residual pass (mult.jl:55-57 literally)
     value_direct = None
-    if args.loss_mode == 1:
+    if args.loss_mode == 1 and args.alg == "mult":
         shard.set_loss_mode(0)
         fitter.iterate()
         barrier()
@@ -304,11 +364,7 @@ def run_ours(args, cfg, name):
             torch.cuda.synchronize()
             marks.append(time.perf_counter())
 
-        sh2 = cmf.DeviceShard(N, T, t0, t1, K, L, dtype="f32", device=local_rank)
-        if args.engine is not None:
-            sh2.set_engine(args.engine)
-        sh2.set_loss_mode(args.loss_mode)
-        f2 = cmf.ShardedMultFit(sh2, rank, world, dist)
+        sh2, f2 = make_shard()
         sh2.set_data(Xh, t0)                      # H2D of this rank's columns from pinned host memory
         f2.setup_data_norm()
         mark()
@@ -348,6 +404,7 @@ def run_ours(args, cfg, name):
     pk = peaks()
     Fc = flops_contraction(N, T, K, L)
     # dominant kernel = the contraction class with the largest device time in the timed region
+    sweep_ms, sweep_n = prof.pop("sweep", (0.0, 0))
     dom = max(prof, key=lambda k: prof[k][0])
     dom_ms, dom_n = prof[dom]
     per_launch_ms = dom_ms / max(dom_n, 1)
@@ -398,28 +455,47 @@ def run_ours(args, cfg, name):
            "note": "whole-iteration algorithmic bytes s*(2NT + 4KT + 6KNL) per GPU over the step time (the % HBM figure the metric asks for)"}
 
     cpu = None
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and args.alg == "hals":
+        Ts = int(min(T, 4096))
+        sec = cpu_iteration_time_hals(cfg, Ts)
+        cpu = {"value": 1.0 / (sec * T / Ts), "unit": "iterations/s", "cores": int(os.environ.get("OMP_NUM_THREADS", host_cores())),
+               "kind": "port", "sample": f"one literal Float64 HALS iteration (plain-C restatement of hals.jl) on a T={Ts} slice (same N,K,L), extrapolated x{T / Ts:.0f}"}
+    elif world == 1 and not args.no_cpu:
         Ts = cpu_sample_T(cfg)
         sec = cpu_iteration_time(cfg, Ts, 1, 1)
         cpu = {"value": 1.0 / (sec * T / Ts), "unit": "iterations/s", "cores": cpu_threads(), "kind": "port",
                "sample": f"one literal Float64 MU iteration on a T={Ts} slice (same N,K,L), extrapolated x{T / Ts:.0f}"}
 
+    critical = None
+    if args.alg == "hals":
+        # the H sweep (hals.jl:121-154) is a chain of T dependent steps per component: neither HBM nor tensor bound, and no
+        # GPU count shortens it; on a sharded fit it runs on rank 0 over all T columns (gather Q / scatter H around it)
+        per_sweep = sweep_ms / max(sweep_n, 1)
+        critical = {"kernel": "hals_h_wave_kernel (cooperative wavefront over (component, 1024-column chunk))",
+                    "dependent_column_steps": T + (K - 1) * L, "ms_per_sweep": per_sweep, "sweeps": sweep_n,
+                    "us_per_1024_columns": per_sweep * 1e3 / (T / 1024.0) if sweep_n else None,
+                    "ns_per_column": per_sweep * 1e6 / T if sweep_n else None,
+                    "share_of_step": sweep_ms / (ms_per_step * args.steps) if ms > 0 else None,
+                    "note": "measured on rank 0 (the sweep runs there over all T columns); exact reference order k outer / t inner"}
     line = {
         "metric": "CNMF iterations/sec", "value": value, "unit": "iterations/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{name}: MU N={N} T={T} K={K} L={L}", "alg": "mult", "parallelism": f"T-shard x{world}",
+        "config": {"workload": f"{name}: {'MU' if args.alg == 'mult' else 'HALS'} N={N} T={T} K={K} L={L}", "alg": args.alg,
+                   "parallelism": f"T-shard x{world}", "collectives": ("NCCL inside libcmf_sm100 (cmf_create_rank)" if args.collectives == "lib" else "torch.distributed between the split-phase calls") if world > 1 else "none",
                    "l2": "inputs (X = %.1f GiB per GPU) exceed the 126 MB L2" % (4.0 * N * (t1 - t0) / 2 ** 30),
                    "seeds": {"data": SEED_DATA, "init": SEED_INIT}, "p_h": P_H, "noise": NOISE,
                    "engine": {0: "SIMT fp32", 1: "tcgen05 split-bf16, time domain (3 MMAs per product, fp32 accumulate)",
                               2: "tcgen05 split-bf16, frequency domain (overlap-save spectrum of X, SIMT FFTs, per-frequency "
                                  "complex products with 3 MMAs per product)"}[engine],
                    "loss": ("algebraic expansion ||X||^2 - 2<numH,H> + <WW',HtHt'> (exact identity, falls back to the direct "
-                            "pass below 25% loss)" if args.loss_mode == 1 else "direct conv + residual pass")},
+                            "pass below 25% loss)" if (args.loss_mode == 1 and args.alg == "mult") else "direct conv + residual pass")},
         "value_direct_loss": value_direct,
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_hbm": hbm, "cpu_baseline": cpu,
         "clocks": clocks, "loss": {"initial": loss0, "final": losses[-1] if losses else None},
     }
+    if critical is not None:
+        line["critical_path"] = critical
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -469,6 +545,9 @@ def main():
                     help="1: loss by the algebraic expansion on resident numH / W W' (default); 0: direct residual pass")
     ap.add_argument("--engine", type=int, default=None, choices=[0, 1, 2],
                     help="contraction engine (default: the library's choice): 0 SIMT, 1 tcgen05 time domain, 2 tcgen05 frequency domain")
+    ap.add_argument("--alg", default="mult", choices=["mult", "hals"])
+    ap.add_argument("--collectives", default="lib", choices=["lib", "host"],
+                    help="multi-GPU: NCCL inside the library behind the reference-facing calls (default) or torch.distributed between the split-phase calls")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -20,6 +20,12 @@ _h = _c.c_void_p
 SIGNATURES = {
     "cmf_create": [_c.POINTER(_h), _i64, _i64, _i64, _i64, _int, _int, _int],
     "cmf_create_shard": [_c.POINTER(_h), _i64, _i64, _i64, _i64, _i64, _i64, _int, _int, _int],
+    "cmf_create_multi": [_c.POINTER(_h), _i64, _i64, _i64, _i64, _int, _int, _int, _c.POINTER(_int)],
+    "cmf_comm_unique_id": [_vp],
+    "cmf_create_rank": [_c.POINTER(_h), _i64, _i64, _i64, _i64, _int, _int, _int, _vp, _int, _int],
+    "cmf_shard_range": [_i64, _int, _int, _c.POINTER(_i64), _c.POINTER(_i64)],
+    "cmf_comm_info": [_h, _c.POINTER(_int), _c.POINTER(_int), _c.POINTER(_i64), _c.POINTER(_i64)],
+    "cmf_exchange_halos": [_h],
     "cmf_destroy": [_h],
     "cmf_set_data": [_h, _vp, _i64],
     "cmf_synth_data": [_h, _c.c_uint64, _i64, _i64, _dbl, _dbl],
@@ -56,6 +62,8 @@ SIGNATURES = {
     "cmf_tensor_conv": [_i64, _i64, _i64, _i64, _int, _vp, _vp, _vp],
     "cmf_tensor_transconv": [_i64, _i64, _i64, _i64, _int, _vp, _vp, _vp],
     "cmf_corr_w": [_i64, _i64, _i64, _i64, _int, _vp, _vp, _vp],
+    "cmf_compute_resids": [_i64, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp],
+    "cmf_shift_and_stack": [_i64, _i64, _i64, _int, _vp, _vp],
 }
 
 _LIB = None

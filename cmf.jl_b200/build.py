@@ -13,6 +13,7 @@ DEPS = SOURCES + [
     os.path.join(HERE, "csrc", "kernels_simt.cuh"),
     os.path.join(HERE, "csrc", "kernels_tc.cuh"),
     os.path.join(HERE, "csrc", "kernels_fd.cuh"),
+    os.path.join(HERE, "csrc", "comm.h"),
     os.path.join(ROOT, "include", "cmf_sm100.h"),
 ]
 
@@ -36,7 +37,7 @@ def build(force=False, verbose=False):
         return SO
     cmd = [
         nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-        "-Xcompiler", "-fPIC", "-shared", "-o", SO, *SOURCES, "-lcuda",
+        "-Xcompiler", "-fPIC", "-shared", "-o", SO, *SOURCES, "-lcuda", "-ldl", "-lpthread",
     ]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -20,6 +21,7 @@
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_fd.cuh"
+#include "comm.h"
 
 namespace {
 
@@ -56,7 +58,10 @@ struct DevBuf {
         n = count;
         if (count) {
             CK(cudaMalloc(&p, count * sizeof(T)));
-            CK(cudaMemset(p, 0, count * sizeof(T)));
+            // the zero-fill runs on the legacy default stream, which the handle's non-blocking stream is not ordered
+            // against: wait for it here (allocation is never on the hot path)
+            CK(cudaMemsetAsync(p, 0, count * sizeof(T), cudaStreamLegacy));
+            CK(cudaStreamSynchronize(cudaStreamLegacy));
         }
     }
     void free() {
@@ -81,6 +86,7 @@ struct cmf_ctx {
     int64_t launches = 0;
     double data_norm = 0.0;
     double data_sumsq_local = 0.0;   // ||X_owned||^2 of this shard
+    double data_sumsq_global = 0.0;  // ||X||^2 over all shards (== local without a communicator)
     int loss_mode = 0;               // 0 = direct residual pass, 1 = algebraic expansion when its inputs are resident
     bool loss_mode_explicit = false; // set by cmf_set_loss_mode: engine changes then leave the mode alone
     double pgd_stepW = 5.0, pgd_stepH = 5.0, pgd_cur_loss = 0.0;   // PGDUpdate state (pgd.jl:147-151)
@@ -110,34 +116,49 @@ struct cmf_ctx {
         prof_events.clear();
     }
     virtual ~cmf_ctx() { prof_clear(); }
-    virtual void get_data(void *X_out, int with_halo) = 0;
-    virtual bool tc_available() = 0;
-    virtual bool fd_available() = 0;
-    virtual void fd_release() = 0;
-    virtual void set_data(const void *X, int64_t first_col) = 0;
-    virtual void synth_data(uint64_t seed, int64_t Kt, int64_t Lt, double p_h, double noise) = 0;
-    virtual double data_sumsq() = 0;
-    virtual void set_factors(const void *W, const void *H, int64_t first_col) = 0;
-    virtual void init_rand(uint64_t seed) = 0;
-    virtual void init_scale_partials(double out[2]) = 0;
-    virtual void scale_factors(double s) = 0;
-    virtual void get_factors(void *W, void *H) = 0;
-    virtual void w_partials() = 0;
-    virtual void w_apply(double l1W, double l2W) = 0;
-    virtual void h_update(double l1H, double l2H) = 0;
-    virtual double loss_partial() = 0;
-    virtual void hals_update_motifs(double l1W, double l2W) = 0;
-    virtual double hals_update_feature_maps(double l1H, double l2H) = 0;
-    virtual void pgd_update_motifs(double l1W, double l2W) = 0;
-    virtual double pgd_update_feature_maps(double l1H, double l2H) = 0;
-    virtual void exchange_buffer(int which, void **p, int64_t *count, int *dt) = 0;
-    virtual void halo_buffers(void **sl, void **sr, void **rl, void **rr, int64_t *count) = 0;
-    virtual void prim_conv(void *out_host) = 0;
-    virtual void prim_transconv(const void *X_host, void *out_host) = 0;
-    virtual void prim_corr(const void *X_host, void *out_host) = 0;
+    // ---- multi-GPU (the reference is single-process: no counterpart)
+    cmf::Comm comm;                  // NCCL communicator of this rank (world == 1: collectives are no-ops)
+    struct cmf_multi *multi = nullptr;   // set on the single-process multi-GPU handle only (cmf_create_multi)
+    int world() const { return comm.world; }
+    int rank() const { return comm.rank; }
+    [[noreturn]] static void no_multi() { throw std::runtime_error("this call is not available on a multi-GPU group handle"); }
+    virtual void get_data(void *, int) { no_multi(); }
+    virtual bool tc_available() { no_multi(); }
+    virtual bool fd_available() { no_multi(); }
+    virtual void fd_release() { no_multi(); }
+    virtual void set_data(const void *, int64_t) { no_multi(); }
+    virtual void synth_data(uint64_t, int64_t, int64_t, double, double) { no_multi(); }
+    virtual double data_sumsq() { no_multi(); }
+    virtual void set_factors(const void *, const void *, int64_t) { no_multi(); }
+    virtual void init_rand(uint64_t) { no_multi(); }
+    virtual void init_scale_partials(double *) { no_multi(); }
+    virtual void scale_factors(double) { no_multi(); }
+    virtual void get_factors(void *, void *) { no_multi(); }
+    virtual void w_partials() { no_multi(); }
+    virtual void w_apply(double, double) { no_multi(); }
+    virtual void h_update(double, double) { no_multi(); }
+    virtual double loss_partial() { no_multi(); }
+    virtual int loss_partial_dev() { no_multi(); }                 // leaves 1 (direct) or 2 (expansion) doubles in scalars()
+    virtual double *scalars() { no_multi(); }                      // device buffer of 8 doubles
+    virtual void hals_update_motifs(double, double) { no_multi(); }
+    virtual double hals_update_feature_maps(double, double) { no_multi(); }
+    virtual void hals_h_prepare() { no_multi(); }                  // Q = denomH - numH on the owned columns
+    virtual void hals_h_local(void **, void **, int64_t *) { no_multi(); }     // device pointers of the local Q and H (owned columns), element count
+    virtual void hals_h_full(void **, void **) { no_multi(); }     // rank 0 of a sharded fit: full-T Q and H buffers (allocated on first use)
+    virtual void hals_h_sweep(int full, double, double) { no_multi(); }
+    virtual void h_changed() { no_multi(); }                       // invalidates what depends on H (after a halo exchange / scatter)
+    virtual void pgd_update_motifs(double, double) { no_multi(); }
+    virtual double pgd_update_feature_maps(double, double) { no_multi(); }
+    virtual void exchange_buffer(int, void **, int64_t *, int *) { no_multi(); }
+    virtual void halo_buffers(void **, void **, void **, void **, int64_t *) { no_multi(); }
+    virtual void prim_conv(void *) { no_multi(); }
+    virtual void prim_transconv(const void *, void *) { no_multi(); }
+    virtual void prim_corr(const void *, void *) { no_multi(); }
+    virtual void prim_resids(void *) { no_multi(); }
+    virtual void prim_shift_and_stack(void *) { no_multi(); }
 };
 
-enum { PROF_CONV = 0, PROF_TRANSCONV = 1, PROF_CORR = 2, PROF_NCLASS = 3 };
+enum { PROF_CONV = 0, PROF_TRANSCONV = 1, PROF_CORR = 2, PROF_SWEEP = 3, PROF_NCLASS = 4 };
 
 namespace {
 
@@ -242,7 +263,7 @@ struct Ctx : cmf_ctx {
     DevBuf<S> X, Hbuf, Wi, Wtmp, numW, denW, GS, Cf, numH, denH, tailC;
     DevBuf<int> progress, lockstep;
     DevBuf<S> tailCt;                  // HALS H sweep: truncated lag tables of all component pairs
-    int hals_grid = 0, hals_grid_ovl = -1;
+    int hals_grid = 0;
     DevBuf<double> exch1, corr_part, loss_part, scal;
     S *H = nullptr;  // owned column 0 inside Hbuf
     int nsplit_w = 1, nsplit_g = 1;
@@ -255,6 +276,22 @@ struct Ctx : cmf_ctx {
     static constexpr int BN = 16 * TN, BT = TY * TT;
 
     int64_t KL() const { return K * L; }
+
+    void hals_setup() {
+        // wavefront H sweep: one cooperative launch, CTA b owns components b, b+grid, ...
+        REQUIRE(L - 1 <= HW_TC, "HALS: L-1 must not exceed the sweep chunk (1024 columns)");
+        const size_t smem = hals_wave_smem_elems<S>(L) * sizeof(S);
+        int per_sm = 0, sms = 0, coop = 0;
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+        REQUIRE(coop != 0, "HALS needs cooperative launch support");
+        CK(cudaFuncSetAttribute(hals_h_wave_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hals_h_wave_kernel<S>, HW_NT, smem));
+        hals_grid = (int)std::min<int64_t>(K, (int64_t)per_sm * sms);
+        REQUIRE(hals_grid >= 1, "HALS: H sweep kernel does not fit on the device");
+        tailC.alloc((size_t)hals_grid * (size_t)(L * L));
+        progress.alloc((size_t)K);
+    }
 
     void init() {
         CK(cudaSetDevice(device));
@@ -274,21 +311,7 @@ struct Ctx : cmf_ctx {
         denH.alloc((size_t)(std::max<int64_t>(Tl * K, Tl)));
         exch1.alloc((size_t)(L * K * K + hal * K + 1));
         scal.alloc(8);
-        if (alg == CMF_HALS) {
-            // wavefront H sweep: one cooperative launch, CTA b owns components b, b+grid, ...
-            REQUIRE(L - 1 <= HW_TC, "HALS: L-1 must not exceed the sweep chunk (1024 columns)");
-            const size_t smem = hals_wave_smem_elems<S>(L) * sizeof(S);
-            int per_sm = 0, sms = 0, coop = 0;
-            CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-            CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
-            REQUIRE(coop != 0, "HALS needs cooperative launch support");
-            CK(cudaFuncSetAttribute(hals_h_wave_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hals_h_wave_kernel<S>, HW_NT, smem));
-            hals_grid = (int)std::min<int64_t>(K, (int64_t)per_sm * sms);
-            REQUIRE(hals_grid >= 1, "HALS: H sweep kernel does not fit on the device");
-            tailC.alloc((size_t)hals_grid * (size_t)(L * L));
-            progress.alloc((size_t)K);
-        }
+        if (alg == CMF_HALS) hals_setup();
         // corr splits: numW (Nin = N) and Gram (Nin = K)
         plan_split(N, Tl + hal, nsplit_w, split_w);
         plan_split(K, Tl + hal, nsplit_g, split_g);
@@ -1196,27 +1219,43 @@ struct Ctx : cmf_ctx {
         gram_valid = false; fds.h_dirty = true;
     }
 
-    double loss_partial() override {
+    double *scalars() override { return scal.p; }
+
+    // Leaves the local loss scalars in scal.p without a host synchronisation and returns how many there are:
+    //   1 (direct pass):  scal[0] = sum of squared residuals over the owned columns (mult.jl:55-57)
+    //   2 (expansion):    scal[0] = <numH, H>, scal[1] = <W W', Htilde Htilde'> over the owned columns
+    // scal[1] is zeroed in the direct case so that a fixed-size all-reduce of two doubles serves both.
+    int loss_partial_dev() override {
         REQUIRE(have_data && have_factors, "loss: data and factors must be set first");
         if (loss_mode == 1 && tc_active()) {
             // frequency-domain engine: numH and W W' are cheap, so the expansion also serves calls that find them stale
             // (the loss at the initial factors, after a W-only step, after the HALS sweep overwrote numH)
             if (!numH_valid && fd_active()) { tc_transconv(); lag_tables(); numH_valid = true; }
-            if (numH_valid) return loss_partial_expansion();
+            if (numH_valid) { loss_partial_expansion_dev(); return 2; }
         }
         int64_t nb = conv_nblocks(0, Tl);
         if (fd_active() && !getenv("CMF_FD_LOSS_TC")) nb = fd_conv_loss();
         else if (tc_active()) nb = tc_conv_loss();
         else launch_conv(Wi.p, H, K, L, -(L - 1), Tl + (L - 1), 0, Tl, 4, nullptr, loss_part.p);  // mult.jl:55-57
         reduce_scalar(loss_part.p, nb, scal.p);
-        return fetch_scalar(scal.p);
+        CK(cudaMemsetAsync(scal.p + 1, 0, sizeof(double), stream));
+        return 1;
+    }
+
+    // local sum of squared residuals (for the expansion: this shard's share of the global identity)
+    double loss_partial() override {
+        const int n = loss_partial_dev();
+        double bc[2];
+        CK(cudaMemcpyAsync(bc, scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        return n == 2 ? data_sumsq_local - 2.0 * bc[0] + bc[1] : bc[0];
     }
 
     // ||conv(W,H) - X||^2 = ||X||^2 - 2 <transconv(W,X), H> + <W W', Htilde Htilde'>, summed over the owned columns
     // (the global sum over shards is exact; a single shard's value is not its own residual).  numH and W W' are
     // resident from the H update with the current W; the Gram of the new H is computed here and reused by the
     // next cmf_w_partials (the halos must not change in between).
-    double loss_partial_expansion() {
+    void loss_partial_expansion_dev() {
         gram_partial();
         gram_valid = true;
         if (getenv("CMF_G_DIRECT"))
@@ -1228,10 +1267,6 @@ struct Ctx : cmf_ctx {
         dot_partial_kernel<S><<<1024, 256, 0, stream>>>(numH.p, H, Tl * K, loss_part.p);
         post_launch();
         reduce_scalar(loss_part.p, 1024, scal.p);
-        double bc[2];
-        CK(cudaMemcpyAsync(bc, scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
-        CK(cudaStreamSynchronize(stream));
-        return data_sumsq_local - 2.0 * bc[0] + bc[1];
     }
 
     // ---------------------------------------------------------------- HALS (src/algs/hals.jl)
@@ -1260,27 +1295,42 @@ struct Ctx : cmf_ctx {
         hals_w_apply(l1W, l2W);
     }
 
-    double hals_update_feature_maps(double l1H, double l2H) override {
+    // Q = transconv(W, R) = denomH - numH on the owned columns (left in numH)
+    void hals_h_prepare() override {
         REQUIRE(have_data && have_factors, "update: data and factors must be set first");
-        REQUIRE(is_first && is_last, "HALS H sweep is single-shard");
         if (tc_active()) tc_transconv();
         else launch_transconv(Wi.p, X.p, numH.p, N, K, L, N, Tl, Tl + (L - 1));
         lag_tables();
         if (fd_active()) fd_denomH();
         else if (tc_active()) { tc_split_H(false); tc_denomH(); }
         else launch_transconv(Cf.p, Hbuf.p, denH.p, K, K, 2 * L - 1, K, Tl, Tl + 2 * (L - 1));
-        if (L > 1) {
+        if (is_last && L > 1) {
             launch_denomH_tail();
         }
         sub_kernel<S><<<(unsigned)cdiv(Tl * K, 256), 256, 0, stream>>>(numH.p, denH.p, numH.p, Tl * K);        // Q
         post_launch();
-        // wavefront sweep (hals.jl:121-154); Delta H goes to denH
+    }
+    void hals_h_local(void **q, void **h, int64_t *count) override { *q = numH.p; *h = H; *count = Tl * K; }
+    // rank 0 of a T-sharded HALS fit holds Q, H and Delta H of ALL columns during the sweep: the sweep is a chain of T
+    // dependent steps per component (hals.jl:124-128) that more GPUs cannot shorten, so the shards' Q are gathered here,
+    // swept once in the reference's order, and the new H is scattered back
+    DevBuf<S> Qfull, Hfull, Dfull;
+    void hals_h_full(void **q, void **h) override {
+        const size_t n = (size_t)(T * K);
+        if (Qfull.n < n) { Qfull.alloc(n); Hfull.alloc(n); Dfull.alloc(n); }
+        *q = Qfull.p; *h = Hfull.p;
+    }
+
+    // wavefront sweep (hals.jl:121-154) over the local shard (single-shard handles) or over the gathered full-T buffers
+    void hals_h_sweep(int full, double l1H, double l2H) override {
+        REQUIRE(full || (is_first && is_last), "the local HALS H sweep needs a single-shard handle");
+        if (progress.n == 0) hals_setup();
         CK(cudaMemsetAsync(progress.p, 0, progress.n * sizeof(int), stream));
         const size_t smem = hals_wave_smem_elems<S>(L) * sizeof(S);
-        const S *cf = Cf.p, *s2 = GS.p, *q = numH.p;
-        S *hh = H, *dd = denH.p, *tc_ = tailC.p;
+        const S *cf = Cf.p, *s2 = GS.p, *q = full ? Qfull.p : numH.p;
+        S *hh = full ? Hfull.p : H, *dd = full ? Dfull.p : denH.p, *tc_ = tailC.p;
         int *pr = progress.p;
-        int64_t Kk = K, Ll = L, Tt = Tl, ks = s2_ks, ldv = s2_ld;
+        int64_t Kk = K, Ll = L, Tt = full ? T : Tl, ks = s2_ks, ldv = s2_ld;
         S a1 = (S)l1H, a2 = (S)l2H;
         int dbg = getenv("CMF_HALS_DEBUG") ? atoi(getenv("CMF_HALS_DEBUG")) : 0;   // 1: phase clocks of the last component; 2 / 4: timing runs without the pull / recurrence
         // truncated lag tables of all component pairs for the pull over the last L-1 columns (skipped when they would not fit: the
@@ -1296,35 +1346,21 @@ struct Ctx : cmf_ctx {
             }
         }
         void *args[] = {&cf, &s2, &q, &hh, &dd, &tc_, &pr, &Kk, &Ll, &Tt, &ks, &ldv, &a1, &a2, &dbg, &ct};
-        // CMF_HALS_OVERLAP=1 (fp32, experimental): the recurrence of cell c runs in its own warp while the other warps stage and
-        // pull cell c+1 (hals_h_wave_ovl_kernel, bit-identical results).  Measured: no gain yet (223.6 vs 219.1 ms per sweep at
-        // config-5 shape, T = 2^20) -- the recurrence warp shares its scheduler with four busy pull warps and slows down by about as
-        // much as the overlap saves; it stays opt-in until the pull team leaves that scheduler free.
-        bool ovl = false;
-        if constexpr (std::is_same<S, float>::value) {
-            const char *e = getenv("CMF_HALS_OVERLAP");
-            ovl = dbg == 0 && e && atoi(e) == 1;
-            if (ovl) {
-                const size_t smem_o = smem + (size_t)2 * HW_TC * sizeof(S);
-                if (hals_grid_ovl < 0) {
-                    int per_sm = 0, sms = 0;
-                    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-                    cudaError_t e1 = cudaFuncSetAttribute(hals_h_wave_ovl_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_o);
-                    cudaError_t e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hals_h_wave_ovl_kernel<S>, HW_NT_OVL, smem_o);
-                    hals_grid_ovl = (e1 == cudaSuccess && e2 == cudaSuccess) ? (int)std::min<int64_t>(K, (int64_t)per_sm * sms) : 0;
-                    if (e1 != cudaSuccess || e2 != cudaSuccess) cudaGetLastError();
-                }
-                // same tailC scratch (one L*L table per CTA): the overlapped grid must not exceed the plain one
-                if (hals_grid_ovl >= 1 && hals_grid_ovl <= hals_grid)
-                    CK(cudaLaunchCooperativeKernel((void *)hals_h_wave_ovl_kernel<S>, dim3((unsigned)hals_grid_ovl), dim3(HW_NT_OVL), args, smem_o, stream));
-                else ovl = false;
-            }
-        }
-        if (!ovl)
+        prof_begin(PROF_SWEEP);
         CK(cudaLaunchCooperativeKernel((void *)hals_h_wave_kernel<S>, dim3((unsigned)hals_grid), dim3(HW_NT), args, smem, stream));
+        prof_end();
         post_launch();
+    }
+    void h_changed() override {
         gram_valid = false; fds.h_dirty = true;
         numH_valid = false;
+    }
+
+    double hals_update_feature_maps(double l1H, double l2H) override {
+        REQUIRE(is_first && is_last, "single-shard entry; sharded fits go through the communicator path");
+        hals_h_prepare();
+        hals_h_sweep(0, l1H, l2H);
+        h_changed();
         return loss_partial();                                                // hals.jl:41
     }
 
@@ -1409,6 +1445,26 @@ struct Ctx : cmf_ctx {
         CK(cudaMemcpyAsync(out_host, Wtmp.p, Wtmp.n * sizeof(S), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
     }
+    // compute_resids (src/common.jl:58-59): conv(W,H) - X through the conv kernel's residual epilogue
+    void prim_resids(void *out_host) override {
+        REQUIRE(have_data && have_factors, "compute_resids: data and factors must be set");
+        DevBuf<S> out;
+        out.alloc((size_t)(N * Tl));
+        launch_conv(Wi.p, H, K, L, -(L - 1), Tl + (L - 1), 0, Tl, 2, out.p, nullptr);
+        CK(cudaMemcpyAsync(out_host, out.p, out.n * sizeof(S), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+    }
+    // shift_and_stack (src/common.jl:133-142): Htilde[(l*K+k), t] = H[k, t-l], zero for t < l (materialised only here, for tests
+    // and small problems: the fit itself addresses the same rows through overlapping windows of H)
+    void prim_shift_and_stack(void *out_host) override {
+        REQUIRE(have_factors, "shift_and_stack: factors must be set");
+        DevBuf<S> out;
+        out.alloc((size_t)(KL() * Tl));
+        shift_stack_kernel<S><<<(unsigned)cdiv(KL() * Tl, 256), 256, 0, stream>>>(H, out.p, K, L, Tl);
+        post_launch();
+        CK(cudaMemcpyAsync(out_host, out.p, out.n * sizeof(S), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+    }
 };
 
 cmf_ctx *make_ctx(int64_t N, int64_t T, int64_t t0, int64_t t1, int64_t K, int64_t L, int dtype, int alg, int device) {
@@ -1420,7 +1476,7 @@ cmf_ctx *make_ctx(int64_t N, int64_t T, int64_t t0, int64_t t1, int64_t K, int64
     const bool sharded = !(t0 == 0 && t1 == T);
     if (sharded) {
         REQUIRE(t1 - t0 >= L - 1, "each shard needs at least L-1 columns");
-        if (alg != CMF_MULT) throw CmfError(CMF_ERR_UNSUPPORTED, "HALS and PGD are single-shard only in this version");
+        if (alg == CMF_PGD) throw CmfError(CMF_ERR_UNSUPPORTED, "PGD is single-shard only in this version");
     }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1458,21 +1514,23 @@ int guarded(F &&f) {
     }
 }
 
-void use(cmf_handle h) {
-    REQUIRE(h != nullptr, "null handle");
-    CK(cudaSetDevice(h->device));
-}
-
-// The expansion loss cancels like 1/loss^2 (error ~2e-6/loss^2 relative, measured): at or below 25 % relative loss
-// (or when the expansion went negative) switch the handle back to the direct residual pass and re-evaluate with it.
-double guarded_loss(cmf_handle h, double sumsq) {
-    double loss = std::sqrt(sumsq) / h->data_norm;
-    if (h->loss_mode == 1 && !(loss > 0.25)) {
-        h->loss_mode = 0;
-        loss = std::sqrt(h->loss_partial()) / h->data_norm;
+// Every ABI call runs on the handle's device and leaves the caller's current device as it found it.
+struct DevGuard {
+    int prev = -1;
+    explicit DevGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        CK(cudaSetDevice(dev));
     }
-    return loss;
-}
+    ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DevGuard(const DevGuard &) = delete;
+    DevGuard &operator=(const DevGuard &) = delete;
+};
+// only restores the caller's current device on exit (constructors: the argument checks come before any CUDA call)
+struct DevRestore {
+    int prev = -1;
+    DevRestore() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
+    ~DevRestore() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 // src/model.jl:91-107
 bool converged(const double *loss_hist, int64_t n, int patience, double tol) {
@@ -1481,6 +1539,288 @@ bool converged(const double *loss_hist, int64_t n, int patience, double tol) {
         if (!(std::fabs(loss_hist[i] - loss_hist[i - 1]) < tol)) return false;
     return true;
 }
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU: T-sharding with NCCL inside the library (the reference is single-process)
+// ------------------------------------------------------------------------------------------
+#define NK(call)                                                                                   \
+    do {                                                                                           \
+        ncclResult_t r__ = (call);                                                                 \
+        if (r__ != ncclSuccess)                                                                    \
+            throw CmfError(CMF_ERR_NCCL, std::string(#call) + ": " + NcclApi::get().GetErrorString(r__)); \
+    } while (0)
+
+NcclApi &nccl() {
+    NcclApi &a = NcclApi::get();
+    if (!a.ok()) throw CmfError(CMF_ERR_NCCL, "NCCL is not available: " + a.why);
+    return a;
+}
+
+// balanced contiguous partition of the time axis (the same rule as cmf.jl_b200/sharded.py ShardPlan)
+void shard_range(int64_t T, int world, int rank, int64_t *t0, int64_t *t1) {
+    const int64_t base = T / world, rem = T % world;
+    *t0 = rank * base + std::min<int64_t>(rank, rem);
+    *t1 = *t0 + base + (rank < rem ? 1 : 0);
+}
+
+ncclDataType_t nccl_dt(const cmf_ctx *h) { return h->dtype == CMF_F64 ? ncclFloat64 : ncclFloat32; }
+size_t elem_size(const cmf_ctx *h) { return h->dtype == CMF_F64 ? 8 : 4; }
+
+void c_allreduce(cmf_ctx *h, void *buf, size_t count, ncclDataType_t dt, ncclRedOp_t op = ncclSum) {
+    if (h->world() == 1) return;
+    NK(nccl().AllReduce(buf, buf, count, dt, op, h->comm.comm, h->stream));
+}
+
+// all-reduce of a few host doubles through the handle's scalar buffer (slots 4..7); synchronises the stream
+void c_allreduce_host(cmf_ctx *h, double *vals, int n, ncclRedOp_t op = ncclSum) {
+    if (h->world() == 1) return;
+    REQUIRE(n <= 4, "at most 4 scalars");
+    double *d = h->scalars() + 4;
+    CK(cudaMemcpyAsync(d, vals, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    c_allreduce(h, d, (size_t)n, ncclFloat64, op);
+    CK(cudaMemcpyAsync(vals, d, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+}
+
+// L-1 columns of H each way (left neighbour's right halo <- my first L-1 columns; right neighbour's left halo <- my last)
+void c_halo_exchange(cmf_ctx *h) {
+    if (h->world() == 1 || h->L <= 1) return;
+    void *sl, *sr, *rl, *rr;
+    int64_t cnt;
+    h->halo_buffers(&sl, &sr, &rl, &rr, &cnt);
+    NcclApi &a = nccl();
+    const ncclDataType_t dt = nccl_dt(h);
+    const int r = h->rank(), w = h->world();
+    NK(a.GroupStart());
+    if (r + 1 < w) {
+        NK(a.Send(sr, (size_t)cnt, dt, r + 1, h->comm.comm, h->stream));
+        NK(a.Recv(rr, (size_t)cnt, dt, r + 1, h->comm.comm, h->stream));
+    }
+    if (r > 0) {
+        NK(a.Send(sl, (size_t)cnt, dt, r - 1, h->comm.comm, h->stream));
+        NK(a.Recv(rl, (size_t)cnt, dt, r - 1, h->comm.comm, h->stream));
+    }
+    NK(a.GroupEnd());
+}
+
+// ||X||_F over all shards (mult.jl:13, hals.jl:23)
+void r_data_norm(cmf_ctx *h) {
+    double ss = h->data_sumsq_local;
+    c_allreduce_host(h, &ss, 1);
+    h->data_sumsq_global = ss;
+    h->data_norm = std::sqrt(ss);
+    h->pgd_cur_loss = h->data_norm;
+}
+
+// <X, est> and ||est||^2 of the alpha rescale (src/model.jl:119-120), summed over shards
+void r_init_scale_partials(cmf_ctx *h, double out[2]) {
+    h->init_scale_partials(out);
+    c_allreduce_host(h, out, 2);
+}
+
+// sum of squared residuals over ALL shards: one fixed-size all-reduce of the two loss scalars, one read-back
+double r_loss_sumsq(cmf_ctx *h) {
+    const int n = h->loss_partial_dev();
+    double *d = h->scalars();
+    c_allreduce(h, d, 2, ncclFloat64);
+    double v[2];
+    CK(cudaMemcpyAsync(v, d, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return n == 2 ? h->data_sumsq_global - 2.0 * v[0] + v[1] : v[0];
+}
+
+// The expansion loss cancels like 1/loss^2 (error ~2e-6/loss^2 relative, measured): at or below 25 % relative loss
+// (or when the expansion went negative) switch the handle back to the direct residual pass and re-evaluate with it.
+// Every rank sees the same all-reduced value, so every rank takes the same branch.
+double r_guarded_loss(cmf_ctx *h) {
+    double loss = std::sqrt(r_loss_sumsq(h)) / h->data_norm;
+    if (h->loss_mode == 1 && !(loss > 0.25)) {
+        h->loss_mode = 0;
+        loss = std::sqrt(r_loss_sumsq(h)) / h->data_norm;
+    }
+    return loss;
+}
+
+// update_motifs! (mult.jl:23-39 / hals.jl:31-34 / pgd.jl:158-178) on this rank's shard
+void r_update_motifs(cmf_ctx *h, double l1W, double l2W) {
+    if (h->alg == CMF_PGD) { h->pgd_update_motifs(l1W, l2W); return; }
+    h->w_partials();
+    if (h->world() > 1) {
+        void *p; int64_t cnt; int dt;
+        h->exchange_buffer(0, &p, &cnt, &dt);
+        c_allreduce(h, p, (size_t)cnt, dt == CMF_F64 ? ncclFloat64 : ncclFloat32);     // numW            (K*N*L)
+        h->exchange_buffer(1, &p, &cnt, &dt);
+        c_allreduce(h, p, (size_t)cnt, ncclFloat64);                                   // Gram + H tail   (K*K*L + (L-1)*K doubles)
+    }
+    h->w_apply(l1W, l2W);                                                              // identical update on every rank
+}
+
+// HALS H sweep of a T-sharded fit: gather Q and H on rank 0, sweep once in the reference's order, scatter H
+void r_hals_sweep_sharded(cmf_ctx *h, double l1H, double l2H) {
+    NcclApi &a = nccl();
+    const ncclDataType_t dt = nccl_dt(h);
+    const size_t es = elem_size(h);
+    const int w = h->world(), r = h->rank();
+    void *ql, *hl, *qf = nullptr, *hf = nullptr;
+    int64_t cnt;
+    h->hals_h_local(&ql, &hl, &cnt);
+    if (r == 0) h->hals_h_full(&qf, &hf);
+    for (int pass = 0; pass < 2; ++pass) {          // 0: gather Q and H, 1: scatter H
+        if (pass == 1 && r == 0) h->hals_h_sweep(1, l1H, l2H);
+        NK(a.GroupStart());
+        if (r == 0) {
+            for (int p = 1; p < w; ++p) {
+                int64_t a0, a1;
+                shard_range(h->T, w, p, &a0, &a1);
+                const size_t off = (size_t)(a0 * h->K) * es, c = (size_t)((a1 - a0) * h->K);
+                if (pass == 0) {
+                    NK(a.Recv((char *)qf + off, c, dt, p, h->comm.comm, h->stream));
+                    NK(a.Recv((char *)hf + off, c, dt, p, h->comm.comm, h->stream));
+                } else {
+                    NK(a.Send((char *)hf + off, c, dt, p, h->comm.comm, h->stream));
+                }
+            }
+        } else if (pass == 0) {
+            NK(a.Send(ql, (size_t)cnt, dt, 0, h->comm.comm, h->stream));
+            NK(a.Send(hl, (size_t)cnt, dt, 0, h->comm.comm, h->stream));
+        } else {
+            NK(a.Recv(hl, (size_t)cnt, dt, 0, h->comm.comm, h->stream));
+        }
+        NK(a.GroupEnd());
+        if (r == 0) {
+            if (pass == 0) {
+                CK(cudaMemcpyAsync(qf, ql, (size_t)cnt * es, cudaMemcpyDeviceToDevice, h->stream));
+                CK(cudaMemcpyAsync(hf, hl, (size_t)cnt * es, cudaMemcpyDeviceToDevice, h->stream));
+            } else {
+                CK(cudaMemcpyAsync(hl, hf, (size_t)cnt * es, cudaMemcpyDeviceToDevice, h->stream));
+            }
+        }
+    }
+}
+
+// loss = update_feature_maps! (mult.jl:42-58 / hals.jl:37-42 / pgd.jl:181-203)
+double r_update_feature_maps(cmf_ctx *h, double l1H, double l2H) {
+    if (h->alg == CMF_PGD) {
+        const double loss = std::sqrt(h->pgd_update_feature_maps(l1H, l2H)) / h->data_norm;
+        if (h->loss_mode == 1 && !(loss > 0.25)) h->loss_mode = 0;   // PGD adapts its step on this value: no re-evaluation
+        return loss;
+    }
+    if (h->alg == CMF_HALS) {
+        h->hals_h_prepare();
+        if (h->world() == 1) h->hals_h_sweep(0, l1H, l2H);
+        else r_hals_sweep_sharded(h, l1H, l2H);
+        h->h_changed();
+    } else {
+        h->h_update(l1H, l2H);
+    }
+    c_halo_exchange(h);
+    return r_guarded_loss(h);
+}
+
+// src/algs/alternating.jl:16-71 on one rank (every rank runs the same loop: the loss is all-reduced, and the elapsed
+// time that decides `max_time` is rank 0's, so all ranks take the same branches)
+void r_fit(cmf_ctx *h, int64_t max_itr, double max_time, int eval_mode, int check_convergence, int patience, double tol,
+           double l1W, double l2W, double l1H, double l2H, std::vector<double> &loss_hist, std::vector<double> &time_hist,
+           int64_t cap, int *converged_early) {
+    *converged_early = 0;
+    loss_hist.clear(); time_hist.clear();
+    loss_hist.push_back(r_guarded_loss(h));   // alternating.jl:37
+    time_hist.push_back(0.0);
+    int64_t itr = 1;
+    const bool timed = max_time < 1e300;
+    while ((max_itr < 0 || itr <= max_itr) && time_hist.back() <= max_time) {   // alternating.jl:45
+        ++itr;
+        REQUIRE((int64_t)loss_hist.size() < cap, "history capacity exhausted");
+        auto t_start = std::chrono::steady_clock::now();
+        if (!eval_mode) r_update_motifs(h, l1W, l2W);
+        const double loss = r_update_feature_maps(h, l1H, l2H);
+        double dur = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+        if (timed && h->world() > 1) {          // rank 0's clock decides for everyone
+            if (h->rank() != 0) dur = 0.0;
+            c_allreduce_host(h, &dur, 1);
+        }
+        time_hist.push_back(time_hist.back() + dur);
+        loss_hist.push_back(loss);
+        if (check_convergence && converged(loss_hist.data(), (int64_t)loss_hist.size(), patience, tol)) {   // alternating.jl:63-66
+            *converged_early = 1;
+            break;
+        }
+    }
+}
+
+void r_set_engine(cmf_ctx *h, int engine) {
+    REQUIRE(engine >= 0 && engine <= 2, "engine must be 0 (SIMT), 1 (tcgen05, time domain) or 2 (tcgen05, frequency domain)");
+    if (engine == 2 && !h->fd_available())
+        throw CmfError(CMF_ERR_UNSUPPORTED, "the frequency-domain engine needs an fp32 handle with K <= 128, L <= 256, N % 8 == 0 on sm_100 and room for the spectrum of X");
+    if (engine < 2) h->fd_release();               // the spectrum of X and the time-domain planes never coexist
+    if (engine >= 1 && !h->tc_available())
+        throw CmfError(CMF_ERR_UNSUPPORTED, "tcgen05 engine needs an fp32 MultUpdate handle with K <= 128 and N % 8 == 0 on sm_100");
+    h->engine = engine;
+    if (!h->loss_mode_explicit) h->loss_mode = (engine == 2) ? 1 : 0;   // the expansion is the default of engine 2 only
+}
+
+// every rank must run the same engine (the collectives are matched by program order): take the minimum of what the
+// ranks selected by themselves (shard lengths and free memory may differ by a little)
+void r_agree_engine(cmf_ctx *h) {
+    if (h->world() == 1) return;
+    double e = (double)h->engine;
+    c_allreduce_host(h, &e, 1, ncclMin);
+    if ((int)e != h->engine) r_set_engine(h, (int)e);
+}
+
+void attach_comm(cmf_ctx *h, ncclComm_t comm, int rank, int world, bool owned) {
+    int64_t a0, a1;
+    shard_range(h->T, world, rank, &a0, &a1);
+    REQUIRE(a0 == h->t0 && a1 == h->t1, "the handle's column range is not the balanced shard of this rank (use cmf_shard_range)");
+    h->comm.comm = comm; h->comm.rank = rank; h->comm.world = world; h->comm.owned = owned;
+    r_agree_engine(h);
+}
+
+}  // namespace
+
+// single-process multi-GPU group: one rank context per device, one worker thread per rank
+struct cmf_multi {
+    std::vector<cmf_ctx *> ranks;
+    std::vector<ncclComm_t> comms;
+    std::unique_ptr<cmf::Workers> workers;
+};
+
+namespace {
+
+struct MultiCtx : cmf_ctx {
+    cmf_multi m;
+    ~MultiCtx() override {
+        if (m.workers) {
+            try {
+                m.workers->run_all([&](int i) {
+                    cmf_ctx *r = m.ranks[(size_t)i];
+                    if (!r) return;
+                    cudaSetDevice(r->device);
+                    delete r;
+                    if ((size_t)i < m.comms.size() && m.comms[(size_t)i]) NcclApi::get().CommDestroy(m.comms[(size_t)i]);
+                });
+            } catch (...) {}
+        }
+    }
+};
+
+// runs f(rank context) on the handle itself or, for a group handle, on every rank concurrently (worker threads)
+template <typename F>
+void on_ranks(cmf_handle h, F &&f) {
+    REQUIRE(h != nullptr, "null handle");
+    if (h->multi) {
+        cmf_multi *m = h->multi;
+        m->workers->run_all([&](int i) {
+            cmf_ctx *r = m->ranks[(size_t)i];
+            DevGuard g(r->device);
+            f(r);
+        });
+    } else {
+        DevGuard g(h->device);
+        f(h);
+    }
+}
+cmf_ctx *rank0(cmf_handle h) { return h->multi ? h->multi->ranks[0] : h; }
 
 }  // namespace
 
@@ -1494,6 +1834,7 @@ const char *cmf_last_error(void) { return g_err.c_str(); }
 int cmf_create(cmf_handle *out, int64_t N, int64_t T, int64_t K, int64_t L, int dtype, int alg, int device) {
     return guarded([&] {
         REQUIRE(out != nullptr, "null output pointer");
+        DevRestore g;
         *out = make_ctx(N, T, 0, T, K, L, dtype, alg, device);
     });
 }
@@ -1502,80 +1843,192 @@ int cmf_create_shard(cmf_handle *out, int64_t N, int64_t T_global, int64_t t_beg
                      int64_t L, int dtype, int alg, int device) {
     return guarded([&] {
         REQUIRE(out != nullptr, "null output pointer");
+        DevRestore g;
         *out = make_ctx(N, T_global, t_begin, t_end, K, L, dtype, alg, device);
+    });
+}
+
+int cmf_shard_range(int64_t T, int world, int rank, int64_t *t_begin, int64_t *t_end) {
+    return guarded([&] {
+        REQUIRE(t_begin && t_end, "null output");
+        REQUIRE(world >= 1 && rank >= 0 && rank < world && T >= world, "need 0 <= rank < world <= T");
+        shard_range(T, world, rank, t_begin, t_end);
+    });
+}
+
+int cmf_comm_unique_id(void *id_out) {
+    return guarded([&] {
+        REQUIRE(id_out, "null output");
+        ncclUniqueId id;
+        NK(nccl().GetUniqueId(&id));
+        memcpy(id_out, &id, sizeof(id));
+    });
+}
+
+int cmf_create_rank(cmf_handle *out, int64_t N, int64_t T, int64_t K, int64_t L, int dtype, int alg, int device,
+                    const void *unique_id, int rank, int world) {
+    return guarded([&] {
+        REQUIRE(out != nullptr && unique_id != nullptr, "null pointer");
+        REQUIRE(world >= 1 && rank >= 0 && rank < world, "need 0 <= rank < world");
+        DevRestore g;
+        int64_t a0, a1;
+        shard_range(T, world, rank, &a0, &a1);
+        cmf_ctx *c = make_ctx(N, T, a0, a1, K, L, dtype, alg, device);
+        try {
+            ncclUniqueId id;
+            memcpy(&id, unique_id, sizeof(id));
+            ncclComm_t comm = nullptr;
+            if (world > 1) NK(nccl().CommInitRank(&comm, world, id, rank));
+            attach_comm(c, comm, rank, world, true);
+        } catch (...) { delete c; throw; }
+        *out = c;
+    });
+}
+
+int cmf_create_multi(cmf_handle *out, int64_t N, int64_t T, int64_t K, int64_t L, int dtype, int alg, int ngpu,
+                     const int *devices) {
+    return guarded([&] {
+        REQUIRE(out != nullptr, "null output pointer");
+        REQUIRE(ngpu >= 1 && ngpu <= 64, "ngpu must be in 1..64");
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw CmfError(CMF_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) + "); libcmf_sm100 has no CPU fallback");
+        std::vector<int> devs((size_t)ngpu);
+        for (int i = 0; i < ngpu; ++i) {
+            devs[(size_t)i] = devices ? devices[i] : i;
+            REQUIRE(devs[(size_t)i] >= 0 && devs[(size_t)i] < ndev, "bad device ordinal in the device list");
+        }
+        if (ngpu == 1) {
+            DevRestore g;
+            *out = make_ctx(N, T, 0, T, K, L, dtype, alg, devs[0]);
+            return;
+        }
+        int prev = 0;
+        cudaGetDevice(&prev);
+        auto *mc = new MultiCtx();
+        mc->N = N; mc->T = T; mc->t0 = 0; mc->t1 = T; mc->Tl = T; mc->K = K; mc->L = L;
+        mc->dtype = dtype; mc->alg = alg; mc->device = devs[0];
+        mc->multi = &mc->m;
+        try {
+            mc->m.ranks.assign((size_t)ngpu, nullptr);
+            mc->m.comms.assign((size_t)ngpu, nullptr);
+            mc->m.workers.reset(new Workers(ngpu));
+            NK(nccl().CommInitAll(mc->m.comms.data(), ngpu, devs.data()));
+            cudaSetDevice(prev);
+            mc->m.workers->run_all([&](int i) {
+                DevGuard g(devs[(size_t)i]);
+                int64_t a0, a1;
+                shard_range(T, ngpu, i, &a0, &a1);
+                mc->m.ranks[(size_t)i] = make_ctx(N, T, a0, a1, K, L, dtype, alg, devs[(size_t)i]);
+            });
+            mc->m.workers->run_all([&](int i) {
+                cmf_ctx *r = mc->m.ranks[(size_t)i];
+                DevGuard g(r->device);
+                attach_comm(r, mc->m.comms[(size_t)i], i, ngpu, false);
+            });
+        } catch (...) {
+            cudaSetDevice(prev);
+            delete mc;
+            throw;
+        }
+        *out = mc;
+    });
+}
+
+int cmf_comm_info(cmf_handle h, int *rank_out, int *world_out, int64_t *t_begin, int64_t *t_end) {
+    return guarded([&] {
+        REQUIRE(h, "null handle");
+        if (rank_out) *rank_out = h->multi ? 0 : h->rank();
+        if (world_out) *world_out = h->multi ? (int)h->multi->ranks.size() : h->world();
+        if (t_begin) *t_begin = h->t0;
+        if (t_end) *t_end = h->t1;
     });
 }
 
 int cmf_destroy(cmf_handle h) {
     return guarded([&] {
         if (!h) return;
-        cudaSetDevice(h->device);
+        if (h->multi) { delete h; return; }
+        DevGuard g(h->device);
+        ncclComm_t comm = (h->comm.owned ? h->comm.comm : nullptr);
         delete h;
+        if (comm) NcclApi::get().CommDestroy(comm);
     });
 }
 
 int cmf_set_data(cmf_handle h, const void *X, int64_t first_col) {
-    return guarded([&] { use(h); h->set_data(X, first_col); });
+    return guarded([&] { on_ranks(h, [&](cmf_ctx *r) { r->set_data(X, first_col); r_data_norm(r); }); });
 }
 int cmf_synth_data(cmf_handle h, uint64_t seed, int64_t K_true, int64_t L_true, double p_h, double noise) {
-    return guarded([&] { use(h); h->synth_data(seed, K_true, L_true, p_h, noise); });
+    return guarded([&] { on_ranks(h, [&](cmf_ctx *r) { r->synth_data(seed, K_true, L_true, p_h, noise); r_data_norm(r); }); });
 }
 int cmf_data_sumsq(cmf_handle h, double *out) {
-    return guarded([&] { use(h); REQUIRE(out, "null output"); REQUIRE(h->have_data, "no data"); *out = h->data_sumsq(); });
+    return guarded([&] {
+        REQUIRE(out, "null output");
+        cmf_ctx *r = rank0(h);
+        REQUIRE(r->have_data, "no data");
+        *out = (h->multi || r->world() > 1) ? r->data_sumsq_global : r->data_sumsq_local;
+    });
 }
 int cmf_set_data_norm(cmf_handle h, double norm) {
-    return guarded([&] { use(h); h->data_norm = norm; });
+    return guarded([&] { on_ranks(h, [&](cmf_ctx *r) { r->data_norm = norm; r->data_sumsq_global = norm * norm; }); });
 }
 int cmf_set_factors(cmf_handle h, const void *W, const void *H, int64_t first_col) {
-    return guarded([&] { use(h); h->set_factors(W, H, first_col); });
+    return guarded([&] { on_ranks(h, [&](cmf_ctx *r) { r->set_factors(W, H, first_col); }); });
+}
+int cmf_exchange_halos(cmf_handle h) {
+    return guarded([&] { on_ranks(h, [&](cmf_ctx *r) { c_halo_exchange(r); r->h_changed(); }); });
 }
 int cmf_init_rand(cmf_handle h, uint64_t seed) {
-    return guarded([&] { use(h); h->init_rand(seed); });
+    return guarded([&] { on_ranks(h, [&](cmf_ctx *r) { r->init_rand(seed); }); });
 }
 int cmf_init_scale_partials(cmf_handle h, double out[2]) {
-    return guarded([&] { use(h); REQUIRE(out, "null output"); h->init_scale_partials(out); });
+    return guarded([&] {
+        REQUIRE(out, "null output");
+        on_ranks(h, [&](cmf_ctx *r) {
+            double v[2];
+            r_init_scale_partials(r, v);
+            if (!h->multi || r->rank() == 0) { out[0] = v[0]; out[1] = v[1]; }
+        });
+    });
 }
 int cmf_scale_factors(cmf_handle h, double s) {
-    return guarded([&] { use(h); h->scale_factors(s); });
+    return guarded([&] { on_ranks(h, [&](cmf_ctx *r) { r->scale_factors(s); }); });
 }
 int cmf_get_factors(cmf_handle h, void *W_out, void *H_out) {
-    return guarded([&] { use(h); REQUIRE(h->have_factors, "no factors"); h->get_factors(W_out, H_out); });
+    return guarded([&] {
+        const bool grp = h && h->multi;
+        on_ranks(h, [&](cmf_ctx *r) {
+            REQUIRE(r->have_factors, "no factors");
+            void *Hp = H_out;
+            if (grp && H_out) Hp = (char *)H_out + (size_t)(r->t0 * r->K) * elem_size(r);     // group handle: H_out is K x T
+            r->get_factors((!grp || r->rank() == 0) ? W_out : nullptr, Hp);
+        });
+    });
 }
 
 int cmf_update_motifs(cmf_handle h, double l1W, double l2W) {
-    return guarded([&] {
-        use(h);
-        if (h->alg == CMF_HALS) { h->hals_update_motifs(l1W, l2W); return; }
-        if (h->alg == CMF_PGD) { h->pgd_update_motifs(l1W, l2W); return; }
-        REQUIRE(h->is_first && h->is_last, "sharded handles use the split-phase calls");
-        h->w_partials();
-        h->w_apply(l1W, l2W);
-    });
+    return guarded([&] { on_ranks(h, [&](cmf_ctx *r) { r_update_motifs(r, l1W, l2W); }); });
 }
 
 int cmf_update_feature_maps(cmf_handle h, double l1H, double l2H, double *loss_out) {
     return guarded([&] {
-        use(h);
-        double loss;
-        if (h->alg == CMF_HALS) {
-            loss = guarded_loss(h, h->hals_update_feature_maps(l1H, l2H));
-        } else if (h->alg == CMF_PGD) {
-            loss = std::sqrt(h->pgd_update_feature_maps(l1H, l2H)) / h->data_norm;
-        } else {
-            REQUIRE(h->is_first && h->is_last, "sharded handles use the split-phase calls");
-            h->h_update(l1H, l2H);
-            loss = guarded_loss(h, h->loss_partial());
-        }
-        if (loss_out) *loss_out = loss;
+        on_ranks(h, [&](cmf_ctx *r) {
+            const double loss = r_update_feature_maps(r, l1H, l2H);
+            if (loss_out && (r->rank() == 0 || !h->multi)) *loss_out = loss;
+        });
     });
 }
 
 int cmf_loss(cmf_handle h, double *loss_out) {
     return guarded([&] {
-        use(h);
         REQUIRE(loss_out, "null output");
-        REQUIRE(h->is_first && h->is_last, "sharded handles use cmf_loss_partial");
-        *loss_out = guarded_loss(h, h->loss_partial());
+        on_ranks(h, [&](cmf_ctx *r) {
+            REQUIRE(r->world() > 1 || (r->is_first && r->is_last), "shards without a communicator use cmf_loss_partial");
+            const double loss = r_guarded_loss(r);
+            if (r->rank() == 0 || !h->multi) *loss_out = loss;
+        });
     });
 }
 
@@ -1583,94 +2036,92 @@ int cmf_fit(cmf_handle h, int64_t max_itr, double max_time, int eval_mode, int c
             double tol, double l1W, double l2W, double l1H, double l2H, double *loss_hist, double *time_hist,
             int64_t cap, int64_t *n_hist, int *converged_early) {
     return guarded([&] {
-        use(h);
         REQUIRE(loss_hist && time_hist && n_hist, "null history pointers");
         REQUIRE(patience >= 1, "patience must be >= 1 (src/algs/alternating.jl:30)");
         REQUIRE(cap >= 1, "history capacity must be >= 1");
-        REQUIRE(h->is_first && h->is_last, "cmf_fit drives a single shard; sharded fits use the split-phase calls");
         if (converged_early) *converged_early = 0;
-        int64_t n = 0;
-        loss_hist[n] = guarded_loss(h, h->loss_partial());   // alternating.jl:37
-        time_hist[n] = 0.0;
-        ++n;
-        int64_t itr = 1;
-        while ((max_itr < 0 || itr <= max_itr) && time_hist[n - 1] <= max_time) {   // alternating.jl:45
-            ++itr;
-            REQUIRE(n < cap, "history capacity exhausted");
-            auto t_start = std::chrono::steady_clock::now();
-            double loss;
-            if (h->alg == CMF_HALS) {
-                if (!eval_mode) h->hals_update_motifs(l1W, l2W);
-                loss = guarded_loss(h, h->hals_update_feature_maps(l1H, l2H));
-            } else if (h->alg == CMF_PGD) {
-                if (!eval_mode) h->pgd_update_motifs(l1W, l2W);
-                loss = std::sqrt(h->pgd_update_feature_maps(l1H, l2H)) / h->data_norm;
-                if (h->loss_mode == 1 && !(loss > 0.25)) h->loss_mode = 0;   // PGD adapts its step on this value: no re-evaluation
-            } else {
-                if (!eval_mode) { h->w_partials(); h->w_apply(l1W, l2W); }
-                h->h_update(l1H, l2H);
-                loss = guarded_loss(h, h->loss_partial());
+        on_ranks(h, [&](cmf_ctx *r) {
+            REQUIRE(r->world() > 1 || (r->is_first && r->is_last), "shards without a communicator use the split-phase calls");
+            std::vector<double> lh, th;
+            int early = 0;
+            r_fit(r, max_itr, max_time, eval_mode, check_convergence, patience, tol, l1W, l2W, l1H, l2H, lh, th, cap, &early);
+            if (r->rank() == 0 || !h->multi) {
+                std::copy(lh.begin(), lh.end(), loss_hist);
+                std::copy(th.begin(), th.end(), time_hist);
+                *n_hist = (int64_t)lh.size();
+                if (converged_early) *converged_early = early;
             }
-            const double dur = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
-            time_hist[n] = time_hist[n - 1] + dur;
-            loss_hist[n] = loss;
-            ++n;
-            if (check_convergence && converged(loss_hist, n, patience, tol)) {   // alternating.jl:63-66
-                if (converged_early) *converged_early = 1;
-                break;
-            }
-        }
-        *n_hist = n;
+        });
     });
 }
 
 int cmf_w_partials(cmf_handle h) {
-    return guarded([&] { use(h); h->w_partials(); });
+    return guarded([&] { REQUIRE(h && !h->multi, "single-rank call"); DevGuard g(h->device); h->w_partials(); });
 }
 int cmf_w_apply(cmf_handle h, double l1W, double l2W) {
-    return guarded([&] { use(h); h->w_apply(l1W, l2W); });
+    return guarded([&] { REQUIRE(h && !h->multi, "single-rank call"); DevGuard g(h->device); h->w_apply(l1W, l2W); });
 }
 int cmf_h_update(cmf_handle h, double l1H, double l2H) {
-    return guarded([&] { use(h); REQUIRE(h->alg == CMF_MULT, "the split-phase H update is MultUpdate only"); h->h_update(l1H, l2H); });
+    return guarded([&] {
+        REQUIRE(h && !h->multi, "single-rank call");
+        DevGuard g(h->device);
+        REQUIRE(h->alg == CMF_MULT, "the split-phase H update is MultUpdate only");
+        h->h_update(l1H, l2H);
+    });
 }
 int cmf_loss_partial(cmf_handle h, double *sumsq_out) {
-    return guarded([&] { use(h); REQUIRE(sumsq_out, "null output"); *sumsq_out = h->loss_partial(); });
+    return guarded([&] { REQUIRE(h && !h->multi, "single-rank call"); REQUIRE(sumsq_out, "null output"); DevGuard g(h->device); *sumsq_out = h->loss_partial(); });
 }
 int cmf_exchange_buffer(cmf_handle h, int which, void **dev_ptr, int64_t *count, int *dtype) {
-    return guarded([&] { use(h); REQUIRE(dev_ptr && count && dtype, "null output"); h->exchange_buffer(which, dev_ptr, count, dtype); });
+    return guarded([&] { REQUIRE(h && !h->multi, "single-rank call"); REQUIRE(dev_ptr && count && dtype, "null output"); h->exchange_buffer(which, dev_ptr, count, dtype); });
 }
 int cmf_halo_buffers(cmf_handle h, void **sl, void **sr, void **rl, void **rr, int64_t *count) {
-    return guarded([&] { use(h); REQUIRE(sl && sr && rl && rr && count, "null output"); h->halo_buffers(sl, sr, rl, rr, count); });
+    return guarded([&] { REQUIRE(h && !h->multi, "single-rank call"); REQUIRE(sl && sr && rl && rr && count, "null output"); h->halo_buffers(sl, sr, rl, rr, count); });
 }
 int cmf_sync(cmf_handle h) {
-    return guarded([&] { use(h); CK(cudaStreamSynchronize(h->stream)); });
+    return guarded([&] { on_ranks(h, [&](cmf_ctx *r) { CK(cudaStreamSynchronize(r->stream)); }); });
 }
 int cmf_launch_count(cmf_handle h, int64_t *out) {
-    return guarded([&] { REQUIRE(h && out, "null argument"); *out = h->launches; });
+    return guarded([&] {
+        REQUIRE(h && out, "null argument");
+        if (!h->multi) { *out = h->launches; return; }
+        int64_t n = 0;
+        for (cmf_ctx *r : h->multi->ranks) n += r->launches;
+        *out = n;
+    });
 }
 int cmf_stream(cmf_handle h, void **stream_out) {
-    return guarded([&] { REQUIRE(h && stream_out, "null argument"); *stream_out = (void *)h->stream; });
+    return guarded([&] { REQUIRE(h && stream_out, "null argument"); *stream_out = (void *)rank0(h)->stream; });
 }
 int cmf_get_data(cmf_handle h, void *X_out, int with_halo) {
-    return guarded([&] { use(h); REQUIRE(X_out, "null output"); REQUIRE(h->have_data, "no data"); h->get_data(X_out, with_halo); });
+    return guarded([&] {
+        REQUIRE(X_out, "null output");
+        const bool grp = h && h->multi;
+        on_ranks(h, [&](cmf_ctx *r) {
+            REQUIRE(r->have_data, "no data");
+            r->get_data(grp ? (char *)X_out + (size_t)(r->t0 * r->N) * elem_size(r) : X_out, grp ? 0 : with_halo);
+        });
+    });
 }
 int cmf_profile(cmf_handle h, int enable) {
     return guarded([&] {
-        use(h);
-        CK(cudaStreamSynchronize(h->stream));
-        h->prof_clear();
-        h->profiling = enable != 0;
+        on_ranks(h, [&](cmf_ctx *r) {
+            CK(cudaStreamSynchronize(r->stream));
+            r->prof_clear();
+            r->profiling = enable != 0;
+        });
     });
 }
 int cmf_profile_read(cmf_handle h, int which, double *ms_total, int64_t *count) {
     return guarded([&] {
-        use(h);
-        REQUIRE(ms_total && count, "null output");
-        REQUIRE(which >= 0 && which < PROF_NCLASS, "which must be 0 (conv), 1 (transconv) or 2 (corr)");
-        CK(cudaStreamSynchronize(h->stream));
+        REQUIRE(h && ms_total && count, "null output");
+        REQUIRE(which >= 0 && which < PROF_NCLASS, "which must be 0 (conv), 1 (transconv), 2 (corr) or 3 (HALS H sweep)");
+        cmf_ctx *r = rank0(h);
+        DevGuard g(r->device);
+        CK(cudaStreamSynchronize(r->stream));
         double tot = 0.0;
         int64_t n = 0;
-        for (auto &e : h->prof_events) {
+        for (auto &e : r->prof_events) {
             if (e.which != which) continue;
             float ms = 0.f;
             CK(cudaEventElapsedTime(&ms, e.a, e.b));
@@ -1683,7 +2134,8 @@ int cmf_profile_read(cmf_handle h, int which, double *ms_total, int64_t *count) 
 }
 int cmf_set_stream(cmf_handle h, void *stream) {
     return guarded([&] {
-        use(h);
+        REQUIRE(h && !h->multi, "single-rank call");
+        DevGuard g(h->device);
         CK(cudaStreamSynchronize(h->stream));
         if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
         h->own_stream = false;
@@ -1691,39 +2143,32 @@ int cmf_set_stream(cmf_handle h, void *stream) {
     });
 }
 int cmf_set_engine(cmf_handle h, int engine) {
-    return guarded([&] {
-        REQUIRE(h, "null handle");
-        REQUIRE(engine >= 0 && engine <= 2, "engine must be 0 (SIMT), 1 (tcgen05, time domain) or 2 (tcgen05, frequency domain)");
-        use(h);
-        if (engine == 2 && !h->fd_available())
-            throw CmfError(CMF_ERR_UNSUPPORTED, "the frequency-domain engine needs an fp32 handle with K <= 128, L <= 256, N % 8 == 0 on sm_100 and room for the spectrum of X");
-        if (engine < 2) h->fd_release();               // the spectrum of X and the time-domain planes never coexist
-        if (engine >= 1 && !h->tc_available())
-            throw CmfError(CMF_ERR_UNSUPPORTED, "tcgen05 engine needs an fp32 MultUpdate handle with K <= 128 and N % 8 == 0 on sm_100");
-        h->engine = engine;
-        if (!h->loss_mode_explicit) h->loss_mode = (engine == 2) ? 1 : 0;   // the expansion is the default of engine 2 only
-    });
+    return guarded([&] { on_ranks(h, [&](cmf_ctx *r) { r_set_engine(r, engine); }); });
 }
 
 int cmf_set_loss_mode(cmf_handle h, int mode) {
     return guarded([&] {
-        REQUIRE(h, "null handle");
         REQUIRE(mode == 0 || mode == 1, "loss mode must be 0 (direct) or 1 (expansion)");
-        h->loss_mode = mode;
-        h->loss_mode_explicit = true;
+        on_ranks(h, [&](cmf_ctx *r) { r->loss_mode = mode; r->loss_mode_explicit = true; });
     });
 }
 int cmf_get_loss_mode(cmf_handle h, int *mode_out) {
-    return guarded([&] { REQUIRE(h && mode_out, "null argument"); *mode_out = h->loss_mode; });
+    return guarded([&] { REQUIRE(h && mode_out, "null argument"); *mode_out = rank0(h)->loss_mode; });
 }
 int cmf_get_engine(cmf_handle h, int *engine_out) {
-    return guarded([&] { REQUIRE(h && engine_out, "null argument"); *engine_out = h->engine; });
+    return guarded([&] { REQUIRE(h && engine_out, "null argument"); *engine_out = rank0(h)->engine; });
+}
+
+static int current_device() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) d = 0;
+    return d;
 }
 
 int cmf_tensor_conv(int64_t N, int64_t T, int64_t K, int64_t L, int dtype, const void *W, const void *H, void *out) {
     return guarded([&] {
         REQUIRE(W && H && out, "null pointer");
-        cmf_ctx *c = make_ctx(N, T, 0, T, K, L, dtype, CMF_MULT, 0);
+        cmf_ctx *c = make_ctx(N, T, 0, T, K, L, dtype, CMF_MULT, current_device());
         try { c->set_factors(W, H, 0); c->prim_conv(out); } catch (...) { delete c; throw; }
         delete c;
     });
@@ -1731,7 +2176,7 @@ int cmf_tensor_conv(int64_t N, int64_t T, int64_t K, int64_t L, int dtype, const
 int cmf_tensor_transconv(int64_t N, int64_t T, int64_t K, int64_t L, int dtype, const void *W, const void *X, void *out) {
     return guarded([&] {
         REQUIRE(W && X && out, "null pointer");
-        cmf_ctx *c = make_ctx(N, T, 0, T, K, L, dtype, CMF_MULT, 0);
+        cmf_ctx *c = make_ctx(N, T, 0, T, K, L, dtype, CMF_MULT, current_device());
         try {
             std::vector<char> Hz((size_t)(K * T) * (dtype == CMF_F64 ? 8 : 4), 0);
             c->set_factors(W, Hz.data(), 0);
@@ -1743,11 +2188,31 @@ int cmf_tensor_transconv(int64_t N, int64_t T, int64_t K, int64_t L, int dtype, 
 int cmf_corr_w(int64_t N, int64_t T, int64_t K, int64_t L, int dtype, const void *H, const void *X, void *out) {
     return guarded([&] {
         REQUIRE(H && X && out, "null pointer");
-        cmf_ctx *c = make_ctx(N, T, 0, T, K, L, dtype, CMF_MULT, 0);
+        cmf_ctx *c = make_ctx(N, T, 0, T, K, L, dtype, CMF_MULT, current_device());
         try {
             std::vector<char> Wz((size_t)(K * N * L) * (dtype == CMF_F64 ? 8 : 4), 0);
             c->set_factors(Wz.data(), H, 0);
             c->prim_corr(X, out);
+        } catch (...) { delete c; throw; }
+        delete c;
+    });
+}
+int cmf_compute_resids(int64_t N, int64_t T, int64_t K, int64_t L, int dtype, const void *X, const void *W, const void *H, void *out) {
+    return guarded([&] {
+        REQUIRE(X && W && H && out, "null pointer");
+        cmf_ctx *c = make_ctx(N, T, 0, T, K, L, dtype, CMF_MULT, current_device());
+        try { c->set_data(X, 0); c->set_factors(W, H, 0); c->prim_resids(out); } catch (...) { delete c; throw; }
+        delete c;
+    });
+}
+int cmf_shift_and_stack(int64_t K, int64_t T, int64_t L, int dtype, const void *H, void *out) {
+    return guarded([&] {
+        REQUIRE(H && out, "null pointer");
+        cmf_ctx *c = make_ctx(8, T, 0, T, K, L, dtype, CMF_MULT, current_device());
+        try {
+            std::vector<char> Wz((size_t)(K * 8 * L) * (dtype == CMF_F64 ? 8 : 4), 0);
+            c->set_factors(Wz.data(), H, 0);
+            c->prim_shift_and_stack(out);
         } catch (...) { delete c; throw; }
         delete c;
     });

@@ -700,6 +700,15 @@ __global__ void w_internal_to_julia(const S *__restrict__ Wi, S *__restrict__ Wj
 }
 
 // tail[c][k] (double) = H[Tl-(L-1)+c][k]; zeros when this shard is not the last one
+// shift_and_stack (src/common.jl:133-142) on t-major storage: out[t][l*K + k] = H[t-l][k], zero for t < l
+template <typename S>
+__global__ void shift_stack_kernel(const S *__restrict__ H, S *__restrict__ out, int64_t K, int64_t L, int64_t T) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= K * L * T) return;
+    const int64_t j = e % (K * L), t = e / (K * L), l = j / K, k = j % K;
+    out[e] = (t >= l) ? H[(t - l) * K + k] : S(0);
+}
+
 template <typename S>
 __global__ void h_tail_kernel(const S *__restrict__ H, double *__restrict__ tail, int64_t K, int64_t L,
                               int64_t Tl, int is_last) {
@@ -1206,370 +1215,6 @@ __global__ void __launch_bounds__(HW_NT) hals_h_wave_kernel(const S *__restrict_
 }
 
 #undef HW_MARK
-
-// EXPERIMENTAL (CMF_HALS_OVERLAP=1, off by default: validated bit-identical, but not faster yet -- see cmf_sm100.cu).
-// The same sweep with the recurrence of cell c overlapped with the staging and pull of cell c+1 (fp32 handles): 640 threads,
-// warpgroups 0-3 are the pull team (named barrier 1 over 512 threads), warp 16 is the recurrence warp, the two sides hand the
-// double-buffered (qeff, hch) pair over through the shared counters ready_c / done_c.  Arithmetic and order of every
-// operation are those of hals_h_wave_kernel, so the results are bit-identical (tests/test_gpu_tc.py).
-constexpr int HW_NT_OVL = HW_NT + 128;
-#define HW_TEAM_SYNC() asm volatile("bar.sync 1, %0;" ::"n"(HW_NT) : "memory")
-#define HW_ALL_SYNC() asm volatile("bar.sync 2, %0;" ::"n"(HW_NT_OVL) : "memory")     // both roles, from different program points
-template <typename S>
-__global__ void __launch_bounds__(HW_NT_OVL, 1) hals_h_wave_ovl_kernel(const S *__restrict__ Cf, const S *__restrict__ S2,
-                                                             const S *__restrict__ Q, S *__restrict__ H, S *__restrict__ D,
-                                                             S *__restrict__ tailC_all /*[grid][L*L]*/, int *progress /*[K]*/,
-                                                             int64_t K, int64_t L, int64_t T, int64_t Ks, int64_t ld,
-                                                             S l1, S l2, int debug, const S *__restrict__ Ct /*tail tables or nullptr*/) {
-    constexpr int HW_KB = hw_kb<S>();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    S *qeff = reinterpret_cast<S *>(smem_raw);       // [HW_TC]
-    S *pend = qeff + HW_TC;                          // ring of RB entries
-    S *ckk = pend + (2 * L + 32);                    // Cf[k,k,s], s = 0..L-1
-    S *ckk32 = ckk + L;                              // [32] C[k,k,j] zero padded (register-window recurrence, L <= 32)
-    S *hch = ckk32 + 32;                             // [HW_TC] H of the current cell
-    S *Cs = hch + HW_TC;                             // [(2L-1)][HW_KB] lag-table slice of the pull phase
-    S *Dwin = Cs + (2 * L + 6) * HW_KB;              // [HW_KB][8 planes][QP] transposed Delta window of the pull phase (Cs: lag rows padded to a multiple of 8)
-    const int RB = (int)(2 * L + 32);
-    const size_t WWs = HW_TC + 2 * (size_t)(L - 1), QPs = ((WWs + 7) >> 3) | 1;
-    const size_t dwin_elems = (size_t)HW_KB * 8 * QPs > (size_t)4 * HW_TC ? (size_t)HW_KB * 8 * QPs : (size_t)4 * HW_TC;
-    S *qeffB = Dwin + dwin_elems;                     // second (qeff, hch) pair: cell c uses pair c & 1
-    S *hchB = qeffB + HW_TC;
-    __shared__ volatile int ready_c, done_c;         // cells whose (qeff, hch) are ready / fully written back
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int64_t nC = (T + HW_TC - 1) / HW_TC;
-    const int64_t Tint = T - (L - 1);                // columns t < Tint have the full lag window (w = L)
-    S *tailC = tailC_all + (size_t)blockIdx.x * (size_t)(L * L);
-
-    // per-component tables (all 640 threads take part, in both roles)
-    auto setup_component = [&](int64_t k) {
-        // per-component tables
-        for (int64_t s = tid; s < L; s += nthr) ckk[s] = Cf[((s + L - 1) * K + k) * K + k];
-        if (tid < 32) ckk32[tid] = (tid >= 1 && tid < L) ? Cf[((tid + L - 1) * K + k) * K + k] : S(0);
-        // tailC[w][s] = C_w[k,k,s] = sum_{l<w, l-s>=0} S2[(l,k)][(l-s,k)],  w = 1..L-1, s = 0..L-1
-        for (int64_t idx = tid; idx < L * L; idx += nthr) {
-            const int64_t w = idx / L, s = idx % L;
-            double acc = 0.0;
-            for (int64_t l = s; l < w; ++l) acc += (double)S2[(l * Ks + k) * ld + (l - s) * Ks + k];
-            tailC[idx] = (S)acc;
-        }
-        for (int i = tid; i < RB; i += nthr) pend[i] = S(0);
-        if (tid == 0) { ready_c = 0; done_c = 0; }
-        HW_ALL_SYNC();
-
-    };
-    // Warpgroups 0-3 (512 threads) stage and pull, warp 16 runs the recurrence and the write-back.  The two roles never share
-    // code after this branch, so the register budgets below hold for the whole role (the recurrence keeps a 64-entry register
-    // window; the pull needs far fewer registers).
-    if (tid < HW_NT) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-        for (int64_t k = blockIdx.x; k < K; k += gridDim.x) {
-            setup_component(k);
-            // ================================================================ pull team: stage + pull + H prefetch of cell c
-            const int nthr = HW_NT;
-            for (int64_t c = 0; c < nC; ++c) {
-                const int64_t t0 = c * HW_TC;
-                S *qeff_c = (c & 1) ? qeffB : qeff, *hch_c = (c & 1) ? hchB : hch;
-                // ---- wait: component k-1 must have finished cell min(c+1, nC-1), and the recurrence warp must be done with
-                //      the buffers of cell c-2
-                if (tid == 0) {
-                    if (k > 0) {
-                        const int need = (int)((c + 2 < nC) ? c + 2 : nC);
-                        volatile int *pr = progress + (k - 1);
-                        while (*pr < need) { __nanosleep(64); }
-                    }
-                    while (done_c < (int)c - 1) { __nanosleep(32); }
-                }
-                HW_TEAM_SYNC();
-                __threadfence();
-            // ---- pull: corrections from all earlier components, HW_KB components at a time through shared memory.
-            //      Register tiling: thread (cg, kq) owns the 8 consecutive columns 8*cg .. 8*cg+7 and a quarter of the
-            //      staged components; along the lag loop the 8 Delta values slide through registers, so each step costs
-            //      one new Delta load + one (broadcast) table load for 8 FMAs.  The Delta window is stored transposed and
-            //      split into 8 planes (index i -> plane i&7, slot i>>3) so that lanes read consecutive words.
-            {
-                const int WW = HW_TC + 2 * (int)(L - 1);
-                const int QP = ((WW + 7) >> 3) | 1;            // slots per plane (odd)
-                const int WWQ = 8 * QP;                        // words per staged component
-                const int cg = tid & (HW_TC / 8 - 1), kq = tid >> 7;       // column group, component quarter
-                constexpr int NKQ = HW_NT / (HW_TC / 8);                   // 4 groups of components per staged block
-                constexpr int KQ = HW_KB / NKQ;
-                S a8[8];
-#pragma unroll
-                for (int r = 0; r < 8; ++r) a8[r] = S(0);
-                for (int64_t kp0 = 0; kp0 < k; kp0 += HW_KB) {
-                    const int kb = (int)((k - kp0 < HW_KB) ? k - kp0 : HW_KB);
-                    HW_TEAM_SYNC();
-                    // 8 loads in flight per thread: Delta comes from L2 (written by other SMs), a dependent load per
-                    // element would expose its latency 68 times per staged block
-                    if (sizeof(S) == 4 && (K & 3) == 0) {
-                        // 128-bit loads: 4 staged components per load (kp0 is a multiple of HW_KB, rows of Delta are K long)
-                        constexpr int KB4 = HW_KB / 4;
-                        for (int base = tid; base < WW * KB4; base += nthr * 4) {
-                            float4 v4[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int idx = base + u * nthr;
-                                const int k4 = (idx % KB4) * 4, i = idx / KB4;
-                                const int64_t t = t0 - (L - 1) + i;
-                                v4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (idx < WW * KB4 && k4 < kb && t >= 0 && t < Tint)
-                                    v4[u] = __ldcg(reinterpret_cast<const float4 *>(D + t * K + kp0 + k4));
-                            }
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int idx = base + u * nthr;
-                                const int k4 = (idx % KB4) * 4, i = idx / KB4;
-                                if (idx < WW * KB4) {
-                                    const int ad = (i & 7) * QP + (i >> 3);
-                                    Dwin[(k4 + 0) * WWQ + ad] = (S)((k4 + 0 < kb) ? v4[u].x : 0.f);
-                                    Dwin[(k4 + 1) * WWQ + ad] = (S)((k4 + 1 < kb) ? v4[u].y : 0.f);
-                                    Dwin[(k4 + 2) * WWQ + ad] = (S)((k4 + 2 < kb) ? v4[u].z : 0.f);
-                                    Dwin[(k4 + 3) * WWQ + ad] = (S)((k4 + 3 < kb) ? v4[u].w : 0.f);
-                                }
-                            }
-                        }
-                    } else
-                    for (int base = tid; base < WW * HW_KB; base += nthr * 8) {
-                        S v8[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int idx = base + u * nthr;
-                            const int kk = idx % HW_KB, i = idx / HW_KB;
-                            const int64_t t = t0 - (L - 1) + i;
-                            v8[u] = S(0);
-                            if (idx < WW * HW_KB && kk < kb && t >= 0 && t < Tint) v8[u] = __ldcg(D + t * K + kp0 + kk);   // tail columns: slow path below
-                        }
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int idx = base + u * nthr;
-                            const int kk = idx % HW_KB, i = idx / HW_KB;
-                            if (idx < WW * HW_KB) Dwin[kk * WWQ + (i & 7) * QP + (i >> 3)] = v8[u];
-                        }
-                    }
-                    const int nlp = (2 * (int)L - 1 + 7) & ~7;                 // lag rows padded with zeros to a multiple of 8
-                    for (int idx = tid; idx < nlp * HW_KB; idx += nthr) {
-                        const int kk = idx % HW_KB;
-                        const int64_t j = idx / HW_KB;
-                        Cs[idx] = (kk < kb && j < 2 * L - 1) ? Cf[(j * K + kp0 + kk) * K + k] : S(0);
-                    }
-                    HW_TEAM_SYNC();
-                    // two staged components per pass (they share the index arithmetic); the window of 8 Delta values per
-                    // component is a circular register file whose rotation is compile-time: the lag loop is unrolled by 8,
-                    // slot (r - jj) & 7 holds window index ib + r - j at step j = j0 + jj, and step jj refills slot -jj.
-                    for (int kk = kq * KQ; kk < kq * KQ + KQ && kk < kb; kk += 2) {
-                        const bool two = kk + 1 < kb;
-                        const S *dwa = Dwin + kk * WWQ, *dwb = two ? dwa + WWQ : dwa;
-                        const int ib = 8 * cg + 2 * (int)(L - 1);
-                        const int nl = 2 * (int)L - 1;
-                        S da[8], db[8];
-                        da[0] = S(0); db[0] = S(0);
-#pragma unroll
-                        for (int o = 1; o < 8; ++o) {
-                            const int ad = ((ib + o) & 7) * QP + ((ib + o) >> 3);
-                            da[o] = dwa[ad]; db[o] = dwb[ad];
-                        }
-                        // the padded lag rows of Cs are zero, so whole groups of 8 steps run without a branch (window
-                        // indices below 0 are clamped: their table entries are zero)
-                        const int kkb = two ? kk + 1 : kk;
-                        const S cbs = two ? S(1) : S(0);
-                        for (int j0 = 0; j0 < nl; j0 += 8) {
-#pragma unroll
-                            for (int jj = 0; jj < 8; ++jj) {
-                                const int j = j0 + jj;
-                                const int in = max(ib - j, 0);         // window index entering at this step (column r = 0)
-                                const int ad = (in & 7) * QP + (in >> 3);
-                                da[(8 - jj) & 7] = dwa[ad]; db[(8 - jj) & 7] = dwb[ad];
-                                const S ca = Cs[j * HW_KB + kk], cb = Cs[j * HW_KB + kkb] * cbs;
-#pragma unroll
-                                for (int r = 0; r < 8; ++r) {
-                                    a8[r] = fma(da[(r - jj + 8) & 7], ca, a8[r]);
-                                    a8[r] = fma(db[(r - jj + 8) & 7], cb, a8[r]);
-                                }
-                            }
-                        }
-                    }
-                }
-                // reduce the component groups: red[kq][column] (reuses the Delta window space), then add Q
-                HW_TEAM_SYNC();
-                S *red = Dwin;
-#pragma unroll
-                for (int r = 0; r < 8; ++r) red[kq * HW_TC + 8 * cg + r] = a8[r];
-                HW_TEAM_SYNC();
-                for (int col = tid; col < HW_TC; col += nthr) {
-                    const int64_t tp = t0 + col;
-                    S acc = (tp < T) ? Q[tp * K + k] : S(0);
-#pragma unroll
-                    for (int g = 0; g < NKQ; ++g) acc += red[g * HW_TC + col];
-                    qeff_c[col] = acc;
-                }
-                HW_TEAM_SYNC();
-                // truncated tail columns t >= Tint (only the last chunks see them): the tables C_w[k',k,dd] come precomputed
-                // (hals_tail_table_kernel) as Ct[w-1][dd+L-1][k][k']; work item = (column, block of earlier components),
-                // block sums go through shared memory and are added in a fixed order (deterministic)
-                if (Ct != nullptr) {
-                    if (k > 0 && t0 + HW_TC + (L - 1) > Tint) {
-                        const int64_t c_lo = (t0 > Tint - (L - 1)) ? t0 : Tint - (L - 1);
-                        const int64_t c_hi = (t0 + HW_TC < T) ? t0 + HW_TC : T;
-                        const int ncol = (int)(c_hi - c_lo);
-                        const int CH = (int)((k + 15) / 16 > 16 ? (k + 15) / 16 : 16);
-                        const int nch = (int)((k + CH - 1) / CH);
-                        S *part = Dwin;                            // [nch][HW_TC], nch <= 16
-                        if (ncol > 0) {
-                            for (int it = tid; it < ncol * nch; it += nthr) {
-                                const int ci = it % ncol, ch = it / ncol;
-                                const int64_t tp = c_lo + ci;
-                                int64_t ta = (tp - (L - 1) > Tint) ? tp - (L - 1) : Tint;
-                                if (ta < 0) ta = 0;
-                                const int64_t tb = tp + (L - 1) < T - 1 ? tp + (L - 1) : T - 1;
-                                const int64_t kp_lo = (int64_t)ch * CH, kp_hi = (kp_lo + CH < k) ? kp_lo + CH : k;
-                                double accd = 0.0;
-                                for (int64_t t = ta; t <= tb; ++t) {
-                                    const int64_t dd = tp - t, w = T - t;
-                                    const S *ct = Ct + ((((w - 1) * (2 * L - 1) + (dd + L - 1)) * K + k) * K);
-                                    const S *dr = D + t * K;
-                                    for (int64_t kp = kp_lo; kp < kp_hi; ++kp) accd += (double)__ldcg(dr + kp) * (double)ct[kp];
-                                }
-                                part[ch * HW_TC + ci] = (S)accd;
-                            }
-                            HW_TEAM_SYNC();
-                            for (int ci = tid; ci < ncol; ci += nthr) {
-                                double sacc = 0.0;
-                                for (int ch = 0; ch < nch; ++ch) sacc += (double)part[ch * HW_TC + ci];
-                                qeff_c[(int)(c_lo - t0) + ci] += (S)sacc;
-                            }
-                        }
-                    }
-                } else
-                for (int col = tid; col < HW_TC; col += nthr) {
-                    const int64_t tp = t0 + col;
-                    if (tp < T && tp + (L - 1) >= Tint) {
-                        double accd = 0.0;
-                        const int64_t ta = (tp - (L - 1) > Tint) ? tp - (L - 1) : Tint;
-                        const int64_t tb = tp + (L - 1) < T - 1 ? tp + (L - 1) : T - 1;
-                        for (int64_t t = (ta > 0 ? ta : 0); t <= tb; ++t) {
-                            const int64_t dd = tp - t;
-                            const int64_t w = T - t;    // C_w[k',k,dd] = sum_{l<w, 0<=l-dd<L} S2[(l,k')][(l-dd,k)]
-                            for (int64_t kp = 0; kp < k; ++kp) {
-                                const S d = __ldcg(D + t * K + kp);
-                                if (d == S(0)) continue;
-                                double cw = 0.0;
-                                for (int64_t l = (dd > 0 ? dd : 0); l < w && l - dd < L; ++l)
-                                    cw += (double)S2[(l * Ks + kp) * ld + (l - dd) * Ks + k];
-                                accd += (double)d * cw;
-                            }
-                        }
-                        qeff_c[col] += (S)accd;
-                    }
-                }
-            }
-                HW_TEAM_SYNC();
-            // ---- sweep: the sequential recurrence of component k over this chunk (warp 0), entirely in shared
-            //      memory: H of the chunk is prefetched by all threads, results are written back by all threads
-            for (int col = tid; col < HW_TC; col += nthr) {
-                const int64_t tp = t0 + col;
-                hch_c[col] = (tp < T) ? H[tp * K + k] : S(0);
-            }
-                HW_TEAM_SYNC();
-                if (tid == 0) { __threadfence_block(); ready_c = (int)(c + 1); }
-            }
-            HW_ALL_SYNC();
-        }
-    } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
-        for (int64_t k = blockIdx.x; k < K; k += gridDim.x) {
-            setup_component(k);
-            if (tid < HW_NT + 32) {
-            // ================================================================ recurrence warp: sweep + write-back + publish of cell c
-            const int lane = tid & 31;
-            S Pw[32];                             // register window of pending corrections (L <= 32)
-            S creg[sizeof(S) == 4 ? 32 : 1];      // C[k,k,j] in registers (fp32)
-#pragma unroll
-            for (int j = 0; j < 32; ++j) Pw[j] = S(0);
-            if (sizeof(S) == 4) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) creg[j % (sizeof(S) == 4 ? 32 : 1)] = ckk32[j];
-            }
-            bool ring_mode = false;               // true once the window lives in the shared ring (tail / partial blocks / L > 32)
-            for (int64_t c = 0; c < nC; ++c) {
-                const int64_t t0 = c * HW_TC;
-                S *qeff_c = (c & 1) ? qeffB : qeff, *hch_c = (c & 1) ? hchB : hch;
-                if (lane == 0) { while (ready_c < (int)(c + 1)) { __nanosleep(32); } }
-                __syncwarp();
-                __threadfence_block();
-            {
-                
-                const int n = (int)((t0 + HW_TC < T) ? HW_TC : T - t0);
-                int i = 0;
-                if (L <= 32 && !ring_mode) {
-                    // register-window recurrence over whole blocks of 32 interior columns
-                    const S c0i = ckk[0], inv_i = S(1) / (c0i + (S)CMF_EPS + l2);
-                    while (i + 32 <= n && t0 + i + 32 <= Tint) {
-                        if (sizeof(S) == 4) hals_recurrence_block<S, 32>(hch_c, qeff_c, Pw, creg, c0i, inv_i, l1, i, lane);   // table in registers
-                        else hals_recurrence_block<S, 32>(hch_c, qeff_c, Pw, ckk32, c0i, inv_i, l1, i, lane);                  // fp64: table in shared memory
-                        i += 32;
-                    }
-                    if (i < n) {
-                        // the rest (truncated tail of the sequence / partial block) runs on the shared ring: hand the window over
-                        int slot0 = (int)((t0 + i) % RB);
-                        if (lane == 0) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) { int ps = slot0 + j; if (ps >= RB) ps -= RB; pend[ps] = Pw[j]; }
-                        }
-                        ring_mode = true;
-                        __syncwarp();
-                    }
-                }
-                {
-                int slot = (int)((t0 + i) % RB);
-                for (; i < n; ++i) {
-                    const int64_t t = t0 + i;
-                    const int w = (int)((T - t < L) ? (T - t) : L);
-                    const S c0 = (w == (int)L) ? ckk[0] : tailC[w * L + 0];
-                    const S h = hch_c[i];
-                    const S q = qeff_c[i] + pend[slot];
-                    S v = (h * c0 - q - l1) / (c0 + (S)CMF_EPS + l2);
-                    v = v > S(0) ? v : S(0);
-                    const S d = v - h;
-                    __syncwarp();
-                    if (lane == 0) {
-                        hch_c[i] = v;
-                        qeff_c[i] = d;            // Delta H of this column (qeff_c[i] is dead now)
-                        pend[slot] = S(0);
-                    }
-                    if (d != S(0)) {
-                        const S *ctab = (w == (int)L) ? ckk : tailC + (size_t)w * L;
-                        for (int sft = 1 + lane; sft < w; sft += 32) {
-                            int ps = slot + sft;
-                            if (ps >= RB) ps -= RB;
-                            pend[ps] += d * ctab[sft];
-                        }
-                    }
-                    if (++slot == RB) slot = 0;
-                    __syncwarp();
-                }
-                }
-            }
-                __syncwarp();
-                for (int col = lane; col < HW_TC; col += 32) {
-                    const int64_t tp = t0 + col;
-                    if (tp < T) {
-                        H[tp * K + k] = hch_c[col];
-                        D[tp * K + k] = qeff_c[col];
-                    }
-                }
-                // ---- publish (every lane fences its own H / Delta stores, then one lane raises the counters)
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) { atomicExch(progress + k, (int)(c + 1)); done_c = (int)(c + 1); }
-            }
-            }
-            HW_ALL_SYNC();
-        }
-    }
-}
-#undef HW_TEAM_SYNC
-#undef HW_ALL_SYNC
 
 // Projected gradient descent pieces (src/algs/pgd.jl:224-255, SquareLoss):
 //   g = 2*(den - num) + 2*l2*x + l1*sign(x)      gradient of ||conv - X||^2 plus Square/Absolute penalties (:30-32,:77-88)

@@ -30,7 +30,7 @@ from ._lib import F32, F64, HALS, MULT, PGD, CMFError, check, fptr, julia_array,
 _REG_ALIASES = {"l1_W": "l1W", "l2_W": "l2W", "l1_H": "l1H", "l2_H": "l2H"}
 _INIT_ALIASES = {"initW": "W_init", "initH": "H_init"}
 _KNOWN = {"l1W", "l2W", "l1H", "l2H", "seed", "W_init", "H_init", "check_convergence", "patience",
-          "eval_mode", "tol", "verbose", "dtype", "device", "layout", "printer", "engine", "loss_mode"}
+          "eval_mode", "tol", "verbose", "dtype", "device", "layout", "printer", "engine", "loss_mode", "ngpu", "devices"}
 
 
 def _normalise_kwargs(kwargs):
@@ -102,7 +102,10 @@ class AbstractCFUpdate:
 
     _ALG = None
 
-    def __init__(self, data, W, H, dtype="f64", device=0, sync_host=True, engine=None, loss_mode=None):
+    def __init__(self, data, W, H, dtype="f64", device=0, sync_host=True, engine=None, loss_mode=None, ngpu=1,
+                 devices=None):
+        """``ngpu > 1``: the rule spans ``ngpu`` GPUs (time axis sharded inside the library, NCCL collectives driven
+        from this one thread -- cmf_create_multi); every other argument and every method is unchanged."""
         lib = _lib.load()
         self.dtype = parse_dtype(dtype)
         data = np.asarray(data)
@@ -116,7 +119,13 @@ class AbstractCFUpdate:
         self.N, self.T, self.K, self.L = N, data.shape[1], K, L
         self.sync_host = sync_host
         self._h = ctypes.c_void_p()
-        check(lib.cmf_create(ctypes.byref(self._h), N, self.T, K, L, self.dtype, self._ALG, device))
+        ngpu = int(ngpu or 1)
+        if ngpu > 1:
+            devs = (ctypes.c_int * ngpu)(*(devices if devices is not None else range(ngpu)))
+            check(lib.cmf_create_multi(ctypes.byref(self._h), N, self.T, K, L, self.dtype, self._ALG, ngpu, devs))
+        else:
+            check(lib.cmf_create(ctypes.byref(self._h), N, self.T, K, L, self.dtype, self._ALG,
+                                 device if devices is None else devices[0]))
         if engine is not None:
             check(lib.cmf_set_engine(self._h, int(engine)))
         if loss_mode is not None:
@@ -298,7 +307,8 @@ def fit_cnmf(data, L=10, K=5, alg=MultUpdate, max_itr=100, max_time=math.inf, **
     rule and runs the alternating loop -- the loop itself is ONE call into the library (cmf_fit).
 
     Extra keywords of this implementation: ``dtype`` ("f64" default, "f32"), ``device``,
-    ``layout`` ("LNK" default -- W returned as L x N x K as in the README -- or "KNL")."""
+    ``layout`` ("LNK" default -- W returned as L x N x K as in the README -- or "KNL"), ``ngpu`` / ``devices``
+    (the fit runs T-sharded over that many GPUs inside the same single library call; MultUpdate and HALSUpdate)."""
     kw = _normalise_kwargs(kwargs)
     printer = kw.get("printer", print)
     verbose = kw.get("verbose", False)
@@ -330,7 +340,8 @@ def fit_cnmf(data, L=10, K=5, alg=MultUpdate, max_itr=100, max_time=math.inf, **
         raise ValueError(f"W_init must be {(K, N, L)} and H_init {(K, T)}; got {W0.shape}, {H0.shape}")
 
     rule = rule_cls(data, W0, H0, dtype=dtype, device=device, sync_host=False,
-                    engine=kw.get("engine"), loss_mode=kw.get("loss_mode"))  # model.jl:79
+                    engine=kw.get("engine"), loss_mode=kw.get("loss_mode"),
+                    ngpu=kw.get("ngpu", 1), devices=kw.get("devices"))  # model.jl:79
     try:
         if need_rescale:
             _rescale(rule)
@@ -405,6 +416,27 @@ def corr_w(H, X, L, dtype="f64"):
     out = np.empty((K, N, L), dtype=np_dtype(dt), order="F")
     Hj, Xj = julia_array(H, dt), julia_array(X, dt)
     check(_lib.load().cmf_corr_w(N, T, K, L, dt, fptr(Hj), fptr(Xj), fptr(out)))
+    return out
+
+
+def compute_resids(data, W, H, dtype="f64"):
+    """src/common.jl:58-59: tensor_conv(W, H) - data."""
+    dt = parse_dtype(dtype)
+    K, N, L = W.shape
+    T = H.shape[1]
+    out = np.empty((N, T), dtype=np_dtype(dt), order="F")
+    Xj, Wj, Hj = julia_array(data, dt), julia_array(W, dt), julia_array(H, dt)
+    check(_lib.load().cmf_compute_resids(N, T, K, L, dt, fptr(Xj), fptr(Wj), fptr(Hj), fptr(out)))
+    return out
+
+
+def shift_and_stack(H, L, dtype="f64"):
+    """src/common.jl:133-142: (K*L) x T matrix whose row l*K + k is H[k, :] shifted right by l columns."""
+    dt = parse_dtype(dtype)
+    K, T = H.shape
+    out = np.empty((K * L, T), dtype=np_dtype(dt), order="F")
+    Hj = julia_array(H, dt)
+    check(_lib.load().cmf_shift_and_stack(K, T, L, dt, fptr(Hj), fptr(out)))
     return out
 
 

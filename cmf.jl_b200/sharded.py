@@ -61,7 +61,11 @@ class _CudaView:
 class DeviceShard:
     """One rank's shard on one GPU: a libcmf_sm100 handle plus torch views of its exchange buffers."""
 
-    def __init__(self, N, T, t0, t1, K, L, dtype="f32", device=0, use_torch_stream=True, alg="mult"):
+    def __init__(self, N, T, t0, t1, K, L, dtype="f32", device=0, use_torch_stream=True, alg="mult", comm=None,
+                 ngpu=None, devices=None):
+        """``comm=(unique_id_bytes, rank, world)``: the handle of one rank with the NCCL communicator INSIDE the library
+        (cmf_create_rank; t0/t1 must be the balanced shard of that rank).  ``ngpu=n``: one group handle driving n GPUs
+        from this process (cmf_create_multi; t0/t1 = 0/T).  Neither: a plain (shard) handle whose collectives the host does."""
         import torch
 
         self.torch = torch
@@ -70,16 +74,45 @@ class DeviceShard:
         self.dtype = parse_dtype(dtype)
         self.device = device
         self._h = ctypes.c_void_p()
+        self.group = bool(ngpu and ngpu > 1)
+        self.in_library_comm = comm is not None or self.group
         algc = {"mult": _lib.MULT, "hals": _lib.HALS}[alg]
-        if t0 == 0 and t1 == T:
+        if self.group:
+            devs = (ctypes.c_int * ngpu)(*(devices if devices is not None else range(ngpu)))
+            check(lib.cmf_create_multi(ctypes.byref(self._h), N, T, K, L, self.dtype, algc, ngpu, devs))
+            self.t0, self.t1 = 0, T
+        elif comm is not None:
+            uid, rank, world = comm
+            buf = ctypes.create_string_buffer(bytes(uid), 128)
+            check(lib.cmf_create_rank(ctypes.byref(self._h), N, T, K, L, self.dtype, algc, device, buf, rank, world))
+            a, b = ctypes.c_int64(), ctypes.c_int64()
+            check(lib.cmf_comm_info(self._h, None, None, ctypes.byref(a), ctypes.byref(b)))
+            assert (a.value, b.value) == (t0, t1), "ShardPlan and cmf_shard_range disagree"
+        elif t0 == 0 and t1 == T:
             check(lib.cmf_create(ctypes.byref(self._h), N, T, K, L, self.dtype, algc, device))
         else:
             check(lib.cmf_create_shard(ctypes.byref(self._h), N, T, t0, t1, K, L, self.dtype, algc, device))
-        if use_torch_stream:
+        if use_torch_stream and not self.group:
             with torch.cuda.device(device):
                 s = torch.cuda.current_stream().cuda_stream
             check(lib.cmf_set_stream(self._h, ctypes.c_void_p(s)))
-        self._views()
+        if not self.group:
+            self._views()
+
+    @staticmethod
+    def unique_id():
+        """128-byte NCCL id for cmf_create_rank (rank 0 creates it, the host hands it to the other ranks)."""
+        buf = ctypes.create_string_buffer(128)
+        check(_lib.load().cmf_comm_unique_id(buf))
+        return bytes(buf.raw)
+
+    def exchange_halos(self):
+        check(_lib.load().cmf_exchange_halos(self._h))
+
+    def loss(self):
+        out = ctypes.c_double()
+        check(_lib.load().cmf_loss(self._h, ctypes.byref(out)))
+        return out.value
 
     def _views(self):
         torch, lib = self.torch, _lib.load()
@@ -131,6 +164,7 @@ class DeviceShard:
         check(_lib.load().cmf_synth_data(self._h, seed, K_true, L_true, p_h, noise))
 
     def data_sumsq(self):
+        """||X||^2 of the owned columns; over ALL columns on handles whose collectives run inside the library."""
         out = ctypes.c_double()
         check(_lib.load().cmf_data_sumsq(self._h, ctypes.byref(out)))
         return out.value
@@ -149,9 +183,9 @@ class DeviceShard:
         check(_lib.load().cmf_profile(self._h, int(enable)))
 
     def profile_read(self):
-        """{class: (total_ms, launches)} for conv / transconv / corr."""
+        """{class: (total_ms, launches)} for conv / transconv / corr / sweep (HALS H sweep)."""
         res = {}
-        for which, name in enumerate(("conv", "transconv", "corr")):
+        for which, name in enumerate(("conv", "transconv", "corr", "sweep")):
             ms, n = ctypes.c_double(), ctypes.c_int64()
             check(_lib.load().cmf_profile_read(self._h, which, ctypes.byref(ms), ctypes.byref(n)))
             res[name] = (ms.value, n.value)
@@ -304,11 +338,54 @@ class ShardedMultFit:
         loss = self.loss()                       # all-reduce of one double
         if getattr(s, "loss_mode", 0) == 1 and not loss > 0.25:
             s.set_loss_mode(0)                   # the expansion cancels like 1/loss^2 (same rule on every rank)
+            loss = self.loss()                   # re-evaluate with the direct pass, as the library's own loop does
         return loss
 
     def fit(self, max_itr=100, check_convergence=True, patience=3, tol=1e-4, **reg):
         """src/algs/alternating.jl:16-71 over shards (every rank takes the same branch because the
         loss is all-reduced)."""
+        from .model import converged
+
+        loss_hist = [self.loss()]
+        itr = 1
+        while itr <= max_itr:
+            itr += 1
+            loss_hist.append(self.iterate(**reg))
+            if check_convergence and converged(loss_hist, patience, tol):
+                break
+        return loss_hist
+
+
+class LibraryFit:
+    """The same fit steps as ``ShardedMultFit`` with every collective INSIDE libcmf_sm100 (NCCL bound by the library:
+    ``DeviceShard(comm=...)`` under torchrun, or ``DeviceShard(ngpu=...)`` in one process).  The host only calls the
+    reference-facing entry points: update_motifs! / update_feature_maps! / compute_loss (alternating.jl:37,52,54)."""
+
+    def __init__(self, shard):
+        self.shard = shard
+
+    def setup_data_norm(self):
+        self.data_norm = math.sqrt(self.shard.data_sumsq())       # all-reduced by cmf_set_data / cmf_synth_data
+        return self.data_norm
+
+    def rescale_init(self):
+        dot, nrm2 = self.shard.init_scale_partials()              # all-reduced by the library
+        s = math.sqrt(abs(dot / nrm2))
+        self.shard.scale_factors(s)
+        return s
+
+    def exchange_halos(self):
+        self.shard.exchange_halos()
+
+    def loss(self):
+        return self.shard.loss()
+
+    def iterate(self, l1W=0.0, l2W=0.0, l1H=0.0, l2H=0.0, eval_mode=False):
+        if not eval_mode:
+            self.shard.update_motifs(l1W, l2W)
+        return self.shard.update_feature_maps(l1H, l2H)
+
+    def fit(self, max_itr=100, check_convergence=True, patience=3, tol=1e-4, **reg):
         from .model import converged
 
         loss_hist = [self.loss()]

@@ -16,13 +16,24 @@
  *  - Every function returns 0 on success, non-zero on error; the message is available from
  *    cmf_last_error() (thread-local).  No C++ exception crosses this boundary.  There is no
  *    CPU fallback: without a CUDA device every compute entry point fails with CMF_ERR_CUDA.
- *  - One host thread per handle.
+ *  - One host thread per handle; the call blocks the caller (a Julia task inside `ccall`).  Every call
+ *    runs on the handle's device(s) and restores the caller's current CUDA device before returning.
  *
- * Sharding (time axis): a handle may own the column range
- * [t_begin, t_end) of a global problem of T columns.  The exchange steps between ranks
- * (all-reduce of the W-side partials, L-1 column halo exchange of H, all-reduce of the loss
- * partial) are done by the HOST with whatever collective library it has (torch.distributed /
- * NCCL.jl / MPI) on the device pointers exposed by cmf_exchange_buffer / cmf_halo_buffers.
+ * Multi-GPU (time axis sharding; the reference is single-process): rank r owns the
+ * columns [t_r, t_{r+1}) of X and H, W is replicated.  The collectives (all-reduce of the W-side partials,
+ * L-1 column halo exchange of H, all-reduce of the loss scalars, gather/scatter around the HALS H sweep)
+ * run INSIDE the library over NCCL (bound at run time with dlopen), so the same reference-facing calls --
+ * cmf_set_data, cmf_set_factors, cmf_update_motifs, cmf_update_feature_maps, cmf_loss, cmf_fit,
+ * cmf_get_factors -- drive one GPU or many:
+ *   - cmf_create_multi: ONE process, one calling thread, `ngpu` devices (ncclCommInitAll + one worker thread
+ *     and one stream per device inside the library; Julia never needs `Distributed`).  Host arrays are the
+ *     full N x T / K x T arrays, exactly as for cmf_create.
+ *   - cmf_create_rank: one process per GPU (torchrun / MPI style); rank 0 obtains cmf_comm_unique_id, the
+ *     host passes the 128 bytes to the other ranks by its own means, every rank calls the same sequence of
+ *     library calls (they meet inside the collectives).  Host arrays cover the rank's own columns.
+ * The older split-phase calls (cmf_w_partials ... cmf_loss_partial on handles from cmf_create_shard, with the
+ * HOST doing the collectives on the pointers from cmf_exchange_buffer / cmf_halo_buffers) are kept for hosts
+ * that bring their own collective library, and for the CPU (gloo) tests of the step logic.
  */
 #ifndef CMF_SM100_H
 #define CMF_SM100_H
@@ -43,7 +54,8 @@ enum {
     CMF_OK = 0,
     CMF_ERR_ARG = 1,   /* bad dimensions / null pointer / wrong state                  */
     CMF_ERR_CUDA = 2,  /* CUDA runtime error (including "no device")                   */
-    CMF_ERR_UNSUPPORTED = 3
+    CMF_ERR_UNSUPPORTED = 3,
+    CMF_ERR_NCCL = 4   /* NCCL missing or a collective failed                           */
 };
 
 /* ---- lifecycle ---------------------------------------------------------------------- */
@@ -57,9 +69,31 @@ int cmf_create(cmf_handle *out, int64_t N, int64_t T, int64_t K, int64_t L, int 
 
 /* Same, for one time-shard [t_begin, t_end) of a T_global-column problem (no reference
  * counterpart: the reference is single-process).  Needs t_end - t_begin >= L-1.
- * HALS and PGD are single-shard only in this version (CMF_ERR_UNSUPPORTED otherwise). */
+ * PGD is single-shard only in this version (CMF_ERR_UNSUPPORTED otherwise). */
 int cmf_create_shard(cmf_handle *out, int64_t N, int64_t T_global, int64_t t_begin, int64_t t_end,
                      int64_t K, int64_t L, int dtype, int alg, int device);
+
+/* The rule constructor (src/model.jl:79) for `ngpu` GPUs driven from ONE host thread: the time axis is
+ * split into balanced contiguous shards, one per device (`devices` = CUDA ordinals, NULL = 0..ngpu-1).
+ * The returned group handle takes the same calls as a cmf_create handle with the full host arrays;
+ * ngpu == 1 is cmf_create.  MultUpdate and HALSUpdate. */
+int cmf_create_multi(cmf_handle *out, int64_t N, int64_t T, int64_t K, int64_t L, int dtype, int alg,
+                     int ngpu, const int *devices);
+
+/* One process per GPU: the balanced shard of `rank` among `world` ranks on `device`, with its own NCCL
+ * communicator built from the 128-byte id that rank 0 got from cmf_comm_unique_id (collective: every
+ * rank must call it).  Host arrays passed to this handle start at global column `first_col` as for
+ * cmf_create_shard; cmf_get_factors returns the rank's own columns of H. */
+int cmf_comm_unique_id(void *id_out_128_bytes);
+int cmf_create_rank(cmf_handle *out, int64_t N, int64_t T, int64_t K, int64_t L, int dtype, int alg,
+                    int device, const void *unique_id_128_bytes, int rank, int world);
+/* The partition rule of both constructors: columns [*t_begin, *t_end) of rank `rank`. */
+int cmf_shard_range(int64_t T, int world, int rank, int64_t *t_begin, int64_t *t_end);
+/* rank / world / column range of a handle (group handles report rank 0, world = ngpu, the full range). */
+int cmf_comm_info(cmf_handle h, int *rank_out, int *world_out, int64_t *t_begin, int64_t *t_end);
+/* Re-sends the L-1 column halos of H between neighbouring ranks (after cmf_set_factors from host arrays
+ * that hold only the rank's own columns); a no-op without a communicator. */
+int cmf_exchange_halos(cmf_handle h);
 
 int cmf_destroy(cmf_handle h);
 
@@ -164,7 +198,7 @@ int cmf_set_stream(cmf_handle h, void *stream);
 /* Per-kernel-class CUDA-event timing on the handle's stream (bench.py's roofline numbers):
  * cmf_profile(h, 1) starts recording an event pair around every launch of the three contraction
  * kernels; cmf_profile_read returns the summed device time and launch count of class
- * `which` (0 = conv/residual/loss, 1 = transposed conv for numH, 2 = correlation for numW). */
+ * `which` (0 = conv/residual/loss, 1 = transposed conv for numH, 2 = correlation for numW, 3 = HALS H sweep). */
 int cmf_profile(cmf_handle h, int enable);
 int cmf_profile_read(cmf_handle h, int which, double *ms_total, int64_t *count);
 /* Selects the contraction engine: 0 = SIMT kernels (fp64 and fp32); 1 = tcgen05 tensor-core kernels in the
@@ -201,6 +235,13 @@ int cmf_tensor_transconv(int64_t N, int64_t T, int64_t K, int64_t L, int dtype, 
 /* numW of src/algs/mult.jl:31-34                  out: K x N x L */
 int cmf_corr_w(int64_t N, int64_t T, int64_t K, int64_t L, int dtype, const void *H,
                const void *X, void *out);
+/* compute_resids(data, W, H) = tensor_conv(W,H) - data   src/common.jl:58-59     out: N x T */
+int cmf_compute_resids(int64_t N, int64_t T, int64_t K, int64_t L, int dtype, const void *X,
+                       const void *W, const void *H, void *out);
+/* shift_and_stack(H, L)   src/common.jl:133-142   out: (K*L) x T, row l*K + k holds H[k, :] shifted right by l
+ * (the fit never materialises it -- it addresses the same rows through overlapping windows of H; this entry
+ * point exists for callers and tests that want the matrix itself) */
+int cmf_shift_and_stack(int64_t K, int64_t T, int64_t L, int dtype, const void *H, void *out);
 
 #ifdef __cplusplus
 }

@@ -70,7 +70,7 @@ def test_argument_validation(lib):
     assert L.cmf_create(ctypes.byref(h), 0, 10, 2, 5, 0, 0, 0) == 1
     assert L.cmf_create(ctypes.byref(h), 4, 10, 2, 5, 7, 0, 0) == 1  # bad dtype
     assert L.cmf_create_shard(ctypes.byref(h), 4, 100, 0, 2, 2, 5, 0, 0, 0) == 1   # shard < L-1
-    assert L.cmf_create_shard(ctypes.byref(h), 4, 100, 0, 50, 2, 5, 0, 1, 0) == 3  # sharded HALS
+    assert L.cmf_create_shard(ctypes.byref(h), 4, 100, 0, 50, 2, 5, 0, 2, 0) == 3  # sharded PGD
     assert L.cmf_update_motifs(None, 0.0, 0.0) == 1
     assert L.cmf_destroy(None) == 0
 

@@ -53,6 +53,23 @@ PRIM_DIMS = [(13, 57, 3, 5), (1, 1, 1, 1), (5, 7, 2, 7), (130, 300, 20, 9), (500
 
 @pytest.mark.parametrize("dims", PRIM_DIMS)
 @pytest.mark.parametrize("dtype,tol", [("f64", 1e-12), ("f32", 2e-5)])
+def test_resids_and_shift_and_stack_match_oracle(cmf, orc, dims, dtype, tol):
+    # compute_resids (src/common.jl:58-59) and shift_and_stack (:133-142) as callable primitives
+    N, T, K, L = dims
+    W, H, X = _rand(*dims, seed=sum(dims) + 1)
+    ref = orc.po.compute_resids(X, W, H)
+    got = cmf.compute_resids(X, W, H, dtype)
+    assert np.max(np.abs(got - ref)) < tol * max(np.max(np.abs(orc.po.tensor_conv(W, H))), 1.0)
+    Hs = cmf.shift_and_stack(H, L, dtype)
+    assert Hs.shape == (K * L, T)
+    assert np.array_equal(Hs, orc.po.shift_and_stack(H, L).astype(Hs.dtype))     # pure data movement: bit-exact
+    # the tconv3 identity of notebooks/benchmarks.ipynb:96 on the device primitives: conv(W,H) = W_unf * Htilde
+    W_unf = np.concatenate([W[:, :, l].T for l in range(L)], axis=1)             # N x (L*K), column l*K + k
+    assert _relerr(W_unf @ Hs.astype(np.float64), orc.po.tensor_conv(W, H)) < 10 * tol
+
+
+@pytest.mark.parametrize("dims", PRIM_DIMS)
+@pytest.mark.parametrize("dtype,tol", [("f64", 1e-12), ("f32", 2e-5)])
 def test_primitives_match_oracle(cmf, orc, dims, dtype, tol):
     N, T, K, L = dims
     W, H, X = _rand(*dims, seed=sum(dims))
