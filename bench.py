@@ -250,14 +250,14 @@ def run_ours(args, cfg, name):
     # collectives: "lib" = NCCL inside libcmf_sm100 (the reference-facing calls drive all ranks; one process per GPU under
     # torchrun, the 128-byte NCCL id travels over torch.distributed), "host" = the older split-phase calls with
     # torch.distributed doing the collectives between them
-    uid = None
-    if world > 1 and args.collectives == "lib":
+    def new_uid():      # an NCCL id builds ONE communicator: a fresh one per handle
         box = [cmf.DeviceShard.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
-        uid = box[0]
+        return box[0]
 
     def make_shard():
         if world > 1 and args.collectives == "lib":
+            uid = new_uid()
             sh = cmf.DeviceShard(N, T, t0, t1, K, L, dtype="f32", device=local_rank, alg=args.alg, comm=(uid, rank, world))
         else:
             sh = cmf.DeviceShard(N, T, t0, t1, K, L, dtype="f32", device=local_rank, alg=args.alg)

@@ -25,11 +25,11 @@ def main():
     X, _, _ = po.synthetic_sequences(K=3, N=N, L=L, T=T, rng=np.random.default_rng(21))
     W0, H0 = po.init_rand(X, L, K, np.random.default_rng(22))
     reg = dict(l1W=0.1, l2W=0.5, l1H=0.1, l2H=0.2)
-    box = [cmf.DeviceShard.unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(box, src=0)
     plan = cmf.ShardPlan(T, world, L)
     t0, t1 = plan.ranges[rank]
     for dtype, tol in (("f64", 1e-9), ("f32", 1e-4)):
+        box = [cmf.DeviceShard.unique_id() if rank == 0 else None]      # an NCCL id builds ONE communicator
+        dist.broadcast_object_list(box, src=0)
         sh = cmf.DeviceShard(N, T, t0, t1, K, L, dtype=dtype, device=int(os.environ["LOCAL_RANK"]), alg=alg,
                              comm=(box[0], rank, world), use_torch_stream=False)
         sh.set_data(X, 0)

@@ -355,3 +355,34 @@ def test_gen_synthetic_and_parameter_sweep(cmf):
     assert set(sweep) == {(4, 2, "mult"), (6, 2, "mult"), (4, 2, ":hals"), (6, 2, ":hals")}
     for r in sweep.values():
         assert r.loss_hist[-1] < r.loss_hist[0]
+
+
+def test_cuda_fp64_matches_exact_rational_pin(cmf):
+    # The pin that is not floating-point code checking floating-point code: one MU iteration and one HALS iteration on the
+    # reference's toy data (datasets/toy.jl:5-48) computed in exact rational arithmetic (oracle/exact_pin.py,
+    # tests/golden/make_exact_pin.py) vs the fp64 CUDA path through the plugin boundary.
+    g = np.load(os.path.join(GOLD, "exact_pin_toy.npz"))
+    X, W0, H0 = g["X"], g["W0"], g["H0"]
+    l1W, l2W, l1H, l2H = (float(v) for v in g["reg"])
+    for rule_cls, key in ((cmf.MultUpdate, "mu"), (cmf.HALSUpdate, "hals")):
+        W, H = W0.copy(), H0.copy()
+        rule = rule_cls(X, W, H, dtype="f64")
+        rule.update_motifs(X, W, H, l1W=l1W, l2W=l2W)
+        loss = rule.update_feature_maps(X, W, H, l1H=l1H, l2H=l2H)
+        rule.close()
+        We, He, le = g[key + "_W"], g[key + "_H"], float(g[key + "_loss"])
+        assert abs(loss - le) < 1e-11 * le, (key, loss, le)
+        assert np.max(np.abs(W - We)) < 1e-11 * np.max(We) and np.max(np.abs(H - He)) < 1e-11 * np.max(He), key
+
+
+def test_cuda_fp32_close_to_exact_rational_pin(cmf):
+    g = np.load(os.path.join(GOLD, "exact_pin_toy.npz"))
+    X, W0, H0 = g["X"], g["W0"], g["H0"]
+    l1W, l2W, l1H, l2H = (float(v) for v in g["reg"])
+    for rule_cls, key in ((cmf.MultUpdate, "mu"), (cmf.HALSUpdate, "hals")):
+        W, H = W0.copy(), H0.copy()
+        rule = rule_cls(X, W, H, dtype="f32")
+        rule.update_motifs(X, W, H, l1W=l1W, l2W=l2W)
+        loss = rule.update_feature_maps(X, W, H, l1H=l1H, l2H=l2H)
+        rule.close()
+        assert abs(loss - float(g[key + "_loss"])) < 1e-5 * float(g[key + "_loss"]), key

@@ -249,3 +249,65 @@ def test_mu_iteration_in_the_frequency_domain_equals_literal(reg):
         Wf, Hf, loss_f = rs.mu_iteration_overlap_save(X, Wf, Hf, **reg)
         assert abs(loss_l - loss_f) < 1e-11
     assert np.allclose(Wl, Wf, rtol=1e-9, atol=1e-13) and np.allclose(Hl, Hf, rtol=1e-9, atol=1e-13)
+
+
+# ---- exact-arithmetic pin (oracle/exact_pin.py): rational restatement written from the Julia sources ----------------------
+def _exact_case(tiles):
+    from fractions import Fraction as Fr
+
+    from oracle import exact_pin as ex
+
+    X, Wt, Ht = ex.toy_data_exact(tiles)
+    N, T, K, L = ex.dims(Wt, Ht)
+    W0, H0 = ex.rational_init(K, N, L, T)
+    reg_x = dict(l1W=Fr(1, 10), l2W=Fr(1, 2), l1H=Fr(1, 10), l2H=Fr(1, 5))
+    f = lambda a: np.asfortranarray(np.asarray(ex.to_float(a), dtype=np.float64))
+    return ex, X, W0, H0, reg_x, f
+
+
+def test_exact_pin_toy_data_matches_oracle_toy():
+    from oracle import exact_pin as ex
+
+    X, W, H = ex.toy_data_exact(5)
+    Xo, Wo, Ho = po.toy_data()
+    assert np.array_equal(np.asarray(ex.to_float(X)), Xo) and np.array_equal(np.asarray(ex.to_float(W)), Wo)
+    assert np.array_equal(np.asarray(ex.to_float(H)), Ho)
+
+
+@pytest.mark.parametrize("oracle_name", ["numpy", "c"])
+def test_exact_pin_mu_iteration(oracle_name):
+    # one MultUpdate iteration (mult.jl:23-58) in exact rationals vs the floating-point oracles: rounding error only
+    ex, X, W0, H0, reg_x, f = _exact_case(2)
+    We, He, le = ex.mu_iteration(X, W0, H0, **reg_x)
+    o = po if oracle_name == "numpy" else co
+    Xf, W, H = f(X), f(W0), f(H0)
+    rule = o.MultUpdate(Xf, W, H)
+    rule.update_motifs(Xf, W, H, l1W=0.1, l2W=0.5)
+    loss = rule.update_feature_maps(Xf, W, H, l1H=0.1, l2H=0.2)
+    assert abs(loss - le) < 1e-13 * le
+    assert np.max(np.abs(W - f(We)) / f(We)) < 1e-13 and np.max(np.abs(H - f(He)) / f(He)) < 1e-13
+
+
+@pytest.mark.parametrize("oracle_name", ["numpy", "c"])
+def test_exact_pin_hals_iteration(oracle_name):
+    # one HALSUpdate iteration (hals.jl:18-154, persistent residual, both sweeps) in exact rationals vs the oracles
+    ex, X, W0, H0, reg_x, f = _exact_case(5)
+    We, He, Re, le = ex.hals_iteration(X, W0, H0, None, **reg_x)
+    o = po if oracle_name == "numpy" else co
+    Xf, W, H = f(X), f(W0), f(H0)
+    rule = o.HALSUpdate(Xf, W, H)
+    rule.update_motifs(Xf, W, H, l1W=0.1, l2W=0.5)
+    loss = rule.update_feature_maps(Xf, W, H, l1H=0.1, l2H=0.2)
+    assert abs(loss - le) < 1e-13 * le
+    assert np.max(np.abs(W - f(We))) < 1e-13 and np.max(np.abs(H - f(He))) < 1e-12
+    assert (f(He) == 0).sum() > 0            # the clamp at zero (hals.jl:153) is exercised: exact zeros stay exact zeros
+    assert np.array_equal(H == 0, f(He) == 0)
+
+
+def test_exact_pin_fixture_is_current():
+    # tests/golden/exact_pin_toy.npz (what the GPU tests compare with) is what oracle/exact_pin.py produces
+    ex, X, W0, H0, reg_x, f = _exact_case(5)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "exact_pin_toy.npz"))
+    assert np.array_equal(g["X"], f(X)) and np.array_equal(g["W0"], f(W0)) and np.array_equal(g["H0"], f(H0))
+    We, He, Re, le = ex.hals_iteration(X, W0, H0, None, **reg_x)
+    assert np.array_equal(g["hals_W"], f(We)) and np.array_equal(g["hals_H"], f(He)) and float(g["hals_loss"]) == le
