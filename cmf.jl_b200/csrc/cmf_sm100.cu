@@ -115,9 +115,16 @@ struct cmf_ctx {
         for (auto &e : prof_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
         prof_events.clear();
     }
-    virtual ~cmf_ctx() { prof_clear(); }
+    virtual ~cmf_ctx() {
+        prof_clear();
+        if (ev_a) cudaEventDestroy(ev_a);
+        if (ev_b) cudaEventDestroy(ev_b);
+        if (comm_stream) cudaStreamDestroy(comm_stream);
+    }
     // ---- multi-GPU (the reference is single-process: no counterpart)
     cmf::Comm comm;                  // NCCL communicator of this rank (world == 1: collectives are no-ops)
+    cudaStream_t comm_stream = nullptr;  // side stream for collectives that overlap with kernels of the main stream
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     struct cmf_multi *multi = nullptr;   // set on the single-process multi-GPU handle only (cmf_create_multi)
     int world() const { return comm.world; }
     int rank() const { return comm.rank; }
@@ -136,6 +143,9 @@ struct cmf_ctx {
     virtual void get_factors(void *, void *) { no_multi(); }
     virtual void w_partials() { no_multi(); }
     virtual void w_apply(double, double) { no_multi(); }
+    virtual void w_denom_rows(int64_t, int64_t) { no_multi(); }
+    virtual void w_update_rows(double, double, int64_t, int64_t) { no_multi(); }
+    virtual void w_rows_buffers(void **, void **, int64_t *) { no_multi(); }
     virtual void h_update(double, double) { no_multi(); }
     virtual double loss_partial() { no_multi(); }
     virtual int loss_partial_dev() { no_multi(); }                 // leaves 1 (direct) or 2 (expansion) doubles in scalars()
@@ -773,9 +783,10 @@ struct Ctx : cmf_ctx {
         }
     }
     // plain GEMM out[m*ldo + n] = sum_k A[m][k] B[n][k] on tensor cores (operands given as hi/lo tensor maps)
-    void tc_plain(const CUtensorMap *mA, const CUtensorMap *mB, S *out, int64_t Mrows, int64_t Ncols, int64_t Kdim, int64_t ldo) {
+    void tc_plain(const CUtensorMap *mA, const CUtensorMap *mB, S *out, int64_t Mrows, int64_t Ncols, int64_t Kdim, int64_t ldo, bool sym = false) {
         if constexpr (std::is_same<S, float>::value) {
             tc::Params q = tc_base_params();
+            q.sym = (sym && !getenv("CMF_S2_FULL")) ? 1 : 0;
             q.tiles_n = cdiv(Ncols, tc::BN);
             q.nkb = cdiv(Kdim, tc::BK);
             q.units = q.tiles_n * cdiv(Mrows, tc::BM);
@@ -783,10 +794,15 @@ struct Ctx : cmf_ctx {
             const unsigned grid = (unsigned)std::min<int64_t>(q.units, tcs.num_sms);
             tc::tc_kernel<tc::TC_PLAIN><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(mA[0], mA[1], mB[0], mB[1], q);
             post_launch();
+            if (q.sym) {
+                tc::mirror_upper_kernel<<<dim3((unsigned)cdiv(Mrows, 256), (unsigned)Mrows), 256, 0, stream>>>(out, Mrows, ldo);
+                post_launch();
+            }
         }
     }
     // denomW = G * Wi (mult.jl:28,33): G is built straight into bf16 planes in the K-dim order of Wc
-    void tc_denomW() {
+    void tc_denomW(int64_t j0 = 0, int64_t j1 = -1) {
+        if (j1 < 0) j1 = KL();
         if constexpr (std::is_same<S, float>::value) {
             if (getenv("CMF_G_DIRECT"))          // element-wise form (kept for A/B)
                 tc::build_G_split_kernel<<<(unsigned)cdiv(KL() * tcs.KLp, 256), 256, 0, stream>>>(
@@ -796,7 +812,16 @@ struct Ctx : cmf_ctx {
                     exch1.p, exch1.p + L * K * K, tcs.Gc_hi.p, tcs.Gc_lo.p, K, L, tcs.Kp, tcs.KLp);
             post_launch();
             tc_split_W();
-            tc_plain(tcs.mGc, tcs.mWcB, denW.p, KL(), N, tcs.KLp, N);
+            if (j0 == 0 && j1 == KL()) {
+                tc_plain(tcs.mGc, tcs.mWcB, denW.p, KL(), N, tcs.KLp, N);
+            } else {
+                // rows [j0, j1) of G only (the W update is sharded by rows over the ranks): A maps over that row block
+                CUtensorMap mg[2];
+                __nv_bfloat16 *gc[2] = {tcs.Gc_hi.p, tcs.Gc_lo.p};
+                for (int i = 0; i < 2; ++i)
+                    mg[i] = make_map_2d(gc[i] + j0 * tcs.KLp, (uint64_t)tcs.KLp, (uint64_t)(j1 - j0), (uint64_t)tcs.KLp * 2, tc::BK, tc::BM, CU_TENSOR_MAP_SWIZZLE_64B);
+                tc_plain(mg, tcs.mWcB, denW.p + j0 * N, j1 - j0, N, tcs.KLp, N);
+            }
         }
     }
     // Gram partial Rg[d][k][k'] = sum_u H[u][k] H[u+d][k'] via tensor cores (needs tc_split_H(true) and (false) done)
@@ -1156,16 +1181,25 @@ struct Ctx : cmf_ctx {
     void w_apply(double l1W, double l2W) override {
         if (alg == CMF_HALS) { hals_w_apply(l1W, l2W); return; }
         REQUIRE(alg == CMF_MULT, "the split-phase W update serves MultUpdate and HALSUpdate");
+        w_denom_rows(0, KL());
+        w_update_rows(l1W, l2W, 0, KL());
+    }
+    // denomW = G * Wi (mult.jl:28,33) for the unfolded rows [j0, j1)
+    void w_denom_rows(int64_t j0, int64_t j1) override {
         if (tc_active()) {
-            tc_denomW();                                                          // denomW = G * Wi on tensor cores
+            tc_denomW(j0, j1);                                                    // on tensor cores
         } else {
             build_G();
-            launch_gemm<false>(GS.p, Wi.p, denW.p, KL(), N, KL(), KL(), N, N);   // denomW = G * Wi (mult.jl:28,33)
+            launch_gemm<false>(GS.p + j0 * KL(), Wi.p, denW.p + j0 * N, j1 - j0, N, KL(), KL(), N, N);
         }
-        launch_mu(Wi.p, numW.p, denW.p, l1W, l2W, KL() * N);                  // mult.jl:37-38
+    }
+    // mult.jl:37-38 on the rows [j0, j1) (the whole update when the range is everything)
+    void w_update_rows(double l1W, double l2W, int64_t j0, int64_t j1) override {
+        launch_mu(Wi.p + j0 * N, numW.p + j0 * N, denW.p + j0 * N, l1W, l2W, (j1 - j0) * N);
         mark_w_dirty();
         numH_valid = false;
     }
+    void w_rows_buffers(void **numw, void **w, int64_t *row_elems) override { *numw = numW.p; *w = Wi.p; *row_elems = N; }
 
     // layout of the W W' product held in GS: S2[(l*s2_ks + k)*s2_ld + l'*s2_ks + k']
     int64_t s2_ks = 0, s2_ld = 0;
@@ -1173,7 +1207,7 @@ struct Ctx : cmf_ctx {
     void lag_tables() {
         if (tc_active()) {
             tc_split_W();
-            tc_plain(tcs.mWu, tcs.mWuB, GS.p, tcs.rows_u, tcs.rows_u, N, tcs.rows_u);   // S2 = Wu Wu' on tensor cores
+            tc_plain(tcs.mWu, tcs.mWuB, GS.p, tcs.rows_u, tcs.rows_u, N, tcs.rows_u, true);   // S2 = Wu Wu' on tensor cores (lower tiles + mirror)
             s2_ks = tcs.Kp; s2_ld = tcs.rows_u;
         } else {
             launch_gemm<true>(Wi.p, Wi.p, GS.p, KL(), KL(), N, N, N, KL());              // S2 = Wi Wi'
@@ -1645,6 +1679,29 @@ double r_guarded_loss(cmf_ctx *h) {
 void r_update_motifs(cmf_ctx *h, double l1W, double l2W) {
     if (h->alg == CMF_PGD) { h->pgd_update_motifs(l1W, l2W); return; }
     h->w_partials();
+    const int64_t KL = h->K * h->L;
+    if (h->world() > 1 && h->alg == CMF_MULT && KL % h->world() == 0 && !getenv("CMF_W_REPLICATED")) {
+        // MultUpdate: the W update is sharded by unfolded rows j = l*K + k (contiguous row blocks of numW / W):
+        // reduce-scatter of numW on the side stream while this rank forms its rows of denomW = G W, update of those
+        // rows, all-gather of W.  Same bytes on the wire as an all-reduce; G W, the ratio update and the eps floor cost 1/world.
+        NcclApi &a = nccl();
+        void *p; int64_t cnt; int dt;
+        h->exchange_buffer(1, &p, &cnt, &dt);
+        c_allreduce(h, p, (size_t)cnt, ncclFloat64);                                   // Gram + H tail (small, needed by G)
+        void *nw, *w; int64_t row;
+        h->w_rows_buffers(&nw, &w, &row);
+        const int64_t rows = KL / h->world(), j0 = rows * h->rank(), chunk = rows * row;
+        const size_t es = elem_size(h);
+        CK(cudaEventRecord(h->ev_a, h->stream));
+        CK(cudaStreamWaitEvent(h->comm_stream, h->ev_a, 0));
+        NK(a.ReduceScatter(nw, (char *)nw + (size_t)(j0 * row) * es, (size_t)chunk, nccl_dt(h), ncclSum, h->comm.comm, h->comm_stream));
+        CK(cudaEventRecord(h->ev_b, h->comm_stream));
+        h->w_denom_rows(j0, j0 + rows);
+        CK(cudaStreamWaitEvent(h->stream, h->ev_b, 0));
+        h->w_update_rows(l1W, l2W, j0, j0 + rows);
+        NK(a.AllGather((char *)w + (size_t)(j0 * row) * es, w, (size_t)chunk, nccl_dt(h), h->comm.comm, h->stream));
+        return;
+    }
     if (h->world() > 1) {
         void *p; int64_t cnt; int dt;
         h->exchange_buffer(0, &p, &cnt, &dt);
@@ -1773,6 +1830,11 @@ void attach_comm(cmf_ctx *h, ncclComm_t comm, int rank, int world, bool owned) {
     shard_range(h->T, world, rank, &a0, &a1);
     REQUIRE(a0 == h->t0 && a1 == h->t1, "the handle's column range is not the balanced shard of this rank (use cmf_shard_range)");
     h->comm.comm = comm; h->comm.rank = rank; h->comm.world = world; h->comm.owned = owned;
+    if (world > 1 && !h->comm_stream) {
+        CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
+    }
     r_agree_engine(h);
 }
 

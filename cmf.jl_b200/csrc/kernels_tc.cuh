@@ -74,7 +74,16 @@ struct Params {
     int64_t b_off, nbc;        // FQX: first block and number of blocks of the chunk this launch covers
     int64_t MR;                // FQT / FQC / FQX: rows per frequency of the A operand / output (2 Kq = 128 or 256)
     int mtiles;                // FQT / FQC: 128-row tiles per frequency (MR / 128); the tiles of one column tile are adjacent units
+    int sym;                   // PLAIN: the product is symmetric (A == B): tiles strictly above the diagonal are skipped, the caller mirrors
 };
+
+// Completes a symmetric product computed with Params::sym: the tiles strictly above the diagonal (column tile nt, row
+// tile mt with nt*BN >= (mt+1)*BM) take their values from the mirrored entries.
+__global__ void mirror_upper_kernel(float *__restrict__ S, int64_t rows, int64_t ld) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, a = blockIdx.y;
+    if (b >= rows || a >= rows) return;
+    if ((b / 256) * 256 >= (a / 128 + 1) * 128) S[a * ld + b] = S[b * ld + a];
+}
 
 // ---------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -201,6 +210,10 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
     // A unit is a sequence of segments (CORR: fp64 flush segments of FLUSH_T columns; others: one),
     // a segment is a range of k-blocks [kb0, kb0 + kbn), consumed in promotion chunks of PROMO k-blocks.
     auto n_segments = [&](int64_t unit) -> int64_t {
+        if (MODE == TC_PLAIN && p.sym) {      // every role skips the same tiles: no segment, no pipeline traffic
+            const int64_t nt = unit % p.tiles_n, mt = unit / p.tiles_n;
+            return (nt * BN >= (mt + 1) * BM) ? 0 : 1;
+        }
         if (MODE != TC_CORR) return 1;
         const int64_t sp = unit / (p.tiles_m * p.tiles_n);
         const int64_t ta = sp * p.split_len, tb = min(p.tau_hi, ta + p.split_len);
