@@ -21,6 +21,7 @@
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_fd.cuh"
+#include "kernels_hals.cuh"
 #include "comm.h"
 
 namespace {
@@ -1355,6 +1356,51 @@ struct Ctx : cmf_ctx {
         *q = Qfull.p; *h = Hfull.p;
     }
 
+    // second-generation sweep (kernels_hals.cuh): rounds with a grid barrier, lane = component recurrences, 8 x 8 pull blocks.
+    // Returns false when the handle / shape is outside its envelope (the wavefront kernel below then runs).
+    DevBuf<float> h2_Hcm, h2_AD, h2_part;
+    int h2_max_ctas = -1;
+    bool hals2_sweep(const S *Qp, S *Hp, int64_t Tt, const S *ct, double l1H, double l2H) {
+        if constexpr (!std::is_same<S, float>::value) { return false; } else {
+            if (L > hals2::LMAX || K > 128 || (L > 1 && ct == nullptr)) return false;
+            if (const char *e = getenv("CMF_HALS_SWEEP")) { if (atoi(e) == 1) return false; }      // 1: first-generation wavefront kernel
+            const int G = (int)cdiv(K, hals2::GS);
+            const int n_block = G * (G - 1) / 2, n_diag = G, n_rec = (int)cdiv(K, 32);
+            const int grid = n_block + n_diag + n_rec;
+            const size_t smem = hals2::smem_bytes();
+            if (h2_max_ctas < 0) {
+                int per_sm = 0, sms = 0;
+                CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+                cudaError_t e1 = cudaFuncSetAttribute(hals2::hals2_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaError_t e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hals2::hals2_sweep_kernel, hals2::NT, smem);
+                h2_max_ctas = (e1 == cudaSuccess && e2 == cudaSuccess) ? per_sm * sms : 0;
+                if (e1 != cudaSuccess || e2 != cudaSuccess) cudaGetLastError();
+            }
+            if (grid > h2_max_ctas) return false;
+            const int64_t nC = cdiv(Tt, hals2::CW), Tp = nC * hals2::CW;
+            const size_t ncm = (size_t)(K * Tp), npart = (size_t)G * (size_t)K * hals2::RING * hals2::CW;
+            if (h2_Hcm.n < ncm) { h2_Hcm.alloc(ncm); h2_AD.alloc(ncm); }
+            if (h2_part.n < npart) h2_part.alloc(npart);
+            dim3 tb(32, 8), tg((unsigned)cdiv(Tp, 32), (unsigned)cdiv(K, 32));
+            hals2::hals2_prepare_kernel<<<tg, tb, 0, stream>>>(Qp, Hp, h2_AD.p, h2_Hcm.p, K, Tt, Tp);
+            post_launch();
+            hals2::Args a;
+            a.Cf = Cf.p; a.Ct = ct; a.S2 = GS.p; a.Ks = s2_ks; a.ld = s2_ld;
+            a.H_cm = h2_Hcm.p; a.AD_cm = h2_AD.p; a.part = h2_part.p;
+            a.K = K; a.L = L; a.T = Tt; a.Tp = Tp; a.nC = nC;
+            a.l1 = (float)l1H; a.l2 = (float)l2H;
+            a.G = G; a.n_block_items = n_block; a.n_diag_items = n_diag; a.n_rec = n_rec;
+            void *args[] = {&a};
+            prof_begin(PROF_SWEEP);
+            CK(cudaLaunchCooperativeKernel((void *)hals2::hals2_sweep_kernel, dim3((unsigned)grid), dim3(hals2::NT), args, smem, stream));
+            prof_end();
+            post_launch();
+            hals2::hals2_finish_kernel<<<dim3((unsigned)cdiv(Tt, 32), (unsigned)cdiv(K, 32)), tb, 0, stream>>>(h2_Hcm.p, Hp, K, Tt, Tp);
+            post_launch();
+            return true;
+        }
+    }
+
     // wavefront sweep (hals.jl:121-154) over the local shard (single-shard handles) or over the gathered full-T buffers
     void hals_h_sweep(int full, double l1H, double l2H) override {
         REQUIRE(full || (is_first && is_last), "the local HALS H sweep needs a single-shard handle");
@@ -1379,6 +1425,7 @@ struct Ctx : cmf_ctx {
                 ct = tailCt.p;
             }
         }
+        if (hals2_sweep(q, hh, Tt, ct, l1H, l2H)) return;     // round-based kernel (fp32, L <= 32, K <= 128)
         void *args[] = {&cf, &s2, &q, &hh, &dd, &tc_, &pr, &Kk, &Ll, &Tt, &ks, &ldv, &a1, &a2, &dbg, &ct};
         prof_begin(PROF_SWEEP);
         CK(cudaLaunchCooperativeKernel((void *)hals_h_wave_kernel<S>, dim3((unsigned)hals_grid), dim3(HW_NT), args, smem, stream));

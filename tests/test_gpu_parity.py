@@ -386,3 +386,52 @@ def test_cuda_fp32_close_to_exact_rational_pin(cmf):
         loss = rule.update_feature_maps(X, W, H, l1H=l1H, l2H=l2H)
         rule.close()
         assert abs(loss - float(g[key + "_loss"])) < 1e-5 * float(g[key + "_loss"]), key
+
+
+# ---- config-5 shape of the components (K = 128, L = 32): HALS against the plain-C oracle ---------------------------------------
+@pytest.fixture(scope="module")
+def c5shape(orc):
+    N, T, K, L = 32, 3000, 128, 32
+    X, _, _ = orc.po.synthetic_sequences(K=6, N=N, L=L, T=T, p_h=0.3, noise_scale=0.5, rng=np.random.default_rng(5))
+    W0, H0 = orc.po.init_rand(X, L, K, np.random.default_rng(6))
+    reg = dict(l1W=0.05, l2W=0.1, l1H=0.05, l2H=0.1)
+    ref = orc.co.fit(orc.co.HALSUpdate, X, W0, H0, 10, check_convergence=False, **reg)
+    return X, W0, H0, reg, ref
+
+
+def test_hals_c5_component_shape_fp64(cmf, c5shape):
+    X, W0, H0, reg, ref = c5shape
+    r = cmf.fit_cnmf(X, L=32, K=128, alg="hals", max_itr=10, W_init=W0, H_init=H0, check_convergence=False, layout="KNL", **reg)
+    assert np.allclose(r.loss_hist, ref.loss_hist, rtol=1e-9, atol=0)
+    assert np.allclose(r.W, ref.W, rtol=1e-7, atol=1e-10) and np.allclose(r.H, ref.H, rtol=1e-7, atol=1e-10)
+
+
+@pytest.mark.parametrize("sweep", ["2", "1"])
+def test_hals_c5_component_shape_fp32(cmf, c5shape, monkeypatch, sweep):
+    # sweep 2 = round-based kernel (kernels_hals.cuh: lane = component recurrences, 8 x 8 pull blocks; 140 CTAs at K = 128),
+    # sweep 1 = first-generation wavefront kernel; both against the oracle at the north-star's fp32 bar
+    X, W0, H0, reg, ref = c5shape
+    monkeypatch.setenv("CMF_HALS_SWEEP", sweep)
+    r = cmf.fit_cnmf(X, L=32, K=128, alg="hals", max_itr=10, W_init=W0, H_init=H0, check_convergence=False, layout="KNL",
+                     dtype="f32", **reg)
+    rel = np.abs(np.asarray(r.loss_hist) - np.asarray(ref.loss_hist)) / np.asarray(ref.loss_hist)
+    assert rel.max() < 1e-4, rel
+
+
+@pytest.mark.parametrize("dims", [(24, 5000, 9, 6), (16, 2600, 40, 32), (16, 1500, 128, 17), (8, 900, 3, 1), (12, 1024, 20, 8)])
+def test_hals_round_kernel_equals_wavefront_kernel(cmf, dims, monkeypatch):
+    # one HALS iteration from the same factors with the two H-sweep kernels: same sequential order, different order of the
+    # floating-point sums in the pull (fixed in both) -> agreement to fp32 rounding, identical zero pattern up to rounding
+    N, T, K, L = dims
+    W, H, X = _rand(N, T, K, L, seed=sum(dims))
+    out = {}
+    for sweep in ("1", "2"):
+        monkeypatch.setenv("CMF_HALS_SWEEP", sweep)
+        Wc, Hc = W.copy(), H.copy()
+        rule = cmf.HALSUpdate(X, Wc, Hc, dtype="f32", engine=0)
+        rule.update_motifs(X, Wc, Hc, l2W=0.1)
+        loss = rule.update_feature_maps(X, Wc, Hc, l1H=0.05, l2H=0.1)
+        rule.close()
+        out[sweep] = (Hc, loss)
+    assert abs(out["1"][1] - out["2"][1]) < 1e-5 * out["1"][1]
+    assert np.max(np.abs(out["1"][0] - out["2"][0])) < 2e-4 * np.max(np.abs(out["1"][0]))

@@ -311,3 +311,24 @@ def test_exact_pin_fixture_is_current():
     assert np.array_equal(g["X"], f(X)) and np.array_equal(g["W0"], f(W0)) and np.array_equal(g["H0"], f(H0))
     We, He, Re, le = ex.hals_iteration(X, W0, H0, None, **reg_x)
     assert np.array_equal(g["hals_W"], f(We)) and np.array_equal(g["hals_H"], f(He)) and float(g["hals_loss"]) == le
+
+
+# ---- round schedule of the second-generation HALS H sweep (cmf.jl_b200/csrc/kernels_hals.cuh) replayed on the CPU ------------
+@pytest.mark.parametrize("dims", [(6, 150, 11, 4, 16, 4), (5, 97, 9, 5, 8, 2), (4, 64, 3, 1, 16, 8), (5, 200, 20, 6, 32, 8),
+                                  (4, 40, 5, 7, 8, 4), (4, 300, 17, 9, 8, 8)])
+def test_hals2_round_schedule_equals_sequential_sweep(dims):
+    # every read of the replay is checked against the round its data was written in (bulk-synchronous rounds: strictly
+    # earlier), ring slots against the chunk they hold; the result must be the k-outer / t-inner sweep of hals.jl:121-154
+    from oracle import hals2_schedule as h2
+
+    N, T, K, L, CW, GS = dims
+    rng = np.random.default_rng(N + T + K)
+    W = rng.random((K, N, L))
+    H = rng.random((K, T)) * (rng.random((K, T)) < 0.6)
+    X = rng.random((N, T))
+    R = po.tensor_conv(W, H) - X
+    ref = rs.hals_H_sweep_gram(R, W, H, 0.05, 0.1)
+    got, n_rounds = h2.sweep(po.tensor_transconv(W, R), H, W, 0.05, 0.1, CW=CW, GS=GS, STAG=4)
+    assert n_rounds == -(-T // CW) + 4 * (K - 1) + 3
+    assert np.max(np.abs(got - ref)) < 1e-12
+    assert np.array_equal(got == 0, ref == 0)
