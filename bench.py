@@ -255,9 +255,12 @@ def run_ours(args, cfg, name):
         dist.broadcast_object_list(box, src=0)
         return box[0]
 
+    have_comm = []
+
     def make_shard():
         if world > 1 and args.collectives == "lib":
-            uid = new_uid()
+            uid = None if have_comm else new_uid()      # later handles reuse the process's communicator
+            have_comm.append(True)
             sh = cmf.DeviceShard(N, T, t0, t1, K, L, dtype="f32", device=local_rank, alg=args.alg, comm=(uid, rank, world))
         else:
             sh = cmf.DeviceShard(N, T, t0, t1, K, L, dtype="f32", device=local_rank, alg=args.alg)

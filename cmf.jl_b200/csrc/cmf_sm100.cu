@@ -11,7 +11,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
+#include <tuple>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -158,6 +161,7 @@ struct cmf_ctx {
     virtual void hals_h_full(void **, void **) { no_multi(); }     // rank 0 of a sharded fit: full-T Q and H buffers (allocated on first use)
     virtual void hals_h_sweep(int full, double, double) { no_multi(); }
     virtual void h_changed() { no_multi(); }                       // invalidates what depends on H (after a halo exchange / scatter)
+    virtual void set_pgd_loss(int, const void *) { no_multi(); }
     virtual void pgd_update_motifs(double, double) { no_multi(); }
     virtual double pgd_update_feature_maps(double, double) { no_multi(); }
     virtual void exchange_buffer(int, void **, int64_t *, int *) { no_multi(); }
@@ -936,6 +940,7 @@ struct Ctx : cmf_ctx {
         a.Wi = Wsrc; a.H = Hsrc; a.X = X.p; a.out = out; a.partial = partial;
         a.N = N; a.K = Kc; a.L = Lc; a.t_lo = t_lo; a.t_hi = t_hi; a.h_lo = h_lo; a.h_hi = h_hi;
         a.flags = flags; a.seed = seed; a.t_global0 = t0; a.noise = noise;
+        a.mask = pgd_mask.n ? pgd_mask.p : nullptr; a.lossf = pgd_loss;
         const int Lpad = (int)(cdiv(Lc, 8) * 8);
         const int HW = BT + Lpad - 1;
         const size_t ws_bytes = (size_t)CONV_LC * BN * sizeof(S);
@@ -1358,7 +1363,7 @@ struct Ctx : cmf_ctx {
 
     // second-generation sweep (kernels_hals.cuh): rounds with a grid barrier, lane = component recurrences, 8 x 8 pull blocks.
     // Returns false when the handle / shape is outside its envelope (the wavefront kernel below then runs).
-    DevBuf<float> h2_Hcm, h2_AD, h2_part;
+    DevBuf<float> h2_Hcm, h2_AD, h2_part, h2_coef;
     int h2_max_ctas = -1;
     bool hals2_sweep(const S *Qp, S *Hp, int64_t Tt, const S *ct, double l1H, double l2H) {
         if constexpr (!std::is_same<S, float>::value) { return false; } else {
@@ -1378,18 +1383,27 @@ struct Ctx : cmf_ctx {
             }
             if (grid > h2_max_ctas) return false;
             const int64_t nC = cdiv(Tt, hals2::CW), Tp = nC * hals2::CW;
-            const size_t ncm = (size_t)(K * Tp), npart = (size_t)G * (size_t)K * hals2::RING * hals2::CW;
+            const size_t ncm = (size_t)hals2::cells_elems(K, nC), npart = (size_t)G * (size_t)K * hals2::RING * hals2::CW;
             if (h2_Hcm.n < ncm) { h2_Hcm.alloc(ncm); h2_AD.alloc(ncm); }
             if (h2_part.n < npart) h2_part.alloc(npart);
             dim3 tb(32, 8), tg((unsigned)cdiv(Tp, 32), (unsigned)cdiv(K, 32));
             hals2::hals2_prepare_kernel<<<tg, tb, 0, stream>>>(Qp, Hp, h2_AD.p, h2_Hcm.p, K, Tt, Tp);
             post_launch();
+            if (h2_coef.n < (size_t)(K * 64)) h2_coef.alloc((size_t)(K * 64));
+            hals2::hals2_coef_kernel<<<(unsigned)cdiv(K * 64, 256), 256, 0, stream>>>(Cf.p, h2_coef.p, K, L, (float)l2H);
+            post_launch();
             hals2::Args a;
+            a.coef = h2_coef.p;
             a.Cf = Cf.p; a.Ct = ct; a.S2 = GS.p; a.Ks = s2_ks; a.ld = s2_ld;
             a.H_cm = h2_Hcm.p; a.AD_cm = h2_AD.p; a.part = h2_part.p;
-            a.K = K; a.L = L; a.T = Tt; a.Tp = Tp; a.nC = nC;
+            a.K = K; a.L = L; a.T = Tt; a.nC = nC;
             a.l1 = (float)l1H; a.l2 = (float)l2H;
             a.G = G; a.n_block_items = n_block; a.n_diag_items = n_diag; a.n_rec = n_rec;
+            DevBuf<long long> dbgbuf;
+            const bool dbg2 = getenv("CMF_HALS_DEBUG") && atoi(getenv("CMF_HALS_DEBUG")) == 1;
+            if (dbg2) dbgbuf.alloc((size_t)8 * grid);
+            a.dbg = dbg2 ? dbgbuf.p : nullptr;
+            a.dbg_mode = getenv("CMF_HALS_DBGMODE") ? atoi(getenv("CMF_HALS_DBGMODE")) : 0;
             void *args[] = {&a};
             prof_begin(PROF_SWEEP);
             CK(cudaLaunchCooperativeKernel((void *)hals2::hals2_sweep_kernel, dim3((unsigned)grid), dim3(hals2::NT), args, smem, stream));
@@ -1397,6 +1411,26 @@ struct Ctx : cmf_ctx {
             post_launch();
             hals2::hals2_finish_kernel<<<dim3((unsigned)cdiv(Tt, 32), (unsigned)cdiv(K, 32)), tb, 0, stream>>>(h2_Hcm.p, Hp, K, Tt, Tp);
             post_launch();
+            if (dbg2) {      // kcycles of work per active round (barrier waits excluded): worst and mean CTA of every role
+                std::vector<long long> hv((size_t)8 * grid);
+                CK(cudaMemcpyAsync(hv.data(), dbgbuf.p, hv.size() * sizeof(long long), cudaMemcpyDeviceToHost, stream));
+                CK(cudaStreamSynchronize(stream));
+                fprintf(stderr, "hals2: SM clock over the launch %lld MHz (clock64 / globaltimer, CTA 0)\n", hv[7]);
+                const char *names[3] = {"block items", "diagonal items", "recurrence warps"};
+                const int lo[4] = {0, n_block, n_block + n_diag, grid};
+                for (int r = 0; r < 3; ++r) {
+                    double worst = 0.0, mean = 0.0; int cnt = 0, wi = -1;
+                    double phw[5] = {0, 0, 0, 0, 0};
+                    for (int i = lo[r]; i < lo[r + 1]; ++i) {
+                        if (hv[8 * i + 1] == 0) continue;
+                        const double v = (double)hv[8 * i] / (double)hv[8 * i + 1] / 1e3;
+                        if (v > worst) { worst = v; wi = i - lo[r]; for (int q = 0; q < 5; ++q) phw[q] = (double)hv[8 * i + 2 + q] / (double)hv[8 * i + 1] / 1e3; }
+                        mean += v; ++cnt;
+                    }
+                    fprintf(stderr, "hals2 %s: %d CTAs, kcycles of work per active round: mean %.1f, worst %.1f (item %d; phases stage %.1f pull %.1f tail/store %.1f final %.1f, barrier wait %.1f); rounds %lld, chunks %lld\n",
+                            names[r], lo[r + 1] - lo[r], cnt ? mean / cnt : 0.0, worst, wi, phw[0], phw[1], phw[2], phw[3], phw[4], (long long)(nC + 4 * (K - 1) + 3), (long long)nC);
+                }
+            }
             return true;
         }
     }
@@ -1459,8 +1493,47 @@ struct Ctx : cmf_ctx {
         pgd_cur_loss = loss;
     }
 
+    // ---- PGD with the pluggable losses of pgd.jl:28-70 (AbsoluteLoss, MaskedLoss): the loss gradient d D / d est is not
+    // linear in (X, est) any more (sign) or carries a mask, so the Gram forms do not apply and the path follows pgd.jl:224-255
+    // literally: conv + loss-gradient epilogue into an N x T scratch, then the W-side correlation (pgd.jl:206-214) resp. the
+    // transposed conv (:218-221) of that scratch, on the SIMT kernels in the handle's type.
+    int pgd_loss = 0;                 // 0 SquareLoss, 1 AbsoluteLoss
+    DevBuf<S> pgd_mask, pgd_ge;       // mask [t][N] (empty = none), loss-gradient scratch [t][N] incl. a zero right halo
+    bool pgd_general() const { return pgd_loss != 0 || pgd_mask.n != 0; }
+    void set_pgd_loss(int lossf, const void *mask_host) override {
+        REQUIRE(alg == CMF_PGD, "the pluggable loss belongs to PGDUpdate handles");
+        REQUIRE(lossf == 0 || lossf == 1, "loss_func must be 0 (SquareLoss) or 1 (AbsoluteLoss)");
+        pgd_loss = lossf;
+        if (mask_host) {
+            pgd_mask.alloc((size_t)(N * Tl));
+            CK(cudaMemcpyAsync(pgd_mask.p, mask_host, pgd_mask.n * sizeof(S), cudaMemcpyHostToDevice, stream));
+            CK(cudaStreamSynchronize(stream));
+        } else pgd_mask.free();
+        if (pgd_general() && pgd_ge.n == 0) pgd_ge.alloc((size_t)((Tl + (L - 1)) * N));
+    }
+    void pgd_loss_gradient() {       // pgd.jl:231: grad!(loss_func, est, est, data)
+        launch_conv(Wi.p, H, K, L, -(L - 1), Tl + (L - 1), 0, Tl, 32, pgd_ge.p, nullptr);
+    }
+    double pgd_loss_eval() {         // pgd.jl:244-245: tensor_conv!(est, W, H); eval(loss_func, data, est)
+        const int nb = conv_nblocks(0, Tl);
+        launch_conv(Wi.p, H, K, L, -(L - 1), Tl + (L - 1), 0, Tl, 64, nullptr, loss_part.p);
+        reduce_scalar(loss_part.p, nb, scal.p);
+        return fetch_scalar(scal.p);
+    }
+
     void pgd_update_motifs(double l1W, double l2W) override {
         REQUIRE(is_first && is_last, "PGD is single-shard");
+        if (pgd_general()) {
+            pgd_loss_gradient();
+            launch_corr(pgd_ge.p, N, N, Tl + (L - 1), nsplit_w, split_w, denW.p, nullptr);          // gradW (pgd.jl:206-214)
+            pgd_penalty_kernel<S><<<(unsigned)cdiv(KL() * N, 256), 256, 0, stream>>>(denW.p, Wi.p, (S)l1W, (S)l2W, KL() * N);
+            post_launch();
+            pgd_step(Wi.p, denW.p, KL() * N, pgd_stepW);
+            mark_w_dirty();
+            numH_valid = false;
+            pgd_adapt(pgd_loss_eval(), pgd_stepW);
+            return;
+        }
         w_partials();
         if (tc_active()) tc_denomW();
         else { build_G(); launch_gemm<false>(GS.p, Wi.p, denW.p, KL(), N, KL(), KL(), N, N); }
@@ -1474,6 +1547,17 @@ struct Ctx : cmf_ctx {
 
     double pgd_update_feature_maps(double l1H, double l2H) override {
         REQUIRE(is_first && is_last, "PGD is single-shard");
+        if (pgd_general()) {
+            pgd_loss_gradient();
+            launch_transconv(Wi.p, pgd_ge.p, denH.p, N, K, L, N, Tl, Tl + (L - 1));                   // gradH (pgd.jl:218-221)
+            pgd_penalty_kernel<S><<<(unsigned)cdiv(Tl * K, 256), 256, 0, stream>>>(denH.p, H, (S)l1H, (S)l2H, Tl * K);
+            post_launch();
+            pgd_step(H, denH.p, Tl * K, pgd_stepH);
+            gram_valid = false; fds.h_dirty = true;
+            numH_valid = false;
+            pgd_adapt(pgd_loss_eval(), pgd_stepH);
+            return pgd_cur_loss;
+        }
         if (tc_active()) tc_transconv();
         else launch_transconv(Wi.p, X.p, numH.p, N, K, L, N, Tl, Tl + (L - 1));
         lag_tables();
@@ -1974,21 +2058,39 @@ int cmf_comm_unique_id(void *id_out) {
     });
 }
 
+// One communicator per (device, rank, world) of this process is kept alive and reused by later handles created with
+// unique_id == NULL (building one costs ~0.5 s; a fit does not need a new one).  Communicators in the cache live until exit.
+struct CommKey { int device, rank, world; bool operator<(const CommKey &o) const { return std::tie(device, rank, world) < std::tie(o.device, o.rank, o.world); } };
+static std::map<CommKey, ncclComm_t> g_comm_cache;
+static std::mutex g_comm_mu;
+
 int cmf_create_rank(cmf_handle *out, int64_t N, int64_t T, int64_t K, int64_t L, int dtype, int alg, int device,
                     const void *unique_id, int rank, int world) {
     return guarded([&] {
-        REQUIRE(out != nullptr && unique_id != nullptr, "null pointer");
+        REQUIRE(out != nullptr, "null pointer");
         REQUIRE(world >= 1 && rank >= 0 && rank < world, "need 0 <= rank < world");
         DevRestore g;
         int64_t a0, a1;
         shard_range(T, world, rank, &a0, &a1);
         cmf_ctx *c = make_ctx(N, T, a0, a1, K, L, dtype, alg, device);
         try {
-            ncclUniqueId id;
-            memcpy(&id, unique_id, sizeof(id));
             ncclComm_t comm = nullptr;
-            if (world > 1) NK(nccl().CommInitRank(&comm, world, id, rank));
-            attach_comm(c, comm, rank, world, true);
+            if (world > 1) {
+                std::lock_guard<std::mutex> lk(g_comm_mu);
+                const CommKey key{device, rank, world};
+                if (unique_id == nullptr) {
+                    auto it = g_comm_cache.find(key);
+                    REQUIRE(it != g_comm_cache.end(), "unique_id == NULL reuses this process's communicator for (device, rank, world), but none exists yet");
+                    comm = it->second;
+                } else {
+                    ncclUniqueId id;
+                    memcpy(&id, unique_id, sizeof(id));
+                    CK(cudaSetDevice(device));
+                    NK(nccl().CommInitRank(&comm, world, id, rank));
+                    g_comm_cache[key] = comm;            // replaces (and leaks until exit) an older one: it may still serve a live handle
+                }
+            }
+            attach_comm(c, comm, rank, world, false);
         } catch (...) { delete c; throw; }
         *out = c;
     });
@@ -2272,6 +2374,10 @@ static int current_device() {
     int d = 0;
     if (cudaGetDevice(&d) != cudaSuccess) d = 0;
     return d;
+}
+
+int cmf_set_pgd_loss(cmf_handle h, int loss_func, const void *mask) {
+    return guarded([&] { REQUIRE(h && !h->multi, "single-rank call"); DevGuard g(h->device); h->set_pgd_loss(loss_func, mask); });
 }
 
 int cmf_tensor_conv(int64_t N, int64_t T, int64_t K, int64_t L, int dtype, const void *W, const void *H, void *out) {

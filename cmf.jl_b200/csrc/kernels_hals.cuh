@@ -44,6 +44,7 @@ constexpr int GS = 8;           // components per group
 constexpr int STAG = 4;         // chunks between consecutive components
 constexpr int RING = 32;        // chunks a block partial stays alive: written in round c+32g-1, read no later than c+32g+28
 constexpr int LMAX = 32;
+static_assert(CW == 4 * NT, "the hand-over loop covers a chunk with one float4 per thread");
 constexpr int WIN = CW + 2 * (LMAX - 1);      // staged window of Delta H (columns t0-(L-1) .. t0+CW+(L-1)-1), sized for L = 32
 constexpr int QP = ((WIN + 7) >> 3) | 1;      // slots per plane of the 8-plane layout (odd: conflict-free)
 constexpr int WINQ = 8 * QP;                  // words per staged source
@@ -53,42 +54,104 @@ struct Args {
     const float *Ct;      // [w-1][dd+L-1][k][k'] truncated tables (w = 1..L-1), nullptr when L == 1
     const float *S2;      // W W' (truncated self tables of the tail job)
     int64_t Ks, ld;       // addressing of S2
-    float *H_cm;          // [K][Tp]  H, component-major (old value until the recurrence overwrites it with the new one)
-    float *AD_cm;         // [K][Tp]  Q (from hals2_prepare_kernel), then a (hand-over to the recurrence), then Delta H
-    float *part;          // [G][K][RING][CW] block partials, indexed by source group
-    int64_t K, L, T, Tp, nC;
+    float *H_cm;          // cells (see cell_at): H, old value until the recurrence overwrites it with the new one
+    float *AD_cm;         // cells: Q (from hals2_prepare_kernel), then a (hand-over to the recurrence), then Delta H
+    float *part;          // [RING][G][K][CW] block partials, indexed by ring slot and source group
+    const float *coef;    // [K][64] self lag table of every component scaled by 1/(c0+eps+l2): 16 even-aligned pairs (cs[2m], cs[2m+1]), then
+                          // 16 odd-aligned pairs (cs[2m+1], cs[2m+2]) (hals2_coef_kernel); cs[0] = cs[32] = 0
+    int64_t K, L, T, nC;
     float l1, l2;
     int G;                // groups of 8 components
     int n_block_items, n_diag_items, n_rec;
+    int dbg_mode;         // timing experiments (wrong results): bit 1 = the recurrence skips its global loads and stores
+    long long *dbg;       // optional [grid][8]: cycles spent working (barrier waits excluded), rounds with work
 };
 
 __device__ __forceinline__ float ldcg(const float *p) { return __ldcg(p); }
 
-// Stages Delta H of `nsrc` sources (components k0 .. k0+nsrc-1) over the window of chunk c into the 8-plane layout.
-// Columns outside [0, Tint) read as zero (sources in the truncated tail go through the tail tables instead).
-__device__ __forceinline__ void stage_window(float *Dwin, const Args &a, int64_t k0, int nsrc, int64_t c, int64_t Tint) {
+// Working layout of H and of the Q / a / Delta H array: CELLS of CW columns of one component, ordered by the round that
+// works on them: cell (k, c) lives at slice d = c + STAG*k, position k inside the slice.  What one round touches is then
+// contiguous (the 32 cells of a recurrence warp are 128 KB, all the cells of a round 512 KB at K = 128), where a plain
+// component-major array would spread a warp's lanes over rows 4*Tp bytes apart -- one 2 MB page per lane, all in the same
+// TLB set (measured: every load of the kernel then took ~4000 cycles).
+__host__ __device__ __forceinline__ int64_t cell_at(int64_t k, int64_t t, int64_t K) {
+    const int64_t c = t / CW;
+    return ((c + (int64_t)STAG * k) * K + k) * CW + (t - c * CW);
+}
+__host__ __device__ __forceinline__ int64_t cells_elems(int64_t K, int64_t nC) { return (nC + (int64_t)STAG * (K - 1)) * K * CW; }
+__device__ __forceinline__ int64_t part_at(int64_t slot, int64_t gp, int64_t k, int64_t K, int G) { return ((slot * G + gp) * K + k) * CW; }
+
+// FP32 on sm_100 runs at full rate only through the packed FFMA2 (two fp32 FMAs per instruction on a 64-bit register
+// pair; a scalar FFMA occupies the same issue slots).  The pull therefore processes the staged sources two at a time: the
+// window holds (source 2p, source 2p+1) pairs, the table (C[2p], C[2p+1]) pairs, and every accumulator is a pair
+// (contribution of the even source, contribution of the odd source) that is added up at the end.
+//
+// Staging of Delta H of `nsrc` sources (components k0 .. k0+nsrc-1) over the window of chunk c, columns
+// [c*CW - (L-1), (c+1)*CW + (L-1)), into the 8-plane pair layout (an odd last source is paired with zeros; columns outside
+// [0, Tint) are zero: sources in the truncated tail go through the tail tables instead).  Split in two halves so that the
+// loads (128-bit, from L2 / HBM: written by other SMs in earlier rounds, > 1000 cycles away) can be in flight while other
+// work runs: stage_load fills registers, stage_store scatters them into shared memory.  Address arithmetic is per 4 columns.
+constexpr int SCH = (WIN + 3 + 3) / 4;                   // aligned 4-column pieces covering a window
+constexpr int SIT = (SCH + NT - 1) / NT;                 // pieces per thread and source
+struct StageRegs { float4 va[GS / 2][SIT], vb[GS / 2][SIT]; };
+
+__device__ __forceinline__ void stage_load(StageRegs &r, const Args &a, int64_t k0, int nsrc, int64_t c, int64_t Tint) {
     const int Lm = (int)a.L - 1, WW = CW + 2 * Lm;
-    const int64_t tbase = c * CW - Lm;
-    for (int idx = threadIdx.x; idx < nsrc * WW; idx += NT) {
-        const int s = idx / WW, i = idx - s * WW;
-        const int64_t t = tbase + i;
-        float v = 0.f;
-        if (t >= 0 && t < Tint) v = ldcg(a.AD_cm + (k0 + s) * a.Tp + t);
-        Dwin[s * WINQ + (i & 7) * QP + (i >> 3)] = v;
+    const int64_t tbase = c * CW - Lm, ta0 = tbase - (((tbase % 4) + 4) % 4);     // first aligned piece
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int p = 0; p < GS / 2; ++p) {
+#pragma unroll
+        for (int it = 0; it < SIT; ++it) {
+            r.va[p][it] = z4; r.vb[p][it] = z4;
+            const int64_t t = ta0 + 4 * (int64_t)(threadIdx.x + it * NT);
+            if (2 * p < nsrc && t < tbase + WW && t >= 0 && t < Tint) {
+                const int64_t cc = t >> 10, col = t & (CW - 1), ka = k0 + 2 * p;
+                static_assert(CW == 1024, "shift / mask above");
+                r.va[p][it] = __ldcg(reinterpret_cast<const float4 *>(a.AD_cm + ((cc + (int64_t)STAG * ka) * a.K + ka) * CW + col));
+                if (2 * p + 1 < nsrc)
+                    r.vb[p][it] = __ldcg(reinterpret_cast<const float4 *>(a.AD_cm + ((cc + (int64_t)STAG * (ka + 1)) * a.K + ka + 1) * CW + col));
+            }
+        }
     }
 }
 
-// acc[r][q] += sum over the staged sources and lags of D[src][t'+(L-1)-j] * tab[src][j][q],  t' = 8*cgp + r, q = 0..NTG-1.
-// tab: [nsrc][NLP][8] floats (lag rows padded with zeros to NLP = a multiple of 8), tq0 = first target column of the table.
+__device__ __forceinline__ void stage_store(float2 *Dwin2, const StageRegs &r, const Args &a, int nsrc, int64_t c, int64_t Tint) {
+    const int Lm = (int)a.L - 1, WW = CW + 2 * Lm;
+    const int64_t tbase = c * CW - Lm, ta0 = tbase - (((tbase % 4) + 4) % 4);
+#pragma unroll
+    for (int p = 0; p < GS / 2; ++p) {
+        if (2 * p >= nsrc) break;
+        float2 *dst = Dwin2 + p * WINQ;
+#pragma unroll
+        for (int it = 0; it < SIT; ++it) {
+            const int64_t t = ta0 + 4 * (int64_t)(threadIdx.x + it * NT);
+            const float xa[4] = {r.va[p][it].x, r.va[p][it].y, r.va[p][it].z, r.va[p][it].w};
+            const float xb[4] = {r.vb[p][it].x, r.vb[p][it].y, r.vb[p][it].z, r.vb[p][it].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = (int)(t + e - tbase);
+                if (i >= 0 && i < WW) {
+                    const bool ok = t + e >= 0 && t + e < Tint;      // the piece may straddle Tint: zero beyond it
+                    dst[(i & 7) * QP + (i >> 3)] = make_float2(ok ? xa[e] : 0.f, ok ? xb[e] : 0.f);
+                }
+            }
+        }
+    }
+}
+
+// acc[r][q] (pair: even / odd source) += D[src][t'+(L-1)-j] * tab[src][j][q] over `npair` staged source pairs and all lags,
+// t' = 8*cgp + r, q = 0..NTG-1.  tab2: [npair][NLP][8] pairs (lag rows padded with zeros to NLP = a multiple of 8), tq0 = first
+// target column of the table.
 template <int NTG>
-__device__ __forceinline__ void pull_tile(float (&acc)[8][NTG], const float *Dwin, const float *tab, int nsrc, int L, int cgp, int tq0) {
+__device__ __forceinline__ void pull_tile(float2 (&acc)[8][NTG], const float2 *Dwin2, const float2 *tab2, int npair, int L, int cgp, int tq0) {
     const int nl = 2 * L - 1, NLP = (nl + 7) & ~7;
     const int ib = 8 * cgp + 2 * (L - 1);
-    for (int s = 0; s < nsrc; ++s) {
-        const float *dw = Dwin + s * WINQ;
-        const float *tb = tab + (size_t)s * NLP * 8 + tq0;
-        float w[8];
-        w[0] = 0.f;
+    for (int sp = 0; sp < npair; ++sp) {
+        const float2 *dw = Dwin2 + sp * WINQ;
+        const float2 *tb = tab2 + (size_t)sp * NLP * 8 + tq0;
+        float2 w[8];
+        w[0] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int o = 1; o < 8; ++o) { const int i = ib + o; w[o] = dw[(i & 7) * QP + (i >> 3)]; }
         for (int j0 = 0; j0 < nl; j0 += 8) {
@@ -97,61 +160,110 @@ __device__ __forceinline__ void pull_tile(float (&acc)[8][NTG], const float *Dwi
                 const int j = j0 + jj;
                 const int in = max(ib - j, 0);              // window index entering at this step (column r = 0); padded lags multiply by zero
                 w[(8 - jj) & 7] = dw[(in & 7) * QP + (in >> 3)];
-                float cq[NTG];
+                float2 cq[NTG];
 #pragma unroll
                 for (int q = 0; q < NTG; ++q) cq[q] = tb[j * 8 + q];
 #pragma unroll
                 for (int r = 0; r < 8; ++r)
 #pragma unroll
-                    for (int q = 0; q < NTG; ++q) acc[r][q] = fmaf(w[(r - jj + 8) & 7], cq[q], acc[r][q]);
+                    for (int q = 0; q < NTG; ++q) acc[r][q] = __ffma2_rn(w[(r - jj + 8) & 7], cq[q], acc[r][q]);
             }
         }
     }
 }
 
-// table slice tab[s][j][q] = C[k0s+s, k0t+q, j-(L-1)] (zero where the pair is not a (source < target) pair or out of range)
-__device__ __forceinline__ void load_table(float *tab, const Args &a, int64_t k0s, int64_t k0t, bool diagonal) {
+// table slice as source pairs: tab2[p][j][q] = (C[k0s+2p, k0t+q, j-(L-1)], C[k0s+2p+1, k0t+q, j-(L-1)]), zero where the pair is
+// not a (source < target) pair or out of range
+__device__ __forceinline__ void load_table(float2 *tab2, const Args &a, int64_t k0s, int64_t k0t, bool diagonal) {
     const int L = (int)a.L, nl = 2 * L - 1, NLP = (nl + 7) & ~7;
+    float *tab = reinterpret_cast<float *>(tab2);
     for (int idx = threadIdx.x; idx < GS * NLP * 8; idx += NT) {
         const int q = idx & 7, j = (idx >> 3) % NLP, s = idx / (8 * NLP);
         const int64_t ks = k0s + s, kt = k0t + q;
         float v = 0.f;
         if (j < nl && ks < a.K && kt < a.K && (!diagonal || ks < kt)) v = a.Cf[((int64_t)j * a.K + ks) * a.K + kt];
-        tab[idx] = v;
+        tab[2 * (((s >> 1) * NLP + j) * 8 + q) + (s & 1)] = v;
     }
 }
 
-// 16 columns of the lane's recurrence (HH = which half of the 32-slot pending window they occupy: static register indices).
-// an / hn hold a and h of these columns on entry and of the next 16 columns on exit (prefetch).
-template <int HH>
-__device__ __forceinline__ void rec_half(float (&p)[32], const float (&cs)[32], float4 (&an)[4], float4 (&hn)[4], float *adp, float *hp,
-                                         int64_t t0, int i0, int nv, bool on, bool more) {
-    float av[16], hv[16];
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-        av[4 * v] = an[v].x; av[4 * v + 1] = an[v].y; av[4 * v + 2] = an[v].z; av[4 * v + 3] = an[v].w;
-        hv[4 * v] = hn[v].x; hv[4 * v + 1] = hn[v].y; hv[4 * v + 2] = hn[v].z; hv[4 * v + 3] = hn[v].w;
-    }
-    if (more && on) {
+// 64-bit register pairs for the recurrence: the coefficient pairs and the pending window stay packed for the whole kernel
+// (as float2 the compiler splits them into scalars and rebuilds the aligned pairs FFMA2 needs with two moves per use)
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float x, float y) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
+__device__ __forceinline__ float lo_of(u64 v) { float x, y; asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); return x; }
+__device__ __forceinline__ float hi_of(u64 v) { float x, y; asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); return y; }
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
+// The recurrence warp streams a and h of its 32 cells through a shared-memory ring filled with cp.async (no registers held
+// by loads in flight): RSTG stages of 16 columns, RPRE stages ahead of the one being consumed -- the cells were written by
+// other SMs one round earlier and a load of such a line takes well over 1000 cycles (measured), one stage of compute ~700.
+constexpr int RSTG = 8, RPRE = 6, RLS = 20;         // lane stride of a stage in floats (16 + 4: conflict-free 128-bit shared loads)
+__device__ __forceinline__ void cp_async16(float *smem_dst, const float *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// issues the copies of half `h` (16 columns starting at column 16*h of the lane's cell) into its ring stage; always commits
+__device__ __forceinline__ void rec_fetch(float *ring, const float *adp, const float *hp, int64_t t0, int h, int lane, bool on) {
+    if (on && h < CW / 16) {
+        float *st = ring + (h % RSTG) * (2 * 32 * RLS) + lane * RLS;
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-            an[v] = __ldcg(reinterpret_cast<const float4 *>(adp + t0 + i0 + 16) + v);
-            hn[v] = __ldcg(reinterpret_cast<const float4 *>(hp + t0 + i0 + 16) + v);
+            cp_async16(st + 4 * v, adp + t0 + 16 * h + 4 * v);
+            cp_async16(st + 32 * RLS + 4 * v, hp + t0 + 16 * h + 4 * v);
         }
     }
+    cp_async_commit();
+}
+
+// 16 columns of the lane's recurrence (HH = which half of the 32-slot pending window they occupy: static register indices).
+// The pending window is kept as 16 register pairs (p[2m], p[2m+1]) and updated with FFMA2: for an even column u the pair of
+// slots (u+2m, u+2m+1) takes d * (cs[2m], cs[2m+1]) (csE), for an odd one the pair (u+2m+1, u+2m+2) takes
+// d * (cs[2m+1], cs[2m+2]) (csO); cs[0] = cs[32] = 0, so the freshly cleared slot u is touched with a zero coefficient only.
+// FULL: every column of the half is an interior column of every active lane (no masks).
+template <int HH, bool FULL>
+__device__ __forceinline__ void rec_half(u64 (&p2)[16], const u64 (&csE)[16], const u64 (&csO)[16], float *ring, float *adp, float *hp,
+                                         int64_t t0, int h, int lane, int nv, bool on) {
+    float av[16], hv[16];
+    cp_async_wait<RPRE - 1>();                          // the copies of half h (this lane's own) have landed
+    {
+        const float *st = ring + (h % RSTG) * (2 * 32 * RLS) + lane * RLS;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const float4 x = *reinterpret_cast<const float4 *>(st + 4 * v), y = *reinterpret_cast<const float4 *>(st + 32 * RLS + 4 * v);
+            av[4 * v] = x.x; av[4 * v + 1] = x.y; av[4 * v + 2] = x.z; av[4 * v + 3] = x.w;
+            hv[4 * v] = y.x; hv[4 * v + 1] = y.y; hv[4 * v + 2] = y.z; hv[4 * v + 3] = y.w;
+        }
+    }
+    rec_fetch(ring, adp, hp, t0, h + RPRE, lane, on);   // stage (h + RPRE) % RSTG was consumed RSTG - RPRE halves ago
+    const int i0 = 16 * h;
 #pragma unroll
     for (int uu = 0; uu < 16; ++uu) {
         constexpr int base = HH * 16;
         const int u = base + uu;
-        const bool ok = i0 + uu < nv;
-        float vn = av[uu] - p[u];
+        const float plo = lo_of(p2[u >> 1]), phi = hi_of(p2[u >> 1]);
+        const float pu = (u & 1) ? phi : plo;
+        float vn = av[uu] - pu;
         vn = vn > 0.f ? vn : 0.f;
-        const float d = ok ? vn - hv[uu] : 0.f;
-        hv[uu] = ok ? vn : hv[uu];
-        av[uu] = ok ? d : av[uu];                       // tail columns keep the raw qeff for the tail job
-        p[u] = 0.f;                                     // this slot now stands for column t + 32
+        float d = vn - hv[uu];
+        if (FULL) {
+            hv[uu] = vn;
+            av[uu] = d;
+        } else {
+            const bool ok = i0 + uu < nv;
+            d = ok ? d : 0.f;
+            hv[uu] = ok ? vn : hv[uu];
+            av[uu] = ok ? d : av[uu];                   // tail columns keep the raw qeff for the tail job
+        }
+        p2[u >> 1] = (u & 1) ? pack2(plo, 0.f) : pack2(0.f, phi);   // this slot now stands for column t + 32
+        const u64 dd = pack2(d, d);
 #pragma unroll
-        for (int j = 1; j < 32; ++j) p[(u + j) & 31] = fmaf(d, cs[j], p[(u + j) & 31]);
+        for (int m = 0; m < 16; ++m) {
+            if (u & 1) { const int x = ((u + 2 * m + 1) & 31) >> 1; p2[x] = ffma2(dd, csO[m], p2[x]); }
+            else       { const int x = ((u + 2 * m) & 31) >> 1;     p2[x] = ffma2(dd, csE[m], p2[x]); }
+        }
     }
     if (on) {
 #pragma unroll
@@ -166,19 +278,29 @@ __global__ void __launch_bounds__(NT, 1) hals2_sweep_kernel(Args a) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int L = (int)a.L, Lm = L - 1;
-    const int64_t K = a.K, T = a.T, Tp = a.Tp, nC = a.nC;
+    const int64_t K = a.K, T = a.T, nC = a.nC;
     const int64_t Tint = T - Lm;                               // columns t < Tint use the full lag window
     const int64_t n_rounds = nC + (int64_t)STAG * (K - 1) + 3;
     const int b = blockIdx.x, tid = threadIdx.x;
     const float eps = 2.220446049250313e-16f;
+    long long wk_cyc = 0, wk_rounds = 0, wk_t0 = 0, ph_t = 0, ph[5] = {0, 0, 0, 0, 0};
+    const long long kern_t0 = clock64();
+    unsigned long long kern_ns0 = 0;
+    if (a.dbg && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(kern_ns0));
+#define H2_BEGIN() do { if (a.dbg && tid == 0) { wk_t0 = clock64(); ph_t = wk_t0; } } while (0)
+#define H2_END() do { if (a.dbg && tid == 0) { wk_cyc += clock64() - wk_t0; ++wk_rounds; } } while (0)
+#define H2_PHASE(i) do { if (a.dbg && tid == 0) { const long long n_ = clock64(); ph[i] += n_ - ph_t; ph_t = n_; } } while (0)
+#define H2_REPORT() do { if (a.dbg && tid == 0) { a.dbg[8 * b] = wk_cyc; a.dbg[8 * b + 1] = wk_rounds; for (int i_ = 0; i_ < 5; ++i_) a.dbg[8 * b + 2 + i_] = ph[i_]; \
+        unsigned long long ns1_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns1_)); \
+        a.dbg[8 * b + 7] = (long long)((double)(clock64() - kern_t0) * 1000.0 / (double)(ns1_ - kern_ns0)); } } while (0)   /* SM MHz over the launch */
 
     if (b < a.n_block_items) {
         // ============================================================ block item (g, g'), g' < g
         int g = 1, rem = b;
         while (rem >= g) { rem -= g; ++g; }                     // items enumerated as (1,0), (2,0), (2,1), (3,0), ...
         const int gp = rem;
-        float *Dwin = reinterpret_cast<float *>(smem_raw);      // [8][WINQ]
-        float *tab = Dwin + GS * WINQ;                          // [8][NLP][8]
+        float2 *Dwin = reinterpret_cast<float2 *>(smem_raw);    // [4 source pairs][WINQ]
+        float2 *tab = Dwin + (GS / 2) * WINQ;                   // [4][NLP][8]
         load_table(tab, a, (int64_t)gp * GS, (int64_t)g * GS, false);
         __syncthreads();
         const int cgp = tid & 127, th = tid >> 7;               // column group (8 columns), half of the targets
@@ -187,62 +309,112 @@ __global__ void __launch_bounds__(NT, 1) hals2_sweep_kernel(Args a) {
         for (int64_t s = 0; s < n_rounds; ++s) {
             const int64_t c = s + 1 - (int64_t)STAG * GS * g;
             if (c >= 0 && c < nC) {
-                stage_window(Dwin, a, (int64_t)gp * GS, nsrc, c, Tint);
+                H2_BEGIN();
+                {
+                    StageRegs sr;
+                    stage_load(sr, a, (int64_t)gp * GS, nsrc, c, Tint);
+                    stage_store(Dwin, sr, a, nsrc, c, Tint);
+                }
                 __syncthreads();
-                float acc[8][4];
+                H2_PHASE(0);
+                float2 acc[8][4];
 #pragma unroll
                 for (int r = 0; r < 8; ++r)
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[r][q] = 0.f;
-                pull_tile<4>(acc, Dwin, tab, nsrc, L, cgp, th * 4);
+                    for (int q = 0; q < 4; ++q) acc[r][q] = make_float2(0.f, 0.f);
+                pull_tile<4>(acc, Dwin, tab, (nsrc + 1) / 2, L, cgp, th * 4);
+                H2_PHASE(1);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int64_t kt = (int64_t)g * GS + th * 4 + q;
                     if (kt < K) {
-                        float *o = a.part + (((int64_t)gp * K + kt) * RING + (c % RING)) * CW + 8 * cgp;
-                        *reinterpret_cast<float4 *>(o) = make_float4(acc[0][q], acc[1][q], acc[2][q], acc[3][q]);
-                        *reinterpret_cast<float4 *>(o + 4) = make_float4(acc[4][q], acc[5][q], acc[6][q], acc[7][q]);
+                        float *o = a.part + part_at(c % RING, gp, kt, K, a.G) + 8 * cgp;
+                        *reinterpret_cast<float4 *>(o) = make_float4(acc[0][q].x + acc[0][q].y, acc[1][q].x + acc[1][q].y, acc[2][q].x + acc[2][q].y, acc[3][q].x + acc[3][q].y);
+                        *reinterpret_cast<float4 *>(o + 4) = make_float4(acc[4][q].x + acc[4][q].y, acc[5][q].x + acc[5][q].y, acc[6][q].x + acc[6][q].y, acc[7][q].x + acc[7][q].y);
                     }
                 }
                 __syncthreads();
+                H2_PHASE(2);
+                H2_END();
             }
             grid.sync();
         }
+        H2_REPORT();
     } else if (b < a.n_block_items + a.n_diag_items) {
         // ============================================================ diagonal item (g): finalises qeff of its 8 targets
         const int g = b - a.n_block_items;
-        float *Dwin = reinterpret_cast<float *>(smem_raw);      // [8][WINQ]
-        float *tab = Dwin + GS * WINQ;                          // [8][NLP][8]
-        float *qsum = tab + GS * (((2 * LMAX - 1) + 7) & ~7) * 8;   // [CW]
+        float2 *Dwin0 = reinterpret_cast<float2 *>(smem_raw);   // 2 x [4 source pairs][WINQ]: the window of the next target loads
+        float2 *tab = Dwin0 + 2 * (GS / 2) * WINQ;              // [4][NLP][8]                 while the current one is pulled
+        float *qsum = reinterpret_cast<float *>(tab + (GS / 2) * (((2 * LMAX - 1) + 7) & ~7) * 8);   // [CW]
         load_table(tab, a, (int64_t)g * GS, (int64_t)g * GS, true);
         __syncthreads();
         const int cgp = tid & 127, th = tid >> 7;
+        // target i of the group is active in round s when its chunk c = s - STAG*k exists
+        auto active = [&](int i, int64_t s) -> bool {
+            const int64_t k = (int64_t)g * GS + i, c = s - (int64_t)STAG * k;
+            return i < GS && k < K && c >= 0 && c < nC;
+        };
         for (int64_t s = 0; s < n_rounds; ++s) {
+            H2_BEGIN();
+            int buf = 0;
+            {
+                // window of the first active target of the round (the later ones are loaded during the previous target's pull)
+                int first = 0;
+                while (first < GS && !active(first, s)) ++first;
+                if (first > 0 && first < GS) {
+                    StageRegs sr;
+                    const int64_t cf = s - (int64_t)STAG * ((int64_t)g * GS + first);
+                    stage_load(sr, a, (int64_t)g * GS, first, cf, Tint);
+                    stage_store(Dwin0, sr, a, first, cf, Tint);
+                }
+            }
             for (int i = 0; i < GS; ++i) {
                 const int64_t k = (int64_t)g * GS + i;
                 const int64_t c = s - (int64_t)STAG * k;
                 if (k >= K || c < 0 || c >= nC) continue;      // uniform over the CTA
+                float2 *Dwin = Dwin0 + buf * (GS / 2) * WINQ;
+                // loads of the NEXT active target's window go out now and are stored into the other buffer after this pull
+                int nxt = i + 1;
+                while (nxt < GS && !active(nxt, s)) ++nxt;
+                const int64_t cn = s - (int64_t)STAG * ((int64_t)g * GS + nxt);
+                StageRegs srn;
+                if (nxt < GS) stage_load(srn, a, (int64_t)g * GS, nxt, cn, Tint);
                 const int64_t t0 = c * CW;
-                // ---- pull from the earlier components of the own group (sources g*8 .. k-1): the two thread halves split the sources
-                float acc[8][1];
+                // the loads of the hand-over (Q, H and the block partials of this cell: L2 / HBM) are issued now and consumed
+                // after the pull, so their latency hides behind it
+                const int col = 4 * tid;
+                const int64_t t = t0 + col;
+                const float4 q4 = __ldcg(reinterpret_cast<const float4 *>(a.AD_cm + cell_at(k, t, K)));      // Q[k][t..t+3]
+                const float4 h4 = __ldcg(reinterpret_cast<const float4 *>(a.H_cm + cell_at(k, t, K)));
+                float4 pv[16];
 #pragma unroll
-                for (int r = 0; r < 8; ++r) acc[r][0] = 0.f;
+                for (int gp = 0; gp < 16; ++gp)
+                    pv[gp] = (gp < g) ? __ldcg(reinterpret_cast<const float4 *>(a.part + part_at(c % RING, gp, k, K, a.G) + col))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                // ---- pull from the earlier components of the own group (sources g*8 .. k-1): the two thread halves split the sources
+                float2 acc[8][1];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) acc[r][0] = make_float2(0.f, 0.f);
+                __syncthreads();                                // this target's window is complete in shared memory
                 if (i > 0) {
-                    stage_window(Dwin, a, (int64_t)g * GS, i, c, Tint);
-                    __syncthreads();
-                    const int s_lo = th == 0 ? 0 : (i + 1) / 2, s_hi = th == 0 ? (i + 1) / 2 : i;
-                    if (s_hi > s_lo) pull_tile<1>(acc, Dwin + s_lo * WINQ, tab + (size_t)s_lo * (((2 * L - 1) + 7) & ~7) * 8, s_hi - s_lo, L, cgp, i);
+                    H2_PHASE(0);
+                    const int npair = (i + 1) / 2;              // the two thread halves split the source pairs
+                    const int p_lo = th == 0 ? 0 : (npair + 1) / 2, p_hi = th == 0 ? (npair + 1) / 2 : npair;
+                    if (p_hi > p_lo) pull_tile<1>(acc, Dwin + p_lo * WINQ, tab + (size_t)p_lo * (((2 * L - 1) + 7) & ~7) * 8, p_hi - p_lo, L, cgp, i);
                 }
                 if (th == 1) {
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) qsum[8 * cgp + r] = acc[r][0];
+                    for (int r = 0; r < 8; ++r) qsum[8 * cgp + r] = acc[r][0].x + acc[r][0].y;
                 }
                 __syncthreads();
                 if (th == 0) {
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) qsum[8 * cgp + r] += acc[r][0];
+                    for (int r = 0; r < 8; ++r) qsum[8 * cgp + r] += acc[r][0].x + acc[r][0].y;
                 }
+                if (nxt < GS) stage_store(Dwin0 + (buf ^ 1) * (GS / 2) * WINQ, srn, a, nxt, cn, Tint);
+                buf ^= 1;
                 __syncthreads();
+                H2_PHASE(1);
                 // ---- truncated tail: sources t >= Tint of ALL earlier components with the tables C_w (w = T - t); work item =
                 //      (target column, block of earlier components), block sums added in a fixed order (deterministic)
                 if (k > 0 && Lm > 0 && t0 + CW + Lm > Tint) {
@@ -251,7 +423,7 @@ __global__ void __launch_bounds__(NT, 1) hals2_sweep_kernel(Args a) {
                     const int ncol = (int)(c_hi - c_lo);          // <= 2 (L-1)
                     const int CH = (int)((k + 15) / 16 > 8 ? (k + 15) / 16 : 8);
                     const int nch = (int)((k + CH - 1) / CH);     // <= 16
-                    float *tpart = Dwin;                          // [nch][64]
+                    float *tpart = reinterpret_cast<float *>(Dwin);  // [nch][64] (this target's window: its pull is done)
                     if (ncol > 0) {
                         for (int it = tid; it < ncol * nch; it += NT) {
                             const int ci = it % ncol, ch = it / ncol;
@@ -264,7 +436,7 @@ __global__ void __launch_bounds__(NT, 1) hals2_sweep_kernel(Args a) {
                             for (int64_t t = ta; t <= tb; ++t) {
                                 const int64_t dd = tp - t, w = T - t;
                                 const float *ct = a.Ct + ((((w - 1) * (2 * a.L - 1) + (dd + Lm)) * K + k) * K);
-                                for (int64_t kp = kp_lo; kp < kp_hi; ++kp) accd += (double)ldcg(a.AD_cm + kp * Tp + t) * (double)ct[kp];
+                                for (int64_t kp = kp_lo; kp < kp_hi; ++kp) accd += (double)ldcg(a.AD_cm + cell_at(kp, t, K)) * (double)ct[kp];
                             }
                             tpart[ch * 64 + ci] = (float)accd;
                         }
@@ -277,22 +449,35 @@ __global__ void __launch_bounds__(NT, 1) hals2_sweep_kernel(Args a) {
                     }
                     __syncthreads();
                 }
+                H2_PHASE(2);
                 // ---- Q + the block partials in the fixed order g' = 0 .. g-1 + the own-group pull, and the hand-over
                 const float c0 = a.Cf[((int64_t)Lm * K + k) * K + k];
                 const float inv = 1.f / (c0 + eps + a.l2);
-                for (int col = tid; col < CW; col += NT) {
-                    const int64_t t = t0 + col;
-                    if (t >= T) continue;
-                    float q = ldcg(a.AD_cm + k * Tp + t);                                    // Q[k][t]
-                    for (int gp = 0; gp < g; ++gp) q += ldcg(a.part + (((int64_t)gp * K + k) * RING + (c % RING)) * CW + col);
-                    q += qsum[col];
-                    const float h = ldcg(a.H_cm + k * Tp + t);
-                    a.AD_cm[k * Tp + t] = (t < Tint) ? (h * c0 - q - a.l1) * inv : q;        // tail columns keep the raw qeff
+                {
+                    // 4 consecutive columns per thread (CW == 4 * NT)
+                    float qv[4] = {q4.x, q4.y, q4.z, q4.w};
+                    const float hv4[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+                    for (int gp = 0; gp < 16; ++gp) {
+                        if (gp < g) { qv[0] += pv[gp].x; qv[1] += pv[gp].y; qv[2] += pv[gp].z; qv[3] += pv[gp].w; }
+                    }
+                    float ov[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float q = qv[e] + qsum[col + e];
+                        ov[e] = (t + e < Tint) ? (hv4[e] * c0 - q - a.l1) * inv : q;          // tail columns keep the raw qeff
+                    }
+                    *reinterpret_cast<float4 *>(a.AD_cm + cell_at(k, t, K)) = make_float4(ov[0], ov[1], ov[2], ov[3]);
                 }
+                H2_PHASE(3);
                 __syncthreads();
             }
+            H2_END();
+            if (a.dbg && tid == 0) ph_t = clock64();
             grid.sync();
+            H2_PHASE(4);
         }
+        H2_REPORT();
     } else {
         // ============================================================ recurrence warp: lane = component
         const int rb = b - a.n_block_items - a.n_diag_items;
@@ -303,38 +488,59 @@ __global__ void __launch_bounds__(NT, 1) hals2_sweep_kernel(Args a) {
         const int lane = tid;
         const int64_t k = (int64_t)rb * 32 + lane;
         const bool live = k < K;
-        float cs[32], p[32];
+        u64 csE[16], csO[16], p2[16];
         float c0 = 1.f, inv = 1.f;
         if (live) {
             c0 = a.Cf[((int64_t)Lm * K + k) * K + k];
             inv = 1.f / (c0 + eps + a.l2);
         }
+        {
+            // both alignments of the coefficient pairs come from memory as 64-bit loads: pairs built in registers from one set of
+            // scalars are rebuilt by the compiler with two moves per FFMA2 instead of being kept
+            const u64 *cp = reinterpret_cast<const u64 *>(a.coef + (live ? k : 0) * 64);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            cs[j] = (live && j >= 1 && j < L) ? a.Cf[((int64_t)(j + Lm) * K + k) * K + k] * inv : 0.f;
-            p[j] = 0.f;
+            for (int m = 0; m < 16; ++m) {
+                csE[m] = live ? __ldg(cp + m) : 0ull;
+                csO[m] = live ? __ldg(cp + 16 + m) : 0ull;
+                p2[m] = pack2(0.f, 0.f);
+            }
         }
-        float *adp = a.AD_cm + (live ? k : 0) * Tp;
-        float *hp = a.H_cm + (live ? k : 0) * Tp;
+        float *adp = a.AD_cm, *hp = a.H_cm;               // cell bases are added per round (t0 below is the offset of the cell)
         for (int64_t s = 0; s < n_rounds; ++s) {
             const int64_t c = s - 1 - (int64_t)STAG * k;
-            const bool on = live && c >= 0 && c < nC;
-            if (__any_sync(0xffffffffu, on)) {
-                const int64_t t0 = on ? c * CW : 0;
+            const bool on_ = live && c >= 0 && c < nC;
+            const bool on = on_ && !(a.dbg_mode & 2);
+            if (__any_sync(0xffffffffu, on_)) {
+                H2_BEGIN();
                 // interior columns of this chunk (the truncated tail is left to the tail job)
                 int nv = 0;
-                if (on) { const int64_t r = Tint - t0; nv = (int)(r < 0 ? 0 : (r > CW ? CW : r)); }
-                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                float4 an[4], hn[4];                             // the next 16 columns (prefetched one half-block ahead: L2 hits)
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    an[v] = on ? __ldcg(reinterpret_cast<const float4 *>(adp + t0) + v) : z4;
-                    hn[v] = on ? __ldcg(reinterpret_cast<const float4 *>(hp + t0) + v) : z4;
+                if (on_) { const int64_t r = Tint - c * CW; nv = (int)(r < 0 ? 0 : (r > CW ? CW : r)); }
+                const int64_t t0 = on_ ? cell_at(k, c * CW, K) : 0;      // offset of the cell inside the working arrays
+                float *ring = reinterpret_cast<float *>(smem_raw);          // [RSTG][2][32][RLS]
+                // a lane that is off (not started / finished) runs the same instructions on zeros and stores nothing; the
+                // mask-free path needs every active lane to be on a full interior chunk (all but the last chunk of a component)
+                const bool full = __all_sync(0xffffffffu, !on_ || nv == CW);
+#pragma unroll 1
+                for (int h = 0; h < RPRE; ++h) rec_fetch(ring, adp, hp, t0, h, lane, on);
+                if (!on) {                                                  // zeros for the lanes that do not load
+                    for (int h = 0; h < RSTG; ++h)
+                        for (int v = 0; v < 16; ++v) { ring[h * (2 * 32 * RLS) + lane * RLS + v] = 0.f; ring[h * (2 * 32 * RLS) + 32 * RLS + lane * RLS + v] = 0.f; }
                 }
-                for (int i0 = 0; i0 < CW; i0 += 32) {
-                    rec_half<0>(p, cs, an, hn, adp, hp, t0, i0, nv, on, i0 + 16 < CW);
-                    rec_half<1>(p, cs, an, hn, adp, hp, t0, i0 + 16, nv, on, i0 + 32 < CW);
+                if (full) {
+#pragma unroll 1
+                    for (int h = 0; h < CW / 16; h += 2) {
+                        rec_half<0, true>(p2, csE, csO, ring, adp, hp, t0, h, lane, nv, on);
+                        rec_half<1, true>(p2, csE, csO, ring, adp, hp, t0, h + 1, lane, nv, on);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int h = 0; h < CW / 16; h += 2) {
+                        rec_half<0, false>(p2, csE, csO, ring, adp, hp, t0, h, lane, nv, on);
+                        rec_half<1, false>(p2, csE, csO, ring, adp, hp, t0, h + 1, lane, nv, on);
+                    }
                 }
+                cp_async_wait<0>();
+                H2_END();
             }
             // ---- tail job of component k: the last L-1 columns with the truncated tables, one round after its last chunk
             if (live && Lm > 0 && s == nC + (int64_t)STAG * k + 1) {
@@ -347,30 +553,49 @@ __global__ void __launch_bounds__(NT, 1) hals2_sweep_kernel(Args a) {
                     double pend = 0.0;
                     for (int64_t sft = 1; sft <= Lm && t - sft >= 0; ++sft) {
                         const int64_t ts = t - sft, ws = T - ts;
-                        const float d = ldcg(a.AD_cm + k * Tp + ts);
+                        const float d = ldcg(a.AD_cm + cell_at(k, ts, K));
                         if (d == 0.f) continue;
                         double cw;
                         if (ws >= a.L) cw = (double)a.Cf[((int64_t)(sft + Lm) * K + k) * K + k];
                         else { cw = 0.0; for (int64_t l = sft; l < ws; ++l) cw += (double)a.S2[(l * a.Ks + k) * a.ld + (l - sft) * a.Ks + k]; }
                         pend += (double)d * cw;
                     }
-                    const float h = ldcg(a.H_cm + k * Tp + t);
-                    const float q = ldcg(a.AD_cm + k * Tp + t) + (float)pend;
+                    const float h = ldcg(a.H_cm + cell_at(k, t, K));
+                    const float q = ldcg(a.AD_cm + cell_at(k, t, K)) + (float)pend;
                     const float c0f = (float)c0w;
                     float vn = (h * c0f - q - a.l1) / (c0f + eps + a.l2);
                     vn = vn > 0.f ? vn : 0.f;
-                    a.H_cm[k * Tp + t] = vn;
-                    a.AD_cm[k * Tp + t] = vn - h;
+                    a.H_cm[cell_at(k, t, K)] = vn;
+                    a.AD_cm[cell_at(k, t, K)] = vn - h;
                 }
             }
             grid.sync();
         }
+        H2_REPORT();
     }
+#undef H2_BEGIN
+#undef H2_END
+#undef H2_REPORT
+#undef H2_PHASE
+}
+
+// coefficient pairs of the recurrence lanes: coef[k][0..31] = (cs[2m], cs[2m+1]), coef[k][32..63] = (cs[2m+1], cs[2m+2]), m = 0..15,
+// cs[j] = C[k,k,j] / (C[k,k,0] + eps + l2) for 1 <= j < L, zero otherwise
+__global__ void hals2_coef_kernel(const float *__restrict__ Cf, float *__restrict__ coef, int64_t K, int64_t L, float l2) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= K * 64) return;
+    const int64_t k = e / 64;
+    const int i = (int)(e % 64), m = (i & 31) >> 1, half = i & 1;
+    const int j = (i < 32) ? 2 * m + half : 2 * m + 1 + half;
+    const int64_t Lm = L - 1;
+    const float c0 = Cf[(Lm * K + k) * K + k];
+    const float inv = 1.f / (c0 + 2.220446049250313e-16f + l2);
+    coef[e] = (j >= 1 && j < L) ? Cf[((j + Lm) * K + k) * K + k] * inv : 0.f;
 }
 
 // Q and H into the component-major working arrays (AD_cm <- Q', H_cm <- H')
 __global__ void hals2_prepare_kernel(const float *__restrict__ Q, const float *__restrict__ H, float *__restrict__ AD_cm,
-                                     float *__restrict__ H_cm, int64_t K, int64_t T, int64_t Tp) {
+                                     float *__restrict__ H_cm, int64_t K, int64_t T, int64_t Tp) {      // Tp = nC * CW
     __shared__ float tq[32][33], thh[32][33];
     const int64_t t0 = (int64_t)blockIdx.x * 32, k0 = (int64_t)blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -382,7 +607,7 @@ __global__ void hals2_prepare_kernel(const float *__restrict__ Q, const float *_
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int64_t k = k0 + r, t = t0 + threadIdx.x;
-        if (k < K && t < Tp) { AD_cm[k * Tp + t] = tq[threadIdx.x][r]; H_cm[k * Tp + t] = thh[threadIdx.x][r]; }
+        if (k < K && t < Tp) { const int64_t o = cell_at(k, t, K); AD_cm[o] = tq[threadIdx.x][r]; H_cm[o] = thh[threadIdx.x][r]; }
     }
 }
 
@@ -392,7 +617,7 @@ __global__ void hals2_finish_kernel(const float *__restrict__ H_cm, float *__res
     const int64_t t0 = (int64_t)blockIdx.x * 32, k0 = (int64_t)blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int64_t k = k0 + r, t = t0 + threadIdx.x;
-        tile[r][threadIdx.x] = (k < K && t < T) ? H_cm[k * Tp + t] : 0.f;
+        tile[r][threadIdx.x] = (k < K && t < T) ? H_cm[cell_at(k, t, K)] : 0.f;
     }
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -402,7 +627,9 @@ __global__ void hals2_finish_kernel(const float *__restrict__ H_cm, float *__res
 }
 
 inline size_t smem_bytes() {
-    return (size_t)(GS * WINQ + GS * (((2 * LMAX - 1) + 7) & ~7) * 8 + CW) * sizeof(float);
+    // two window buffers (diagonal items double-buffer their staging), the table slice, the per-cell sums; the recurrence ring fits inside
+    static_assert(RSTG * 2 * 32 * RLS <= 2 * GS * WINQ, "recurrence ring");
+    return (size_t)(2 * GS * WINQ + GS * (((2 * LMAX - 1) + 7) & ~7) * 8 + CW) * sizeof(float);
 }
 
 }  // namespace hals2

@@ -59,7 +59,10 @@ __global__ void reduce_sum_kernel(const double *__restrict__ in, int64_t n, doub
 //   smem: H window of KC components  Hs[KC][BT + Lpad - 1], W chunk Ws[LC][BN] of one k.
 //   flags: bit0 store est, bit1 store est - X, bit2 accumulate sum((est-X)^2) into partial[block],
 //          bit3 synth epilogue out = max(0, est + noise*gauss(seed, n, t_global)),
-//          bit4 partial[2b] = <est,X>, partial[2b+1] = ||est||^2 (init_rand rescale, src/model.jl:119-120).
+//          bit4 partial[2b] = <est,X>, partial[2b+1] = ||est||^2 (init_rand rescale, src/model.jl:119-120),
+//          bit5 store the loss gradient d D / d est of PGD's pluggable losses (src/algs/pgd.jl:28-70): 2 (est - X) for SquareLoss
+//               (lossf 0), sign(est - X) for AbsoluteLoss (lossf 1), times mask[t][n] when a MaskedLoss wraps it,
+//          bit6 accumulate the loss itself into partial[block]: sum (m (X - est))^2 resp. sum |m (X - est)| (pgd.jl:33-35,43-45,67-69).
 // ------------------------------------------------------------------------------------------
 template <typename S>
 struct ConvArgs {
@@ -76,6 +79,8 @@ struct ConvArgs {
     int64_t t_global0;    // global index of local column 0 (synth)
     double noise;         // synth
     int KC;               // components staged per H window
+    const S *mask;        // flags 32|64: optional mask [t][N] (nullptr = all ones)
+    int lossf;            // flags 32|64: 0 SquareLoss, 1 AbsoluteLoss
 };
 
 __device__ __forceinline__ uint64_t mix64(uint64_t z) {
@@ -191,11 +196,17 @@ __global__ void __launch_bounds__(16 * TY) conv_kernel(ConvArgs<S> a) {
                 if (a.flags & 2) a.out[t * N + n] = r;
                 part = fma(r, r, part);
             }
+            if (a.flags & 96) {
+                const S r = e - a.X[t * N + n];
+                const S m = a.mask ? a.mask[t * N + n] : S(1);
+                if (a.flags & 32) a.out[t * N + n] = (a.lossf == 0 ? S(2) * r : (r > S(0) ? S(1) : (r < S(0) ? S(-1) : S(0)))) * m;
+                if (a.flags & 64) { const S mr = m * r; part += (a.lossf == 0) ? mr * mr : (mr < S(0) ? -mr : mr); }
+            }
         }
         sq += (double)part;
         dxe += (double)pdot;
     }
-    if (a.flags & 4) {
+    if (a.flags & (4 | 64)) {
         sq = block_sum(sq, red);
         if (tid == 0) a.partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = sq;
     }
@@ -1227,6 +1238,15 @@ __global__ void pgd_grad_kernel(S *g, const S *den, const S *num, const S *__res
     const S sg = xv > S(0) ? S(1) : (xv < S(0) ? S(-1) : S(0));
     g[i] = S(2) * (den[i] - num[i]) + S(2) * l2 * xv + l1 * sg;      // g may alias den
 }
+// g += 2*l2*x + l1*sign(x): the Square / Absolute penalties on top of a gradient that is already in g (pgd.jl:77-88)
+template <typename S>
+__global__ void pgd_penalty_kernel(S *g, const S *__restrict__ x, S l1, S l2, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const S v = x[i];
+    g[i] += S(2) * l2 * v + l1 * (v > S(0) ? S(1) : (v < S(0) ? S(-1) : S(0)));
+}
+
 template <typename S>
 __global__ void pgd_step_kernel(S *__restrict__ x, const S *__restrict__ g, double step, const double *__restrict__ nrm2, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

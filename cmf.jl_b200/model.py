@@ -30,7 +30,7 @@ from ._lib import F32, F64, HALS, MULT, PGD, CMFError, check, fptr, julia_array,
 _REG_ALIASES = {"l1_W": "l1W", "l2_W": "l2W", "l1_H": "l1H", "l2_H": "l2H"}
 _INIT_ALIASES = {"initW": "W_init", "initH": "H_init"}
 _KNOWN = {"l1W", "l2W", "l1H", "l2H", "seed", "W_init", "H_init", "check_convergence", "patience",
-          "eval_mode", "tol", "verbose", "dtype", "device", "layout", "printer", "engine", "loss_mode", "ngpu", "devices"}
+          "eval_mode", "tol", "verbose", "dtype", "device", "layout", "printer", "engine", "loss_mode", "ngpu", "devices", "loss_func", "mask"}
 
 
 def _normalise_kwargs(kwargs):
@@ -206,6 +206,17 @@ class PGDUpdate(AbstractCFUpdate):
     weight; the reference defaults are ``penaltiesW=[SquarePenalty(1)]`` and ``penaltiesH=[]`` (pgd.jl:161,185)."""
     _ALG = PGD
 
+    def __init__(self, data, W, H, loss_func="square", mask=None, **kw):
+        """``loss_func``: "square" (SquareLoss, pgd.jl:28-35) or "absolute" (AbsoluteLoss, :38-45); ``mask`` (N x T) wraps it in a
+        MaskedLoss (:59-70).  Both run on the device (cmf_set_pgd_loss)."""
+        super().__init__(data, W, H, **kw)
+        lf = {"square": 0, "absolute": 1, 0: 0, 1: 1}[loss_func]
+        if lf != 0 or mask is not None:
+            m = None if mask is None else julia_array(np.asarray(mask), self.dtype)
+            if m is not None and m.shape != (self.N, self.T):
+                raise ValueError(f"mask must be {(self.N, self.T)}, got {m.shape}")
+            check(_lib.load().cmf_set_pgd_loss(self._h, lf, None if m is None else fptr(m)))
+
     def update_motifs(self, data, W, H, l1W=0.0, l2W=1.0, **kwargs):
         return super().update_motifs(data, W, H, l1W=l1W, l2W=l2W, **kwargs)
 
@@ -339,9 +350,12 @@ def fit_cnmf(data, L=10, K=5, alg=MultUpdate, max_itr=100, max_time=math.inf, **
     if W0.shape != (K, N, L) or H0.shape != (K, T):
         raise ValueError(f"W_init must be {(K, N, L)} and H_init {(K, T)}; got {W0.shape}, {H0.shape}")
 
+    extra = {}
+    if rule_cls is PGDUpdate:
+        extra = dict(loss_func=kw.get("loss_func", "square"), mask=kw.get("mask"))
     rule = rule_cls(data, W0, H0, dtype=dtype, device=device, sync_host=False,
                     engine=kw.get("engine"), loss_mode=kw.get("loss_mode"),
-                    ngpu=kw.get("ngpu", 1), devices=kw.get("devices"))  # model.jl:79
+                    ngpu=kw.get("ngpu", 1), devices=kw.get("devices"), **extra)  # model.jl:79
     try:
         if need_rescale:
             _rescale(rule)

@@ -82,8 +82,8 @@ class DeviceShard:
             check(lib.cmf_create_multi(ctypes.byref(self._h), N, T, K, L, self.dtype, algc, ngpu, devs))
             self.t0, self.t1 = 0, T
         elif comm is not None:
-            uid, rank, world = comm
-            buf = ctypes.create_string_buffer(bytes(uid), 128)
+            uid, rank, world = comm      # uid None: reuse the communicator this process already built for (device, rank, world)
+            buf = ctypes.create_string_buffer(bytes(uid), 128) if uid is not None else None
             check(lib.cmf_create_rank(ctypes.byref(self._h), N, T, K, L, self.dtype, algc, device, buf, rank, world))
             a, b = ctypes.c_int64(), ctypes.c_int64()
             check(lib.cmf_comm_info(self._h, None, None, ctypes.byref(a), ctypes.byref(b)))

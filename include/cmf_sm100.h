@@ -83,7 +83,8 @@ int cmf_create_multi(cmf_handle *out, int64_t N, int64_t T, int64_t K, int64_t L
 /* One process per GPU: the balanced shard of `rank` among `world` ranks on `device`, with its own NCCL
  * communicator built from the 128-byte id that rank 0 got from cmf_comm_unique_id (collective: every
  * rank must call it).  Host arrays passed to this handle start at global column `first_col` as for
- * cmf_create_shard; cmf_get_factors returns the rank's own columns of H. */
+ * cmf_create_shard; cmf_get_factors returns the rank's own columns of H.  The communicator is kept by the process and
+ * reused by later handles of the same (device, rank, world) created with unique_id == NULL (every rank must then do so). */
 int cmf_comm_unique_id(void *id_out_128_bytes);
 int cmf_create_rank(cmf_handle *out, int64_t N, int64_t T, int64_t K, int64_t L, int dtype, int alg,
                     int device, const void *unique_id_128_bytes, int rank, int world);
@@ -223,6 +224,13 @@ int cmf_set_loss_mode(cmf_handle h, int mode);
 int cmf_get_loss_mode(cmf_handle h, int *mode_out);
 /* The engine currently selected (0 / 1 / 2). */
 int cmf_get_engine(cmf_handle h, int *engine_out);
+
+/* PGDUpdate's pluggable loss (src/algs/pgd.jl:28-70; keyword `loss_func` of update_motifs! / update_feature_maps!, pgd.jl:160,183):
+ * loss_func 0 = SquareLoss (default), 1 = AbsoluteLoss; `mask` = NULL or a column-major N x T host array of the handle dtype that
+ * wraps the loss in a MaskedLoss (gradient multiplied by the mask, loss evaluated on mask.*data and mask.*est).  With either, the
+ * update follows pgd.jl:224-255 literally (conv + loss-gradient epilogue, then the correlation / transposed conv of that gradient);
+ * the loss returned by cmf_update_feature_maps is sqrt(eval(loss_func) / ||data||^2) as pgd.jl:202.  PGD handles only. */
+int cmf_set_pgd_loss(cmf_handle h, int loss_func, const void *mask);
 
 /* ---- primitives (tests; one-shot, host in / host out) ----------------------------------- */
 

@@ -345,6 +345,34 @@ def test_pgd_fp32_engines_loss_within_1e4(cmf, orc):
         assert rel.max() < F32_LOSS_RTOL, (engine, rel.max())
 
 
+@pytest.mark.parametrize("loss_func,masked", [("square", True), ("absolute", False), ("absolute", True)])
+def test_pgd_masked_and_absolute_losses(cmf, orc, loss_func, masked):
+    # the pluggable losses of PGD (src/algs/pgd.jl:28-70) on the device -- MaskedLoss (the configuration
+    # of the reference's own test script, test/test.jl:28-44) and AbsoluteLoss -- against the oracle's PGDUpdate(loss_func=, mask=)
+    X, W0, H0 = _config1(orc, N=60, T=400)
+    mask = (np.random.default_rng(3).random(X.shape) < 0.8).astype(np.float64) if masked else None
+    reg = dict(l1W=0.05, l2W=1.0, l1H=0.02, l2H=0.1)
+    ref = orc.po.fit(orc.po.PGDUpdate(X, W0, H0, loss_func=loss_func, mask=mask), X, W0, H0, 30, check_convergence=False, **reg)
+    r = cmf.fit_cnmf(X, L=10, K=5, alg="pgd", max_itr=30, W_init=W0, H_init=H0, check_convergence=False, layout="KNL",
+                     loss_func=loss_func, mask=mask, **reg)
+    assert np.allclose(r.loss_hist, ref.loss_hist, rtol=F64_RTOL), (r.loss_hist[-3:], ref.loss_hist[-3:])
+    assert np.allclose(r.W, ref.W, rtol=1e-7, atol=1e-11) and np.allclose(r.H, ref.H, rtol=1e-7, atol=1e-11)
+    if loss_func == "square":       # fp32 (the sign() of AbsoluteLoss flips on rounding-level residuals, so only the smooth loss is held to 1e-4)
+        r32 = cmf.fit_cnmf(X, L=10, K=5, alg="pgd", max_itr=30, W_init=W0, H_init=H0, check_convergence=False, layout="KNL",
+                           dtype="f32", loss_func=loss_func, mask=mask, **reg)
+        rel = np.abs(np.asarray(r32.loss_hist) - np.asarray(ref.loss_hist)) / np.asarray(ref.loss_hist)
+        assert rel.max() < F32_LOSS_RTOL, rel.max()
+    # rule-level interface
+    rule = cmf.PGDUpdate(X, W0.copy(), H0.copy(), loss_func=loss_func, mask=mask)
+    ro = orc.po.PGDUpdate(X, W0, H0, loss_func=loss_func, mask=mask)
+    Wg, Hg, Wo, Ho = W0.copy(), H0.copy(), W0.copy(), H0.copy()
+    for _ in range(2):
+        rule.update_motifs(X, Wg, Hg)
+        ro.update_motifs(X, Wo, Ho)
+        assert abs(rule.update_feature_maps(X, Wg, Hg) - ro.update_feature_maps(X, Wo, Ho)) < 1e-10
+    rule.close()
+
+
 def test_gen_synthetic_and_parameter_sweep(cmf):
     # README.md:14-23: data = CMF.gen_synthetic(N=500, T=2000); fit_cnmf(data; L=10, K=5, alg=:hals)
     data = cmf.gen_synthetic(N=60, T=300, K=3, L=8, seed=7)
