@@ -150,6 +150,7 @@ struct cmf_ctx {
     virtual void w_denom_rows(int64_t, int64_t) { no_multi(); }
     virtual void w_update_rows(double, double, int64_t, int64_t) { no_multi(); }
     virtual void w_rows_buffers(void **, void **, int64_t *) { no_multi(); }
+    virtual void fd_denomH_prefetch() {}
     virtual void h_update(double, double) { no_multi(); }
     virtual double loss_partial() { no_multi(); }
     virtual int loss_partial_dev() { no_multi(); }                 // leaves 1 (direct) or 2 (expansion) doubles in scalars()
@@ -261,13 +262,14 @@ struct FdState {
     bool wx_dirty = true;
     CUtensorMap mXfK[2], mXfMN[2], mAw[2], mAh[2], mHfMN[2], mAc[2], mHf2K[2], mAwm[2], mHcK[2];
     bool x_dirty = true, w_dirty = true, h_dirty = true;   // h_dirty: Ah does not hold the spectrum of the current H
+    bool hf2_valid = false;               // Hf holds the denomH blocking (hop V2) of the current H (prefetched while W is all-gathered)
     std::string why;                      // reason the engine is unavailable
     void release() {
         Xf_hi.free(); Xf_lo.free(); Ah_hi.free(); Ah_lo.free(); Aw_hi.free(); Aw_lo.free(); Of.free(); Df.free();
         Hf_hi.free(); Hf_lo.free(); Gf.free(); Ac_hi.free(); Ac_lo.free();
         Yf.free(); Awm_hi.free(); Awm_lo.free(); nbc = 0; wx_dirty = true;
         ok = tried = false;
-        x_dirty = w_dirty = h_dirty = true;
+        x_dirty = w_dirty = h_dirty = true; hf2_valid = false;
     }
 };
 
@@ -477,9 +479,8 @@ struct Ctx : cmf_ctx {
                 Cf.p, f.Ac_hi.p, f.Ac_lo.p, K, K, 2 * L - 1, f.B, f.logB, f.MR, f.Kq, 0, f.Kq);
             post_launch();
             const int C = fd_cols_h();
-            fd::fft_h_kernel<<<dim3((unsigned)f.nblk2, (unsigned)(f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
-                H, f.Hf_hi.p, f.Hf_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V2, f.nblk2, C, 1, -(L - 1), f.Kq);
-            post_launch();
+            fd_denomH_prefetch();
+            f.hf2_valid = false;                                   // consumed below; Hf is shared with the Gram / loss passes
             tc::Params q = tc_base_params();
             q.nprod = 3;
             q.tiles_n = cdiv(f.nblk2, tc::BN);
@@ -495,12 +496,26 @@ struct Ctx : cmf_ctx {
             post_launch();
         }
     }
+    // the H-only part of fd_denomH: spectrum of the blocks of H (hop V2, both halos).  Depends on H alone, so a sharded fit runs it
+    // while the all-gather of the new W is in flight (r_update_motifs).
+    void fd_denomH_prefetch() override {
+        if constexpr (std::is_same<S, float>::value) {
+            FdState &f = fds;
+            if (!fd_active() || f.hf2_valid) return;
+            const int C = fd_cols_h();
+            fd::fft_h_kernel<<<dim3((unsigned)f.nblk2, (unsigned)(f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
+                H, f.Hf_hi.p, f.Hf_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V2, f.nblk2, C, 1, -(L - 1), f.Kq);
+            post_launch();
+            f.hf2_valid = true;
+        }
+    }
     // sum of squared residuals (mult.jl:55-57) through the frequency domain: Xhat^ = W^ H^ per frequency for a chunk of
     // blocks (TC_FQX), inverse transform, subtract X, sum of squares (ifft_resid_kernel); returns the number of partials.
     // ~5x cheaper than the time-domain TC_CONV pass at c4, and free of the cancellation of the expansion.
     int64_t fd_conv_loss() {
         if constexpr (std::is_same<S, float>::value) {
             FdState &f = fds;
+            f.hf2_valid = false;
             const int64_t ntile32 = cdiv(N, 32);
             if (f.Awm_hi.n == 0) {
                 const size_t aw = (size_t)f.F * 2 * f.MR * (size_t)N + 64;
@@ -571,6 +586,7 @@ struct Ctx : cmf_ctx {
     void fd_gram() {
         if constexpr (std::is_same<S, float>::value) {
             FdState &f = fds;
+            f.hf2_valid = false;
             fd_spectrum_H();
             const int C = fd_cols_h();
             fd::fft_h_kernel<<<dim3((unsigned)f.nblkp, (unsigned)(f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
@@ -1102,7 +1118,7 @@ struct Ctx : cmf_ctx {
         have_factors = true;
         mark_w_dirty();
         numH_valid = false;
-        gram_valid = false; fds.h_dirty = true;
+        gram_valid = false; fds.h_dirty = true; fds.hf2_valid = false;
         pgd_stepW = pgd_stepH = 5.0;            // a new rule instance (pgd.jl:147-149)
         pgd_cur_loss = data_norm;
     }
@@ -1121,7 +1137,7 @@ struct Ctx : cmf_ctx {
         have_factors = true;
         mark_w_dirty();
         numH_valid = false;
-        gram_valid = false; fds.h_dirty = true;
+        gram_valid = false; fds.h_dirty = true; fds.hf2_valid = false;
     }
 
     void init_scale_partials(double out[2]) override {
@@ -1144,7 +1160,7 @@ struct Ctx : cmf_ctx {
         post_launch();
         mark_w_dirty();
         numH_valid = false;
-        gram_valid = false; fds.h_dirty = true;
+        gram_valid = false; fds.h_dirty = true; fds.hf2_valid = false;
     }
 
     void get_factors(void *Wo, void *Ho) override {
@@ -1256,7 +1272,7 @@ struct Ctx : cmf_ctx {
         }
         launch_mu(H, numH.p, denH.p, l1H, l2H, Tl * K);                       // mult.jl:51-52
         numH_valid = (alg == CMF_MULT);
-        gram_valid = false; fds.h_dirty = true;
+        gram_valid = false; fds.h_dirty = true; fds.hf2_valid = false;
     }
 
     double *scalars() override { return scal.p; }
@@ -1467,7 +1483,7 @@ struct Ctx : cmf_ctx {
         post_launch();
     }
     void h_changed() override {
-        gram_valid = false; fds.h_dirty = true;
+        gram_valid = false; fds.h_dirty = true; fds.hf2_valid = false;
         numH_valid = false;
     }
 
@@ -1553,7 +1569,7 @@ struct Ctx : cmf_ctx {
             pgd_penalty_kernel<S><<<(unsigned)cdiv(Tl * K, 256), 256, 0, stream>>>(denH.p, H, (S)l1H, (S)l2H, Tl * K);
             post_launch();
             pgd_step(H, denH.p, Tl * K, pgd_stepH);
-            gram_valid = false; fds.h_dirty = true;
+            gram_valid = false; fds.h_dirty = true; fds.hf2_valid = false;
             numH_valid = false;
             pgd_adapt(pgd_loss_eval(), pgd_stepH);
             return pgd_cur_loss;
@@ -1570,7 +1586,7 @@ struct Ctx : cmf_ctx {
         pgd_grad_kernel<S><<<(unsigned)cdiv(Tl * K, 256), 256, 0, stream>>>(denH.p, denH.p, numH.p, H, (S)l1H, (S)l2H, Tl * K);
         post_launch();
         pgd_step(H, denH.p, Tl * K, pgd_stepH);
-        gram_valid = false; fds.h_dirty = true;
+        gram_valid = false; fds.h_dirty = true; fds.hf2_valid = false;
         numH_valid = true;                                                              // W unchanged: the expansion loss may reuse numH / W W'
         pgd_adapt(loss_partial(), pgd_stepH);
         return pgd_cur_loss;                                                            // caller: sqrt(cur_loss / datanorm^2), pgd.jl:202
@@ -1830,7 +1846,14 @@ void r_update_motifs(cmf_ctx *h, double l1W, double l2W) {
         h->w_denom_rows(j0, j0 + rows);
         CK(cudaStreamWaitEvent(h->stream, h->ev_b, 0));
         h->w_update_rows(l1W, l2W, j0, j0 + rows);
-        NK(a.AllGather((char *)w + (size_t)(j0 * row) * es, w, (size_t)chunk, nccl_dt(h), h->comm.comm, h->stream));
+        // all-gather of W on the side stream; the one piece of the H half-step that does not need W (the spectrum of H for
+        // denomH) runs meanwhile
+        CK(cudaEventRecord(h->ev_a, h->stream));
+        CK(cudaStreamWaitEvent(h->comm_stream, h->ev_a, 0));
+        NK(a.AllGather((char *)w + (size_t)(j0 * row) * es, w, (size_t)chunk, nccl_dt(h), h->comm.comm, h->comm_stream));
+        CK(cudaEventRecord(h->ev_b, h->comm_stream));
+        if (h->alg == CMF_MULT) h->fd_denomH_prefetch();
+        CK(cudaStreamWaitEvent(h->stream, h->ev_b, 0));
         return;
     }
     if (h->world() > 1) {

@@ -631,15 +631,35 @@ __global__ void __launch_bounds__(256) denomH_tail_prefix_kernel(const S *__rest
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Lm = (int)(L - 1);
     S pre = S(0);
-    for (int w = 1; w <= Lm; ++w) {
-        const int64_t l = w - 1, lp = l - d;
-        if (live && lp >= 0 && lp < L) pre += S2[(l * Ks + k) * ld + lp * Ks + kp];
+    // the S2 entries a thread walks (one per w) do not depend on one another: 8 loads in flight ahead of the running sum
+    // (a dependent ~1 us load per step made this kernel latency-bound)
+    S nxt[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int64_t l = q, lp = l - d;
+        nxt[q] = (live && q < Lm && lp >= 0 && lp < L) ? S2[(l * Ks + k) * ld + lp * Ks + kp] : S(0);
+    }
+    for (int w0 = 1; w0 <= Lm; w0 += 8) {
+        S cur[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) cur[q] = nxt[q];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int64_t l = w0 - 1 + 8 + q, lp = l - d;
+            nxt[q] = (live && l < Lm && lp >= 0 && lp < L) ? S2[(l * Ks + k) * ld + lp * Ks + kp] : S(0);
+        }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int w = w0 + q;
+        if (w > Lm) break;
+        pre += cur[q];
         const int64_t u = Tl - w + d;
         double v = 0.0;
         if (live && pre != S(0) && u >= h_lo) v = (double)(pre * H[u * K + kp]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0) tail_sm[warp * Lm + (w - 1)] = v;
+    }
     }
     __syncthreads();
     for (int w = threadIdx.x + 1; w <= Lm; w += blockDim.x) {

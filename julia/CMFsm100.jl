@@ -32,11 +32,20 @@ dtype_code(::Type{Float32}) = CMF_F32
 """Opaque device handle; the finalizer releases all device memory (ownership rule of include/cmf_sm100.h)."""
 mutable struct Handle
     ptr::Ptr{Cvoid}
-    function Handle(N, T, K, L, dtype::Cint, alg::Cint, device::Integer=0)
+    function Handle(N, T, K, L, dtype::Cint, alg::Cint, device::Integer=0; ngpu::Integer=1, devices=nothing)
         out = Ref{Ptr{Cvoid}}(C_NULL)
+        if ngpu > 1
+            # the fit spans `ngpu` GPUs: time axis sharded INSIDE the library (NCCL communicators, one worker thread and one
+            # stream per device), driven from this one Julia task -- no `Distributed`, same calls as a single-GPU handle
+            devs = devices === nothing ? C_NULL : convert(Vector{Cint}, devices)
+            GC.@preserve devs check(ccall((:cmf_create_multi, LIB), Cint,
+                        (Ref{Ptr{Cvoid}}, Int64, Int64, Int64, Int64, Cint, Cint, Cint, Ptr{Cint}),
+                        out, N, T, K, L, dtype, alg, ngpu, devs))
+        else
         check(ccall((:cmf_create, LIB), Cint,
                     (Ref{Ptr{Cvoid}}, Int64, Int64, Int64, Int64, Cint, Cint, Cint),
                     out, N, T, K, L, dtype, alg, device))
+        end
         h = new(out[])
         finalizer(h) do x
             x.ptr == C_NULL || ccall((:cmf_destroy, LIB), Cint, (Ptr{Cvoid},), x.ptr)
@@ -64,10 +73,17 @@ alg_code(::Type{SM100Update{:hals}}) = CMF_HALS
 alg_code(::Type{SM100Update{:pgd}}) = CMF_PGD
 
 """`Rule(data, W, H)` -- src/model.jl:79, src/algs/mult.jl:11-20, src/algs/hals.jl:18-28."""
-function (::Type{R})(data::Matrix{T}, W::Array{T,3}, H::Matrix{T}; sync_host=true, device=0) where {R<:SM100Update,T<:Union{Float32,Float64}}
+function (::Type{R})(data::Matrix{T}, W::Array{T,3}, H::Matrix{T}; sync_host=true, device=0, ngpu=1, devices=nothing,
+                     loss_func=:square, mask=nothing) where {R<:SM100Update,T<:Union{Float32,Float64}}
     K, N, L = size(W)
     @assert size(data) == (N, size(H, 2)) && size(H, 1) == K
-    h = Handle(N, size(data, 2), K, L, dtype_code(T), alg_code(R), device)
+    h = Handle(N, size(data, 2), K, L, dtype_code(T), alg_code(R), device; ngpu=ngpu, devices=devices)
+    if R === SM100PGDUpdate && (loss_func != :square || mask !== nothing)
+        # PGD's pluggable losses (src/algs/pgd.jl:28-70): AbsoluteLoss and / or a MaskedLoss around it, on the device
+        m = mask === nothing ? nothing : convert(Matrix{T}, mask)
+        GC.@preserve m check(ccall((:cmf_set_pgd_loss, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+                                   h.ptr, loss_func == :absolute ? 1 : 0, m === nothing ? C_NULL : pointer(m)))
+    end
     GC.@preserve data W H begin
         check(ccall((:cmf_set_data, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), h.ptr, data, 0))
         check(ccall((:cmf_set_factors, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64), h.ptr, W, H, 0))
@@ -120,8 +136,28 @@ function tensor_conv(W::Array{T,3}, H::Matrix{T}) where {T}
     return est
 end
 
+"""compute_resids(data, W, H) = tensor_conv(W, H) - data on the device -- src/common.jl:58-59."""
+function compute_resids(data::Matrix{T}, W::Array{T,3}, H::Matrix{T}) where {T}
+    K, N, L = size(W); Tt = size(H, 2)
+    out = zeros(T, N, Tt)
+    GC.@preserve data W H out check(ccall((:cmf_compute_resids, LIB), Cint,
+        (Int64, Int64, Int64, Int64, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), N, Tt, K, L, dtype_code(T), data, W, H, out))
+    return out
+end
+
+"""shift_and_stack(H, L) on the device -- src/common.jl:133-142 (the fit itself never materialises it)."""
+function shift_and_stack(H::Matrix{T}, L::Integer) where {T}
+    K, Tt = size(H)
+    out = zeros(T, K * L, Tt)
+    GC.@preserve H out check(ccall((:cmf_shift_and_stack, LIB), Cint,
+        (Int64, Int64, Int64, Cint, Ptr{Cvoid}, Ptr{Cvoid}), K, Tt, L, dtype_code(T), H, out))
+    return out
+end
+
 """
-    fit_cnmf_sm100(data; L=10, K=5, alg=:mult, max_itr=100, max_time=Inf, kwargs...)
+    fit_cnmf_sm100(data; L=10, K=5, alg=:mult, max_itr=100, max_time=Inf, ngpu=1, kwargs...)
+
+`ngpu > 1` runs the same fit T-sharded over that many GPUs inside the same single `cmf_fit` call (MultUpdate, HALSUpdate).
 
 Drop-in for `CMF.fit_cnmf` (src/model.jl:58-85).  Accepts both API generations (SURVEY.md Appendix C):
 `alg` as `:mult`/`:hals` or a rule type, regularisers as `l1_H…` (README) or `l1H…` (current src),
@@ -134,7 +170,8 @@ function fit_cnmf_sm100(data::Matrix{T}; L::Integer=10, K::Integer=5, alg=:mult,
         haskey(kw, a) && (kw[b] = pop!(kw, a))
     end
     known = (:l1W, :l2W, :l1H, :l2H, :seed, :W_init, :H_init, :check_convergence, :patience, :eval_mode, :tol, :verbose,
-             :engine, :loss_mode)      # sm100 extras: contraction engine 0/1/2 and loss evaluation 0/1 (include/cmf_sm100.h)
+             :engine, :loss_mode, :ngpu, :devices, :loss_func, :mask)      # sm100 extras (include/cmf_sm100.h): contraction engine 0/1/2, loss
+                                                                            # evaluation 0/1, GPUs of the fit, PGD loss (pgd.jl:160,183)
     for k in keys(kw)
         k in known || @warn "fit_cnmf_sm100: unknown keyword $k ignored (CMF.jl ignores it silently)"
     end
@@ -143,7 +180,8 @@ function fit_cnmf_sm100(data::Matrix{T}; L::Integer=10, K::Integer=5, alg=:mult,
     W0, H0 = init_rand(data, L, K, tensor_conv)                  # model.jl:70
     W0 = convert(Array{T,3}, get(kw, :W_init, W0)); H0 = convert(Matrix{T}, get(kw, :H_init, H0))   # model.jl:72-73
     R = alg isa Symbol ? ALGS[alg] : alg
-    rule = R(data, W0, H0; sync_host=false)                      # model.jl:79
+    rule = R(data, W0, H0; sync_host=false, ngpu=get(kw, :ngpu, 1), devices=get(kw, :devices, nothing),
+             loss_func=get(kw, :loss_func, :square), mask=get(kw, :mask, nothing))   # model.jl:79
     haskey(kw, :engine) && check(ccall((:cmf_set_engine, LIB), Cint, (Ptr{Cvoid}, Cint), rule.h.ptr, kw[:engine]))
     haskey(kw, :loss_mode) && check(ccall((:cmf_set_loss_mode, LIB), Cint, (Ptr{Cvoid}, Cint), rule.h.ptr, kw[:loss_mode]))
     cap = isfinite(max_itr) ? Int(max_itr) + 1 : 1_000_001
