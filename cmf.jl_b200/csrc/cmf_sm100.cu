@@ -1380,6 +1380,7 @@ struct Ctx : cmf_ctx {
     // second-generation sweep (kernels_hals.cuh): rounds with a grid barrier, lane = component recurrences, 8 x 8 pull blocks.
     // Returns false when the handle / shape is outside its envelope (the wavefront kernel below then runs).
     DevBuf<float> h2_Hcm, h2_AD, h2_part, h2_coef;
+    DevBuf<unsigned> h2_bar;
     int h2_max_ctas = -1;
     bool hals2_sweep(const S *Qp, S *Hp, int64_t Tt, const S *ct, double l1H, double l2H) {
         if constexpr (!std::is_same<S, float>::value) { return false; } else {
@@ -1408,7 +1409,10 @@ struct Ctx : cmf_ctx {
             if (h2_coef.n < (size_t)(K * 64)) h2_coef.alloc((size_t)(K * 64));
             hals2::hals2_coef_kernel<<<(unsigned)cdiv(K * 64, 256), 256, 0, stream>>>(Cf.p, h2_coef.p, K, L, (float)l2H);
             post_launch();
+            if (h2_bar.n == 0) h2_bar.alloc(32);
+            CK(cudaMemsetAsync(h2_bar.p, 0, sizeof(unsigned), stream));
             hals2::Args a;
+            a.barrier = h2_bar.p;
             a.coef = h2_coef.p;
             a.Cf = Cf.p; a.Ct = ct; a.S2 = GS.p; a.Ks = s2_ks; a.ld = s2_ld;
             a.H_cm = h2_Hcm.p; a.AD_cm = h2_AD.p; a.part = h2_part.p;
@@ -1417,7 +1421,7 @@ struct Ctx : cmf_ctx {
             a.G = G; a.n_block_items = n_block; a.n_diag_items = n_diag; a.n_rec = n_rec;
             DevBuf<long long> dbgbuf;
             const bool dbg2 = getenv("CMF_HALS_DEBUG") && atoi(getenv("CMF_HALS_DEBUG")) == 1;
-            if (dbg2) dbgbuf.alloc((size_t)8 * grid);
+            if (dbg2) dbgbuf.alloc((size_t)12 * grid);
             a.dbg = dbg2 ? dbgbuf.p : nullptr;
             a.dbg_mode = getenv("CMF_HALS_DBGMODE") ? atoi(getenv("CMF_HALS_DBGMODE")) : 0;
             void *args[] = {&a};
@@ -1428,7 +1432,7 @@ struct Ctx : cmf_ctx {
             hals2::hals2_finish_kernel<<<dim3((unsigned)cdiv(Tt, 32), (unsigned)cdiv(K, 32)), tb, 0, stream>>>(h2_Hcm.p, Hp, K, Tt, Tp);
             post_launch();
             if (dbg2) {      // kcycles of work per active round (barrier waits excluded): worst and mean CTA of every role
-                std::vector<long long> hv((size_t)8 * grid);
+                std::vector<long long> hv((size_t)12 * grid);
                 CK(cudaMemcpyAsync(hv.data(), dbgbuf.p, hv.size() * sizeof(long long), cudaMemcpyDeviceToHost, stream));
                 CK(cudaStreamSynchronize(stream));
                 fprintf(stderr, "hals2: SM clock over the launch %lld MHz (clock64 / globaltimer, CTA 0)\n", hv[7]);
@@ -1437,12 +1441,15 @@ struct Ctx : cmf_ctx {
                 for (int r = 0; r < 3; ++r) {
                     double worst = 0.0, mean = 0.0; int cnt = 0, wi = -1;
                     double phw[5] = {0, 0, 0, 0, 0};
+                    long long mx = 0, slow = 0, rds = 0;
                     for (int i = lo[r]; i < lo[r + 1]; ++i) {
-                        if (hv[8 * i + 1] == 0) continue;
-                        const double v = (double)hv[8 * i] / (double)hv[8 * i + 1] / 1e3;
-                        if (v > worst) { worst = v; wi = i - lo[r]; for (int q = 0; q < 5; ++q) phw[q] = (double)hv[8 * i + 2 + q] / (double)hv[8 * i + 1] / 1e3; }
+                        if (hv[12 * i + 1] == 0) continue;
+                        const double v = (double)hv[12 * i] / (double)hv[12 * i + 1] / 1e3;
+                        if (v > worst) { worst = v; wi = i - lo[r]; for (int q = 0; q < 5; ++q) phw[q] = (double)hv[12 * i + 2 + q] / (double)hv[12 * i + 1] / 1e3; }
                         mean += v; ++cnt;
+                        mx = std::max(mx, hv[12 * i + 8]); slow += hv[12 * i + 9]; rds += hv[12 * i + 1];
                     }
+                    fprintf(stderr, "hals2 %s: slowest single round %.1f kcycles, %.2f%% of the (CTA, round) pairs above 90 kcycles\n", names[r], mx / 1e3, rds ? 100.0 * slow / rds : 0.0);
                     fprintf(stderr, "hals2 %s: %d CTAs, kcycles of work per active round: mean %.1f, worst %.1f (item %d; phases stage %.1f pull %.1f tail/store %.1f final %.1f, barrier wait %.1f); rounds %lld, chunks %lld\n",
                             names[r], lo[r + 1] - lo[r], cnt ? mean / cnt : 0.0, worst, wi, phw[0], phw[1], phw[2], phw[3], phw[4], (long long)(nC + 4 * (K - 1) + 3), (long long)nC);
                 }

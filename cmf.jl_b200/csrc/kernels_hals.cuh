@@ -45,6 +45,7 @@ constexpr int STAG = 4;         // chunks between consecutive components
 constexpr int RING = 32;        // chunks a block partial stays alive: written in round c+32g-1, read no later than c+32g+28
 constexpr int LMAX = 32;
 static_assert(CW == 4 * NT, "the hand-over loop covers a chunk with one float4 per thread");
+constexpr int KMAX = 128;        // components (the tail paths walk them in 4 passes of 32 lanes)
 constexpr int WIN = CW + 2 * (LMAX - 1);      // staged window of Delta H (columns t0-(L-1) .. t0+CW+(L-1)-1), sized for L = 32
 constexpr int QP = ((WIN + 7) >> 3) | 1;      // slots per plane of the 8-plane layout (odd: conflict-free)
 constexpr int WINQ = 8 * QP;                  // words per staged source
@@ -63,8 +64,9 @@ struct Args {
     float l1, l2;
     int G;                // groups of 8 components
     int n_block_items, n_diag_items, n_rec;
-    int dbg_mode;         // timing experiments (wrong results): bit 1 = the recurrence skips its global loads and stores
-    long long *dbg;       // optional [grid][8]: cycles spent working (barrier waits excluded), rounds with work
+    int dbg_mode;         // timing experiments (wrong results): 2 = the recurrence skips its global loads and stores, 4 = no role does any work (barrier cost)
+    unsigned *barrier;    // grid barrier counter (zero before the launch)
+    long long *dbg;       // optional [grid][12]: cycles spent working (barrier waits excluded), rounds with work
 };
 
 __device__ __forceinline__ float ldcg(const float *p) { return __ldcg(p); }
@@ -274,8 +276,28 @@ __device__ __forceinline__ void rec_half(u64 (&p2)[16], const u64 (&csE)[16], co
     }
 }
 
+// Grid barrier between rounds: one release-add per CTA on a global counter and an acquire spin until the whole grid has arrived.
+// (cooperative_groups' grid.sync() cost ~15 us per round in this kernel -- two fences and an atomic with return per CTA;
+// the launch stays cooperative so that all CTAs are co-resident.)  The counter is zeroed by the host before the launch.
+struct GridBarrier {
+    unsigned *ctr;
+    unsigned target;
+    __device__ __forceinline__ void sync() {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            target += gridDim.x;
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+            unsigned v;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+            } while ((int)(v - target) < 0);
+        }
+        __syncthreads();
+    }
+};
+
 __global__ void __launch_bounds__(NT, 1) hals2_sweep_kernel(Args a) {
-    cg::grid_group grid = cg::this_grid();
+    GridBarrier grid{a.barrier, 0u};
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int L = (int)a.L, Lm = L - 1;
     const int64_t K = a.K, T = a.T, nC = a.nC;
@@ -283,16 +305,16 @@ __global__ void __launch_bounds__(NT, 1) hals2_sweep_kernel(Args a) {
     const int64_t n_rounds = nC + (int64_t)STAG * (K - 1) + 3;
     const int b = blockIdx.x, tid = threadIdx.x;
     const float eps = 2.220446049250313e-16f;
-    long long wk_cyc = 0, wk_rounds = 0, wk_t0 = 0, ph_t = 0, ph[5] = {0, 0, 0, 0, 0};
+    long long wk_cyc = 0, wk_rounds = 0, wk_t0 = 0, ph_t = 0, ph[5] = {0, 0, 0, 0, 0}, wk_max = 0, wk_slow = 0;
     const long long kern_t0 = clock64();
     unsigned long long kern_ns0 = 0;
     if (a.dbg && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(kern_ns0));
 #define H2_BEGIN() do { if (a.dbg && tid == 0) { wk_t0 = clock64(); ph_t = wk_t0; } } while (0)
-#define H2_END() do { if (a.dbg && tid == 0) { wk_cyc += clock64() - wk_t0; ++wk_rounds; } } while (0)
+#define H2_END() do { if (a.dbg && tid == 0) { const long long d_ = clock64() - wk_t0; wk_cyc += d_; ++wk_rounds; if (d_ > wk_max) wk_max = d_; if (d_ > 90000) ++wk_slow; } } while (0)
 #define H2_PHASE(i) do { if (a.dbg && tid == 0) { const long long n_ = clock64(); ph[i] += n_ - ph_t; ph_t = n_; } } while (0)
-#define H2_REPORT() do { if (a.dbg && tid == 0) { a.dbg[8 * b] = wk_cyc; a.dbg[8 * b + 1] = wk_rounds; for (int i_ = 0; i_ < 5; ++i_) a.dbg[8 * b + 2 + i_] = ph[i_]; \
+#define H2_REPORT() do { if (a.dbg && tid == 0) { a.dbg[12 * b] = wk_cyc; a.dbg[12 * b + 1] = wk_rounds; for (int i_ = 0; i_ < 5; ++i_) a.dbg[12 * b + 2 + i_] = ph[i_]; a.dbg[12 * b + 8] = wk_max; a.dbg[12 * b + 9] = wk_slow; \
         unsigned long long ns1_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns1_)); \
-        a.dbg[8 * b + 7] = (long long)((double)(clock64() - kern_t0) * 1000.0 / (double)(ns1_ - kern_ns0)); } } while (0)   /* SM MHz over the launch */
+        a.dbg[12 * b + 7] = (long long)((double)(clock64() - kern_t0) * 1000.0 / (double)(ns1_ - kern_ns0)); } } while (0)   /* SM MHz over the launch */
 
     if (b < a.n_block_items) {
         // ============================================================ block item (g, g'), g' < g
@@ -308,7 +330,7 @@ __global__ void __launch_bounds__(NT, 1) hals2_sweep_kernel(Args a) {
         const int nsrc = (int)(nleft < GS ? nleft : GS);
         for (int64_t s = 0; s < n_rounds; ++s) {
             const int64_t c = s + 1 - (int64_t)STAG * GS * g;
-            if (c >= 0 && c < nC) {
+            if (c >= 0 && c < nC && !(a.dbg_mode & 4)) {
                 H2_BEGIN();
                 {
                     StageRegs sr;
@@ -361,7 +383,7 @@ __global__ void __launch_bounds__(NT, 1) hals2_sweep_kernel(Args a) {
                 // window of the first active target of the round (the later ones are loaded during the previous target's pull)
                 int first = 0;
                 while (first < GS && !active(first, s)) ++first;
-                if (first > 0 && first < GS) {
+                if (first > 0 && first < GS && !(a.dbg_mode & 4)) {
                     StageRegs sr;
                     const int64_t cf = s - (int64_t)STAG * ((int64_t)g * GS + first);
                     stage_load(sr, a, (int64_t)g * GS, first, cf, Tint);
@@ -371,7 +393,7 @@ __global__ void __launch_bounds__(NT, 1) hals2_sweep_kernel(Args a) {
             for (int i = 0; i < GS; ++i) {
                 const int64_t k = (int64_t)g * GS + i;
                 const int64_t c = s - (int64_t)STAG * k;
-                if (k >= K || c < 0 || c >= nC) continue;      // uniform over the CTA
+                if (k >= K || c < 0 || c >= nC || (a.dbg_mode & 4)) continue;      // uniform over the CTA
                 float2 *Dwin = Dwin0 + buf * (GS / 2) * WINQ;
                 // loads of the NEXT active target's window go out now and are stored into the other buffer after this pull
                 int nxt = i + 1;
@@ -421,31 +443,48 @@ __global__ void __launch_bounds__(NT, 1) hals2_sweep_kernel(Args a) {
                     const int64_t c_lo = (t0 > Tint - Lm) ? t0 : Tint - Lm;
                     const int64_t c_hi = (t0 + CW < T) ? t0 + CW : T;
                     const int ncol = (int)(c_hi - c_lo);          // <= 2 (L-1)
-                    const int CH = (int)((k + 15) / 16 > 8 ? (k + 15) / 16 : 8);
-                    const int nch = (int)((k + CH - 1) / CH);     // <= 16
-                    float *tpart = reinterpret_cast<float *>(Dwin);  // [nch][64] (this target's window: its pull is done)
-                    if (ncol > 0) {
-                        for (int it = tid; it < ncol * nch; it += NT) {
-                            const int ci = it % ncol, ch = it / ncol;
-                            const int64_t tp = c_lo + ci;
-                            int64_t ta = (tp - Lm > Tint) ? tp - Lm : Tint;
-                            if (ta < 0) ta = 0;
-                            const int64_t tb = tp + Lm < T - 1 ? tp + Lm : T - 1;
-                            const int64_t kp_lo = (int64_t)ch * CH, kp_hi = (kp_lo + CH < k) ? kp_lo + CH : k;
-                            double accd = 0.0;
-                            for (int64_t t = ta; t <= tb; ++t) {
-                                const int64_t dd = tp - t, w = T - t;
-                                const float *ct = a.Ct + ((((w - 1) * (2 * a.L - 1) + (dd + Lm)) * K + k) * K);
-                                for (int64_t kp = kp_lo; kp < kp_hi; ++kp) accd += (double)ldcg(a.AD_cm + cell_at(kp, t, K)) * (double)ct[kp];
+                    // Delta H of the tail columns of all earlier components -> shared memory (this target's window buffer: its pull
+                    // is done), then one warp per target column: lanes over the earlier components (table rows are contiguous in
+                    // k'), 4 source columns in flight, fixed shuffle tree
+                    float *dt = reinterpret_cast<float *>(Dwin);  // [k][Lm]
+                    const int ntl = (int)k * Lm;
+                    for (int base = tid; base < ntl; base += NT * 8) {
+                        float v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int idx = base + u * NT;
+                            v[u] = (idx < ntl) ? ldcg(a.AD_cm + cell_at(idx / Lm, Tint + idx % Lm, K)) : 0.f;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) { const int idx = base + u * NT; if (idx < ntl) dt[idx] = v[u]; }
+                    }
+                    __syncthreads();
+                    const int wv = tid >> 5, ln = tid & 31;
+                    for (int ci = wv; ci < ncol; ci += NT / 32) {
+                        const int64_t tp = c_lo + ci;
+                        const int64_t ta = (tp - Lm > Tint) ? tp - Lm : Tint;
+                        const int64_t tb = tp + Lm < T - 1 ? tp + Lm : T - 1;
+                        double accd = 0.0;
+                        for (int64_t tq = ta; tq <= tb; tq += 4) {
+                            float cv[4][4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int64_t t = tq + u, w = T - t;
+                                const float *ct = a.Ct + ((((w - 1) * (2 * a.L - 1) + (tp - t + Lm)) * K + k) * K);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) { const int kp = ln + 32 * e; cv[u][e] = (t <= tb && kp < k) ? __ldg(ct + kp) : 0.f; }
                             }
-                            tpart[ch * 64 + ci] = (float)accd;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int64_t t = tq + u;
+                                if (t > tb) break;
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) { const int kp = ln + 32 * e; if (kp < k) accd += (double)dt[kp * Lm + (int)(t - Tint)] * (double)cv[u][e]; }
+                            }
                         }
-                        __syncthreads();
-                        for (int ci = tid; ci < ncol; ci += NT) {
-                            double sacc = 0.0;
-                            for (int ch = 0; ch < nch; ++ch) sacc += (double)tpart[ch * 64 + ci];
-                            qsum[(int)(c_lo - t0) + ci] += (float)sacc;
-                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) accd += __shfl_xor_sync(0xffffffffu, accd, o);
+                        if (ln == 0) qsum[(int)(c_lo - t0) + ci] += (float)accd;
                     }
                     __syncthreads();
                 }
@@ -510,7 +549,7 @@ __global__ void __launch_bounds__(NT, 1) hals2_sweep_kernel(Args a) {
             const int64_t c = s - 1 - (int64_t)STAG * k;
             const bool on_ = live && c >= 0 && c < nC;
             const bool on = on_ && !(a.dbg_mode & 2);
-            if (__any_sync(0xffffffffu, on_)) {
+            if (__any_sync(0xffffffffu, on_) && !(a.dbg_mode & 4)) {
                 H2_BEGIN();
                 // interior columns of this chunk (the truncated tail is left to the tail job)
                 int nv = 0;
@@ -542,31 +581,39 @@ __global__ void __launch_bounds__(NT, 1) hals2_sweep_kernel(Args a) {
                 cp_async_wait<0>();
                 H2_END();
             }
-            // ---- tail job of component k: the last L-1 columns with the truncated tables, one round after its last chunk
-            if (live && Lm > 0 && s == nC + (int64_t)STAG * k + 1) {
-                for (int64_t t = (Tint > 0 ? Tint : 0); t < T; ++t) {
-                    const int64_t w = T - t;                     // 1 .. L-1 lags left
-                    // C_w[k,k,sft] = sum_{l<w, l-sft>=0} S2[(l,k)][(l-sft,k)]
-                    double c0w = 0.0;
-                    for (int64_t l = 0; l < w; ++l) c0w += (double)a.S2[(l * a.Ks + k) * a.ld + l * a.Ks + k];
-                    // pending corrections from the earlier columns of this component (interior sources: full table)
-                    double pend = 0.0;
-                    for (int64_t sft = 1; sft <= Lm && t - sft >= 0; ++sft) {
-                        const int64_t ts = t - sft, ws = T - ts;
-                        const float d = ldcg(a.AD_cm + cell_at(k, ts, K));
-                        if (d == 0.f) continue;
-                        double cw;
-                        if (ws >= a.L) cw = (double)a.Cf[((int64_t)(sft + Lm) * K + k) * K + k];
-                        else { cw = 0.0; for (int64_t l = sft; l < ws; ++l) cw += (double)a.S2[(l * a.Ks + k) * a.ld + (l - sft) * a.Ks + k]; }
-                        pend += (double)d * cw;
+            // ---- tail job: the last L-1 columns of one component with the truncated tables, one round after its last chunk.  At most
+            //      one lane of the warp has it in a given round; the whole warp works on it: lane = lag of the pending sum.
+            {
+                const unsigned jm = __ballot_sync(0xffffffffu, live && Lm > 0 && s == nC + (int64_t)STAG * k + 1);
+                if (jm != 0) {
+                    const int64_t kk = (int64_t)rb * 32 + (__ffs(jm) - 1);
+                    __shared__ float tail_d[LMAX];
+                    const int sft = lane + 1;                      // this lane's lag (1 .. L-1)
+                    for (int64_t t = (Tint > 0 ? Tint : 0); t < T; ++t) {
+                        const int64_t w = T - t;                     // 1 .. L-1 lags left; C_w[k,k,0] from the truncated tables
+                        const float c0w = __ldg(a.Ct + ((((w - 1) * (2 * a.L - 1) + Lm) * K + kk) * K + kk));
+                        double pe = 0.0;
+                        const int64_t ts = t - sft;
+                        if (sft <= Lm && ts >= 0) {
+                            const int64_t ws = T - ts;
+                            const float d = (ts >= Tint) ? tail_d[(int)(ts - Tint)] : ldcg(a.AD_cm + cell_at(kk, ts, K));
+                            const float cw = (ws >= a.L) ? __ldg(a.Cf + ((int64_t)(sft + Lm) * K + kk) * K + kk)
+                                                         : __ldg(a.Ct + ((((ws - 1) * (2 * a.L - 1) + (sft + Lm)) * K + kk) * K + kk));
+                            pe = (double)d * (double)cw;
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) pe += __shfl_xor_sync(0xffffffffu, pe, o);
+                        if (lane == 0) {
+                            const float h = ldcg(a.H_cm + cell_at(kk, t, K));
+                            const float q = ldcg(a.AD_cm + cell_at(kk, t, K)) + (float)pe;
+                            float vn = (h * c0w - q - a.l1) / (c0w + eps + a.l2);
+                            vn = vn > 0.f ? vn : 0.f;
+                            a.H_cm[cell_at(kk, t, K)] = vn;
+                            a.AD_cm[cell_at(kk, t, K)] = vn - h;
+                            tail_d[(int)(t - Tint)] = vn - h;
+                        }
+                        __syncwarp();
                     }
-                    const float h = ldcg(a.H_cm + cell_at(k, t, K));
-                    const float q = ldcg(a.AD_cm + cell_at(k, t, K)) + (float)pend;
-                    const float c0f = (float)c0w;
-                    float vn = (h * c0f - q - a.l1) / (c0f + eps + a.l2);
-                    vn = vn > 0.f ? vn : 0.f;
-                    a.H_cm[cell_at(k, t, K)] = vn;
-                    a.AD_cm[cell_at(k, t, K)] = vn - h;
                 }
             }
             grid.sync();
