@@ -57,6 +57,8 @@ SIGNATURES = {
     "cmf_get_engine": [_h, _c.POINTER(_int)],
     "cmf_set_loss_mode": [_h, _int],
     "cmf_get_loss_mode": [_h, _c.POINTER(_int)],
+    "cmf_set_loss_guard": [_h, _dbl, _int],
+    "cmf_get_loss_stats": [_h, _c.POINTER(_i64), _c.POINTER(_i64), _c.POINTER(_int), _c.POINTER(_dbl)],
     "cmf_profile": [_h, _int],
     "cmf_profile_read": [_h, _int, _c.POINTER(_dbl), _c.POINTER(_i64)],
     "cmf_set_pgd_loss": [_h, _int, _vp],

@@ -93,6 +93,17 @@ struct cmf_ctx {
     double data_sumsq_global = 0.0;  // ||X||^2 over all shards (== local without a communicator)
     int loss_mode = 0;               // 0 = direct residual pass, 1 = algebraic expansion when its inputs are resident
     bool loss_mode_explicit = false; // set by cmf_set_loss_mode: engine changes then leave the mode alone
+    // Calibrated expansion (loss_mode 1 at or below `loss_guard`): the expansion's error is a slowly varying bias (the
+    // truncating fp32 adder of the tensor core shrinks numH and the Grams by ~1e-6), so it is measured against the direct
+    // residual pass every `calib_interval` evaluations and subtracted in between; the interval doubles while the
+    // prediction made with the previous bias agrees with the direct pass and halves when it does not.
+    double loss_guard = 0.25;        // relative loss at or below which the expansion needs the calibration
+    int calib_max_interval = 16;
+    bool calib_have = false;
+    double calib_bias = 0.0, calib_last_err = 0.0;
+    int calib_left = 0, calib_interval = 1, calib_fail = 0;
+    int64_t n_loss_direct = 0, n_loss_expansion = 0;
+    void calib_reset() { calib_have = false; calib_left = 0; calib_interval = 1; calib_fail = 0; }
     double pgd_stepW = 5.0, pgd_stepH = 5.0, pgd_cur_loss = 0.0;   // PGDUpdate state (pgd.jl:147-151)
     bool numH_valid = false;         // numH buffer == transconv(current W, X) and GS == W W' of the current W
     bool gram_valid = false;         // exchange buffer 1 holds the local Gram/tail partial of the current H
@@ -1074,6 +1085,7 @@ struct Ctx : cmf_ctx {
         tcs.x_dirty = true;
         fds.x_dirty = true;
         numH_valid = false;
+        calib_reset();
         data_sumsq_local = data_sumsq();
         data_norm = std::sqrt(data_sumsq_local);
         pgd_cur_loss = data_norm;
@@ -1121,6 +1133,7 @@ struct Ctx : cmf_ctx {
         gram_valid = false; fds.h_dirty = true; fds.hf2_valid = false;
         pgd_stepW = pgd_stepH = 5.0;            // a new rule instance (pgd.jl:147-149)
         pgd_cur_loss = data_norm;
+        calib_reset();
     }
 
     void init_rand(uint64_t seed) override {
@@ -1138,6 +1151,7 @@ struct Ctx : cmf_ctx {
         mark_w_dirty();
         numH_valid = false;
         gram_valid = false; fds.h_dirty = true; fds.hf2_valid = false;
+        calib_reset();
     }
 
     void init_scale_partials(double out[2]) override {
@@ -1161,6 +1175,7 @@ struct Ctx : cmf_ctx {
         mark_w_dirty();
         numH_valid = false;
         gram_valid = false; fds.h_dirty = true; fds.hf2_valid = false;
+        calib_reset();
     }
 
     void get_factors(void *Wo, void *Ho) override {
@@ -1807,26 +1822,56 @@ void r_init_scale_partials(cmf_ctx *h, double out[2]) {
 }
 
 // sum of squared residuals over ALL shards: one fixed-size all-reduce of the two loss scalars, one read-back
-double r_loss_sumsq(cmf_ctx *h) {
-    const int n = h->loss_partial_dev();
+double r_loss_sumsq(cmf_ctx *h, bool force_direct = false, bool *expansion_used = nullptr) {
+    const int saved = h->loss_mode;
+    if (force_direct) h->loss_mode = 0;
+    int n;
+    try { n = h->loss_partial_dev(); } catch (...) { h->loss_mode = saved; throw; }
+    h->loss_mode = saved;
     double *d = h->scalars();
     c_allreduce(h, d, 2, ncclFloat64);
     double v[2];
     CK(cudaMemcpyAsync(v, d, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (expansion_used) *expansion_used = (n == 2);
+    ++(n == 2 ? h->n_loss_expansion : h->n_loss_direct);
     return n == 2 ? h->data_sumsq_global - 2.0 * v[0] + v[1] : v[0];
 }
 
-// The expansion loss cancels like 1/loss^2 (error ~2e-6/loss^2 relative, measured): at or below 25 % relative loss
-// (or when the expansion went negative) switch the handle back to the direct residual pass and re-evaluate with it.
-// Every rank sees the same all-reduced value, so every rank takes the same branch.
+// Loss of the current factors, mult.jl:55-57.  With loss_mode 1 the algebraic expansion serves while the relative loss is
+// above `loss_guard` (25 %): its error is ~2e-6/loss^2 relative.  At or below the guard the expansion is CALIBRATED: its
+// error is a bias that moves slowly with the factors, so the direct residual pass is run every `calib_interval`
+// evaluations, the difference is kept and subtracted in between, and at each direct pass the value the previous bias would
+// have predicted is checked against it -- agreement to 5e-6 (relative, on the loss) doubles the interval (up to 16), more
+// than 2e-5 halves it, more than 1e-4 three times in a row returns the handle to the direct pass for good.  Values returned
+// at calibration points are the direct pass itself.  Every rank sees the same all-reduced numbers and takes the same branch.
 double r_guarded_loss(cmf_ctx *h) {
-    double loss = std::sqrt(r_loss_sumsq(h)) / h->data_norm;
-    if (h->loss_mode == 1 && !(loss > 0.25)) {
-        h->loss_mode = 0;
-        loss = std::sqrt(r_loss_sumsq(h)) / h->data_norm;
+    if (h->loss_mode != 1) return std::sqrt(std::max(r_loss_sumsq(h), 0.0)) / h->data_norm;
+    bool exp_used = false;
+    const double se = r_loss_sumsq(h, false, &exp_used);
+    if (!exp_used) return std::sqrt(std::max(se, 0.0)) / h->data_norm;
+    const double g2 = h->loss_guard * h->loss_guard * h->data_sumsq_global;
+    if (!h->calib_have && se > g2) return std::sqrt(se) / h->data_norm;
+    if (h->calib_have && h->calib_left > 0 && se - h->calib_bias > 0.0) {
+        --h->calib_left;
+        return std::sqrt(se - h->calib_bias) / h->data_norm;
     }
-    return loss;
+    const double sd = r_loss_sumsq(h, true);
+    if (h->calib_have && sd > 0.0) {
+        const double err = std::fabs((se - h->calib_bias) - sd) / (2.0 * sd);
+        h->calib_last_err = err;
+        if (err > 1e-4) { h->calib_interval = 1; ++h->calib_fail; }
+        else {
+            h->calib_fail = 0;
+            if (err > 2e-5) h->calib_interval = std::max(1, h->calib_interval / 2);
+            else if (err < 5e-6) h->calib_interval = std::min(h->calib_max_interval, h->calib_interval * 2);
+        }
+        if (h->calib_fail >= 3) { h->loss_mode = 0; h->calib_reset(); }      // the expansion is not reliable on this problem
+    }
+    h->calib_bias = se - sd;
+    h->calib_have = true;
+    h->calib_left = h->calib_interval - 1;
+    return std::sqrt(std::max(sd, 0.0)) / h->data_norm;
 }
 
 // update_motifs! (mult.jl:23-39 / hals.jl:31-34 / pgd.jl:158-178) on this rank's shard
@@ -2390,7 +2435,24 @@ int cmf_set_engine(cmf_handle h, int engine) {
 int cmf_set_loss_mode(cmf_handle h, int mode) {
     return guarded([&] {
         REQUIRE(mode == 0 || mode == 1, "loss mode must be 0 (direct) or 1 (expansion)");
-        on_ranks(h, [&](cmf_ctx *r) { r->loss_mode = mode; r->loss_mode_explicit = true; });
+        on_ranks(h, [&](cmf_ctx *r) { r->loss_mode = mode; r->loss_mode_explicit = true; r->calib_reset(); });
+    });
+}
+int cmf_set_loss_guard(cmf_handle h, double guard, int max_interval) {
+    return guarded([&] {
+        REQUIRE(guard >= 0.0, "loss guard must be >= 0");
+        REQUIRE(max_interval >= 1 && max_interval <= 1024, "calibration interval must be in [1, 1024]");
+        on_ranks(h, [&](cmf_ctx *r) { r->loss_guard = guard; r->calib_max_interval = max_interval; r->calib_reset(); });
+    });
+}
+int cmf_get_loss_stats(cmf_handle h, int64_t *n_direct, int64_t *n_expansion, int *interval, double *last_err) {
+    return guarded([&] {
+        REQUIRE(h, "null handle");
+        cmf_ctx *r = rank0(h);
+        if (n_direct) *n_direct = r->n_loss_direct;
+        if (n_expansion) *n_expansion = r->n_loss_expansion;
+        if (interval) *interval = r->calib_have ? r->calib_interval : 0;
+        if (last_err) *last_err = r->calib_last_err;
     });
 }
 int cmf_get_loss_mode(cmf_handle h, int *mode_out) {

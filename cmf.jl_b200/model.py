@@ -30,7 +30,7 @@ from ._lib import F32, F64, HALS, MULT, PGD, CMFError, check, fptr, julia_array,
 _REG_ALIASES = {"l1_W": "l1W", "l2_W": "l2W", "l1_H": "l1H", "l2_H": "l2H"}
 _INIT_ALIASES = {"initW": "W_init", "initH": "H_init"}
 _KNOWN = {"l1W", "l2W", "l1H", "l2H", "seed", "W_init", "H_init", "check_convergence", "patience",
-          "eval_mode", "tol", "verbose", "dtype", "device", "layout", "printer", "engine", "loss_mode", "ngpu", "devices", "loss_func", "mask"}
+          "eval_mode", "tol", "verbose", "dtype", "device", "layout", "printer", "engine", "loss_mode", "loss_guard", "ngpu", "devices", "loss_func", "mask"}
 
 
 def _normalise_kwargs(kwargs):
@@ -92,6 +92,12 @@ def converged(loss_hist, patience, tol):
 
 # ------------------------------------------------------------------------------------------
 # update rules: the plugin boundary (abstract type AbstractCFUpdate, alternating.jl:8)
+def _loss_stats(h):
+    nd, ne, iv, le = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int(), ctypes.c_double()
+    check(_lib.load().cmf_get_loss_stats(h, ctypes.byref(nd), ctypes.byref(ne), ctypes.byref(iv), ctypes.byref(le)))
+    return dict(direct=nd.value, expansion=ne.value, interval=iv.value, last_err=le.value)
+
+
 # ------------------------------------------------------------------------------------------
 class AbstractCFUpdate:
     """A rule owns an opaque libcmf_sm100 handle: the constructor uploads (data, W, H) exactly like
@@ -103,7 +109,7 @@ class AbstractCFUpdate:
     _ALG = None
 
     def __init__(self, data, W, H, dtype="f64", device=0, sync_host=True, engine=None, loss_mode=None, ngpu=1,
-                 devices=None):
+                 devices=None, loss_guard=None):
         """``ngpu > 1``: the rule spans ``ngpu`` GPUs (time axis sharded inside the library, NCCL collectives driven
         from this one thread -- cmf_create_multi); every other argument and every method is unchanged."""
         lib = _lib.load()
@@ -130,6 +136,8 @@ class AbstractCFUpdate:
             check(lib.cmf_set_engine(self._h, int(engine)))
         if loss_mode is not None:
             check(lib.cmf_set_loss_mode(self._h, int(loss_mode)))
+        if loss_guard is not None:
+            check(lib.cmf_set_loss_guard(self._h, float(loss_guard), 16))
         Xj = julia_array(data, self.dtype)
         check(lib.cmf_set_data(self._h, fptr(Xj), 0))
         self.set_factors(W, H)
@@ -156,6 +164,15 @@ class AbstractCFUpdate:
         out = ctypes.c_int64()
         check(_lib.load().cmf_launch_count(self._h, ctypes.byref(out)))
         return out.value
+
+    def set_loss_guard(self, guard=0.25, max_interval=16):
+        """Relative loss at or below which loss mode 1 calibrates the expansion against the direct pass, and the
+        longest stretch of evaluations between two direct passes (include/cmf_sm100.h)."""
+        check(_lib.load().cmf_set_loss_guard(self._h, float(guard), int(max_interval)))
+
+    def loss_stats(self):
+        """dict(direct=, expansion=, interval=, last_err=): loss evaluations by path and the calibration state."""
+        return _loss_stats(self._h)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -354,7 +371,7 @@ def fit_cnmf(data, L=10, K=5, alg=MultUpdate, max_itr=100, max_time=math.inf, **
     if rule_cls is PGDUpdate:
         extra = dict(loss_func=kw.get("loss_func", "square"), mask=kw.get("mask"))
     rule = rule_cls(data, W0, H0, dtype=dtype, device=device, sync_host=False,
-                    engine=kw.get("engine"), loss_mode=kw.get("loss_mode"),
+                    engine=kw.get("engine"), loss_mode=kw.get("loss_mode"), loss_guard=kw.get("loss_guard"),
                     ngpu=kw.get("ngpu", 1), devices=kw.get("devices"), **extra)  # model.jl:79
     try:
         if need_rescale:
@@ -381,11 +398,18 @@ def fit_cnmf(data, L=10, K=5, alg=MultUpdate, max_itr=100, max_time=math.inf, **
             _emit(printer, "Converged early.")          # alternating.jl:64
         verbose and _emit(printer, " fit!")
         W, H = rule.get_factors()
+        stats = rule.loss_stats()
+        eng, lm = ctypes.c_int(), ctypes.c_int()
+        check(lib.cmf_get_engine(rule._h, ctypes.byref(eng)))
+        check(lib.cmf_get_loss_mode(rule._h, ctypes.byref(lm)))
+        stats.update(engine=eng.value, loss_mode=lm.value)
     finally:
         rule.close()
     if layout == "LNK":
         W = np.ascontiguousarray(W.transpose(2, 1, 0))
-    return CNMF_results(data, W, H, list(time_hist[: n.value]), list(loss_hist[: n.value]), layout)
+    res = CNMF_results(data, W, H, list(time_hist[: n.value]), list(loss_hist[: n.value]), layout)
+    res.engine_info = stats      # not part of the reference struct: which engine / loss path produced loss_hist
+    return res
 
 
 def _host_rescaled(data, W, H, dtype, device):

@@ -141,6 +141,14 @@ class DeviceShard:
         """0 = direct residual pass, 1 = algebraic expansion on resident numH / C (tcgen05 engine only)."""
         check(_lib.load().cmf_set_loss_mode(self._h, int(mode)))
 
+    def set_loss_guard(self, guard=0.25, max_interval=16):
+        check(_lib.load().cmf_set_loss_guard(self._h, float(guard), int(max_interval)))
+
+    def loss_stats(self):
+        from .model import _loss_stats
+
+        return _loss_stats(self._h)
+
     @property
     def loss_mode(self):
         out = ctypes.c_int(0)

@@ -215,13 +215,22 @@ int cmf_set_engine(cmf_handle h, int engine);
  * ||conv(W,H)-X||^2 = ||X||^2 - 2<transconv(W,X),H> + <W W', Htilde Htilde'> on the numH and W W' that the
  * H update leaves resident plus the Gram of the new H, which the next cmf_w_partials reuses (a third of the
  * contraction work is saved; the halos must not change between cmf_loss_partial and cmf_w_partials).  The
- * identity cancels like 1/loss^2, (measured error ~2e-6/loss^2 relative), so callers switch back to 0 when the relative loss drops below 25%
- * (cmf_fit and the sharded host loop do). */
+ * identity cancels like 1/loss^2 (measured error ~2e-6/loss^2 relative: a slowly varying bias from the truncating
+ * fp32 adder of the tensor core).  cmf_loss / cmf_update_feature_maps / cmf_fit therefore use it as it is only while
+ * the relative loss is above the guard (25 %); at or below the guard they CALIBRATE it: the direct pass runs every
+ * `interval` evaluations, the difference to the expansion is kept and subtracted in between, and every direct pass
+ * checks the value the previous difference would have predicted -- the interval doubles (up to max_interval) while
+ * that prediction is within 5e-6 of the direct loss, halves above 2e-5, and the handle returns to mode 0 for good
+ * after three misses above 1e-4.  Split-phase callers (cmf_loss_partial) get the raw expansion and apply their own rule. */
 int cmf_set_loss_mode(cmf_handle h, int mode);
-/* The loss mode currently in force (handles that select the frequency-domain engine by themselves start with 1; the
- * single-shard calls cmf_loss / cmf_update_feature_maps / cmf_fit drop back to 0 and re-evaluate with the direct pass the
- * first time the relative loss is <= 25%; sharded callers apply the same rule to the all-reduced loss). */
+/* The loss mode currently in force (handles that select the frequency-domain engine by themselves start with 1). */
 int cmf_get_loss_mode(cmf_handle h, int *mode_out);
+/* Guard and longest calibration interval of loss mode 1 (defaults 0.25 and 16); a guard above any loss (e.g. 1e30) puts
+ * the handle into the calibrated regime from the first evaluation (bench.py measures that regime this way). */
+int cmf_set_loss_guard(cmf_handle h, double guard, int max_interval);
+/* Loss evaluations so far by the direct pass and by the expansion, the calibration interval in force (0 = not in the
+ * calibrated regime) and the relative error of the last checked prediction.  Any output pointer may be NULL. */
+int cmf_get_loss_stats(cmf_handle h, int64_t *n_direct, int64_t *n_expansion, int *interval, double *last_err);
 /* The engine currently selected (0 / 1 / 2). */
 int cmf_get_engine(cmf_handle h, int *engine_out);
 

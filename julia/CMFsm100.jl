@@ -170,7 +170,7 @@ function fit_cnmf_sm100(data::Matrix{T}; L::Integer=10, K::Integer=5, alg=:mult,
         haskey(kw, a) && (kw[b] = pop!(kw, a))
     end
     known = (:l1W, :l2W, :l1H, :l2H, :seed, :W_init, :H_init, :check_convergence, :patience, :eval_mode, :tol, :verbose,
-             :engine, :loss_mode, :ngpu, :devices, :loss_func, :mask)      # sm100 extras (include/cmf_sm100.h): contraction engine 0/1/2, loss
+             :engine, :loss_mode, :loss_guard, :ngpu, :devices, :loss_func, :mask)      # sm100 extras (include/cmf_sm100.h): contraction engine 0/1/2, loss
                                                                             # evaluation 0/1, GPUs of the fit, PGD loss (pgd.jl:160,183)
     for k in keys(kw)
         k in known || @warn "fit_cnmf_sm100: unknown keyword $k ignored (CMF.jl ignores it silently)"
@@ -184,6 +184,7 @@ function fit_cnmf_sm100(data::Matrix{T}; L::Integer=10, K::Integer=5, alg=:mult,
              loss_func=get(kw, :loss_func, :square), mask=get(kw, :mask, nothing))   # model.jl:79
     haskey(kw, :engine) && check(ccall((:cmf_set_engine, LIB), Cint, (Ptr{Cvoid}, Cint), rule.h.ptr, kw[:engine]))
     haskey(kw, :loss_mode) && check(ccall((:cmf_set_loss_mode, LIB), Cint, (Ptr{Cvoid}, Cint), rule.h.ptr, kw[:loss_mode]))
+    haskey(kw, :loss_guard) && check(ccall((:cmf_set_loss_guard, LIB), Cint, (Ptr{Cvoid}, Cdouble, Cint), rule.h.ptr, kw[:loss_guard], 16))
     cap = isfinite(max_itr) ? Int(max_itr) + 1 : 1_000_001
     loss_hist = zeros(Cdouble, cap); time_hist = zeros(Cdouble, cap)
     n = Ref{Int64}(0); early = Ref{Cint}(0)

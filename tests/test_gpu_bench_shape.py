@@ -50,3 +50,24 @@ def test_mu_100_iterations_at_benchmark_component_shape(cmf, case, engine, loss_
     # the factors themselves: norms within fp32 drift of the float64 run
     assert abs(np.linalg.norm(r.H) - float(g["H_norm"])) < 2e-3 * float(g["H_norm"])
     assert abs(np.linalg.norm(r.W) - float(g["W_norm"])) < 2e-3 * float(g["W_norm"])
+
+
+@pytest.mark.parametrize("case", ["c4shape_sparse", "c3shape_sparse", "c4shape_dense"])
+def test_calibrated_expansion_below_the_guard(cmf, case):
+    """Loss mode 1 below the 25 % guard: the expansion is calibrated against the direct pass every `interval` evaluations
+    (cmf_set_loss_guard).  With the guard lifted above any loss the whole run is in that regime: every entry of loss_hist
+    must still be within 1e-4 of the float64 oracle, most evaluations must have been served by the expansion, and the last
+    checked prediction must have agreed with the direct pass."""
+    g = np.load(os.path.join(GOLD, f"mu_bench_{case}.npz"))
+    N, T, K, L = (int(v) for v in g["dims"])
+    ref = np.asarray(g["loss_hist"])
+    X, W0, H0 = _inputs(case)
+    r = cmf.fit_cnmf(X, L=L, K=K, alg="mult", max_itr=int(g["iters"]), W_init=W0, H_init=H0, check_convergence=False,
+                     layout="KNL", dtype="f32", engine=2, loss_mode=1, loss_guard=1e30)
+    rel = np.abs(np.asarray(r.loss_hist) - ref) / ref
+    info = r.engine_info
+    print(case, "max rel err", rel.max(), "at", int(rel.argmax()), info)
+    assert rel.max() < 1e-4, (case, int(rel.argmax()), float(rel.max()), info)
+    assert info["loss_mode"] == 1 and info["engine"] == 2, info
+    assert info["direct"] <= 0.5 * info["expansion"], info
+    assert info["last_err"] < 2e-5, info
