@@ -940,6 +940,7 @@ struct Ctx : cmf_ctx {
     }
 
     ~Ctx() override {
+        if (tracing) trace_dump();
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 
@@ -952,9 +953,40 @@ struct Ctx : cmf_ctx {
         nsplit = (int)cdiv(tau_hi, split_len);
     }
 
-    void post_launch() {
+    // CMF_TRACE=1: an event after every launch; the destructor prints, per call site, the live stream time between consecutive
+    // events (= the kernel plus whatever gap preceded it, at the clocks of the real run -- ncu's per-kernel times are not)
+    struct TraceEv { cudaEvent_t e; const char *fn; int line; };
+    std::vector<TraceEv> trace;
+    const bool tracing = getenv("CMF_TRACE") && atoi(getenv("CMF_TRACE")) > 0;
+    void post_launch(const char *fn = __builtin_FUNCTION(), int line = __builtin_LINE()) {
         ++launches;
         CK(cudaGetLastError());
+        if (tracing) {
+            TraceEv t; t.fn = fn; t.line = line;
+            cudaEventCreate(&t.e);
+            cudaEventRecord(t.e, stream);
+            trace.push_back(t);
+        }
+    }
+    void trace_dump() {
+        if (trace.size() < 2) return;
+        cudaStreamSynchronize(stream);
+        struct Agg { double ms = 0.0; int64_t n = 0; };
+        std::map<std::pair<std::string, int>, Agg> agg;
+        const size_t skip = getenv("CMF_TRACE_SKIP") ? (size_t)atoll(getenv("CMF_TRACE_SKIP")) : 0;
+        double total = 0.0;
+        for (size_t i = std::max<size_t>(1, skip); i < trace.size(); ++i) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, trace[i - 1].e, trace[i].e) != cudaSuccess) continue;
+            Agg &g = agg[{trace[i].fn, trace[i].line}];
+            g.ms += ms; ++g.n; total += ms;
+        }
+        fprintf(stderr, "CMF_TRACE: %zu launches, %.3f ms between the first and last traced event (launches before #%zu skipped)\n", trace.size(), total, skip);
+        for (auto &kv : agg)
+            fprintf(stderr, "CMF_TRACE %-28s:%-5d n=%-6lld total %10.3f ms  mean %9.4f ms  %5.1f%%\n", kv.first.first.c_str(), kv.first.second,
+                    (long long)kv.second.n, kv.second.ms, kv.second.ms / (double)kv.second.n, 100.0 * kv.second.ms / total);
+        for (auto &t : trace) cudaEventDestroy(t.e);
+        trace.clear();
     }
 
     // ---------------------------------------------------------------- kernel launch helpers

@@ -58,9 +58,9 @@ def role(n):
 
 
 out = ["# ncu launch list, frequency-domain engine (default), FULL c4 size (N=4096, T=4194304, K=64, L=100, fp32 MU, 1 GPU)\n",
-       '    CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu"',
-       "    $CMD && ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_final_c4.csv $CMD\n",
-       f"Raw list: `profiles/r1_launches_c4_full_fd.csv` ({len(ks)} launches).  One MU iteration with the expansion loss (the default of",
+       '    CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-calibrated"',
+       f"    $CMD && ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/{__import__('os').path.basename(src)} $CMD\n",
+       f"Raw list: `profiles/{__import__('os').path.basename(src)}` ({len(ks)} launches).  One MU iteration with the expansion loss (the default of",
        "`bench.py`), taken from the timed region; per-launch times under ncu are cold-cache and serialised: compare shares.",
        f"The plain (un-profiled) run of the same command measured **{plain['ms_per_step']:.2f} ms/iteration** with CUDA events; its live",
        f"per-launch times of the two products: numW (`TC_FQC`) {km['corr']['total_ms'] / km['corr']['launches']:.2f} ms, numH (`TC_FQT`) "
