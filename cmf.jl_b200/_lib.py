@@ -62,6 +62,7 @@ SIGNATURES = {
     "cmf_profile": [_h, _int],
     "cmf_profile_read": [_h, _int, _c.POINTER(_dbl), _c.POINTER(_i64)],
     "cmf_set_pgd_loss": [_h, _int, _vp],
+    "cmf_set_pgd_constraints": [_h, _int, _int],
     "cmf_tensor_conv": [_i64, _i64, _i64, _i64, _int, _vp, _vp, _vp],
     "cmf_tensor_transconv": [_i64, _i64, _i64, _i64, _int, _vp, _vp, _vp],
     "cmf_corr_w": [_i64, _i64, _i64, _i64, _int, _vp, _vp, _vp],

@@ -174,6 +174,7 @@ struct cmf_ctx {
     virtual void hals_h_sweep(int full, double, double) { no_multi(); }
     virtual void h_changed() { no_multi(); }                       // invalidates what depends on H (after a halo exchange / scatter)
     virtual void set_pgd_loss(int, const void *) { no_multi(); }
+    virtual void set_pgd_constraints(int, int) { no_multi(); }
     virtual void pgd_update_motifs(double, double) { no_multi(); }
     virtual double pgd_update_feature_maps(double, double) { no_multi(); }
     virtual void exchange_buffer(int, void **, int64_t *, int *) { no_multi(); }
@@ -383,29 +384,44 @@ struct Ctx : cmf_ctx {
             if (K > fd::KQ_MAX || L > 256 || N < 16) { f.why = "needs K <= 128, L <= 256, N >= 16"; return; }
             f.Kq = (K <= 64) ? 64 : 128;
             f.MR = 2 * f.Kq;
-            int B = 64, logB = 6;
-            while (B < 4 * L) { B *= 2; ++logB; }
+            int B0 = 64;
+            while (B0 < 4 * L) B0 *= 2;
+            int forced = 0;
             if (const char *e = getenv("CMF_FD_B")) {
                 const int want = atoi(e);
-                if (want >= 4 * L && want >= 64 && want <= 1024 && (want & (want - 1)) == 0) { B = want; logB = 0; while ((1 << logB) < B) ++logB; }
+                if (want >= 4 * L && want >= 64 && want <= 1024 && (want & (want - 1)) == 0) forced = want;
             }
-            f.B = B; f.logB = logB; f.V = B - (int)L + 1; f.F = B / 2 + 1;
-            f.nblk = cdiv(Tl, f.V);
-            f.nblkp = cdiv(f.nblk, 16) * 16;
-            const size_t xf = (size_t)f.F * (size_t)f.nblkp * 2 * (size_t)N + 64;
-            const size_t ah = (size_t)f.F * (size_t)f.nblkp * 2 * f.MR + 64;
-            const size_t aw = (size_t)f.F * f.MR * 2 * (size_t)N + 64;
-            f.V2 = B - 2 * (int)L + 2;
-            f.nblk2 = cdiv(Tl, f.V2);
-            const size_t of = (size_t)f.F * (size_t)std::max(f.nblkp, f.nblk2) * f.MR, df = (size_t)f.F * f.MR * (size_t)N;
-            // Hf serves the Gram partial (nblkp blocks) and, later on the same stream, denomH (nblk2 blocks)
-            const size_t hf = (size_t)f.F * (size_t)std::max(f.nblkp, f.nblk2) * 2 * f.Kq + 256, gf = (size_t)f.F * f.MR * f.Kq;
-            const size_t ac = (size_t)f.F * f.MR * f.MR;
-            const size_t need = 4 * (xf + ah + aw + hf + ac) + 4 * (of + df + gf);
             tcs.X_hi.free(); tcs.X_lo.free(); tcs.x_dirty = true;
             size_t free_b = 0, total_b = 0;
             CK(cudaMemGetInfo(&free_b, &total_b));
-            if (need + ((size_t)1 << 30) > free_b) { f.why = "not enough device memory for the spectrum of X"; return; }
+            // what this handle allocates later, beside the spectra: the HALS round kernel's component-major copies of H and
+            // Delta H and its ring of block partials; the direct loss pass's spectrum of W and a minimal chunk buffer
+            size_t later = (size_t)1 << 30;
+            if (alg == CMF_HALS) later += (size_t)2 * (size_t)(Tl + 2048) * (size_t)K * 4 + (size_t)hals2::RING * (size_t)cdiv(K, hals2::GS) * (size_t)K * hals2::CW * 4;
+            size_t xf = 0, ah = 0, aw = 0, of = 0, df = 0, hf = 0, gf = 0, ac = 0;
+            bool fits = false;
+            // smallest power of two >= 4L first (fastest FFT kernels); the next one moves fewer bytes (hop / length grows), so it
+            // is the fallback when the first does not fit beside the data
+            for (int B = forced ? forced : B0; B <= (forced ? forced : std::min(2 * B0, 1024)); B *= 2) {
+                int logB = 0;
+                while ((1 << logB) < B) ++logB;
+                f.B = B; f.logB = logB; f.V = B - (int)L + 1; f.F = B / 2 + 1;
+                f.nblk = cdiv(Tl, f.V);
+                f.nblkp = cdiv(f.nblk, 16) * 16;
+                xf = (size_t)f.F * (size_t)f.nblkp * 2 * (size_t)N + 64;
+                ah = (size_t)f.F * (size_t)f.nblkp * 2 * f.MR + 64;
+                aw = (size_t)f.F * f.MR * 2 * (size_t)N + 64;
+                f.V2 = B - 2 * (int)L + 2;
+                f.nblk2 = cdiv(Tl, f.V2);
+                of = (size_t)f.F * (size_t)std::max(f.nblkp, f.nblk2) * f.MR; df = (size_t)f.F * f.MR * (size_t)N;
+                // Hf serves the Gram partial (nblkp blocks) and, later on the same stream, denomH (nblk2 blocks)
+                hf = (size_t)f.F * (size_t)std::max(f.nblkp, f.nblk2) * 2 * f.Kq + 256; gf = (size_t)f.F * f.MR * f.Kq;
+                ac = (size_t)f.F * f.MR * f.MR;
+                const size_t need = 4 * (xf + ah + aw + hf + ac) + 4 * (of + df + gf);
+                const size_t loss_pass = 4 * aw + (size_t)256 * (size_t)f.F * 2 * (size_t)N * sizeof(float);
+                if (need + later + loss_pass <= free_b) { fits = true; break; }
+            }
+            if (!fits) { f.why = "not enough device memory for the spectrum of X"; return; }
             f.Xf_hi.alloc(xf); f.Xf_lo.alloc(xf);
             f.Ah_hi.alloc(ah); f.Ah_lo.alloc(ah);
             f.Aw_hi.alloc(aw); f.Aw_lo.alloc(aw);
@@ -447,7 +463,7 @@ struct Ctx : cmf_ctx {
         }
         return 16;
     }
-    size_t fd_smem(int C) const { return ((size_t)fds.B * (size_t)C + (size_t)fds.B / 2) * sizeof(float2); }
+    size_t fd_smem(int C) const { return ((size_t)fds.B * (size_t)C + (size_t)fds.B) * sizeof(float2); }   // tile + full-circle twiddle table
 
     void fd_build_X() {
         if constexpr (std::is_same<S, float>::value) {
@@ -666,9 +682,8 @@ struct Ctx : cmf_ctx {
             CK(cudaGetDeviceProperties(&prop, device));
             if (prop.major != 10) return;                         // tcgen05 needs sm_100
             t.num_sms = prop.multiProcessorCount;
-            const size_t hw_elems = (size_t)((Tl + 2 * hal) * t.Kp + t.KLp + 64);
-            t.Hw_hi.alloc(hw_elems); t.Hw_lo.alloc(hw_elems);
-            t.Hm_hi.alloc(hw_elems); t.Hm_lo.alloc(hw_elems);
+            // the bf16 planes of H (4 x the size of H in bf16) are allocated on first use (tc_h_planes): a handle that runs on
+            // the frequency-domain engine never touches them
             t.Wc_hi.alloc((size_t)(N * t.KLp)); t.Wc_lo.alloc((size_t)(N * t.KLp));
             t.Wu_hi.alloc((size_t)(t.rows_u * N)); t.Wu_lo.alloc((size_t)(t.rows_u * N));
             t.groups_c = cdiv(2 * L - 1, t.G);
@@ -677,20 +692,14 @@ struct Ctx : cmf_ctx {
             t.Gc_hi.alloc((size_t)(KL() * t.KLp)); t.Gc_lo.alloc((size_t)(KL() * t.KLp));
             if (GS.n < (size_t)(t.rows_u * t.rows_u)) GS.alloc((size_t)(t.rows_u * t.rows_u));
             // tensor maps (index 0 = hi plane, 1 = lo plane)
-            __nv_bfloat16 *wc[2] = {t.Wc_hi.p, t.Wc_lo.p}, *hw[2] = {t.Hw_hi.p, t.Hw_lo.p}, *hm[2] = {t.Hm_hi.p, t.Hm_lo.p};
+            __nv_bfloat16 *wc[2] = {t.Wc_hi.p, t.Wc_lo.p};
             __nv_bfloat16 *wu[2] = {t.Wu_hi.p, t.Wu_lo.p};
             for (int i = 0; i < 2; ++i) {
                 t.mWc[i] = make_map_2d(wc[i], (uint64_t)t.KLp, (uint64_t)N, (uint64_t)t.KLp * 2, tc::BK, tc::BM, CU_TENSOR_MAP_SWIZZLE_64B);
-                // overlapping-row "window" map: row t starts at element t*Kp and is KLp long
-                t.mHw[i] = make_map_2d(hw[i], (uint64_t)t.KLp, (uint64_t)t.hrows, (uint64_t)t.Kp * 2, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
-                t.mHm[i] = make_map_mn(hm[i], (uint64_t)t.hrows, (uint64_t)t.Kp * 2, (uint64_t)(t.KLp / 64), tc::BK, 2);
                 t.mWu[i] = make_map_2d(wu[i], (uint64_t)N, (uint64_t)t.rows_u, (uint64_t)N * 2, tc::BK, tc::BM, CU_TENSOR_MAP_SWIZZLE_64B);
-                // Gram: "X" = H rows from owned column 0 (owned + right halo), [t][Kp] MN-major
-                t.mHmn[i] = make_map_mn(hw[i] + hal * t.Kp, (uint64_t)(Tl + hal), (uint64_t)t.Kp * 2, (uint64_t)cdiv(t.Kp, 64), tc::BK, 4);
-                // denomH: A = C table rows (d'*Kp + k) x Kp, "X" = H rows from the left halo on, K-major
+                // denomH: A = C table rows (d'*Kp + k) x Kp
                 __nv_bfloat16 *cc[2] = {t.Cc_hi.p, t.Cc_lo.p};
                 t.mCu[i] = make_map_2d(cc[i], (uint64_t)t.Kp, (uint64_t)t.rows_c, (uint64_t)t.Kp * 2, tc::BK, tc::BM, CU_TENSOR_MAP_SWIZZLE_64B);
-                t.mHk[i] = make_map_2d(hw[i], (uint64_t)t.Kp, (uint64_t)(Tl + 2 * hal), (uint64_t)t.Kp * 2, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
                 __nv_bfloat16 *gc[2] = {t.Gc_hi.p, t.Gc_lo.p};
                 t.mWuB[i] = make_map_2d(wu[i], (uint64_t)N, (uint64_t)t.rows_u, (uint64_t)N * 2, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
                 t.mWcB[i] = make_map_2d(wc[i], (uint64_t)t.KLp, (uint64_t)N, (uint64_t)t.KLp * 2, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
@@ -768,8 +777,30 @@ struct Ctx : cmf_ctx {
             tcs.w_dirty = false;
         }
     }
+    // bf16 hi/lo planes of H for the time-domain tensor-core kernels and the maps over them, on first use
+    void tc_h_planes() {
+        if constexpr (std::is_same<S, float>::value) {
+            TcState &t = tcs;
+            if (t.Hw_hi.n != 0) return;
+            const int64_t hal = L - 1;
+            const size_t hw_elems = (size_t)((Tl + 2 * hal) * t.Kp + t.KLp + 64);
+            t.Hw_hi.alloc(hw_elems); t.Hw_lo.alloc(hw_elems);
+            t.Hm_hi.alloc(hw_elems); t.Hm_lo.alloc(hw_elems);
+            __nv_bfloat16 *hw[2] = {t.Hw_hi.p, t.Hw_lo.p}, *hm[2] = {t.Hm_hi.p, t.Hm_lo.p};
+            for (int i = 0; i < 2; ++i) {
+                // overlapping-row "window" map: row t starts at element t*Kp and is KLp long
+                t.mHw[i] = make_map_2d(hw[i], (uint64_t)t.KLp, (uint64_t)t.hrows, (uint64_t)t.Kp * 2, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
+                t.mHm[i] = make_map_mn(hm[i], (uint64_t)t.hrows, (uint64_t)t.Kp * 2, (uint64_t)(t.KLp / 64), tc::BK, 2);
+                // Gram: "X" = H rows from owned column 0 (owned + right halo), [t][Kp] MN-major
+                t.mHmn[i] = make_map_mn(hw[i] + hal * t.Kp, (uint64_t)(Tl + hal), (uint64_t)t.Kp * 2, (uint64_t)cdiv(t.Kp, 64), tc::BK, 4);
+                // denomH: "X" = H rows from the left halo on, K-major
+                t.mHk[i] = make_map_2d(hw[i], (uint64_t)t.Kp, (uint64_t)(Tl + 2 * hal), (uint64_t)t.Kp * 2, tc::BK, tc::BN, CU_TENSOR_MAP_SWIZZLE_64B);
+            }
+        }
+    }
     void tc_split_H(bool masked) {
         if constexpr (std::is_same<S, float>::value) {
+            tc_h_planes();
             const int64_t rows = Tl + 2 * (L - 1);
             tc::split_H_kernel<<<(unsigned)cdiv(rows * tcs.Kp, 256), 256, 0, stream>>>(
                 Hbuf.p, masked ? tcs.Hm_hi.p : tcs.Hw_hi.p, masked ? tcs.Hm_lo.p : tcs.Hw_lo.p, rows, K, tcs.Kp,
@@ -1551,12 +1582,22 @@ struct Ctx : cmf_ctx {
 
     // ---------------------------------------------------------------- PGD (src/algs/pgd.jl, SquareLoss)
     // The gradients are the MU quantities again: dW = 2 (denomW - numW), dH = 2 (denomH - numH) (pgd.jl:206-221).
-    void pgd_step(S *x, S *g, int64_t n, double &step) {
+    int pgd_constrW = 0, pgd_constrH = 0;     // 0 NonnegConstraint (pgd.jl:91-95), 1 UnitNormConstraint (:98-110)
+    DevBuf<double> un_part;
+    // `inner` = elements between consecutive components in memory (N for Wi rows (l, k), 1 for H[t][K])
+    void pgd_step(S *x, S *g, int64_t n, double &step, int constr, int64_t inner) {
         dot_partial_kernel<S><<<1024, 256, 0, stream>>>(g, g, n, loss_part.p);
         post_launch();
         reduce_scalar(loss_part.p, 1024, scal.p + 2);                                   // ||grad||^2 stays on the device
-        pgd_step_kernel<S><<<(unsigned)cdiv(n, 256), 256, 0, stream>>>(x, g, step, scal.p + 2, n);   // pgd.jl:236-240
+        pgd_step_kernel<S><<<(unsigned)cdiv(n, 256), 256, 0, stream>>>(x, g, step, scal.p + 2, n, constr == 0 ? 1 : 0);   // pgd.jl:236-241
         post_launch();
+        if (constr == 1) {
+            if (un_part.n == 0) un_part.alloc((size_t)K * UN_CHUNKS);
+            unit_norm_partial_kernel<S><<<dim3(UN_CHUNKS, (unsigned)K), 256, 0, stream>>>(x, un_part.p, K, inner, n / K);
+            post_launch();
+            unit_norm_apply_kernel<S><<<(unsigned)cdiv(n, 256), 256, 0, stream>>>(x, un_part.p, K, inner, n);
+            post_launch();
+        }
     }
     void pgd_adapt(double loss, double &step) {
         step *= (loss < pgd_cur_loss) ? 1.05 : 0.70;                                    // pgd.jl:247-251
@@ -1570,6 +1611,11 @@ struct Ctx : cmf_ctx {
     int pgd_loss = 0;                 // 0 SquareLoss, 1 AbsoluteLoss
     DevBuf<S> pgd_mask, pgd_ge;       // mask [t][N] (empty = none), loss-gradient scratch [t][N] incl. a zero right halo
     bool pgd_general() const { return pgd_loss != 0 || pgd_mask.n != 0; }
+    void set_pgd_constraints(int cw, int ch) override {
+        REQUIRE(alg == CMF_PGD, "cmf_set_pgd_constraints: PGD handles only");
+        REQUIRE((cw == 0 || cw == 1) && (ch == 0 || ch == 1), "constraint must be 0 (NonnegConstraint) or 1 (UnitNormConstraint)");
+        pgd_constrW = cw; pgd_constrH = ch;
+    }
     void set_pgd_loss(int lossf, const void *mask_host) override {
         REQUIRE(alg == CMF_PGD, "the pluggable loss belongs to PGDUpdate handles");
         REQUIRE(lossf == 0 || lossf == 1, "loss_func must be 0 (SquareLoss) or 1 (AbsoluteLoss)");
@@ -1598,7 +1644,7 @@ struct Ctx : cmf_ctx {
             launch_corr(pgd_ge.p, N, N, Tl + (L - 1), nsplit_w, split_w, denW.p, nullptr);          // gradW (pgd.jl:206-214)
             pgd_penalty_kernel<S><<<(unsigned)cdiv(KL() * N, 256), 256, 0, stream>>>(denW.p, Wi.p, (S)l1W, (S)l2W, KL() * N);
             post_launch();
-            pgd_step(Wi.p, denW.p, KL() * N, pgd_stepW);
+            pgd_step(Wi.p, denW.p, KL() * N, pgd_stepW, pgd_constrW, N);
             mark_w_dirty();
             numH_valid = false;
             pgd_adapt(pgd_loss_eval(), pgd_stepW);
@@ -1609,7 +1655,7 @@ struct Ctx : cmf_ctx {
         else { build_G(); launch_gemm<false>(GS.p, Wi.p, denW.p, KL(), N, KL(), KL(), N, N); }
         pgd_grad_kernel<S><<<(unsigned)cdiv(KL() * N, 256), 256, 0, stream>>>(denW.p, denW.p, numW.p, Wi.p, (S)l1W, (S)l2W, KL() * N);
         post_launch();
-        pgd_step(Wi.p, denW.p, KL() * N, pgd_stepW);
+        pgd_step(Wi.p, denW.p, KL() * N, pgd_stepW, pgd_constrW, N);
         mark_w_dirty();
         numH_valid = false;
         pgd_adapt(loss_partial(), pgd_stepW);                                           // pgd.jl:244-252
@@ -1622,7 +1668,7 @@ struct Ctx : cmf_ctx {
             launch_transconv(Wi.p, pgd_ge.p, denH.p, N, K, L, N, Tl, Tl + (L - 1));                   // gradH (pgd.jl:218-221)
             pgd_penalty_kernel<S><<<(unsigned)cdiv(Tl * K, 256), 256, 0, stream>>>(denH.p, H, (S)l1H, (S)l2H, Tl * K);
             post_launch();
-            pgd_step(H, denH.p, Tl * K, pgd_stepH);
+            pgd_step(H, denH.p, Tl * K, pgd_stepH, pgd_constrH, 1);
             gram_valid = false; fds.h_dirty = true; fds.hf2_valid = false;
             numH_valid = false;
             pgd_adapt(pgd_loss_eval(), pgd_stepH);
@@ -1639,7 +1685,7 @@ struct Ctx : cmf_ctx {
         }
         pgd_grad_kernel<S><<<(unsigned)cdiv(Tl * K, 256), 256, 0, stream>>>(denH.p, denH.p, numH.p, H, (S)l1H, (S)l2H, Tl * K);
         post_launch();
-        pgd_step(H, denH.p, Tl * K, pgd_stepH);
+        pgd_step(H, denH.p, Tl * K, pgd_stepH, pgd_constrH, 1);
         gram_valid = false; fds.h_dirty = true; fds.hf2_valid = false;
         numH_valid = true;                                                              // W unchanged: the expansion loss may reuse numH / W W'
         pgd_adapt(loss_partial(), pgd_stepH);
@@ -2500,6 +2546,9 @@ static int current_device() {
     return d;
 }
 
+int cmf_set_pgd_constraints(cmf_handle h, int constrW, int constrH) {
+    return guarded([&] { REQUIRE(h && !h->multi, "single-rank call"); h->set_pgd_constraints(constrW, constrH); });
+}
 int cmf_set_pgd_loss(cmf_handle h, int loss_func, const void *mask) {
     return guarded([&] { REQUIRE(h && !h->multi, "single-rank call"); DevGuard g(h->device); h->set_pgd_loss(loss_func, mask); });
 }

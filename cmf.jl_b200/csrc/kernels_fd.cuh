@@ -43,49 +43,88 @@ constexpr int NT = 512;      // threads per CTA (A/B at c4: 256 -> 49, 512 -> 44
 constexpr int KQ_MAX = 128;  // components are padded to Kq = 64 or 128 rows; the A operands / outputs have MROWS = 2 Kq rows per
                              // frequency (m = k real part, m = Kq + k imaginary part), i.e. one or two 128-row tensor-core tiles
 
+// full-circle table tw[m] = exp(-2 pi i m / B), m < B (the radix-8 passes index it up to 7B/8)
 __device__ __forceinline__ void make_twiddles(float2 *tw, int B) {
-    for (int m = threadIdx.x; m < B / 2; m += NT) {
+    for (int m = threadIdx.x; m < B; m += NT) {
         float s, c;
-        sincospif(-2.0f * (float)m / (float)B, &s, &c);   // exp(-2 pi i m / B)
+        sincospif(-2.0f * (float)m / (float)B, &s, &c);
         tw[m] = make_float2(c, s);
     }
 }
 
 __device__ __forceinline__ int rev(int x, int logB) { return (int)(__brev((unsigned)x) >> (32 - logB)); }
 
-// log2(B) radix-2 decimation-in-frequency stages over d[B][C], two stages fused per pass (four rows in registers, the
-// second twiddle of the first stage is the first times -+i): half the shared-memory traffic and barriers of plain
-// radix-2, same bit-reversed output order (X[f] ends up in row rev(f)).  INV uses the conjugate twiddles (no scaling).
 __device__ __forceinline__ float2 cmul(float2 a, float2 w) { return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// multiplication by -i (forward) / +i (inverse), and by the eighth roots w8 = exp(-+ i pi / 4), w8^3
+template <bool INV> __device__ __forceinline__ float2 mul_mi(float2 a) { return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
+template <bool INV> __device__ __forceinline__ float2 mul_w8(float2 a) {
+    const float r = 0.70710678118654752f;
+    return INV ? make_float2((a.x - a.y) * r, (a.x + a.y) * r) : make_float2((a.x + a.y) * r, (a.y - a.x) * r);
+}
+template <bool INV> __device__ __forceinline__ float2 mul_w83(float2 a) {
+    const float r = 0.70710678118654752f;
+    return INV ? make_float2((-a.x - a.y) * r, (a.x - a.y) * r) : make_float2((a.y - a.x) * r, (-a.x - a.y) * r);
+}
 
+// log2(B) radix-2 decimation-in-frequency stages over d[B][C], in place, output in bit-reversed order (X[f] ends up in row
+// rev(f)), THREE stages fused per pass: a thread holds the 8 rows {pos + j n/8} of one block of size n in registers, runs the
+// radix-8 butterfly with the constant eighth roots, and applies the position twiddles on the way out (row m of the butterfly
+// carries w_n^(pos * bitrev3(m)): 7 table reads per 8 points).  B = 512 is three such passes; what is left of log2(B) after
+// the radix-8 passes (blocks of 4 or 2 rows, all twiddles 1) is one radix-4 or radix-2 pass.  INV conjugates every root.
 template <bool INV>
 __device__ __forceinline__ void fft_passes(float2 *d, const float2 *tw, int B, int logB, int C) {
     const int c = threadIdx.x % C, j0 = threadIdx.x / C, jstep = NT / C;
     int s = 0;
-    for (; s + 1 < logB; s += 2) {
-        const int n = B >> s, q = n >> 2, lq = logB - s - 2;      // block size of the first stage, its quarter
-        for (int j = j0; j < B / 4; j += jstep) {
+    for (; s + 2 < logB; s += 3) {
+        const int lq = logB - s - 3, q = 1 << lq, qC = q * C;             // eighth of the block size n = B >> s
+        for (int j = j0; j < (B >> 3); j += jstep) {
             const int pos = j & (q - 1), g = j >> lq;
-            float2 *r0 = d + (size_t)(g * n + pos) * C + c, *r1 = r0 + (size_t)q * C, *r2 = r1 + (size_t)q * C, *r3 = r2 + (size_t)q * C;
-            const float2 a0 = *r0, a1 = *r1, a2 = *r2, a3 = *r3;
-            float2 w1 = tw[pos << s], w2 = tw[pos << (s + 1)];
-            if (INV) { w1.y = -w1.y; w2.y = -w2.y; }
-            const float2 b0 = make_float2(a0.x + a2.x, a0.y + a2.y), b2 = cmul(make_float2(a0.x - a2.x, a0.y - a2.y), w1);
-            const float2 b1 = make_float2(a1.x + a3.x, a1.y + a3.y), uw = cmul(make_float2(a1.x - a3.x, a1.y - a3.y), w1);
-            const float2 b3 = INV ? make_float2(-uw.y, uw.x) : make_float2(uw.y, -uw.x);
-            *r0 = make_float2(b0.x + b1.x, b0.y + b1.y);
-            *r1 = cmul(make_float2(b0.x - b1.x, b0.y - b1.y), w2);
-            *r2 = make_float2(b2.x + b3.x, b2.y + b3.y);
-            *r3 = cmul(make_float2(b2.x - b3.x, b2.y - b3.y), w2);
+            float2 *r = d + ((g << (lq + 3)) + pos) * C + c;
+            float2 a0 = r[0], a1 = r[qC], a2 = r[2 * qC], a3 = r[3 * qC], a4 = r[4 * qC], a5 = r[5 * qC], a6 = r[6 * qC], a7 = r[7 * qC];
+            // stage 1: rows j and j+4, constant root w8^j on the difference
+            float2 t;
+            t = csub(a0, a4); a0 = cadd(a0, a4); a4 = t;
+            t = csub(a1, a5); a1 = cadd(a1, a5); a5 = mul_w8<INV>(t);
+            t = csub(a2, a6); a2 = cadd(a2, a6); a6 = mul_mi<INV>(t);
+            t = csub(a3, a7); a3 = cadd(a3, a7); a7 = mul_w83<INV>(t);
+            // stage 2: rows j and j+2 inside each half, constant root w4^j
+            t = csub(a0, a2); a0 = cadd(a0, a2); a2 = t;
+            t = csub(a1, a3); a1 = cadd(a1, a3); a3 = mul_mi<INV>(t);
+            t = csub(a4, a6); a4 = cadd(a4, a6); a6 = t;
+            t = csub(a5, a7); a5 = cadd(a5, a7); a7 = mul_mi<INV>(t);
+            // stage 3: neighbouring rows
+            t = csub(a0, a1); a0 = cadd(a0, a1); a1 = t;
+            t = csub(a2, a3); a2 = cadd(a2, a3); a3 = t;
+            t = csub(a4, a5); a4 = cadd(a4, a5); a5 = t;
+            t = csub(a6, a7); a6 = cadd(a6, a7); a7 = t;
+            if (lq > 0) {                                                  // position twiddles (all 1 in the last radix-8 pass of 8^m)
+                const int e = pos << s;
+                float2 w;
+#define CMF_TW(m_, a_) w = tw[(m_) * e]; if (INV) w.y = -w.y; a_ = cmul(a_, w);
+                CMF_TW(4, a1) CMF_TW(2, a2) CMF_TW(6, a3) CMF_TW(1, a4) CMF_TW(5, a5) CMF_TW(3, a6) CMF_TW(7, a7)
+#undef CMF_TW
+            }
+            r[0] = a0; r[qC] = a1; r[2 * qC] = a2; r[3 * qC] = a3; r[4 * qC] = a4; r[5 * qC] = a5; r[6 * qC] = a6; r[7 * qC] = a7;
         }
         __syncthreads();
     }
-    if (s < logB) {                                               // odd log2(B): last stage, distance 1, twiddle 1
-        for (int j = j0; j < B / 2; j += jstep) {
-            float2 *r0 = d + (size_t)(2 * j) * C + c, *r1 = r0 + C;
+    if (logB - s == 2) {                                                  // blocks of 4 rows: pos = 0, twiddles 1
+        for (int j = j0; j < (B >> 2); j += jstep) {
+            float2 *r = d + (4 * j) * C + c;
+            float2 a0 = r[0], a1 = r[C], a2 = r[2 * C], a3 = r[3 * C], t;
+            t = csub(a0, a2); a0 = cadd(a0, a2); a2 = t;
+            t = csub(a1, a3); a1 = cadd(a1, a3); a3 = mul_mi<INV>(t);
+            r[0] = cadd(a0, a1); r[C] = csub(a0, a1); r[2 * C] = cadd(a2, a3); r[3 * C] = csub(a2, a3);
+        }
+        __syncthreads();
+    } else if (logB - s == 1) {                                           // blocks of 2 rows
+        for (int j = j0; j < (B >> 1); j += jstep) {
+            float2 *r0 = d + (2 * j) * C + c, *r1 = r0 + C;
             const float2 a = *r0, b = *r1;
-            *r0 = make_float2(a.x + b.x, a.y + b.y);
-            *r1 = make_float2(a.x - b.x, a.y - b.y);
+            *r0 = cadd(a, b);
+            *r1 = csub(a, b);
         }
         __syncthreads();
     }
@@ -106,17 +145,23 @@ __device__ __forceinline__ void pack_pair(float2 *d, int f, int B, int C, int p,
     if (f > 0 && f < B / 2) d[(B - f) * C + p] = make_float2(re.x + im.y, re.y - im.x);
 }
 
+// (a, b) -> packed bf16 pairs hi = bf16(x), lo = bf16(x - hi) (round to nearest, as tc::split_bf16)
+__device__ __forceinline__ void split2(float a, float b, uint32_t &h, uint32_t &l) {
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(hh);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+    h = *reinterpret_cast<const uint32_t *>(&hh);
+    l = *reinterpret_cast<const uint32_t *>(&ll);
+}
 __device__ __forceinline__ void store_split2(__nv_bfloat16 *hi, __nv_bfloat16 *lo, int64_t idx, float a, float b) {
-    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-    const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah)), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
-    __nv_bfloat162 h, l;
-    h.x = ah; h.y = bh; l.x = al; l.y = bl;
-    *reinterpret_cast<__nv_bfloat162 *>(hi + idx) = h;
-    *reinterpret_cast<__nv_bfloat162 *>(lo + idx) = l;
+    uint32_t h, l;
+    split2(a, b, h, l);
+    *reinterpret_cast<uint32_t *>(hi + idx) = h;
+    *reinterpret_cast<uint32_t *>(lo + idx) = l;
 }
 
 // X[t][N] fp32 (xcols rows) -> Xf.  grid (nblkp, ceil(N/32)); 16 complex columns = 32 units per CTA.
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 3)
 fft_x_kernel(const float *__restrict__ X, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int64_t N, int64_t xcols,
              int B, int logB, int V, int64_t nblkp) {
     extern __shared__ float2 fd_smem[];
@@ -148,7 +193,7 @@ fft_x_kernel(const float *__restrict__ X, __nv_bfloat16 *__restrict__ hi, __nv_b
 // full == 0: only the V owned columns of each block, zero padded -> Ah;
 // full != 0: whole blocks over the columns present, t < hcols = Tl + L-1 (owned + right halo) -> Hf.
 // grid (nblkp, 32 / C); C complex columns = 2C components per CTA.
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 3)
 fft_h_kernel(const float *__restrict__ H, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int64_t K, int64_t Tl,
              int64_t hcols, int B, int logB, int V, int64_t nblkp, int C, int full, int64_t t_off, int kq) {
     const int64_t KQ = kq, MROWS = 2 * kq;
@@ -158,37 +203,49 @@ fft_h_kernel(const float *__restrict__ H, __nv_bfloat16 *__restrict__ hi, __nv_b
     const int p = threadIdx.x % C;
     const int k = 2 * ((int)blockIdx.y * C + p);
     make_twiddles(tw, B);
-    for (int i = threadIdx.x / C; i < B; i += NT / C) {
-        const int64_t t = b * V + t_off + i;
-        float2 v = make_float2(0.f, 0.f);
-        if (full ? (t < hcols) : (i < V && t < Tl)) {
-            if (k < K) v.x = H[t * K + k];
-            if (k + 1 < K) v.y = H[t * K + k + 1];
+    {
+        const int i0 = threadIdx.x / C, istep = NT / C;
+        const int64_t tb = b * V + t_off;
+        // rows of the block that hold data: [0, lim) (owned segment, or whatever of the block lies before hcols)
+        const int64_t lim64 = full ? (hcols - tb) : ((Tl - tb < V) ? Tl - tb : V);
+        const int lim = (int)(lim64 < 0 ? 0 : (lim64 > B ? B : lim64));
+        const float *src = H + (tb + i0) * K + k;
+        const bool pair = ((K & 1) == 0) && (k + 1 < K);
+        for (int i = i0; i < B; i += istep, src += (int64_t)istep * K) {
+            float2 v = make_float2(0.f, 0.f);
+            if (i < lim) {
+                if (pair) v = *reinterpret_cast<const float2 *>(src);
+                else { if (k < K) v.x = src[0]; if (k + 1 < K) v.y = src[1]; }
+            }
+            d[i * C + p] = v;
         }
-        d[i * C + p] = v;
     }
     __syncthreads();
     fft_passes<false>(d, tw, B, logB, C);
     for (int f = threadIdx.x / C; f <= B / 2; f += NT / C) {
         float ar, ai, br, bi;
         unpack_pair(d, f, B, logB, C, p, ar, ai, br, bi);
+        uint32_t hr, lr, hi_, li_;
+        split2(ar, br, hr, lr);
+        split2(ai, bi, hi_, li_);
         if (full) {
-            const int64_t r = (((int64_t)f * nblkp + b) * 2) * KQ;
-            store_split2(hi, lo, r + k, ar, br);
-            store_split2(hi, lo, r + KQ + k, ai, bi);
+            const int64_t r = (((int64_t)f * nblkp + b) * 2) * KQ + k;
+            *reinterpret_cast<uint32_t *>(hi + r) = hr; *reinterpret_cast<uint32_t *>(lo + r) = lr;
+            *reinterpret_cast<uint32_t *>(hi + r + KQ) = hi_; *reinterpret_cast<uint32_t *>(lo + r + KQ) = li_;
             continue;
         }
-        const int64_t r = (((int64_t)f * nblkp + b) * 2) * MROWS;
-        store_split2(hi, lo, r + k, ar, br);                       // row (b, re): [ Hr | -Hi ]
-        store_split2(hi, lo, r + KQ + k, -ai, -bi);
-        store_split2(hi, lo, r + MROWS + k, ai, bi);               // row (b, im): [ Hi |  Hr ]
-        store_split2(hi, lo, r + MROWS + KQ + k, ar, br);
+        const int64_t r = (((int64_t)f * nblkp + b) * 2) * MROWS + k;
+        const uint32_t sg = 0x80008000u;                           // -x of a packed bf16 pair (hi and lo planes alike)
+        *reinterpret_cast<uint32_t *>(hi + r) = hr; *reinterpret_cast<uint32_t *>(lo + r) = lr;                                 // row (b, re): [ Hr | -Hi ]
+        *reinterpret_cast<uint32_t *>(hi + r + KQ) = hi_ ^ sg; *reinterpret_cast<uint32_t *>(lo + r + KQ) = li_ ^ sg;
+        *reinterpret_cast<uint32_t *>(hi + r + MROWS) = hi_; *reinterpret_cast<uint32_t *>(lo + r + MROWS) = li_;               // row (b, im): [ Hi |  Hr ]
+        *reinterpret_cast<uint32_t *>(hi + r + MROWS + KQ) = hr; *reinterpret_cast<uint32_t *>(lo + r + MROWS + KQ) = lr;
     }
 }
 
 // Wi[(l*K+k)][N] fp32 -> Aw (rows of ldw elements, imaginary block at column coff: 2N / N for W; 128 / 64 for the
 // K x K lag table C with N = K and L = 2L-1 lags -> Ac).  grid (ceil(N/32), K).
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 3)
 fft_w_kernel(const float *__restrict__ Wi, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int64_t N, int64_t K,
              int64_t L, int B, int logB, int64_t ldw, int64_t coff, int xmode, int kq) {
     const int64_t KQ = kq, MROWS = 2 * kq;
@@ -231,7 +288,7 @@ fft_w_kernel(const float *__restrict__ Wi, __nv_bfloat16 *__restrict__ hi, __nv_
 }
 
 // Of[f][b][m] fp32 -> numH[t][K] (owned columns; V valid outputs per block).  grid (nblk, 32 / C).
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 3)
 ifft_numH_kernel(const float *__restrict__ Of, float *__restrict__ numH, int64_t K, int64_t Tl, int B, int logB, int V,
                  int64_t nblkp, int C, int kq) {
     const int64_t KQ = kq, MROWS = 2 * kq;
@@ -261,7 +318,7 @@ ifft_numH_kernel(const float *__restrict__ Of, float *__restrict__ numH, int64_t
 // sum over the V exact samples of the block and the CTA's 32 units of (Xhat - X)^2.  Block b covers the columns
 // [b*V - (L-1), b*V - (L-1) + B) of H, so sample i >= L-1 of the inverse transform is Xhat at t = b*V + i - (L-1).
 // grid (nbc, ceil(N/32)).
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 3)
 ifft_resid_kernel(const float *__restrict__ Yf, const float *__restrict__ X, double *__restrict__ partial, int64_t N, int64_t Tl,
                   int64_t L, int B, int logB, int V, int64_t nbc, int64_t b0) {
     extern __shared__ float2 fd_smem[];
@@ -314,7 +371,7 @@ ifft_resid_kernel(const float *__restrict__ Yf, const float *__restrict__ X, dou
 // Df[f][m][n] fp32 (row stride ldi) -> out[(l*K+k)*N + n], l < L.  grid (ceil(N/32), K).
 // OutT = float: numW (N even, paired stores);  OutT = double: the Gram partial Rg[d][k][k'] with N = K.
 template <typename OutT>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 3)
 ifft_numW_kernel(const float *__restrict__ Df, OutT *__restrict__ out, int64_t N, int64_t ldi, int64_t K, int64_t L, int B, int logB,
                  int kq) {
     const int64_t KQ = kq, MROWS = 2 * kq;

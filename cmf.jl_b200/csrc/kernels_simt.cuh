@@ -1267,13 +1267,49 @@ __global__ void pgd_penalty_kernel(S *g, const S *__restrict__ x, S l1, S l2, in
     g[i] += S(2) * l2 * v + l1 * (v > S(0) ? S(1) : (v < S(0) ? S(-1) : S(0)));
 }
 
+// pgd.jl:236-241: x -= step / (||g|| + eps) * g, then the projection: NonnegConstraint (x = max(eps, x), :93-95) here, or
+// nothing here and unit_norm_* below for UnitNormConstraint (:98-110)
 template <typename S>
-__global__ void pgd_step_kernel(S *__restrict__ x, const S *__restrict__ g, double step, const double *__restrict__ nrm2, int64_t n) {
+__global__ void pgd_step_kernel(S *__restrict__ x, const S *__restrict__ g, double step, const double *__restrict__ nrm2, int64_t n,
+                                int nonneg) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const S alpha = (S)(step / (sqrt(nrm2[0]) + CMF_EPS));
     const S v = x[i] - alpha * g[i];
-    x[i] = v > (S)CMF_EPS ? v : (S)CMF_EPS;
+    x[i] = (!nonneg || v > (S)CMF_EPS) ? v : (S)CMF_EPS;
+}
+
+// UnitNormConstraint (pgd.jl:98-110): every slice along the first Julia dimension (component k) with ||slice|| > 1 is divided by
+// its norm.  Element e of component k lives at ((e / inner) * K + k) * inner + e % inner  (W: inner = N, rows (l, k); H: inner = 1).
+// grid (UN_CHUNKS, K): fixed chunks and a fixed summation order -> deterministic.
+constexpr int UN_CHUNKS = 64;
+template <typename S>
+__global__ void __launch_bounds__(256) unit_norm_partial_kernel(const S *__restrict__ x, double *__restrict__ part, int64_t K, int64_t inner,
+                                                                 int64_t cnt) {
+    __shared__ double red[256];
+    const int64_t k = blockIdx.y, per = (cnt + UN_CHUNKS - 1) / UN_CHUNKS, e0 = (int64_t)blockIdx.x * per, e1 = min(cnt, e0 + per);
+    double acc = 0.0;
+    for (int64_t e = e0 + threadIdx.x; e < e1; e += 256) {
+        const double v = (double)x[((e / inner) * K + k) * inner + e % inner];
+        acc += v * v;
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[k * UN_CHUNKS + blockIdx.x] = red[0];
+}
+template <typename S>
+__global__ void unit_norm_apply_kernel(S *__restrict__ x, const double *__restrict__ part, int64_t K, int64_t inner, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t k = (i / inner) % K;
+    double ss = 0.0;
+    for (int c = 0; c < UN_CHUNKS; ++c) ss += part[k * UN_CHUNKS + c];
+    const double mag = sqrt(ss);
+    if (mag > 1.0) x[i] = (S)((double)x[i] / mag);
 }
 
 // x[i] = a[i] - b[i]   (P = denomW - numW, Q = denomH - numH: the HALS gradients from the MU quantities)

@@ -30,7 +30,7 @@ from ._lib import F32, F64, HALS, MULT, PGD, CMFError, check, fptr, julia_array,
 _REG_ALIASES = {"l1_W": "l1W", "l2_W": "l2W", "l1_H": "l1H", "l2_H": "l2H"}
 _INIT_ALIASES = {"initW": "W_init", "initH": "H_init"}
 _KNOWN = {"l1W", "l2W", "l1H", "l2H", "seed", "W_init", "H_init", "check_convergence", "patience",
-          "eval_mode", "tol", "verbose", "dtype", "device", "layout", "printer", "engine", "loss_mode", "loss_guard", "ngpu", "devices", "loss_func", "mask"}
+          "eval_mode", "tol", "verbose", "dtype", "device", "layout", "printer", "engine", "loss_mode", "loss_guard", "ngpu", "devices", "loss_func", "mask", "constrW", "constrH"}
 
 
 def _normalise_kwargs(kwargs):
@@ -223,10 +223,14 @@ class PGDUpdate(AbstractCFUpdate):
     weight; the reference defaults are ``penaltiesW=[SquarePenalty(1)]`` and ``penaltiesH=[]`` (pgd.jl:161,185)."""
     _ALG = PGD
 
-    def __init__(self, data, W, H, loss_func="square", mask=None, **kw):
+    def __init__(self, data, W, H, loss_func="square", mask=None, constrW="nonneg", constrH="nonneg", **kw):
         """``loss_func``: "square" (SquareLoss, pgd.jl:28-35) or "absolute" (AbsoluteLoss, :38-45); ``mask`` (N x T) wraps it in a
-        MaskedLoss (:59-70).  Both run on the device (cmf_set_pgd_loss)."""
+        MaskedLoss (:59-70).  Both run on the device (cmf_set_pgd_loss).  ``constrW`` / ``constrH``: "nonneg"
+        (NonnegConstraint, :91-95) or "unitnorm" (UnitNormConstraint, :98-110) -- cmf_set_pgd_constraints."""
         super().__init__(data, W, H, **kw)
+        cmap = {"nonneg": 0, "unitnorm": 1, 0: 0, 1: 1}
+        if cmap[constrW] or cmap[constrH]:
+            check(_lib.load().cmf_set_pgd_constraints(self._h, cmap[constrW], cmap[constrH]))
         lf = {"square": 0, "absolute": 1, 0: 0, 1: 1}[loss_func]
         if lf != 0 or mask is not None:
             m = None if mask is None else julia_array(np.asarray(mask), self.dtype)
@@ -369,7 +373,8 @@ def fit_cnmf(data, L=10, K=5, alg=MultUpdate, max_itr=100, max_time=math.inf, **
 
     extra = {}
     if rule_cls is PGDUpdate:
-        extra = dict(loss_func=kw.get("loss_func", "square"), mask=kw.get("mask"))
+        extra = dict(loss_func=kw.get("loss_func", "square"), mask=kw.get("mask"),
+                     constrW=kw.get("constrW", "nonneg"), constrH=kw.get("constrH", "nonneg"))
     rule = rule_cls(data, W0, H0, dtype=dtype, device=device, sync_host=False,
                     engine=kw.get("engine"), loss_mode=kw.get("loss_mode"), loss_guard=kw.get("loss_guard"),
                     ngpu=kw.get("ngpu", 1), devices=kw.get("devices"), **extra)  # model.jl:79

@@ -240,6 +240,10 @@ int cmf_get_engine(cmf_handle h, int *engine_out);
  * update follows pgd.jl:224-255 literally (conv + loss-gradient epilogue, then the correlation / transposed conv of that gradient);
  * the loss returned by cmf_update_feature_maps is sqrt(eval(loss_func) / ||data||^2) as pgd.jl:202.  PGD handles only. */
 int cmf_set_pgd_loss(cmf_handle h, int loss_func, const void *mask);
+/* PGDUpdate's projections (keywords `constrW` / `constrH` of update_motifs! / update_feature_maps!, pgd.jl:161,183):
+ * 0 = NonnegConstraint (x = max(eps(), x), pgd.jl:91-95; default), 1 = UnitNormConstraint (every component slice whose
+ * 2-norm exceeds 1 is divided by it, pgd.jl:98-110; no non-negativity).  PGD handles only. */
+int cmf_set_pgd_constraints(cmf_handle h, int constrW, int constrH);
 
 /* ---- primitives (tests; one-shot, host in / host out) ----------------------------------- */
 

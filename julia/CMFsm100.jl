@@ -74,7 +74,7 @@ alg_code(::Type{SM100Update{:pgd}}) = CMF_PGD
 
 """`Rule(data, W, H)` -- src/model.jl:79, src/algs/mult.jl:11-20, src/algs/hals.jl:18-28."""
 function (::Type{R})(data::Matrix{T}, W::Array{T,3}, H::Matrix{T}; sync_host=true, device=0, ngpu=1, devices=nothing,
-                     loss_func=:square, mask=nothing) where {R<:SM100Update,T<:Union{Float32,Float64}}
+                     loss_func=:square, mask=nothing, constrW=:nonneg, constrH=:nonneg) where {R<:SM100Update,T<:Union{Float32,Float64}}
     K, N, L = size(W)
     @assert size(data) == (N, size(H, 2)) && size(H, 1) == K
     h = Handle(N, size(data, 2), K, L, dtype_code(T), alg_code(R), device; ngpu=ngpu, devices=devices)
@@ -83,6 +83,9 @@ function (::Type{R})(data::Matrix{T}, W::Array{T,3}, H::Matrix{T}; sync_host=tru
         m = mask === nothing ? nothing : convert(Matrix{T}, mask)
         GC.@preserve m check(ccall((:cmf_set_pgd_loss, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}),
                                    h.ptr, loss_func == :absolute ? 1 : 0, m === nothing ? C_NULL : pointer(m)))
+    end
+    if R === SM100PGDUpdate && (constrW != :nonneg || constrH != :nonneg)     # UnitNormConstraint, src/algs/pgd.jl:98-110
+        check(ccall((:cmf_set_pgd_constraints, LIB), Cint, (Ptr{Cvoid}, Cint, Cint), h.ptr, constrW == :unitnorm ? 1 : 0, constrH == :unitnorm ? 1 : 0))
     end
     GC.@preserve data W H begin
         check(ccall((:cmf_set_data, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), h.ptr, data, 0))

@@ -256,9 +256,11 @@ class PGDUpdate:
     (reference default ``penaltiesW=[SquarePenalty(1)]``, pgd.jl:161), ``l1W`` = AbsolutePenalty weight,
     likewise ``l1H``/``l2H`` (reference default ``penaltiesH=[]``, pgd.jl:185).  ``loss_func`` is "square"
     (SquareLoss, pgd.jl:28-35) or "absolute" (AbsoluteLoss, :38-45); ``mask`` (N x T) wraps it in a MaskedLoss
-    (:59-70: the gradient is multiplied by the mask, the loss is evaluated on mask.*data and mask.*est)."""
+    (:59-70: the gradient is multiplied by the mask, the loss is evaluated on mask.*data and mask.*est).  ``constrW`` /
+    ``constrH`` are "nonneg" (NonnegConstraint, :91-95, the default) or "unitnorm" (UnitNormConstraint, :98-110: every slice
+    along the first dimension -- one component -- whose 2-norm exceeds 1 is divided by it; no non-negativity)."""
 
-    def __init__(self, data, W, H, loss_func="square", mask=None):
+    def __init__(self, data, W, H, loss_func="square", mask=None, constrW="nonneg", constrH="nonneg"):
         self.datanorm = float(np.linalg.norm(data))
         self.est = tensor_conv(W, H)
         self.stepW = 5.0          # pgd.jl:147-148
@@ -266,6 +268,17 @@ class PGDUpdate:
         self.cur_loss = self.datanorm   # pgd.jl:149 (sic: the norm, not its square)
         self.step_incr, self.step_decr = 1.05, 0.70
         self.loss_func, self.mask = loss_func, mask
+        self.constrW, self.constrH = constrW, constrH
+
+    @staticmethod
+    def _project(x, constr):
+        if constr == "nonneg":
+            np.maximum(x, EPSILON, out=x)                 # NonnegConstraint :93-95
+        else:
+            for m in range(x.shape[0]):                   # UnitNormConstraint :101-110
+                mag = float(np.linalg.norm(x[m]))
+                if mag > 1:
+                    x[m] /= mag
 
     def _loss_grad(self, data):
         g = 2.0 * (self.est - data) if self.loss_func == "square" else np.sign(self.est - data)   # :30-32 / :40-42
@@ -275,13 +288,13 @@ class PGDUpdate:
         b, e = (data, self.est) if self.mask is None else (self.mask * data, self.mask * self.est)  # :67-69
         return float(np.linalg.norm(b - e) ** 2) if self.loss_func == "square" else float(np.sum(np.abs(b - e)))
 
-    def _pgd(self, x, grad_fn, step, data, W, H, l1, l2):
+    def _pgd(self, x, grad_fn, step, data, W, H, l1, l2, constr="nonneg"):
         """pgd.jl:224-255."""
         g = grad_fn(self._loss_grad(data))
         g = g + 2.0 * l2 * x + l1 * np.sign(x)            # SquarePenalty :77-79, AbsolutePenalty :86-88
         alpha = step / (np.linalg.norm(g) + EPSILON)      # :236
         x -= alpha * g                                    # :239
-        np.maximum(x, EPSILON, out=x)                     # NonnegConstraint :93-95
+        self._project(x, constr)                          # :241
         self.est = tensor_conv(W, H)                      # :244
         loss = self._loss_eval(data)                      # :245
         step *= self.step_incr if loss < self.cur_loss else self.step_decr   # :247-251
@@ -291,11 +304,11 @@ class PGDUpdate:
     def update_motifs(self, data, W, H, l1W=0.0, l2W=1.0, **_):
         """pgd.jl:158-178; gradient pgd.jl:206-214."""
         L = W.shape[2]
-        self.stepW = self._pgd(W, lambda ge: corr_w(H, ge, L), self.stepW, data, W, H, l1W, l2W)
+        self.stepW = self._pgd(W, lambda ge: corr_w(H, ge, L), self.stepW, data, W, H, l1W, l2W, self.constrW)
 
     def update_feature_maps(self, data, W, H, l1H=0.0, l2H=0.0, **_):
         """pgd.jl:181-203; gradient pgd.jl:218-221."""
-        self.stepH = self._pgd(H, lambda ge: tensor_transconv(W, ge), self.stepH, data, W, H, l1H, l2H)
+        self.stepH = self._pgd(H, lambda ge: tensor_transconv(W, ge), self.stepH, data, W, H, l1H, l2H, self.constrH)
         return float(np.sqrt(self.cur_loss / self.datanorm ** 2))
 
 

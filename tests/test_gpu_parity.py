@@ -373,6 +373,22 @@ def test_pgd_masked_and_absolute_losses(cmf, orc, loss_func, masked):
     rule.close()
 
 
+@pytest.mark.parametrize("constrW,constrH", [("unitnorm", "nonneg"), ("nonneg", "unitnorm"), ("unitnorm", "unitnorm")])
+def test_pgd_unit_norm_constraint(cmf, orc, constrW, constrH):
+    # UnitNormConstraint (src/algs/pgd.jl:98-110) in place of NonnegConstraint on either factor, vs the oracle's restatement
+    X, W0, H0 = _config1(orc, N=60, T=400)
+    reg = dict(l1W=0.0, l2W=1.0, l1H=0.0, l2H=0.05)
+    ref = orc.po.fit(orc.po.PGDUpdate(X, W0, H0, constrW=constrW, constrH=constrH), X, W0, H0, 25, check_convergence=False, **reg)
+    r = cmf.fit_cnmf(X, L=10, K=5, alg="pgd", max_itr=25, W_init=W0, H_init=H0, check_convergence=False, layout="KNL",
+                     constrW=constrW, constrH=constrH, **reg)
+    assert np.allclose(r.loss_hist, ref.loss_hist, rtol=F64_RTOL), (r.loss_hist[-3:], ref.loss_hist[-3:])
+    assert np.allclose(r.W, ref.W, rtol=1e-7, atol=1e-11) and np.allclose(r.H, ref.H, rtol=1e-7, atol=1e-11)
+    if constrW == "unitnorm":
+        assert np.all(np.linalg.norm(r.W.reshape(5, -1), axis=1) <= 1 + 1e-12)
+    if constrH == "unitnorm":
+        assert np.all(np.linalg.norm(r.H, axis=1) <= 1 + 1e-12)
+
+
 def test_gen_synthetic_and_parameter_sweep(cmf):
     # README.md:14-23: data = CMF.gen_synthetic(N=500, T=2000); fit_cnmf(data; L=10, K=5, alg=:hals)
     data = cmf.gen_synthetic(N=60, T=300, K=3, L=8, seed=7)
@@ -383,6 +399,31 @@ def test_gen_synthetic_and_parameter_sweep(cmf):
     assert set(sweep) == {(4, 2, "mult"), (6, 2, "mult"), (4, 2, ":hals"), (6, 2, ":hals")}
     for r in sweep.values():
         assert r.loss_hist[-1] < r.loss_hist[0]
+
+
+def test_gen_synthetic_follows_the_reference_data_model(cmf):
+    """datasets/synthetic.jl:29-61: Dirichlet(0.1) unit weights x Gaussian lag bumps (sigma 0.2 on linspace(-1,1,L), centres
+    U(-1,1)), Exp(1)*Bernoulli(p_h) activations, N(0, noise^2) noise, clipped at 0.  The device generator uses its own
+    counter-based RNG, so the comparison with the oracle's restatement of that file is distributional: pooled over seeds,
+    the first two moments, the clipped fraction and upper quantiles of the data must agree."""
+    from oracle import cnmf_oracle as po
+
+    N, T, K, L, p_h, noise = 160, 3000, 3, 20, 0.3, 0.5
+    dev = np.concatenate([cmf.gen_synthetic(N=N, T=T, K=K, L=L, p_h=p_h, noise_scale=noise, seed=s).ravel() for s in (1, 2, 3, 4)])
+    ref = np.concatenate([po.synthetic_sequences(K=K, N=N, L=L, T=T, p_h=p_h, noise_scale=noise,
+                                                 rng=np.random.default_rng(100 + s))[0].ravel() for s in (1, 2, 3, 4)])
+    assert dev.min() >= 0.0
+    assert abs(dev.mean() - ref.mean()) < 0.06 * ref.mean(), (dev.mean(), ref.mean())
+    assert abs(dev.std() - ref.std()) < 0.08 * ref.std(), (dev.std(), ref.std())
+    assert abs((dev == 0).mean() - (ref == 0).mean()) < 0.02, ((dev == 0).mean(), (ref == 0).mean())
+    for q in (0.5, 0.9, 0.99):
+        a, b = np.quantile(dev, q), np.quantile(ref, q)
+        assert abs(a - b) < 0.08 * b + 0.02, (q, a, b)
+    # noise-free data: every unit's weights sum to one over the components, so sum_t X[n, t] / sum_k,t H-mass is the bump mass
+    clean = cmf.gen_synthetic(N=N, T=T, K=K, L=L, p_h=p_h, noise_scale=0.0, seed=9)
+    clean_ref = po.synthetic_sequences(K=K, N=N, L=L, T=T, p_h=p_h, noise_scale=0.0, rng=np.random.default_rng(9))[0]
+    assert abs(clean.mean() - clean_ref.mean()) < 0.08 * clean_ref.mean(), (clean.mean(), clean_ref.mean())
+    assert abs((clean == 0).mean() - (clean_ref == 0).mean()) < 0.03
 
 
 def test_cuda_fp64_matches_exact_rational_pin(cmf):
