@@ -320,7 +320,7 @@ def run_ours(args, cfg, name):
 
     # secondary: the same iteration with the loss evaluated by the direct conv + residual pass (mult.jl:55-57 literally)
     value_direct = None
-    if args.loss_mode == 1 and args.alg == "mult":
+    if args.loss_mode == 1 and args.alg == "mult" and not args.no_direct:
         shard.set_loss_mode(0)
         fitter.iterate()
         barrier()
@@ -504,7 +504,8 @@ def run_ours(args, cfg, name):
         # the H sweep (hals.jl:121-154) is a chain of T dependent steps per component: neither HBM nor tensor bound, and no
         # GPU count shortens it; on a sharded fit it runs on rank 0 over all T columns (gather Q / scatter H around it)
         per_sweep = sweep_ms / max(sweep_n, 1)
-        critical = {"kernel": "hals_h_wave_kernel (cooperative wavefront over (component, 1024-column chunk))",
+        critical = {"kernel": "hals2_sweep_kernel (cooperative launch in rounds: recurrence warps with lane = component, 8x8 pull blocks, "
+                              "diagonal items; one 1024-column chunk per component per round)",
                     "dependent_column_steps": T + (K - 1) * L, "ms_per_sweep": per_sweep, "sweeps": sweep_n,
                     "us_per_1024_columns": per_sweep * 1e3 / (T / 1024.0) if sweep_n else None,
                     "ns_per_column": per_sweep * 1e6 / T if sweep_n else None,
@@ -521,8 +522,8 @@ def run_ours(args, cfg, name):
                    "engine": {0: "SIMT fp32", 1: "tcgen05 split-bf16, time domain (3 MMAs per product, fp32 accumulate)",
                               2: "tcgen05 split-bf16, frequency domain (overlap-save spectrum of X, SIMT FFTs, per-frequency "
                                  "complex products with 3 MMAs per product)"}[engine],
-                   "loss": ("algebraic expansion ||X||^2 - 2<numH,H> + <WW',HtHt'> (exact identity, falls back to the direct "
-                            "pass below 25% loss)" if (args.loss_mode == 1 and args.alg == "mult") else "direct conv + residual pass")},
+                   "loss": ("algebraic expansion ||X||^2 - 2<numH,H> + <WW',HtHt'> (exact identity; at or below 25% loss it is "
+                            "calibrated against the direct pass every 1..16 evaluations, see value_calibrated_loss)" if (args.loss_mode == 1 and args.alg == "mult") else "direct conv + residual pass")},
         "value_direct_loss": value_direct, "value_calibrated_loss": calibrated,
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_hbm": hbm, "cpu_baseline": cpu,
         "clocks": clocks, "loss": {"initial": loss0, "final": losses[-1] if losses else None},
@@ -583,6 +584,7 @@ def main():
                     help="multi-GPU: NCCL inside the library behind the reference-facing calls (default) or torch.distributed between the split-phase calls")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-direct", action="store_true", help="skip the direct-loss figure")
     ap.add_argument("--no-calibrated", action="store_true", help="skip the calibrated-expansion figure (63 more iterations)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])

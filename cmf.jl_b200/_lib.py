@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libcmf_sm100.so")
+SO_PATH = os.environ.get("CMF_SM100_LIB") or os.path.join(_HERE, "libcmf_sm100.so")   # override: A/B builds of the same ABI
 
 F64, F32 = 0, 1
 MULT, HALS, PGD = 0, 1, 2

@@ -103,9 +103,10 @@ struct cmf_ctx {
     double calib_bias = 0.0, calib_last_err = 0.0;
     int calib_left = 0, calib_interval = 1, calib_fail = 0;
     int64_t n_loss_direct = 0, n_loss_expansion = 0;
-    void calib_reset() { calib_have = false; calib_left = 0; calib_interval = 1; calib_fail = 0; }
+    void calib_reset() { calib_have = false; calib_left = 0; calib_interval = 1; calib_fail = 0; numH_dot_valid = false; }   // called wherever the factors or the data are replaced
     double pgd_stepW = 5.0, pgd_stepH = 5.0, pgd_cur_loss = 0.0;   // PGDUpdate state (pgd.jl:147-151)
     bool numH_valid = false;         // numH buffer == transconv(current W, X) and GS == W W' of the current W
+    bool numH_dot_valid = false;     // scal[4] == <numH, H> of the current numH and H (left there by the MU update of H)
     bool gram_valid = false;         // exchange buffer 1 holds the local Gram/tail partial of the current H
     bool have_data = false, have_factors = false;
     // optional per-kernel-class event timing (bench.py's roofline): class -> list of event pairs
@@ -469,7 +470,7 @@ struct Ctx : cmf_ctx {
         if constexpr (std::is_same<S, float>::value) {
             FdState &f = fds;
             if (!f.x_dirty) return;
-            dim3 grid((unsigned)f.nblkp, (unsigned)cdiv(N, 32));
+            dim3 grid((unsigned)(f.nblkp * cdiv(N, 32)));
             fd::fft_x_kernel<<<grid, fd::NT, fd_smem(16), stream>>>(X.p, f.Xf_hi.p, f.Xf_lo.p, N, Tl + (L - 1), f.B, f.logB, f.V, f.nblkp);
             post_launch();
             f.x_dirty = false;
@@ -518,7 +519,7 @@ struct Ctx : cmf_ctx {
             const unsigned grid = (unsigned)std::min<int64_t>(q.units, tcs.num_sms);
             tc::tc_kernel<tc::TC_FQT><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(f.mAc[0], f.mAc[1], f.mHf2K[0], f.mHf2K[1], q);
             post_launch();
-            fd::ifft_numH_kernel<<<dim3((unsigned)f.nblk2, (unsigned)(f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
+            fd::ifft_numH_kernel<<<(unsigned)(f.nblk2 * (f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
                 f.Of.p, denH.p, K, Tl, f.B, f.logB, f.V2, f.nblk2, C, f.Kq);
             post_launch();
         }
@@ -530,7 +531,7 @@ struct Ctx : cmf_ctx {
             FdState &f = fds;
             if (!fd_active() || f.hf2_valid) return;
             const int C = fd_cols_h();
-            fd::fft_h_kernel<<<dim3((unsigned)f.nblk2, (unsigned)(f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
+            fd::fft_h_kernel<<<(unsigned)(f.nblk2 * (f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
                 H, f.Hf_hi.p, f.Hf_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V2, f.nblk2, C, 1, -(L - 1), f.Kq);
             post_launch();
             f.hf2_valid = true;
@@ -571,7 +572,7 @@ struct Ctx : cmf_ctx {
                 f.wx_dirty = false;
             }
             const int C = fd_cols_h();
-            fd::fft_h_kernel<<<dim3((unsigned)f.nblk, (unsigned)(f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
+            fd::fft_h_kernel<<<(unsigned)(f.nblk * (f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
                 H, f.Hf_hi.p, f.Hf_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V, f.nblk, C, 1, -(L - 1), f.Kq);
             post_launch();
             prof_begin(PROF_CONV);
@@ -588,7 +589,7 @@ struct Ctx : cmf_ctx {
                 const unsigned grid = (unsigned)std::min<int64_t>(q.units, tcs.num_sms);
                 tc::tc_kernel<tc::TC_FQX><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(f.mAwm[0], f.mAwm[1], f.mHcK[0], f.mHcK[1], q);
                 post_launch();
-                fd::ifft_resid_kernel<<<dim3((unsigned)cur, (unsigned)ntile32), fd::NT, fd_smem(16), stream>>>(
+                fd::ifft_resid_kernel<<<(unsigned)(cur * ntile32), fd::NT, fd_smem(16), stream>>>(
                     f.Yf.p, X.p, loss_part.p + b0 * ntile32, N, Tl, L, f.B, f.logB, f.V, cur, b0);
                 post_launch();
             }
@@ -603,7 +604,7 @@ struct Ctx : cmf_ctx {
             FdState &f = fds;
             if (!f.h_dirty) return;
             const int C = fd_cols_h();
-            fd::fft_h_kernel<<<dim3((unsigned)f.nblkp, (unsigned)(f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
+            fd::fft_h_kernel<<<(unsigned)(f.nblkp * (f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
                 H, f.Ah_hi.p, f.Ah_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V, f.nblkp, C, 0, 0, f.Kq);
             post_launch();
             f.h_dirty = false;
@@ -616,7 +617,7 @@ struct Ctx : cmf_ctx {
             f.hf2_valid = false;
             fd_spectrum_H();
             const int C = fd_cols_h();
-            fd::fft_h_kernel<<<dim3((unsigned)f.nblkp, (unsigned)(f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
+            fd::fft_h_kernel<<<(unsigned)(f.nblkp * (f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
                 H, f.Hf_hi.p, f.Hf_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V, f.nblkp, C, 1, 0, f.Kq);
             post_launch();
             tc::Params q = tc_base_params();
@@ -656,7 +657,7 @@ struct Ctx : cmf_ctx {
             prof_end();
             post_launch();
             const int C = fd_cols_h();
-            fd::ifft_numH_kernel<<<dim3((unsigned)f.nblk, (unsigned)(f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
+            fd::ifft_numH_kernel<<<(unsigned)(f.nblk * (f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
                 f.Of.p, numH.p, K, Tl, f.B, f.logB, f.V, f.nblkp, C, f.Kq);
             post_launch();
         }
@@ -1086,6 +1087,23 @@ struct Ctx : cmf_ctx {
         REQUIRE(smem <= 200 * 1024, "transconv: L too large for the shared-memory window");
         dim3 grid((unsigned)cdiv(t_out, BTt), (unsigned)cdiv(Kout, KP));
         const int nthr = best_kg * tg;
+        // small problems (configs 1-2: T = 2000 gives 8 CTAs) do not fill the device over (t, k) tiles alone: split the sum over
+        // units across blockIdx.z into partial outputs and add them in a fixed order (deterministic)
+        int nsplit = 1;
+        a.n_chunk = cdiv(Nin, TR_NC) * TR_NC; a.part_stride = 0;
+        const int64_t ctas = (int64_t)grid.x * grid.y;
+        if (ctas < 296 && Nin >= 64) {
+            const int64_t want = std::min<int64_t>(std::min<int64_t>(cdiv(Nin, 32), cdiv(296, ctas)), 32);
+            a.n_chunk = cdiv(cdiv(Nin, want), TR_NC) * TR_NC;
+            nsplit = (int)cdiv(Nin, a.n_chunk);
+            if (nsplit > 1) {
+                a.part_stride = t_out * Kout;
+                const size_t need = (size_t)nsplit * (size_t)a.part_stride;
+                if (tr_part.n < need) tr_part.alloc(need);
+                a.out = tr_part.p;
+                grid.z = (unsigned)nsplit;
+            }
+        }
 #define LAUNCH_TR(TKV)                                                                             \
     {                                                                                              \
         auto kern = transconv_kernel<S, TKV, 8>;                                                   \
@@ -1097,7 +1115,12 @@ struct Ctx : cmf_ctx {
 #undef LAUNCH_TR
         prof_end();
         post_launch();
+        if (nsplit > 1) {
+            sum_parts_kernel<S><<<(unsigned)cdiv(a.part_stride, 256), 256, 0, stream>>>(tr_part.p, out, a.part_stride, a.part_stride, nsplit);
+            post_launch();
+        }
     }
+    DevBuf<S> tr_part;     // partial outputs of the N-split transposed convolution
 
     // out_S / out_D [(l*K+k)*Nin + n] = sum_tau hm(tau-l)[k] Xin[tau][n]
     void launch_corr(const S *Xin, int64_t Nin, int64_t ldx, int64_t tau_hi, int nsplit, int64_t split_len,
@@ -1124,9 +1147,26 @@ struct Ctx : cmf_ctx {
         post_launch();
     }
 
-    void launch_mu(S *x, const S *num, const S *den, double l1, double l2, int64_t n) {
+    // mult.jl:37-38 / 51-52.  dot_dst != nullptr additionally leaves <num, x'> (new x) there: the expansion loss's <numH, H'>
+    // comes out of the H update for free.  Returns whether the inner product was produced.
+    DevBuf<double> mu_part;
+    bool launch_mu(S *x, const S *num, const S *den, double l1, double l2, int64_t n, double *dot_dst = nullptr) {
+        if constexpr (std::is_same<S, float>::value) {
+            const bool aligned = (((uintptr_t)x | (uintptr_t)num | (uintptr_t)den) & 15) == 0;
+            if (aligned && n % 4 == 0 && n >= 4096) {
+                const unsigned grid = (unsigned)std::min<int64_t>(cdiv(n / 4, 256), 148 * 8);
+                if (dot_dst && mu_part.n == 0) mu_part.alloc(148 * 8);
+                mu_update_vec4_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<float4 *>(x), reinterpret_cast<const float4 *>(num),
+                                                                reinterpret_cast<const float4 *>(den), (float)l1, (float)l2, n / 4,
+                                                                dot_dst ? mu_part.p : nullptr);
+                post_launch();
+                if (dot_dst) reduce_scalar(mu_part.p, grid, dot_dst);
+                return dot_dst != nullptr;
+            }
+        }
         mu_update_kernel<S><<<(unsigned)cdiv(n, 256), 256, 0, stream>>>(x, num, den, (S)l1, (S)l2, n);
         post_launch();
+        return false;
     }
 
     // ---------------------------------------------------------------- data
@@ -1147,7 +1187,7 @@ struct Ctx : cmf_ctx {
     void finish_data() {
         tcs.x_dirty = true;
         fds.x_dirty = true;
-        numH_valid = false;
+        numH_valid = false; numH_dot_valid = false;
         calib_reset();
         data_sumsq_local = data_sumsq();
         data_norm = std::sqrt(data_sumsq_local);
@@ -1192,7 +1232,7 @@ struct Ctx : cmf_ctx {
         CK(cudaStreamSynchronize(stream));
         have_factors = true;
         mark_w_dirty();
-        numH_valid = false;
+        numH_valid = false; numH_dot_valid = false;
         gram_valid = false; fds.h_dirty = true; fds.hf2_valid = false;
         pgd_stepW = pgd_stepH = 5.0;            // a new rule instance (pgd.jl:147-149)
         pgd_cur_loss = data_norm;
@@ -1212,7 +1252,7 @@ struct Ctx : cmf_ctx {
         CK(cudaStreamSynchronize(stream));
         have_factors = true;
         mark_w_dirty();
-        numH_valid = false;
+        numH_valid = false; numH_dot_valid = false;
         gram_valid = false; fds.h_dirty = true; fds.hf2_valid = false;
         calib_reset();
     }
@@ -1236,7 +1276,7 @@ struct Ctx : cmf_ctx {
         scale_kernel<S><<<(unsigned)cdiv((int64_t)Hbuf.n, 256), 256, 0, stream>>>(Hbuf.p, (S)s, (int64_t)Hbuf.n);
         post_launch();
         mark_w_dirty();
-        numH_valid = false;
+        numH_valid = false; numH_dot_valid = false;
         gram_valid = false; fds.h_dirty = true; fds.hf2_valid = false;
         calib_reset();
     }
@@ -1297,7 +1337,7 @@ struct Ctx : cmf_ctx {
     void w_update_rows(double l1W, double l2W, int64_t j0, int64_t j1) override {
         launch_mu(Wi.p + j0 * N, numW.p + j0 * N, denW.p + j0 * N, l1W, l2W, (j1 - j0) * N);
         mark_w_dirty();
-        numH_valid = false;
+        numH_valid = false; numH_dot_valid = false;
     }
     void w_rows_buffers(void **numw, void **w, int64_t *row_elems) override { *numw = numW.p; *w = Wi.p; *row_elems = N; }
 
@@ -1348,7 +1388,8 @@ struct Ctx : cmf_ctx {
         if (is_last && L > 1) {
             launch_denomH_tail();
         }
-        launch_mu(H, numH.p, denH.p, l1H, l2H, Tl * K);                       // mult.jl:51-52
+        // mult.jl:51-52; with the expansion loss in force the update also leaves <numH, H'> in scal[4]
+        numH_dot_valid = launch_mu(H, numH.p, denH.p, l1H, l2H, Tl * K, (loss_mode == 1 && alg == CMF_MULT) ? scal.p + 4 : nullptr);
         numH_valid = (alg == CMF_MULT);
         gram_valid = false; fds.h_dirty = true; fds.hf2_valid = false;
     }
@@ -1364,7 +1405,7 @@ struct Ctx : cmf_ctx {
         if (loss_mode == 1 && tc_active()) {
             // frequency-domain engine: numH and W W' are cheap, so the expansion also serves calls that find them stale
             // (the loss at the initial factors, after a W-only step, after the HALS sweep overwrote numH)
-            if (!numH_valid && fd_active()) { tc_transconv(); lag_tables(); numH_valid = true; }
+            if (!numH_valid && fd_active()) { tc_transconv(); lag_tables(); numH_valid = true; numH_dot_valid = false; }
             if (numH_valid) { loss_partial_expansion_dev(); return 2; }
         }
         int64_t nb = conv_nblocks(0, Tl);
@@ -1398,6 +1439,11 @@ struct Ctx : cmf_ctx {
             s2_dot_G_diag_kernel<S><<<1024, 256, 0, stream>>>(GS.p, s2_ks, s2_ld, exch1.p, exch1.p + L * K * K, K, L, loss_part.p + 1024);
         post_launch();
         reduce_scalar(loss_part.p + 1024, 1024, scal.p + 1);
+        if (numH_dot_valid) {             // produced by the H update itself (consumed once: anything may happen before the next call)
+            CK(cudaMemcpyAsync(scal.p, scal.p + 4, sizeof(double), cudaMemcpyDeviceToDevice, stream));
+            numH_dot_valid = false;
+            return;
+        }
         dot_partial_kernel<S><<<1024, 256, 0, stream>>>(numH.p, H, Tl * K, loss_part.p);
         post_launch();
         reduce_scalar(loss_part.p, 1024, scal.p);
@@ -1421,7 +1467,7 @@ struct Ctx : cmf_ctx {
         kern<<<(unsigned)N, 256, smem, stream>>>(GS.p, numW.p, Wi.p, K, L, N, (S)l1W, (S)l2W);   // hals.jl:90-112
         post_launch();
         mark_w_dirty();
-        numH_valid = false;
+        numH_valid = false; numH_dot_valid = false;
     }
 
     void hals_update_motifs(double l1W, double l2W) override {
@@ -1569,7 +1615,7 @@ struct Ctx : cmf_ctx {
     }
     void h_changed() override {
         gram_valid = false; fds.h_dirty = true; fds.hf2_valid = false;
-        numH_valid = false;
+        numH_valid = false; numH_dot_valid = false;
     }
 
     double hals_update_feature_maps(double l1H, double l2H) override {
@@ -1646,7 +1692,7 @@ struct Ctx : cmf_ctx {
             post_launch();
             pgd_step(Wi.p, denW.p, KL() * N, pgd_stepW, pgd_constrW, N);
             mark_w_dirty();
-            numH_valid = false;
+            numH_valid = false; numH_dot_valid = false;
             pgd_adapt(pgd_loss_eval(), pgd_stepW);
             return;
         }
@@ -1657,7 +1703,7 @@ struct Ctx : cmf_ctx {
         post_launch();
         pgd_step(Wi.p, denW.p, KL() * N, pgd_stepW, pgd_constrW, N);
         mark_w_dirty();
-        numH_valid = false;
+        numH_valid = false; numH_dot_valid = false;
         pgd_adapt(loss_partial(), pgd_stepW);                                           // pgd.jl:244-252
     }
 
@@ -1670,7 +1716,7 @@ struct Ctx : cmf_ctx {
             post_launch();
             pgd_step(H, denH.p, Tl * K, pgd_stepH, pgd_constrH, 1);
             gram_valid = false; fds.h_dirty = true; fds.hf2_valid = false;
-            numH_valid = false;
+            numH_valid = false; numH_dot_valid = false;
             pgd_adapt(pgd_loss_eval(), pgd_stepH);
             return pgd_cur_loss;
         }

@@ -39,6 +39,10 @@
 namespace cmf {
 namespace fd {
 
+#ifndef CMF_FD_MINB
+#define CMF_FD_MINB 3        // CTAs per SM the transforms are compiled for (3 x 512 threads: 40 registers per thread)
+#endif
+constexpr int LD_U = 8;      // global loads a thread keeps in flight while it fills / drains the shared-memory tile
 constexpr int NT = 512;      // threads per CTA (A/B at c4: 256 -> 49, 512 -> 44, 1024 -> 50 ms per iteration)
 constexpr int KQ_MAX = 128;  // components are padded to Kq = 64 or 128 rows; the A operands / outputs have MROWS = 2 Kq rows per
                              // frequency (m = k real part, m = Kq + k imaginary part), i.e. one or two 128-row tensor-core tiles
@@ -160,22 +164,37 @@ __device__ __forceinline__ void store_split2(__nv_bfloat16 *hi, __nv_bfloat16 *l
     *reinterpret_cast<uint32_t *>(lo + idx) = l;
 }
 
-// X[t][N] fp32 (xcols rows) -> Xf.  grid (nblkp, ceil(N/32)); 16 complex columns = 32 units per CTA.
-__global__ void __launch_bounds__(NT, 3)
+// X[t][N] fp32 (xcols rows) -> Xf.  grid nblkp * ceil(N/32) (1-D); 16 complex columns = 32 units per CTA.
+__global__ void __launch_bounds__(NT, CMF_FD_MINB)
 fft_x_kernel(const float *__restrict__ X, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int64_t N, int64_t xcols,
              int B, int logB, int V, int64_t nblkp) {
     extern __shared__ float2 fd_smem[];
     constexpr int C = 16;
     float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;
-    const int64_t b = blockIdx.x;
+    // 1-D grid, unit tile fastest: CTAs that run together read neighbouring 128-byte pieces of the same rows of X
+    const int ny = (int)((N + 31) / 32);
+    const int64_t b = blockIdx.x / ny;
     const int p = threadIdx.x % C;
-    const int64_t n = (int64_t)blockIdx.y * 32 + 2 * p;
+    const int64_t n = (int64_t)(blockIdx.x % ny) * 32 + 2 * p;
     make_twiddles(tw, B);
-    for (int i = threadIdx.x / C; i < B; i += NT / C) {
-        const int64_t t = b * V + i;
-        float2 v = make_float2(0.f, 0.f);
-        if (t < xcols && n < N) v = *reinterpret_cast<const float2 *>(X + t * N + n);
-        d[i * C + p] = v;
+    {
+        // LD_U rows per thread are requested before any is stored: the transforms are bound by the latency of these loads, not by
+        // bandwidth or issue slots (profiles/r2_ncu_fft_kernels.md), so memory-level parallelism is what counts
+        const int i0 = threadIdx.x / C, istep = NT / C;
+        const int64_t lim64 = xcols - b * V;
+        const int lim = (n < N) ? (int)(lim64 < 0 ? 0 : (lim64 > B ? B : lim64)) : 0;
+        const float *src = X + (b * V + i0) * N + n;
+        for (int i = i0; i < B; i += LD_U * istep, src += (int64_t)LD_U * istep * N) {
+            float2 v[LD_U];
+#pragma unroll
+            for (int u = 0; u < LD_U; ++u) {
+                v[u] = make_float2(0.f, 0.f);
+                if (i + u * istep < lim) v[u] = *reinterpret_cast<const float2 *>(src + (int64_t)u * istep * N);
+            }
+#pragma unroll
+            for (int u = 0; u < LD_U; ++u)
+                if (i + u * istep < B) d[(i + u * istep) * C + p] = v[u];
+        }
     }
     __syncthreads();
     fft_passes<false>(d, tw, B, logB, C);
@@ -192,16 +211,17 @@ fft_x_kernel(const float *__restrict__ X, __nv_bfloat16 *__restrict__ hi, __nv_b
 // H[t][K] fp32 (owned column 0 first; block b starts at column b*V + t_off, t_off <= 0 reaches into the left halo).
 // full == 0: only the V owned columns of each block, zero padded -> Ah;
 // full != 0: whole blocks over the columns present, t < hcols = Tl + L-1 (owned + right halo) -> Hf.
-// grid (nblkp, 32 / C); C complex columns = 2C components per CTA.
-__global__ void __launch_bounds__(NT, 3)
+// grid nblkp * (kq / 2 / C) (1-D); C complex columns = 2C components per CTA.
+__global__ void __launch_bounds__(NT, CMF_FD_MINB)
 fft_h_kernel(const float *__restrict__ H, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int64_t K, int64_t Tl,
              int64_t hcols, int B, int logB, int V, int64_t nblkp, int C, int full, int64_t t_off, int kq) {
     const int64_t KQ = kq, MROWS = 2 * kq;
     extern __shared__ float2 fd_smem[];
     float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;
-    const int64_t b = blockIdx.x;
+    const int ny = (kq / 2) / C;                      // 1-D grid, component tile fastest (the tiles of one block share its rows of H)
+    const int64_t b = blockIdx.x / ny;
     const int p = threadIdx.x % C;
-    const int k = 2 * ((int)blockIdx.y * C + p);
+    const int k = 2 * ((int)(blockIdx.x % ny) * C + p);
     make_twiddles(tw, B);
     {
         const int i0 = threadIdx.x / C, istep = NT / C;
@@ -211,13 +231,20 @@ fft_h_kernel(const float *__restrict__ H, __nv_bfloat16 *__restrict__ hi, __nv_b
         const int lim = (int)(lim64 < 0 ? 0 : (lim64 > B ? B : lim64));
         const float *src = H + (tb + i0) * K + k;
         const bool pair = ((K & 1) == 0) && (k + 1 < K);
-        for (int i = i0; i < B; i += istep, src += (int64_t)istep * K) {
-            float2 v = make_float2(0.f, 0.f);
-            if (i < lim) {
-                if (pair) v = *reinterpret_cast<const float2 *>(src);
-                else { if (k < K) v.x = src[0]; if (k + 1 < K) v.y = src[1]; }
+        for (int i = i0; i < B; i += LD_U * istep, src += (int64_t)LD_U * istep * K) {
+            float2 v[LD_U];
+#pragma unroll
+            for (int u = 0; u < LD_U; ++u) {
+                v[u] = make_float2(0.f, 0.f);
+                if (i + u * istep < lim) {
+                    const float *q = src + (int64_t)u * istep * K;
+                    if (pair) v[u] = *reinterpret_cast<const float2 *>(q);
+                    else { if (k < K) v[u].x = q[0]; if (k + 1 < K) v[u].y = q[1]; }
+                }
             }
-            d[i * C + p] = v;
+#pragma unroll
+            for (int u = 0; u < LD_U; ++u)
+                if (i + u * istep < B) d[(i + u * istep) * C + p] = v[u];
         }
     }
     __syncthreads();
@@ -245,7 +272,7 @@ fft_h_kernel(const float *__restrict__ H, __nv_bfloat16 *__restrict__ hi, __nv_b
 
 // Wi[(l*K+k)][N] fp32 -> Aw (rows of ldw elements, imaginary block at column coff: 2N / N for W; 128 / 64 for the
 // K x K lag table C with N = K and L = 2L-1 lags -> Ac).  grid (ceil(N/32), K).
-__global__ void __launch_bounds__(NT, 3)
+__global__ void __launch_bounds__(NT, CMF_FD_MINB)
 fft_w_kernel(const float *__restrict__ Wi, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int64_t N, int64_t K,
              int64_t L, int B, int logB, int64_t ldw, int64_t coff, int xmode, int kq) {
     const int64_t KQ = kq, MROWS = 2 * kq;
@@ -256,14 +283,24 @@ fft_w_kernel(const float *__restrict__ Wi, __nv_bfloat16 *__restrict__ hi, __nv_
     const int p = threadIdx.x % C;
     const int64_t n = (int64_t)blockIdx.x * 32 + 2 * p;
     make_twiddles(tw, B);
-    for (int i = threadIdx.x / C; i < B; i += NT / C) {
-        float2 v = make_float2(0.f, 0.f);
-        if (i < L && n < N) {
-            const float *src = Wi + ((int64_t)i * K + k) * N + n;
-            if ((N & 1) == 0) v = *reinterpret_cast<const float2 *>(src);
-            else { v.x = src[0]; if (n + 1 < N) v.y = src[1]; }
+    {
+        const int i0 = threadIdx.x / C, istep = NT / C;
+        for (int i = i0; i < B; i += LD_U * istep) {
+            float2 v[LD_U];
+#pragma unroll
+            for (int u = 0; u < LD_U; ++u) {
+                const int ii = i + u * istep;
+                v[u] = make_float2(0.f, 0.f);
+                if (ii < L && n < N) {
+                    const float *src = Wi + ((int64_t)ii * K + k) * N + n;
+                    if ((N & 1) == 0) v[u] = *reinterpret_cast<const float2 *>(src);
+                    else { v[u].x = src[0]; if (n + 1 < N) v[u].y = src[1]; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < LD_U; ++u)
+                if (i + u * istep < B) d[(i + u * istep) * C + p] = v[u];
         }
-        d[i * C + p] = v;
     }
     __syncthreads();
     fft_passes<false>(d, tw, B, logB, C);
@@ -287,76 +324,113 @@ fft_w_kernel(const float *__restrict__ Wi, __nv_bfloat16 *__restrict__ hi, __nv_
     }
 }
 
-// Of[f][b][m] fp32 -> numH[t][K] (owned columns; V valid outputs per block).  grid (nblk, 32 / C).
-__global__ void __launch_bounds__(NT, 3)
+// Of[f][b][m] fp32 -> numH[t][K] (owned columns; V valid outputs per block).  grid nblk * (kq / 2 / C) (1-D).
+__global__ void __launch_bounds__(NT, CMF_FD_MINB)
 ifft_numH_kernel(const float *__restrict__ Of, float *__restrict__ numH, int64_t K, int64_t Tl, int B, int logB, int V,
                  int64_t nblkp, int C, int kq) {
     const int64_t KQ = kq, MROWS = 2 * kq;
     extern __shared__ float2 fd_smem[];
     float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;
-    const int64_t b = blockIdx.x;
+    const int ny = (kq / 2) / C;                      // 1-D grid, component tile fastest (the tiles of one block share its rows of H)
+    const int64_t b = blockIdx.x / ny;
     const int p = threadIdx.x % C;
-    const int k = 2 * ((int)blockIdx.y * C + p);
+    const int k = 2 * ((int)(blockIdx.x % ny) * C + p);
     make_twiddles(tw, B);
-    for (int f = threadIdx.x / C; f <= B / 2; f += NT / C) {
-        const float *o = Of + ((int64_t)f * nblkp + b) * MROWS;
-        pack_pair(d, f, B, C, p, *reinterpret_cast<const float2 *>(o + k), *reinterpret_cast<const float2 *>(o + KQ + k));
+    {
+        const int f0 = threadIdx.x / C, fstep = NT / C;
+        const float *o = Of + ((int64_t)f0 * nblkp + b) * MROWS + k;
+        for (int f = f0; f <= B / 2; f += 4 * fstep, o += (int64_t)4 * fstep * nblkp * MROWS) {
+            float2 re[4], im[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (f + u * fstep <= B / 2) {
+                    const float *q = o + (int64_t)u * fstep * nblkp * MROWS;
+                    re[u] = *reinterpret_cast<const float2 *>(q); im[u] = *reinterpret_cast<const float2 *>(q + KQ);
+                }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (f + u * fstep <= B / 2) pack_pair(d, f + u * fstep, B, C, p, re[u], im[u]);
+        }
     }
     __syncthreads();
     fft_passes<true>(d, tw, B, logB, C);
     const float sc = 1.0f / (float)B;
+    const bool pair = ((K & 1) == 0) && (k + 1 < K);
     for (int i = threadIdx.x / C; i < V; i += NT / C) {
         const int64_t t = b * V + i;
         if (t >= Tl) break;
         const float2 z = d[rev(i, logB) * C + p];
-        if (k < K) numH[t * K + k] = z.x * sc;
-        if (k + 1 < K) numH[t * K + k + 1] = z.y * sc;
+        if (pair) *reinterpret_cast<float2 *>(numH + t * K + k) = make_float2(z.x * sc, z.y * sc);
+        else { if (k < K) numH[t * K + k] = z.x * sc; if (k + 1 < K) numH[t * K + k + 1] = z.y * sc; }
     }
 }
 
-// Yf[f][bc][co][n] fp32 (a chunk of nbc blocks starting at block b0) -> partial[bc * gridDim.y + blockIdx.y] =
+// Yf[f][bc][co][n] fp32 (a chunk of nbc blocks starting at block b0) -> partial[bc * ceil(N/32) + unit tile] =
 // sum over the V exact samples of the block and the CTA's 32 units of (Xhat - X)^2.  Block b covers the columns
 // [b*V - (L-1), b*V - (L-1) + B) of H, so sample i >= L-1 of the inverse transform is Xhat at t = b*V + i - (L-1).
-// grid (nbc, ceil(N/32)).
-__global__ void __launch_bounds__(NT, 3)
+// grid nbc * ceil(N/32) (1-D).
+__global__ void __launch_bounds__(NT, CMF_FD_MINB)
 ifft_resid_kernel(const float *__restrict__ Yf, const float *__restrict__ X, double *__restrict__ partial, int64_t N, int64_t Tl,
                   int64_t L, int B, int logB, int V, int64_t nbc, int64_t b0) {
     extern __shared__ float2 fd_smem[];
     __shared__ double red[NT / 32];
     constexpr int C = 16;
     float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;
-    const int64_t bc = blockIdx.x;
+    const int ny = (int)((N + 31) / 32);              // 1-D grid, unit tile fastest
+    const int64_t bc = blockIdx.x / ny;
+    const int by = blockIdx.x % ny;
     const int p = threadIdx.x % C;
-    const int64_t n = (int64_t)blockIdx.y * 32 + 2 * p;
+    const int64_t n = (int64_t)by * 32 + 2 * p;
     make_twiddles(tw, B);
-    for (int f = threadIdx.x / C; f <= B / 2; f += NT / C) {
-        float2 re = make_float2(0.f, 0.f), im = re;
-        if (n < N) {
-            const float *y = Yf + (((int64_t)f * nbc + bc) * 2) * N + n;
-            re = *reinterpret_cast<const float2 *>(y);
-            im = *reinterpret_cast<const float2 *>(y + N);
+    {
+        const int f0 = threadIdx.x / C, fstep = NT / C;
+        const float *y = Yf + (((int64_t)f0 * nbc + bc) * 2) * N + n;
+        for (int f = f0; f <= B / 2; f += 4 * fstep, y += (int64_t)4 * fstep * nbc * 2 * N) {
+            float2 re[4], im[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                re[u] = make_float2(0.f, 0.f); im[u] = re[u];
+                if (f + u * fstep <= B / 2 && n < N) {
+                    const float *q = y + (int64_t)u * fstep * nbc * 2 * N;
+                    re[u] = *reinterpret_cast<const float2 *>(q); im[u] = *reinterpret_cast<const float2 *>(q + N);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (f + u * fstep <= B / 2) pack_pair(d, f + u * fstep, B, C, p, re[u], im[u]);
         }
-        pack_pair(d, f, B, C, p, re, im);
     }
     __syncthreads();
     fft_passes<true>(d, tw, B, logB, C);
     const float sc = 1.0f / (float)B;
-    float acc = 0.f;
     double accd = 0.0;
     if (n < N) {
-        int cnt = 0;
-        for (int i = (int)(L - 1) + threadIdx.x / C; i < B; i += NT / C) {
-            const int64_t t = (b0 + bc) * V + (i - (L - 1));
-            if (t >= Tl) break;
-            const float2 z = d[rev(i, logB) * C + p];
-            const float2 x = *reinterpret_cast<const float2 *>(X + t * N + n);
-            const float r0 = z.x * sc - x.x, r1 = z.y * sc - x.y;
-            acc = fmaf(r0, r0, acc);
-            acc = fmaf(r1, r1, acc);
-            if (++cnt == 8) { accd += (double)acc; acc = 0.f; cnt = 0; }
+        // rows of this thread: i = L-1 + i0 + m*istep; the X loads of 8 rows go out together, their squares are summed in fp32
+        // and every group of 8 rows is added to the fp64 accumulator (same grouping as before)
+        const int istep = NT / C;
+        const int64_t tb = (b0 + bc) * V - (L - 1);
+        for (int i = (int)(L - 1) + threadIdx.x / C; i < B; i += LD_U * istep) {
+            float2 x[LD_U];
+#pragma unroll
+            for (int u = 0; u < LD_U; ++u) {
+                const int ii = i + u * istep;
+                x[u] = make_float2(0.f, 0.f);
+                if (ii < B && tb + ii < Tl) x[u] = *reinterpret_cast<const float2 *>(X + (tb + ii) * N + n);
+            }
+            float acc = 0.f;
+#pragma unroll
+            for (int u = 0; u < LD_U; ++u) {
+                const int ii = i + u * istep;
+                if (ii < B && tb + ii < Tl) {
+                    const float2 z = d[rev(ii, logB) * C + p];
+                    const float r0 = z.x * sc - x[u].x, r1 = z.y * sc - x[u].y;
+                    acc = fmaf(r0, r0, acc);
+                    acc = fmaf(r1, r1, acc);
+                }
+            }
+            accd += (double)acc;
         }
     }
-    accd += (double)acc;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) accd += __shfl_xor_sync(0xffffffffu, accd, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = accd;
@@ -364,14 +438,14 @@ ifft_resid_kernel(const float *__restrict__ Yf, const float *__restrict__ X, dou
     if (threadIdx.x == 0) {
         double s = 0.0;
         for (int w = 0; w < NT / 32; ++w) s += red[w];
-        partial[bc * gridDim.y + blockIdx.y] = s;
+        partial[bc * ny + by] = s;
     }
 }
 
 // Df[f][m][n] fp32 (row stride ldi) -> out[(l*K+k)*N + n], l < L.  grid (ceil(N/32), K).
 // OutT = float: numW (N even, paired stores);  OutT = double: the Gram partial Rg[d][k][k'] with N = K.
 template <typename OutT>
-__global__ void __launch_bounds__(NT, 3)
+__global__ void __launch_bounds__(NT, CMF_FD_MINB)
 ifft_numW_kernel(const float *__restrict__ Df, OutT *__restrict__ out, int64_t N, int64_t ldi, int64_t K, int64_t L, int B, int logB,
                  int kq) {
     const int64_t KQ = kq, MROWS = 2 * kq;
@@ -382,13 +456,23 @@ ifft_numW_kernel(const float *__restrict__ Df, OutT *__restrict__ out, int64_t N
     const int p = threadIdx.x % C;
     const int64_t n = (int64_t)blockIdx.x * 32 + 2 * p;
     make_twiddles(tw, B);
-    for (int f = threadIdx.x / C; f <= B / 2; f += NT / C) {
-        float2 re = make_float2(0.f, 0.f), im = re;
-        if (n < N) {
-            re = *reinterpret_cast<const float2 *>(Df + ((int64_t)f * MROWS + k) * ldi + n);
-            im = *reinterpret_cast<const float2 *>(Df + ((int64_t)f * MROWS + KQ + k) * ldi + n);
+    {
+        const int f0 = threadIdx.x / C, fstep = NT / C;
+        for (int f = f0; f <= B / 2; f += 4 * fstep) {
+            float2 re[4], im[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int ff = f + u * fstep;
+                re[u] = make_float2(0.f, 0.f); im[u] = re[u];
+                if (ff <= B / 2 && n < N) {
+                    re[u] = *reinterpret_cast<const float2 *>(Df + ((int64_t)ff * MROWS + k) * ldi + n);
+                    im[u] = *reinterpret_cast<const float2 *>(Df + ((int64_t)ff * MROWS + KQ + k) * ldi + n);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (f + u * fstep <= B / 2) pack_pair(d, f + u * fstep, B, C, p, re[u], im[u]);
         }
-        pack_pair(d, f, B, C, p, re, im);
     }
     __syncthreads();
     fft_passes<true>(d, tw, B, logB, C);
