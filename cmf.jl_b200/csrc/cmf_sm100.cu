@@ -464,6 +464,8 @@ struct Ctx : cmf_ctx {
         }
         return 16;
     }
+    // scheduling order of the 1-D grids of the transforms: 0 = tile index fastest, block count = block index fastest (CMF_FD_ORDER=1)
+    int64_t fd_order(int64_t nblocks) const { static const int o = getenv("CMF_FD_ORDER") ? atoi(getenv("CMF_FD_ORDER")) : 0; return o ? nblocks : 0; }
     size_t fd_smem(int C) const { return ((size_t)fds.B * (size_t)C + (size_t)fds.B) * sizeof(float2); }   // tile + full-circle twiddle table
 
     void fd_build_X() {
@@ -471,7 +473,7 @@ struct Ctx : cmf_ctx {
             FdState &f = fds;
             if (!f.x_dirty) return;
             dim3 grid((unsigned)(f.nblkp * cdiv(N, 32)));
-            fd::fft_x_kernel<<<grid, fd::NT, fd_smem(16), stream>>>(X.p, f.Xf_hi.p, f.Xf_lo.p, N, Tl + (L - 1), f.B, f.logB, f.V, f.nblkp);
+            fd::fft_x_kernel<<<grid, fd::NT, fd_smem(16), stream>>>(X.p, f.Xf_hi.p, f.Xf_lo.p, N, Tl + (L - 1), f.B, f.logB, f.V, f.nblkp, fd_order(f.nblkp));
             post_launch();
             f.x_dirty = false;
         }
@@ -520,7 +522,7 @@ struct Ctx : cmf_ctx {
             tc::tc_kernel<tc::TC_FQT><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(f.mAc[0], f.mAc[1], f.mHf2K[0], f.mHf2K[1], q);
             post_launch();
             fd::ifft_numH_kernel<<<(unsigned)(f.nblk2 * (f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
-                f.Of.p, denH.p, K, Tl, f.B, f.logB, f.V2, f.nblk2, C, f.Kq);
+                f.Of.p, denH.p, K, Tl, f.B, f.logB, f.V2, f.nblk2, C, f.Kq, fd_order(f.nblk2));
             post_launch();
         }
     }
@@ -532,7 +534,7 @@ struct Ctx : cmf_ctx {
             if (!fd_active() || f.hf2_valid) return;
             const int C = fd_cols_h();
             fd::fft_h_kernel<<<(unsigned)(f.nblk2 * (f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
-                H, f.Hf_hi.p, f.Hf_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V2, f.nblk2, C, 1, -(L - 1), f.Kq);
+                H, f.Hf_hi.p, f.Hf_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V2, f.nblk2, C, 1, -(L - 1), f.Kq, fd_order(f.nblk2));
             post_launch();
             f.hf2_valid = true;
         }
@@ -573,7 +575,7 @@ struct Ctx : cmf_ctx {
             }
             const int C = fd_cols_h();
             fd::fft_h_kernel<<<(unsigned)(f.nblk * (f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
-                H, f.Hf_hi.p, f.Hf_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V, f.nblk, C, 1, -(L - 1), f.Kq);
+                H, f.Hf_hi.p, f.Hf_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V, f.nblk, C, 1, -(L - 1), f.Kq, fd_order(f.nblk));
             post_launch();
             prof_begin(PROF_CONV);
             for (int64_t b0 = 0; b0 < f.nblk; b0 += f.nbc) {
@@ -590,7 +592,7 @@ struct Ctx : cmf_ctx {
                 tc::tc_kernel<tc::TC_FQX><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(f.mAwm[0], f.mAwm[1], f.mHcK[0], f.mHcK[1], q);
                 post_launch();
                 fd::ifft_resid_kernel<<<(unsigned)(cur * ntile32), fd::NT, fd_smem(16), stream>>>(
-                    f.Yf.p, X.p, loss_part.p + b0 * ntile32, N, Tl, L, f.B, f.logB, f.V, cur, b0);
+                    f.Yf.p, X.p, loss_part.p + b0 * ntile32, N, Tl, L, f.B, f.logB, f.V, cur, b0, fd_order(cur));
                 post_launch();
             }
             prof_end();
@@ -605,7 +607,7 @@ struct Ctx : cmf_ctx {
             if (!f.h_dirty) return;
             const int C = fd_cols_h();
             fd::fft_h_kernel<<<(unsigned)(f.nblkp * (f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
-                H, f.Ah_hi.p, f.Ah_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V, f.nblkp, C, 0, 0, f.Kq);
+                H, f.Ah_hi.p, f.Ah_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V, f.nblkp, C, 0, 0, f.Kq, fd_order(f.nblkp));
             post_launch();
             f.h_dirty = false;
         }
@@ -618,7 +620,7 @@ struct Ctx : cmf_ctx {
             fd_spectrum_H();
             const int C = fd_cols_h();
             fd::fft_h_kernel<<<(unsigned)(f.nblkp * (f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
-                H, f.Hf_hi.p, f.Hf_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V, f.nblkp, C, 1, 0, f.Kq);
+                H, f.Hf_hi.p, f.Hf_lo.p, K, Tl, Tl + (L - 1), f.B, f.logB, f.V, f.nblkp, C, 1, 0, f.Kq, fd_order(f.nblkp));
             post_launch();
             tc::Params q = tc_base_params();
             q.nprod = 3;
@@ -658,7 +660,7 @@ struct Ctx : cmf_ctx {
             post_launch();
             const int C = fd_cols_h();
             fd::ifft_numH_kernel<<<(unsigned)(f.nblk * (f.Kq / 2 / C)), fd::NT, fd_smem(C), stream>>>(
-                f.Of.p, numH.p, K, Tl, f.B, f.logB, f.V, f.nblkp, C, f.Kq);
+                f.Of.p, numH.p, K, Tl, f.B, f.logB, f.V, f.nblkp, C, f.Kq, fd_order(f.nblk));
             post_launch();
         }
     }

@@ -167,15 +167,15 @@ __device__ __forceinline__ void store_split2(__nv_bfloat16 *hi, __nv_bfloat16 *l
 // X[t][N] fp32 (xcols rows) -> Xf.  grid nblkp * ceil(N/32) (1-D); 16 complex columns = 32 units per CTA.
 __global__ void __launch_bounds__(NT, CMF_FD_MINB)
 fft_x_kernel(const float *__restrict__ X, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int64_t N, int64_t xcols,
-             int B, int logB, int V, int64_t nblkp) {
+             int B, int logB, int V, int64_t nblkp, int64_t nbx) {
     extern __shared__ float2 fd_smem[];
     constexpr int C = 16;
     float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;
-    // 1-D grid, unit tile fastest: CTAs that run together read neighbouring 128-byte pieces of the same rows of X
+    // 1-D grid over (block, unit tile); nbx = number of blocks when the block index runs fastest, 0 = the tile index runs fastest
     const int ny = (int)((N + 31) / 32);
-    const int64_t b = blockIdx.x / ny;
+    const int64_t b = nbx ? blockIdx.x % nbx : blockIdx.x / ny;
     const int p = threadIdx.x % C;
-    const int64_t n = (int64_t)(blockIdx.x % ny) * 32 + 2 * p;
+    const int64_t n = (int64_t)(nbx ? blockIdx.x / nbx : blockIdx.x % ny) * 32 + 2 * p;
     make_twiddles(tw, B);
     {
         // LD_U rows per thread are requested before any is stored: the transforms are bound by the latency of these loads, not by
@@ -214,14 +214,14 @@ fft_x_kernel(const float *__restrict__ X, __nv_bfloat16 *__restrict__ hi, __nv_b
 // grid nblkp * (kq / 2 / C) (1-D); C complex columns = 2C components per CTA.
 __global__ void __launch_bounds__(NT, CMF_FD_MINB)
 fft_h_kernel(const float *__restrict__ H, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int64_t K, int64_t Tl,
-             int64_t hcols, int B, int logB, int V, int64_t nblkp, int C, int full, int64_t t_off, int kq) {
+             int64_t hcols, int B, int logB, int V, int64_t nblkp, int C, int full, int64_t t_off, int kq, int64_t nbx) {
     const int64_t KQ = kq, MROWS = 2 * kq;
     extern __shared__ float2 fd_smem[];
     float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;
-    const int ny = (kq / 2) / C;                      // 1-D grid, component tile fastest (the tiles of one block share its rows of H)
-    const int64_t b = blockIdx.x / ny;
+    const int ny = (kq / 2) / C;                      // 1-D grid over (block, component tile); nbx as in fft_x_kernel
+    const int64_t b = nbx ? blockIdx.x % nbx : blockIdx.x / ny;
     const int p = threadIdx.x % C;
-    const int k = 2 * ((int)(blockIdx.x % ny) * C + p);
+    const int k = 2 * ((int)(nbx ? blockIdx.x / nbx : blockIdx.x % ny) * C + p);
     make_twiddles(tw, B);
     {
         const int i0 = threadIdx.x / C, istep = NT / C;
@@ -327,14 +327,14 @@ fft_w_kernel(const float *__restrict__ Wi, __nv_bfloat16 *__restrict__ hi, __nv_
 // Of[f][b][m] fp32 -> numH[t][K] (owned columns; V valid outputs per block).  grid nblk * (kq / 2 / C) (1-D).
 __global__ void __launch_bounds__(NT, CMF_FD_MINB)
 ifft_numH_kernel(const float *__restrict__ Of, float *__restrict__ numH, int64_t K, int64_t Tl, int B, int logB, int V,
-                 int64_t nblkp, int C, int kq) {
+                 int64_t nblkp, int C, int kq, int64_t nbx) {
     const int64_t KQ = kq, MROWS = 2 * kq;
     extern __shared__ float2 fd_smem[];
     float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;
-    const int ny = (kq / 2) / C;                      // 1-D grid, component tile fastest (the tiles of one block share its rows of H)
-    const int64_t b = blockIdx.x / ny;
+    const int ny = (kq / 2) / C;                      // 1-D grid over (block, component tile); nbx as in fft_x_kernel
+    const int64_t b = nbx ? blockIdx.x % nbx : blockIdx.x / ny;
     const int p = threadIdx.x % C;
-    const int k = 2 * ((int)(blockIdx.x % ny) * C + p);
+    const int k = 2 * ((int)(nbx ? blockIdx.x / nbx : blockIdx.x % ny) * C + p);
     make_twiddles(tw, B);
     {
         const int f0 = threadIdx.x / C, fstep = NT / C;
@@ -371,14 +371,14 @@ ifft_numH_kernel(const float *__restrict__ Of, float *__restrict__ numH, int64_t
 // grid nbc * ceil(N/32) (1-D).
 __global__ void __launch_bounds__(NT, CMF_FD_MINB)
 ifft_resid_kernel(const float *__restrict__ Yf, const float *__restrict__ X, double *__restrict__ partial, int64_t N, int64_t Tl,
-                  int64_t L, int B, int logB, int V, int64_t nbc, int64_t b0) {
+                  int64_t L, int B, int logB, int V, int64_t nbc, int64_t b0, int64_t nbx) {
     extern __shared__ float2 fd_smem[];
     __shared__ double red[NT / 32];
     constexpr int C = 16;
     float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;
-    const int ny = (int)((N + 31) / 32);              // 1-D grid, unit tile fastest
-    const int64_t bc = blockIdx.x / ny;
-    const int by = blockIdx.x % ny;
+    const int ny = (int)((N + 31) / 32);              // 1-D grid over (block, unit tile); nbx as in fft_x_kernel
+    const int64_t bc = nbx ? blockIdx.x % nbx : blockIdx.x / ny;
+    const int by = (int)(nbx ? blockIdx.x / nbx : blockIdx.x % ny);
     const int p = threadIdx.x % C;
     const int64_t n = (int64_t)by * 32 + 2 * p;
     make_twiddles(tw, B);
