@@ -317,6 +317,7 @@ def run_ours(args, cfg, name):
     ms_per_step = ms / args.steps
     value = 1e3 / ms_per_step
     engine = shard.get_engine()
+    fd_layout = shard.fd_layout()
 
     # secondary: the same iteration with the loss evaluated by the direct conv + residual pass (mult.jl:55-57 literally)
     value_direct = None
@@ -449,19 +450,16 @@ def run_ours(args, cfg, name):
         # frequency-domain engine: the dominant kernel streams the spectrum of X once per launch and is HBM-bound.
         # Algorithmic bytes per launch (one contraction): X once + the small operand + the output,
         # in fp32; the bytes actually moved are the bf16 hi/lo spectrum planes (B/V * (B/2+1)/(B/2) ~ 1.25x of X).
-        Bfft = 64
-        while Bfft < 4 * L:
-            Bfft *= 2
-        V, F = Bfft - L + 1, Bfft // 2 + 1
-        nblkp = -(-(-(-Tl // V)) // 16) * 16
+        Bfft, V, nblkp = fd_layout             # asked from the library (cmf_get_fd_layout) before the handle was closed
+        F = Bfft // 2 + 1
         alg_bytes = 4.0 * (N * Tl + K * Tl + K * N * L)
         moved_bytes = 4.0 * F * nblkp * 2 * N
         exec_flops = 3.0 * 2.0 * 128 * (2 * N) * nblkp * F
         achieved_gbs = alg_bytes / (per_launch_ms * 1e-3) / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture of this workload
         traffic, traffic_note = None, "no ncu capture for this workload / kernel"
-        if name == "c4" and world == 1 and dom in NCU_TRAFFIC_C4_FD:
-            traffic, traffic_note = NCU_TRAFFIC_C4_FD[dom]
+        if name == "c4" and world == 1 and (dom, Bfft) in NCU_TRAFFIC_C4_FD:
+            traffic, traffic_note = NCU_TRAFFIC_C4_FD[(dom, Bfft)]
         roofline = {
             "bound": "hbm", "kernel": dom + (" (TC_FQT: per-frequency conj(W^) X^)" if dom == "transconv" else " (TC_FQC: per-frequency conj(H^) X^)"),
             "achieved": achieved_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved_gbs / pk["hbm"],
@@ -560,9 +558,9 @@ def _tensor_roofline(name, world, dom, engine, achieved_tf, pk, Fc_rank, per_lau
 
 # per-launch DRAM traffic of the frequency-domain kernels at c4 on one GPU, from `ncu --set full` (profiles/); filled per round
 NCU_TRAFFIC_C4_FD = {
-    "transconv": (89.76e9, "ncu --set full, c4, 1 GPU, per launch: 88.42 GB read + 1.34 GB written vs 85.56 GB of spectrum planes + 1.08 GB "
+    ("transconv", 512): (89.76e9, "ncu --set full, c4, 1 GPU, per launch: 88.42 GB read + 1.34 GB written vs 85.56 GB of spectrum planes + 1.08 GB "
                            "operand that must be read and 69.9 GB algorithmic; profiles/r1_ncu_full_fd_kernels.md"),
-    "corr": (90.11e9, "ncu --set full, c4, 1 GPU, per launch: 89.57 GB read + 0.54 GB written vs 85.56 GB of spectrum planes + 2.67 GB "
+    ("corr", 512): (90.11e9, "ncu --set full, c4, 1 GPU, per launch: 89.57 GB read + 0.54 GB written vs 85.56 GB of spectrum planes + 2.67 GB "
                       "operand that must be read and 69.9 GB algorithmic; profiles/r1_ncu_full_fd_kernels.md"),
 }
 

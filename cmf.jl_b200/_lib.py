@@ -55,6 +55,7 @@ SIGNATURES = {
     "cmf_set_stream": [_h, _vp],
     "cmf_set_engine": [_h, _int],
     "cmf_get_engine": [_h, _c.POINTER(_int)],
+    "cmf_get_fd_layout": [_h, _c.POINTER(_int), _c.POINTER(_int), _c.POINTER(_i64)],
     "cmf_set_loss_mode": [_h, _int],
     "cmf_get_loss_mode": [_h, _c.POINTER(_int)],
     "cmf_set_loss_guard": [_h, _dbl, _int],

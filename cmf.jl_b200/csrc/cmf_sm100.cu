@@ -174,6 +174,7 @@ struct cmf_ctx {
     virtual void hals_h_full(void **, void **) { no_multi(); }     // rank 0 of a sharded fit: full-T Q and H buffers (allocated on first use)
     virtual void hals_h_sweep(int full, double, double) { no_multi(); }
     virtual void h_changed() { no_multi(); }                       // invalidates what depends on H (after a halo exchange / scatter)
+    virtual void fd_layout(int *, int *, int64_t *) { no_multi(); }
     virtual void set_pgd_loss(int, const void *) { no_multi(); }
     virtual void set_pgd_constraints(int, int) { no_multi(); }
     virtual void pgd_update_motifs(double, double) { no_multi(); }
@@ -374,6 +375,9 @@ struct Ctx : cmf_ctx {
         return fds.ok;
     }
     void fd_release() override { fds.release(); }
+    void fd_layout(int *B, int *V, int64_t *nblk) override {
+        *B = fd_active() ? fds.B : 0; *V = fd_active() ? fds.V : 0; *nblk = fd_active() ? fds.nblkp : 0;
+    }
     void mark_w_dirty() { tcs.w_dirty = true; fds.w_dirty = true; fds.wx_dirty = true; }
 
     // ---------------------------------------------------------------- frequency-domain engine (fp32, K <= 64, L <= 256)
@@ -385,7 +389,12 @@ struct Ctx : cmf_ctx {
             if (K > fd::KQ_MAX || L > 256 || N < 16) { f.why = "needs K <= 128, L <= 256, N >= 16"; return; }
             f.Kq = (K <= 64) ? 64 : 128;
             f.MR = 2 * f.Kq;
+            // block length: the smallest power of two >= 8L, at most 1024 (>= 4L always: L <= 256).  A/B on B200 with the round-2
+            // transforms, same box: c4 (L = 100) 512 -> 45.9 ms, 1024 -> 43.2 ms per iteration; c3 (L = 50) 256 -> 3.86, 512 -> 3.48,
+            // 1024 -> 3.92 ms: the products move and multiply (B / V)(F / (B/2)) ~ 1.24 / 1.11 / 1.05 times the size of X at
+            // B = 4L.. / 8L.. / 16L.., the transforms get longer
             int B0 = 64;
+            while (B0 < 8 * L && B0 < 1024) B0 *= 2;
             while (B0 < 4 * L) B0 *= 2;
             int forced = 0;
             if (const char *e = getenv("CMF_FD_B")) {
@@ -401,8 +410,8 @@ struct Ctx : cmf_ctx {
             if (alg == CMF_HALS) later += (size_t)2 * (size_t)(Tl + 2048) * (size_t)K * 4 + (size_t)hals2::RING * (size_t)cdiv(K, hals2::GS) * (size_t)K * hals2::CW * 4;
             size_t xf = 0, ah = 0, aw = 0, of = 0, df = 0, hf = 0, gf = 0, ac = 0;
             bool fits = false;
-            // smallest power of two >= 4L first (fastest FFT kernels); the next one moves fewer bytes (hop / length grows), so it
-            // is the fallback when the first does not fit beside the data
+            // the next power of two moves fewer bytes still (hop / length grows), so it is the fallback when the first choice does
+            // not fit beside the data
             for (int B = forced ? forced : B0; B <= (forced ? forced : std::min(2 * B0, 1024)); B *= 2) {
                 int logB = 0;
                 while ((1 << logB) < B) ++logB;
@@ -462,7 +471,7 @@ struct Ctx : cmf_ctx {
             const int c = atoi(e);
             if ((c == 8 || c == 16 || c == 32) && (size_t)fds.B * (size_t)c * sizeof(float2) <= 160 * 1024) return c;
         }
-        return 16;
+        return fds.B >= 1024 ? 8 : 16;          // tiles of <= 64 KB + twiddles: three CTAs per SM (c4 at B = 1024: 44.96 -> 43.23 ms)
     }
     // scheduling order of the 1-D grids of the transforms: 0 = tile index fastest, block count = block index fastest (CMF_FD_ORDER=1)
     int64_t fd_order(int64_t nblocks) const { static const int o = getenv("CMF_FD_ORDER") ? atoi(getenv("CMF_FD_ORDER")) : 0; return o ? nblocks : 0; }
@@ -2583,6 +2592,13 @@ int cmf_get_loss_stats(cmf_handle h, int64_t *n_direct, int64_t *n_expansion, in
 }
 int cmf_get_loss_mode(cmf_handle h, int *mode_out) {
     return guarded([&] { REQUIRE(h && mode_out, "null argument"); *mode_out = rank0(h)->loss_mode; });
+}
+int cmf_get_fd_layout(cmf_handle h, int *block_len, int *hop, int64_t *nblocks) {
+    return guarded([&] {
+        REQUIRE(h && block_len && hop && nblocks, "null argument");
+        cmf_ctx *r = rank0(h);
+        r->fd_layout(block_len, hop, nblocks);
+    });
 }
 int cmf_get_engine(cmf_handle h, int *engine_out) {
     return guarded([&] { REQUIRE(h && engine_out, "null argument"); *engine_out = rank0(h)->engine; });

@@ -155,6 +155,12 @@ class DeviceShard:
         check(_lib.load().cmf_get_loss_mode(self._h, ctypes.byref(out)))
         return out.value
 
+    def fd_layout(self):
+        """(block length, hop, blocks) of the frequency-domain engine on this handle; zeros on the other engines."""
+        b, v, n = ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()
+        check(_lib.load().cmf_get_fd_layout(self._h, ctypes.byref(b), ctypes.byref(v), ctypes.byref(n)))
+        return b.value, v.value, n.value
+
     def get_engine(self):
         out = ctypes.c_int()
         check(_lib.load().cmf_get_engine(self._h, ctypes.byref(out)))

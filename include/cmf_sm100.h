@@ -206,7 +206,7 @@ int cmf_profile_read(cmf_handle h, int which, double *ms_total, int64_t *count);
  * time domain (fp32 data, split-bf16 operands, K <= 128, N % 8 == 0); 2 = frequency-domain engine: numW
  * (mult.jl:32) and numH (mult.jl:47) through the overlap-save spectrum of X (computed once per data set, the
  * circular-convolution idea of src/common.jl:36-50 made exact) with the per-frequency complex products on
- * tcgen05 -- HBM-bound instead of tensor-bound (fp32, K <= 128, L <= 256, room for ~1.25x the size of X in
+ * tcgen05 -- HBM-bound instead of tensor-bound (fp32, K <= 128, L <= 256, room for ~1.1-1.25x the size of X in
  * bf16 hi/lo planes; the time-domain planes of engine 1 are released).  Returns CMF_ERR_UNSUPPORTED when the
  * handle cannot use the engine.  Default: best available (2 for large problems with L >= 8, else 1, else 0). */
 int cmf_set_engine(cmf_handle h, int engine);
@@ -231,6 +231,10 @@ int cmf_set_loss_guard(cmf_handle h, double guard, int max_interval);
 /* Loss evaluations so far by the direct pass and by the expansion, the calibration interval in force (0 = not in the
  * calibrated regime) and the relative error of the last checked prediction.  Any output pointer may be NULL. */
 int cmf_get_loss_stats(cmf_handle h, int64_t *n_direct, int64_t *n_expansion, int *interval, double *last_err);
+/* Overlap-save layout of the frequency-domain engine on this handle (first rank of a group): block length B (the smallest
+ * power of two >= 8L, at most 1024, the next one when memory is short; CMF_FD_B overrides), hop V = B - L + 1 and the number of
+ * blocks (padded to a multiple of 16) whose spectrum the two data-sized products stream.  Zeros when engine 2 is not in force. */
+int cmf_get_fd_layout(cmf_handle h, int *block_len, int *hop, int64_t *nblocks);
 /* The engine currently selected (0 / 1 / 2). */
 int cmf_get_engine(cmf_handle h, int *engine_out);
 
