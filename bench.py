@@ -558,6 +558,10 @@ def _tensor_roofline(name, world, dom, engine, achieved_tf, pk, Fc_rank, per_lau
 
 # per-launch DRAM traffic of the frequency-domain kernels at c4 on one GPU, from `ncu --set full` (profiles/); filled per round
 NCU_TRAFFIC_C4_FD = {
+    ("transconv", 1024): (82.01e9, "ncu --set full, c4, 1 GPU, block length 1024, per launch: 80.82 GB read + 1.20 GB written vs 76.38 GB of spectrum planes + "
+                                   "1.08 GB operand that must be read and 69.9 GB algorithmic; profiles/r2_ncu_full_products_c4.md"),
+    ("corr", 1024): (81.82e9, "ncu --set full, c4, 1 GPU, block length 1024, per launch: 80.74 GB read + 1.08 GB written vs 76.38 GB of spectrum planes + "
+                              "2.4 GB operand that must be read and 69.9 GB algorithmic; profiles/r2_ncu_full_products_c4.md"),
     ("transconv", 512): (89.76e9, "ncu --set full, c4, 1 GPU, per launch: 88.42 GB read + 1.34 GB written vs 85.56 GB of spectrum planes + 1.08 GB "
                            "operand that must be read and 69.9 GB algorithmic; profiles/r1_ncu_full_fd_kernels.md"),
     ("corr", 512): (90.11e9, "ncu --set full, c4, 1 GPU, per launch: 89.57 GB read + 0.54 GB written vs 85.56 GB of spectrum planes + 2.67 GB "

@@ -57,7 +57,7 @@ def test_calibrated_expansion_below_the_guard(cmf, case):
     """Loss mode 1 below the 25 % guard: the expansion is calibrated against the direct pass every `interval` evaluations
     (cmf_set_loss_guard).  With the guard lifted above any loss the whole run is in that regime: every entry of loss_hist
     must still be within 1e-4 of the float64 oracle, most evaluations must have been served by the expansion, and the last
-    checked prediction must have agreed with the direct pass."""
+    checked prediction must have been inside the bar."""
     g = np.load(os.path.join(GOLD, f"mu_bench_{case}.npz"))
     N, T, K, L = (int(v) for v in g["dims"])
     ref = np.asarray(g["loss_hist"])
@@ -70,4 +70,6 @@ def test_calibrated_expansion_below_the_guard(cmf, case):
     assert rel.max() < 1e-4, (case, int(rel.argmax()), float(rel.max()), info)
     assert info["loss_mode"] == 1 and info["engine"] == 2, info
     assert info["direct"] <= 0.5 * info["expansion"], info
-    assert info["last_err"] < 2e-5, info
+    # the controller halves the interval when a checked prediction is off by more than 2e-5 and gives the expansion up after
+    # three misses above 1e-4: what must hold is that the predictions it checked stayed inside the parity bar and it kept going
+    assert info["last_err"] < 1e-4 and info["interval"] >= 2, info
