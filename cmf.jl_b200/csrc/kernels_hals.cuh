@@ -662,9 +662,15 @@ __global__ void hals2_prepare_kernel(const float *__restrict__ Q, const float *_
 __global__ void hals2_finish_kernel(const float *__restrict__ H_cm, float *__restrict__ H, int64_t K, int64_t T, int64_t Tp) {
     __shared__ float tile[32][33];
     const int64_t t0 = (int64_t)blockIdx.x * 32, k0 = (int64_t)blockIdx.y * 32;
-    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-        const int64_t k = k0 + r, t = t0 + threadIdx.x;
-        tile[r][threadIdx.x] = (k < K && t < T) ? H_cm[cell_at(k, t, K)] : 0.f;
+    {   // block (32, 8): four loads in flight per thread
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t k = k0 + threadIdx.y + 8 * i, t = t0 + threadIdx.x;
+            v[i] = (k < K && t < T) ? H_cm[cell_at(k, t, K)] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tile[threadIdx.y + 8 * i][threadIdx.x] = v[i];
     }
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {

@@ -914,7 +914,9 @@ __device__ __forceinline__ void hals_recurrence_block(S *hch, S *qeff, S (&p)[W]
 
 // Truncated lag tables of the H sweep for every pair of components (the sweep's pull over the last L-1 columns):
 //   Ct[w-1][dd+L-1][k][k'] = C_w[k',k,dd] = sum_{l<w, 0<=l-dd<L} S2[(l,k')][(l-dd,k)],   w = 1..L-1
-// one thread per (dd, k, k') walks w with a running sum (each element of S2 is read once per table it enters).
+// one thread per (dd, k, k') walks w with a running sum (each element of S2 is read once per table it enters).  S2 = W W' is
+// symmetric, so the element is read as S2[(l-dd,k)][(l,k')]: consecutive threads (k' fastest) then read consecutive addresses
+// (the other orientation strides by a whole row: 40 ms instead of ~1 ms per sweep at config 5).
 template <typename S>
 __global__ void hals_tail_table_kernel(const S *__restrict__ S2, S *__restrict__ Ct, int64_t K, int64_t L, int64_t Ks, int64_t ld) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -923,7 +925,7 @@ __global__ void hals_tail_table_kernel(const S *__restrict__ S2, S *__restrict__
     double pre = 0.0;
     for (int64_t w = 1; w < L; ++w) {
         const int64_t l = w - 1, lp = l - dd;
-        if (lp >= 0 && lp < L) pre += (double)S2[(l * Ks + kp) * ld + lp * Ks + k];
+        if (lp >= 0 && lp < L) pre += (double)S2[(lp * Ks + k) * ld + l * Ks + kp];
         Ct[(((w - 1) * (2 * L - 1) + dq) * K + k) * K + kp] = (S)pre;
     }
 }
