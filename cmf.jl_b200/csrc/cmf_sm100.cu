@@ -396,6 +396,17 @@ struct Ctx : cmf_ctx {
             int B0 = 64;
             while (B0 < 8 * L && B0 < 1024) B0 *= 2;
             while (B0 < 4 * L) B0 *= 2;
+            // ... unless this shard is so short that the longer block only adds padding: the numH product works on tiles of 256
+            // blocks, so its work goes like F * 256 * ceil(blocks / 256), the numW product's like F * blocks.  A rank of an
+            // 8-GPU c4 fit (524288 columns) has 1270 blocks of 512 (5 tiles, 1 % padding) or 567 blocks of 1024 (3 tiles, 26 %
+            // padding): the shorter block is kept when the longer one does not win at least 3 % on that count.
+            if (B0 / 2 >= 4 * L && B0 / 2 >= 64) {
+                auto work = [&](int B) {
+                    const int64_t nb = cdiv(Tl, (int64_t)(B - (int)L + 1));
+                    return (double)(B / 2 + 1) * (double)(cdiv(nb, tc::BN) * tc::BN + cdiv(nb, 16) * 16);
+                };
+                if (work(B0) > 0.97 * work(B0 / 2)) B0 /= 2;
+            }
             int forced = 0;
             if (const char *e = getenv("CMF_FD_B")) {
                 const int want = atoi(e);
