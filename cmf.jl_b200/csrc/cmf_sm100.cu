@@ -486,6 +486,8 @@ struct Ctx : cmf_ctx {
     }
     // scheduling order of the 1-D grids of the transforms: 0 = tile index fastest, block count = block index fastest (CMF_FD_ORDER=1)
     int64_t fd_order(int64_t nblocks) const { static const int o = getenv("CMF_FD_ORDER") ? atoi(getenv("CMF_FD_ORDER")) : 0; return o ? nblocks : 0; }
+    // complex columns per CTA of the W-side transforms (fft_w / ifft_numW): as for the H side, 8 at B = 1024 keeps three CTAs per SM
+    int fd_cols_w() const { return fds.B >= 1024 ? 8 : 16; }
     size_t fd_smem(int C) const { return ((size_t)fds.B * (size_t)C + (size_t)fds.B) * sizeof(float2); }   // tile + full-circle twiddle table
 
     void fd_build_X() {
@@ -516,7 +518,7 @@ struct Ctx : cmf_ctx {
             tc::tc_kernel<tc::TC_FQC><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(f.mAh[0], f.mAh[1], f.mXfMN[0], f.mXfMN[1], q);
             prof_end();
             post_launch();
-            fd::ifft_numW_kernel<float><<<dim3((unsigned)cdiv(N, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(f.Df.p, numW.p, N, N, K, L, f.B, f.logB, f.Kq);
+            fd::ifft_numW_kernel<float><<<dim3((unsigned)cdiv(N, 2 * fd_cols_w()), (unsigned)K), fd::NT, fd_smem(fd_cols_w()), stream>>>(f.Df.p, numW.p, N, N, K, L, f.B, f.logB, f.Kq, fd_cols_w());
             post_launch();
         }
     }
@@ -525,8 +527,8 @@ struct Ctx : cmf_ctx {
     void fd_denomH() {
         if constexpr (std::is_same<S, float>::value) {
             FdState &f = fds;
-            fd::fft_w_kernel<<<dim3((unsigned)cdiv(K, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(
-                Cf.p, f.Ac_hi.p, f.Ac_lo.p, K, K, 2 * L - 1, f.B, f.logB, f.MR, f.Kq, 0, f.Kq);
+            fd::fft_w_kernel<<<dim3((unsigned)cdiv(K, 2 * fd_cols_w()), (unsigned)K), fd::NT, fd_smem(fd_cols_w()), stream>>>(
+                Cf.p, f.Ac_hi.p, f.Ac_lo.p, K, K, 2 * L - 1, f.B, f.logB, f.MR, f.Kq, 0, f.Kq, fd_cols_w());
             post_launch();
             const int C = fd_cols_h();
             fd_denomH_prefetch();
@@ -589,7 +591,7 @@ struct Ctx : cmf_ctx {
             const size_t need_lp = (size_t)(f.nblk * ntile32);
             if (loss_part.n < need_lp) loss_part.alloc(std::max<size_t>(need_lp, 4096));
             if (f.wx_dirty) {
-                fd::fft_w_kernel<<<dim3((unsigned)cdiv(N, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(Wi.p, f.Awm_hi.p, f.Awm_lo.p, N, K, L, f.B, f.logB, 2 * N, N, 1, f.Kq);
+                fd::fft_w_kernel<<<dim3((unsigned)cdiv(N, 2 * fd_cols_w()), (unsigned)K), fd::NT, fd_smem(fd_cols_w()), stream>>>(Wi.p, f.Awm_hi.p, f.Awm_lo.p, N, K, L, f.B, f.logB, 2 * N, N, 1, f.Kq, fd_cols_w());
                 post_launch();
                 f.wx_dirty = false;
             }
@@ -652,7 +654,7 @@ struct Ctx : cmf_ctx {
             const unsigned grid = (unsigned)std::min<int64_t>(q.units, tcs.num_sms);
             tc::tc_kernel<tc::TC_FQC><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(f.mAh[0], f.mAh[1], f.mHfMN[0], f.mHfMN[1], q);
             post_launch();
-            fd::ifft_numW_kernel<double><<<dim3((unsigned)cdiv(K, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(f.Gf.p, exch1.p, K, f.Kq, K, L, f.B, f.logB, f.Kq);
+            fd::ifft_numW_kernel<double><<<dim3((unsigned)cdiv(K, 2 * fd_cols_w()), (unsigned)K), fd::NT, fd_smem(fd_cols_w()), stream>>>(f.Gf.p, exch1.p, K, f.Kq, K, L, f.B, f.logB, f.Kq, fd_cols_w());
             post_launch();
         }
     }
@@ -662,7 +664,7 @@ struct Ctx : cmf_ctx {
             FdState &f = fds;
             fd_build_X();
             if (f.w_dirty) {
-                fd::fft_w_kernel<<<dim3((unsigned)cdiv(N, 32), (unsigned)K), fd::NT, fd_smem(16), stream>>>(Wi.p, f.Aw_hi.p, f.Aw_lo.p, N, K, L, f.B, f.logB, 2 * N, N, 0, f.Kq);
+                fd::fft_w_kernel<<<dim3((unsigned)cdiv(N, 2 * fd_cols_w()), (unsigned)K), fd::NT, fd_smem(fd_cols_w()), stream>>>(Wi.p, f.Aw_hi.p, f.Aw_lo.p, N, K, L, f.B, f.logB, 2 * N, N, 0, f.Kq, fd_cols_w());
                 post_launch();
                 f.w_dirty = false;
             }

@@ -271,17 +271,16 @@ fft_h_kernel(const float *__restrict__ H, __nv_bfloat16 *__restrict__ hi, __nv_b
 }
 
 // Wi[(l*K+k)][N] fp32 -> Aw (rows of ldw elements, imaginary block at column coff: 2N / N for W; 128 / 64 for the
-// K x K lag table C with N = K and L = 2L-1 lags -> Ac).  grid (ceil(N/32), K).
+// K x K lag table C with N = K and L = 2L-1 lags -> Ac).  grid (ceil(N / 2C), K): C complex columns = 2C units per CTA.
 __global__ void __launch_bounds__(NT, CMF_FD_MINB)
 fft_w_kernel(const float *__restrict__ Wi, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int64_t N, int64_t K,
-             int64_t L, int B, int logB, int64_t ldw, int64_t coff, int xmode, int kq) {
+             int64_t L, int B, int logB, int64_t ldw, int64_t coff, int xmode, int kq, int C) {
     const int64_t KQ = kq, MROWS = 2 * kq;
     extern __shared__ float2 fd_smem[];
-    constexpr int C = 16;
     float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;
     const int64_t k = blockIdx.y;
     const int p = threadIdx.x % C;
-    const int64_t n = (int64_t)blockIdx.x * 32 + 2 * p;
+    const int64_t n = (int64_t)blockIdx.x * (2 * C) + 2 * p;
     make_twiddles(tw, B);
     {
         const int i0 = threadIdx.x / C, istep = NT / C;
@@ -442,19 +441,18 @@ ifft_resid_kernel(const float *__restrict__ Yf, const float *__restrict__ X, dou
     }
 }
 
-// Df[f][m][n] fp32 (row stride ldi) -> out[(l*K+k)*N + n], l < L.  grid (ceil(N/32), K).
+// Df[f][m][n] fp32 (row stride ldi) -> out[(l*K+k)*N + n], l < L.  grid (ceil(N / 2C), K).
 // OutT = float: numW (N even, paired stores);  OutT = double: the Gram partial Rg[d][k][k'] with N = K.
 template <typename OutT>
 __global__ void __launch_bounds__(NT, CMF_FD_MINB)
 ifft_numW_kernel(const float *__restrict__ Df, OutT *__restrict__ out, int64_t N, int64_t ldi, int64_t K, int64_t L, int B, int logB,
-                 int kq) {
+                 int kq, int C) {
     const int64_t KQ = kq, MROWS = 2 * kq;
     extern __shared__ float2 fd_smem[];
-    constexpr int C = 16;
     float2 *d = fd_smem, *tw = fd_smem + (size_t)B * C;
     const int64_t k = blockIdx.y;
     const int p = threadIdx.x % C;
-    const int64_t n = (int64_t)blockIdx.x * 32 + 2 * p;
+    const int64_t n = (int64_t)blockIdx.x * (2 * C) + 2 * p;
     make_twiddles(tw, B);
     {
         const int f0 = threadIdx.x / C, fstep = NT / C;

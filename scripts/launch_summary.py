@@ -31,9 +31,9 @@ def nth(key):
 
 def role(n):
     if "tc_kernel<5>" in n:
-        return ["numW: per-frequency conj(H^) X^ over the spectrum of X (streams 85.6 GB)", "Gram partial of the new H: conj(H^) H^"][min(nth("5"), 1)]
+        return ["numW: per-frequency conj(H^) X^ over the spectrum of X (streams the spectrum planes)", "Gram partial of the new H: conj(H^) H^"][min(nth("5"), 1)]
     if "tc_kernel<4>" in n:
-        return ["numH: per-frequency conj(W^) X^ (streams 85.6 GB)", "denomH: per-frequency conj(C^) H^"][min(nth("4"), 1)]
+        return ["numH: per-frequency conj(W^) X^ (streams the spectrum planes)", "denomH: per-frequency conj(C^) H^"][min(nth("4"), 1)]
     if "tc_kernel<3>" in n:
         return ["denomW = G W (plain tcgen05 GEMM)", "W W^T (plain tcgen05 GEMM)"][min(nth("3"), 1)]
     if "ifft_numW_kernel<float>" in n:
